@@ -1,0 +1,157 @@
+/*
+ * sage_splat.h — C-ABI of libsage_splat.so, the B200-native (sm_100a) 3-D Gaussian-splatting
+ * render-and-collide engine that stands behind SAGE-3D's Python render/collide surface.
+ *
+ * The reference has no FFI: its boundary is Python duck-typing at two seams.
+ * Each entry point below names the reference call it replaces (paths relative to
+ * Code/benchmark/environment_evaluation/ unless noted).  INTEGRATION.md shows the ctypes stub a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - every function returns 0 on success, non-zero on failure; sage_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *     "host" pointers are ordinary (ideally pinned) host memory;
+ *   - calls on one handle are not re-entrant; different handles may be used from different
+ *     threads;  no callbacks;  no allocation after create (sage_scene_reserve excepted);
+ *   - there is NO CPU fallback: every entry point fails loudly without a CUDA device.
+ */
+#ifndef SAGE_SPLAT_H
+#define SAGE_SPLAT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAGE_ABI_VERSION 1
+#define SAGE_TILE 16
+
+typedef struct sage_scene sage_scene;   /* device-resident Gaussian scene + frame workspace */
+typedef struct sage_grid sage_grid;     /* device-resident 2-D obstacle grid */
+typedef struct sage_bodies sage_bodies; /* device-resident collision ellipsoids */
+typedef void* sage_stream_t;
+
+/* Pinhole camera, model -> camera: p_c = R p_m + t; camera axes +x right, +y down, +z forward.
+ * Replaces the state Isaac's Camera holds after cam.set_world_pose(position, orientation)
+ * (simple_env.py:1284; data_pipeline/training_data_construction/generate_images.py:419-421),
+ * focal length 8.0 (simple_env.py:905) and clipping range (0.1, 50) (simple_env.py:899). */
+typedef struct sage_camera {
+    float R[9];      /* row-major */
+    float t[3];
+    float campos[3]; /* camera centre in model space (SH view direction) */
+    float fx, fy, cx, cy;
+    int32_t width, height;
+    float near_z, far_z;
+} sage_camera;
+
+/* Device-side counters of the last frame rendered on a scene. */
+typedef struct sage_frame_stats {
+    int64_t n_gaussians;      /* N */
+    int64_t n_visible;        /* V: survivors of the cull */
+    int64_t n_instances;      /* D: (tile, Gaussian) pairs */
+    int64_t instance_capacity;
+    int64_t algorithmic_bytes;/* N*44 + V*12*(deg+1)^2 + V*32 + D*24 + D*32 + W*H*(3+4*depth) */
+    int32_t overflow;         /* 1: D exceeded instance_capacity; the frame is incomplete */
+    int32_t kernel_launches;  /* kernels of this library launched for the frame */
+} sage_frame_stats;
+
+/* One row of sage_project's debug output (element-wise parity of the projection kernel). */
+typedef struct sage_splat_record {
+    float gx, gy, qa, qb, qc, opacity, z, r, g, b;
+    int32_t tile_x0, tile_y0, tile_x1, tile_y1; /* inclusive tile rectangle after clipping */
+} sage_splat_record;
+
+const char* sage_last_error(void);
+int sage_abi_version(void);
+/* Number of CUDA devices visible to the library (0 => nothing below can work). */
+int sage_device_count(void);
+
+/* ---- scene ------------------------------------------------------------------------------
+ * Upload raw 3DGS attributes (host or device pointers) and repack them once into the engine's
+ * HBM layout.  Stands in for `open_stage(usd_path)` + the USDZ Gaussian payload Isaac loads
+ * (simple_env.py:219-230; generate_images.py:320-327; Data/template.usda:115-124).
+ * sh is [n][(sh_degree+1)^2][3]; quat is (w,x,y,z), not necessarily normalised.
+ * max_instances: capacity of the (tile, Gaussian) lists; <= 0 picks max(8 n, 2^24). */
+int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, const float* xyz,
+                      const float* log_scale, const float* quat_wxyz, const float* opacity_raw,
+                      const float* sh, int64_t max_instances);
+int sage_scene_reserve(sage_scene* s, int64_t max_instances);
+int sage_scene_destroy(sage_scene* s);
+
+/* ---- render -----------------------------------------------------------------------------
+ * One frame: RGB u8 [H,W,3] and (optional) planar depth f32 [H,W] written to *device* buffers,
+ * asynchronously on `stream`.  Replaces world.step(render=True) + cam.get_rgba()
+ * (simple_env.py:1368-1380; generate_images.py:425-428) and
+ * cam.get_current_frame()['distance_to_image_plane'] (simple_env.py:1425-1432).
+ * Only tile rows [row0_tiles, row1_tiles) are produced (multi-GPU tile-row sharding; pass 0 and
+ * ceil(H/16) for the whole frame); rows outside are left untouched.  rgb_dev/depth_dev always
+ * address the full frame. */
+int sage_render(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                uint8_t* rgb_dev, float* depth_dev, sage_stream_t stream);
+
+/* Same frame, but into *host* buffers: render into the scene's internal device frame, copy the
+ * produced rows device->host and synchronise.  This is the call behind env.get_rgb()/get_depth(). */
+int sage_render_host(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                     uint8_t* rgb_host, float* depth_host, sage_stream_t stream);
+
+/* Multi-GPU fused composite+gather: like sage_render, but every finished pixel is stored
+ * straight into each of n_peers frame buffers (peer-mapped device pointers, e.g. opened with
+ * sage_ipc_open) over NVLink, so the strip exchange needs no separate collective copy. */
+int sage_render_peers(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                      int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+                      sage_stream_t stream);
+
+/* Synchronises with the last frame on the scene and returns its counters. */
+int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out);
+
+/* Debug/parity: run only the projection kernel and return its per-Gaussian output to the host. */
+int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                 sage_splat_record* records_host, uint8_t* visible_host);
+
+/* CUDA IPC plumbing for sage_render_peers (64-byte handles exchanged by the host program). */
+int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64]);
+int sage_ipc_open(const uint8_t handle[64], void** dev_ptr_out);
+int sage_ipc_close(void* dev_ptr);
+
+/* ---- 2-D grid collide -------------------------------------------------------------------
+ * Obstacle grid of SemanticMap2DCollisionDetector (collision_detector.py:95-132), uploaded once.
+ * map_host is u8 [H][W] (1 = obstacle). */
+int sage_grid_create(sage_grid** out, int device, const uint8_t* map_host, int H, int W,
+                     double min_x, double max_x, double min_y, double max_y, double scale);
+int sage_grid_destroy(sage_grid* g);
+
+/* Batched check_collision_3d (collision_detector.py:191-237) over P float32 positions [P,3].
+ * np2_promote != 0: NumPy >= 2 scalar promotion (binary32 flip step); 0: NumPy 1.26 (binary64).
+ * pos/hit are HOST pointers (P <= 60 per agent step, simple_env.py:2116-2234); copies included.
+ * first_hit_host (optional, int32[n_segments]): for consecutive segments of lengths
+ * seg_len_host[0..n_segments) the index (within the segment) of the first colliding sample, or
+ * -1 — the reduction _try_direct_movement/_try_short_movement perform by marching. */
+int sage_collide_grid(sage_grid* g, const float* pos_host, int P, int np2_promote,
+                      uint8_t* hit_host, const int32_t* seg_len_host, int n_segments,
+                      int32_t* first_hit_host, sage_stream_t stream);
+/* Double-precision positions (check_collision_at_position, collision_detector.py:263-272). */
+int sage_collide_grid_f64(sage_grid* g, const double* pos_host, int P, uint8_t* hit_host,
+                          sage_stream_t stream);
+/* Device-resident variant: pos_dev f32 [P,3], hit_dev u8 [P]; asynchronous. */
+int sage_collide_grid_dev(sage_grid* g, const float* pos_dev, int P, int np2_promote,
+                          uint8_t* hit_dev, sage_stream_t stream);
+
+/* ---- capsule collide --------------------------------------------------------------------
+ * Collision bodies as ellipsoids (centre, log semi-axes, quaternion wxyz); stands in for the
+ * convex collision payload (Data/template.usda:156-165) and the agent-vs-mesh test the reference
+ * attempts through PhysX (simple_env.py:1878-1931; agent body :238,754-755). */
+int sage_bodies_create(sage_bodies** out, int device, int64_t m, const float* mu,
+                       const float* log_scale, const float* quat_wxyz);
+int sage_bodies_destroy(sage_bodies* b);
+/* pos_host f32 [P,3] -> hit_host u8 [P], first_body_host int32 [P] (optional; smallest index or -1). */
+int sage_collide_capsule(sage_bodies* b, const float* pos_host, int P, float radius, float z0,
+                         float z1, uint8_t* hit_host, int32_t* first_body_host,
+                         sage_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAGE_SPLAT_H */

@@ -1,0 +1,153 @@
+"""CPU oracle bindings — TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this package.  The product package never does.
+
+The C source (``sage_oracle.c``) documents which reference lines each function restates and
+what pins it: grid-collide is pinned by golden vectors generated from the unmodified reference
+class; render and capsule-collide are **parity unpinned** (the reference has no source, test or
+golden vector for them) and this oracle is the frozen specification.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libsage_oracle.so"
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile the oracle with gcc (seconds).  Rebuilds when the source is newer."""
+    src = _HERE / "sage_oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-B", "libsage_oracle.so"], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return _LIB_PATH
+
+
+class Camera(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("campos", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("W", C.c_int32), ("H", C.c_int32), ("near_z", C.c_float), ("far_z", C.c_float)]
+
+
+SPLAT_DTYPE = np.dtype([(k, np.float32) for k in
+                        ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b", "cov_a", "cov_c")])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.so_exp2.restype = C.c_float
+        _lib.so_exp2.argtypes = [C.c_float]
+        _lib.so_exp.restype = C.c_float
+        _lib.so_exp.argtypes = [C.c_float]
+        _lib.so_render.restype = C.c_int
+        _lib.so_abi_version.restype = C.c_int
+    return _lib
+
+
+def make_camera(R, t, campos, fx, fy, cx, cy, W, H, near=0.1, far=50.0) -> Camera:
+    cam = Camera()
+    cam.R[:] = [float(v) for v in np.asarray(R, np.float32).reshape(9)]
+    cam.t[:] = [float(v) for v in np.asarray(t, np.float32).reshape(3)]
+    cam.campos[:] = [float(v) for v in np.asarray(campos, np.float32).reshape(3)]
+    cam.fx, cam.fy, cam.cx, cam.cy = float(fx), float(fy), float(cx), float(cy)
+    cam.W, cam.H = int(W), int(H)
+    cam.near_z, cam.far_z = float(near), float(far)
+    return cam
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, ty=C.c_float):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def exp2(x: float) -> float:
+    return float(lib().so_exp2(C.c_float(x)))
+
+
+def set_threads(n: int) -> None:
+    lib().so_set_threads(C.c_int(n))
+
+
+def project(cam: Camera, xyz, log_scale, quat, opacity_raw, sh):
+    """Per-Gaussian projection.  Returns (records[SPLAT_DTYPE], visible[u8])."""
+    xyz, log_scale, quat, opacity_raw, sh = map(_f32, (xyz, log_scale, quat, opacity_raw, sh))
+    n = xyz.shape[0]
+    nb = sh.shape[1]
+    deg = int(round(np.sqrt(nb))) - 1
+    out = np.zeros(n, dtype=SPLAT_DTYPE)
+    vis = np.zeros(n, dtype=np.uint8)
+    lib().so_project(C.byref(cam), C.c_int64(n), C.c_int(deg), _p(xyz), _p(log_scale), _p(quat),
+                     _p(opacity_raw), _p(sh), out.ctypes.data_as(C.c_void_p), _p(vis, C.c_uint8))
+    return out, vis
+
+
+def render(cam: Camera, xyz, log_scale, quat, opacity_raw, sh, brute: bool = False, want_T: bool = False):
+    """Full frame.  Returns (rgb u8 [H,W,3], depth f32 [H,W], stats dict[, final T f32 [H,W]])."""
+    xyz, log_scale, quat, opacity_raw, sh = map(_f32, (xyz, log_scale, quat, opacity_raw, sh))
+    n = xyz.shape[0]
+    nb = sh.shape[1]
+    deg = int(round(np.sqrt(nb))) - 1
+    H, W = cam.H, cam.W
+    rgb = np.zeros((H, W, 3), np.uint8)
+    depth = np.zeros((H, W), np.float32)
+    fT = np.zeros((H, W), np.float32) if want_T else None
+    stats = np.zeros(3, np.int64)
+    rc = lib().so_render(C.byref(cam), C.c_int64(n), C.c_int(deg), _p(xyz), _p(log_scale), _p(quat),
+                         _p(opacity_raw), _p(sh), C.c_int(1 if brute else 0), _p(rgb, C.c_uint8),
+                         _p(depth), _p(fT) if want_T else None, _p(stats, C.c_int64))
+    if rc != 0:
+        raise RuntimeError(f"so_render failed rc={rc}")
+    st = {"visible": int(stats[0]), "instances": int(stats[1]), "threads": int(stats[2])}
+    return (rgb, depth, st, fT) if want_T else (rgb, depth, st)
+
+
+def collide_grid(grid_map, min_x, max_x, min_y, max_y, scale, pos, np2_promote=None):
+    """Restatement of SemanticMap2DCollisionDetector.check_collision_3d over a batch.
+
+    pos float32 -> ``np2_promote`` picks NumPy>=2 (True) or NumPy 1.26 (False) scalar promotion;
+    pos float64 -> all-double path (promotion-independent).
+    """
+    grid_map = None if grid_map is None else np.ascontiguousarray(grid_map, np.uint8)
+    H, W = (0, 0) if grid_map is None else grid_map.shape
+    pos = np.asarray(pos)
+    mp = None if grid_map is None else _p(grid_map, C.c_uint8)
+    dbl = [C.c_double(float(v)) for v in (min_x, max_x, min_y, max_y, scale)]
+    if pos.dtype == np.float64:
+        pos = np.ascontiguousarray(pos.reshape(-1, 3))
+        hit = np.zeros(pos.shape[0], np.uint8)
+        lib().so_collide_grid_f64(mp, C.c_int(H), C.c_int(W), *dbl, _p(pos, C.c_double),
+                                  C.c_int(pos.shape[0]), _p(hit, C.c_uint8))
+    else:
+        if np2_promote is None:
+            np2_promote = int(np.__version__.split(".")[0]) >= 2
+        pos = _f32(pos).reshape(-1, 3)
+        hit = np.zeros(pos.shape[0], np.uint8)
+        lib().so_collide_grid_f32(mp, C.c_int(H), C.c_int(W), *dbl, _p(pos), C.c_int(pos.shape[0]),
+                                  C.c_int(1 if np2_promote else 0), _p(hit, C.c_uint8))
+    return hit.astype(bool)
+
+
+def collide_capsule(mu, log_scale, quat, pos, radius=0.1, z0=0.6, z1=1.1):
+    mu, log_scale, quat, pos = map(_f32, (mu, log_scale, quat, pos))
+    pos = pos.reshape(-1, 3)
+    m, P = mu.shape[0], pos.shape[0]
+    hit = np.zeros(P, np.uint8)
+    first = np.zeros(P, np.int32)
+    lib().so_collide_capsule(C.c_int64(m), _p(mu), _p(log_scale), _p(quat), _p(pos), C.c_int(P),
+                             C.c_float(radius), C.c_float(z0), C.c_float(z1), _p(hit, C.c_uint8),
+                             _p(first, C.c_int32))
+    return hit.astype(bool), first

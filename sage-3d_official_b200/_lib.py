@@ -1,0 +1,107 @@
+"""ctypes binding of libsage_splat.so (C-ABI: include/sage_splat.h).
+
+There is no CPU fallback: a missing library or a missing CUDA device raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsage_splat.so"
+
+#: every symbol declared in include/sage_splat.h (tests check the .so exports all of them)
+EXPORTS = [
+    "sage_last_error", "sage_abi_version", "sage_device_count",
+    "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy",
+    "sage_render", "sage_render_host", "sage_render_peers", "sage_frame_stats_get", "sage_project",
+    "sage_ipc_export", "sage_ipc_open", "sage_ipc_close",
+    "sage_grid_create", "sage_grid_destroy", "sage_collide_grid", "sage_collide_grid_f64",
+    "sage_collide_grid_dev",
+    "sage_bodies_create", "sage_bodies_destroy", "sage_collide_capsule",
+]
+
+
+class SageError(RuntimeError):
+    pass
+
+
+class CCamera(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("t", C.c_float * 3), ("campos", C.c_float * 3),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32), ("near_z", C.c_float), ("far_z", C.c_float)]
+
+
+class CFrameStats(C.Structure):
+    _fields_ = [("n_gaussians", C.c_int64), ("n_visible", C.c_int64), ("n_instances", C.c_int64),
+                ("instance_capacity", C.c_int64), ("algorithmic_bytes", C.c_int64),
+                ("overflow", C.c_int32), ("kernel_launches", C.c_int32)]
+
+
+class CSplatRecord(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b")] + \
+               [(k, C.c_int32) for k in ("tile_x0", "tile_y0", "tile_x1", "tile_y1")]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
+    import subprocess
+    r = subprocess.run(["make", "-C", str(_HERE / "csrc"), "-j8"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise SageError("building libsage_splat.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise SageError(f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    L.sage_last_error.restype = C.c_char_p
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.sage_scene_create.argtypes = [C.POINTER(vp), i32, i64, i32, vp, vp, vp, vp, vp, i64]
+    L.sage_scene_reserve.argtypes = [vp, i64]
+    L.sage_scene_destroy.argtypes = [vp]
+    L.sage_render.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
+    L.sage_render_host.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
+    L.sage_render_peers.argtypes = [vp, C.POINTER(CCamera), i32, i32, i32, C.POINTER(vp), C.POINTER(vp), vp]
+    L.sage_frame_stats_get.argtypes = [vp, C.POINTER(CFrameStats)]
+    L.sage_project.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp]
+    L.sage_ipc_export.argtypes = [vp, vp]
+    L.sage_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    L.sage_ipc_close.argtypes = [vp]
+    dbl = C.c_double
+    L.sage_grid_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, dbl, dbl, dbl, dbl, dbl]
+    L.sage_grid_destroy.argtypes = [vp]
+    L.sage_collide_grid.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp, vp]
+    L.sage_collide_grid_f64.argtypes = [vp, vp, i32, vp, vp]
+    L.sage_collide_grid_dev.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.sage_bodies_create.argtypes = [C.POINTER(vp), i32, i64, vp, vp, vp]
+    L.sage_bodies_destroy.argtypes = [vp]
+    L.sage_collide_capsule.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name != "sage_last_error":
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SageError(lib().sage_last_error().decode("utf-8", "replace"))
+
+
+def require_gpu() -> None:
+    if lib().sage_device_count() <= 0:
+        raise SageError("no CUDA device visible: sage-3d_official_b200 has no CPU fallback")

@@ -1,0 +1,317 @@
+"""Python surface of the engine: ``render(camera, gaussians) -> (rgb, depth)`` and
+``collide(agent_pose, collision) -> hit`` (BASELINE.json north_star), torch tensors in/out,
+every call funnelled through the C-ABI of ``libsage_splat.so``.
+
+PyTorch is used for device memory and streams only; no tensor arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import CCamera, CFrameStats, CSplatRecord, SageError, check
+from .camera import Camera
+from .scenes import GaussianCloud
+
+TILE = 16
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ccam(cam: Camera) -> CCamera:
+    c = CCamera()
+    c.R[:] = [float(v) for v in np.asarray(cam.R, np.float32).reshape(9)]
+    c.t[:] = [float(v) for v in np.asarray(cam.t, np.float32).reshape(3)]
+    c.campos[:] = [float(v) for v in np.asarray(cam.campos, np.float32).reshape(3)]
+    c.fx, c.fy, c.cx, c.cy = float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy)
+    c.width, c.height = int(cam.width), int(cam.height)
+    c.near_z, c.far_z = float(cam.near), float(cam.far)
+    return c
+
+
+def _stream_ptr(stream=None):
+    torch = _torch()
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _ptr(a) -> C.c_void_p:
+    """Address of a numpy array or torch tensor (host or device)."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())
+
+
+def _as_f32(a):
+    """float32, contiguous; numpy stays numpy, torch stays torch (host or device)."""
+    if isinstance(a, np.ndarray):
+        return np.ascontiguousarray(a, dtype=np.float32)
+    torch = _torch()
+    if not isinstance(a, torch.Tensor):
+        return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+    return a.detach().to(dtype=torch.float32).contiguous()
+
+
+class GaussianScene:
+    """A Gaussian scene resident in HBM (handle of ``sage_scene``)."""
+
+    def __init__(self, gaussians, device: int = 0, max_instances: int = 0):
+        _lib.require_gpu()
+        if isinstance(gaussians, GaussianCloud):
+            parts = gaussians.as_tuple()
+        else:
+            parts = tuple(gaussians)
+        if len(parts) != 5:
+            raise ValueError("gaussians = (xyz[N,3], log_scale[N,3], quat_wxyz[N,4], opacity_raw[N], sh[N,K,3])")
+        xyz, ls, q, op, sh = (_as_f32(p) for p in parts)
+        n = int(xyz.shape[0])
+        if tuple(xyz.shape) != (n, 3) or tuple(ls.shape) != (n, 3) or tuple(q.shape) != (n, 4) \
+                or int(np.prod(op.shape)) != n or sh.ndim != 3 or sh.shape[0] != n or sh.shape[2] != 3:
+            raise ValueError("inconsistent Gaussian attribute shapes")
+        nb = int(sh.shape[1])
+        deg = int(round(np.sqrt(nb))) - 1
+        if (deg + 1) ** 2 != nb or not 0 <= deg <= 3:
+            raise ValueError(f"sh has {nb} coefficients per channel; expected 1, 4, 9 or 16")
+        self.n, self.sh_degree, self.device = n, deg, int(device)
+        self._h = C.c_void_p()
+        check(_lib.lib().sage_scene_create(C.byref(self._h), self.device, n, deg, _ptr(xyz), _ptr(ls),
+                                           _ptr(q), _ptr(op), _ptr(sh), int(max_instances)))
+        self._pinned = {}
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().sage_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, max_instances: int):
+        check(_lib.lib().sage_scene_reserve(self._h, int(max_instances)))
+
+    # -- render --
+    @staticmethod
+    def _rows(cam: Camera, rows):
+        ty = (cam.height + TILE - 1) // TILE
+        if rows is None:
+            return 0, ty
+        r0, r1 = int(rows[0]), int(rows[1])
+        return r0, r1
+
+    def render(self, cam: Camera, rows=None, want_depth: bool = True, out=None, stream=None):
+        """Asynchronous frame into CUDA tensors: (rgb u8 [H,W,3], depth f32 [H,W] | None)."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            rgb = torch.empty((cam.height, cam.width, 3), dtype=torch.uint8, device=dev)
+            depth = torch.empty((cam.height, cam.width), dtype=torch.float32, device=dev) if want_depth else None
+            if rows is not None:
+                rgb.zero_()
+                if depth is not None:
+                    depth.zero_()
+        else:
+            rgb, depth = out
+        r0, r1 = self._rows(cam, rows)
+        cc = _ccam(cam)
+        with torch.cuda.device(dev):
+            check(_lib.lib().sage_render(self._h, C.byref(cc), r0, r1, _ptr(rgb), _ptr(depth), _stream_ptr(stream)))
+        return rgb, depth
+
+    def render_peers(self, cam: Camera, rows, rgb_ptrs: Sequence[int], depth_ptrs: Optional[Sequence[int]], stream=None):
+        """Composite rows straight into several (peer-mapped) frame buffers given as raw addresses."""
+        torch = _torch()
+        n = len(rgb_ptrs)
+        RA = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in rgb_ptrs])
+        DA = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in depth_ptrs]) if depth_ptrs else None
+        cc = _ccam(cam)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_render_peers(self._h, C.byref(cc), int(rows[0]), int(rows[1]), n, RA, DA,
+                                               _stream_ptr(stream)))
+
+    def render_host(self, cam: Camera, rows=None, want_depth: bool = True, stream=None):
+        """Synchronous frame into pinned host memory: (rgb u8 ndarray, depth f32 ndarray | None)."""
+        torch = _torch()
+        key = (cam.height, cam.width)
+        if key not in self._pinned:
+            self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+                                 torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
+        rgb_t, dep_t = self._pinned[key]
+        r0, r1 = self._rows(cam, rows)
+        cc = _ccam(cam)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_render_host(self._h, C.byref(cc), r0, r1, _ptr(rgb_t),
+                                              _ptr(dep_t) if want_depth else C.c_void_p(0), _stream_ptr(stream)))
+        return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
+
+    def stats(self) -> dict:
+        st = CFrameStats()
+        check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in CFrameStats._fields_}
+
+    def project(self, cam: Camera, rows=None):
+        """Projection kernel only (parity/debug): structured records + visibility mask."""
+        rec = (CSplatRecord * max(self.n, 1))()
+        vis = np.zeros(max(self.n, 1), np.uint8)
+        r0, r1 = self._rows(cam, rows)
+        cc = _ccam(cam)
+        check(_lib.lib().sage_project(self._h, C.byref(cc), r0, r1, C.cast(rec, C.c_void_p), _ptr(vis)))
+        dt = np.dtype([(k, np.float32) for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b")] +
+                      [(k, np.int32) for k in ("tile_x0", "tile_y0", "tile_x1", "tile_y1")])
+        arr = np.frombuffer(rec, dtype=dt, count=self.n).copy()
+        return arr, vis[:self.n].astype(bool)
+
+
+class ObstacleGrid:
+    """Device-resident 2-D obstacle grid (handle of ``sage_grid``)."""
+
+    def __init__(self, obstacle_map, min_x, max_x, min_y, max_y, scale, device: int = 0):
+        _lib.require_gpu()
+        self._h = C.c_void_p()
+        m = None if obstacle_map is None else np.ascontiguousarray(obstacle_map, dtype=np.uint8)
+        H, W = (0, 0) if m is None else m.shape
+        check(_lib.lib().sage_grid_create(C.byref(self._h), int(device), _ptr(m), H, W, float(min_x), float(max_x),
+                                          float(min_y), float(max_y), float(scale)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().sage_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, positions, np2_promote: Optional[bool] = None, segments: Optional[Sequence[int]] = None):
+        """Batched check_collision_3d.  float32 positions follow the NumPy promotion mode
+        (default: the running interpreter's); float64 positions take the all-double path.
+        Returns hit mask (bool [P]) and, if ``segments`` is given, first-hit index per segment."""
+        pos = np.asarray(positions)
+        if pos.dtype == np.float64:
+            pos = np.ascontiguousarray(pos.reshape(-1, 3))
+            hit = np.zeros(pos.shape[0], np.uint8)
+            check(_lib.lib().sage_collide_grid_f64(self._h, _ptr(pos), pos.shape[0], _ptr(hit), C.c_void_p(0)))
+            first = None
+            if segments is not None:
+                first = _first_hits(hit, segments)
+            return (hit.astype(bool), first) if segments is not None else hit.astype(bool)
+        if np2_promote is None:
+            np2_promote = int(np.__version__.split(".")[0]) >= 2
+        pos = np.ascontiguousarray(pos, dtype=np.float32).reshape(-1, 3)
+        P = pos.shape[0]
+        hit = np.zeros(P, np.uint8)
+        if segments is None:
+            check(_lib.lib().sage_collide_grid(self._h, _ptr(pos), P, int(bool(np2_promote)), _ptr(hit),
+                                               C.c_void_p(0), 0, C.c_void_p(0), C.c_void_p(0)))
+            return hit.astype(bool)
+        seg = np.ascontiguousarray(segments, dtype=np.int32)
+        first = np.full(seg.shape[0], -1, np.int32)
+        check(_lib.lib().sage_collide_grid(self._h, _ptr(pos), P, int(bool(np2_promote)), _ptr(hit), _ptr(seg),
+                                           seg.shape[0], _ptr(first), C.c_void_p(0)))
+        return hit.astype(bool), first
+
+    def check_device(self, pos_dev, np2_promote: bool = True, stream=None):
+        """positions: CUDA float32 tensor [P,3] -> CUDA uint8 tensor [P] (asynchronous)."""
+        torch = _torch()
+        pos_dev = pos_dev.contiguous()
+        hit = torch.empty(pos_dev.shape[0], dtype=torch.uint8, device=pos_dev.device)
+        check(_lib.lib().sage_collide_grid_dev(self._h, _ptr(pos_dev), int(pos_dev.shape[0]), int(bool(np2_promote)),
+                                               _ptr(hit), _stream_ptr(stream)))
+        return hit
+
+
+def _first_hits(hit, segments):
+    out, s = [], 0
+    for n in segments:
+        idx = np.nonzero(hit[s:s + n])[0]
+        out.append(int(idx[0]) if idx.size else -1)
+        s += n
+    return np.asarray(out, np.int32)
+
+
+class CollisionBodies:
+    """Device-resident collision ellipsoids (handle of ``sage_bodies``)."""
+
+    def __init__(self, mu, log_scale, quat_wxyz, device: int = 0):
+        _lib.require_gpu()
+        mu, ls, q = (_as_f32(a) for a in (mu, log_scale, quat_wxyz))
+        self.m = int(mu.shape[0])
+        self._h = C.c_void_p()
+        check(_lib.lib().sage_bodies_create(C.byref(self._h), int(device), self.m, _ptr(mu), _ptr(ls), _ptr(q)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().sage_bodies_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, positions, radius: float = 0.1, z0: float = 0.6, z1: float = 1.1):
+        """Agent capsule (simple_env.py:238,754-755: r = 0.1, z in [0.6, 1.1]) at each position.
+        Returns (hit bool [P], first_body int32 [P])."""
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        P = pos.shape[0]
+        hit = np.zeros(P, np.uint8)
+        first = np.full(P, -1, np.int32)
+        for s in range(0, P, 256):
+            e = min(P, s + 256)
+            check(_lib.lib().sage_collide_capsule(self._h, _ptr(pos[s:e]), e - s, float(radius), float(z0), float(z1),
+                                                  _ptr(hit[s:e]), _ptr(first[s:e]), C.c_void_p(0)))
+        return hit.astype(bool), first
+
+
+# ---- functional surface (north_star) ---------------------------------------------------------
+
+_scene_cache: dict = {}
+
+
+def render(camera: Camera, gaussians, want_depth: bool = True, rows=None):
+    """``render(camera, gaussians) -> (rgb u8 [H,W,3], depth f32 [H,W])`` as CUDA tensors.
+
+    ``gaussians`` is a resident :class:`GaussianScene`, or raw attributes (GaussianCloud / 5-tuple
+    of arrays or tensors) which are uploaded once and cached by identity.
+    """
+    if isinstance(gaussians, GaussianScene):
+        scene = gaussians
+    else:
+        key = id(gaussians)
+        scene = _scene_cache.get(key)
+        if scene is None:
+            scene = GaussianScene(gaussians)
+            _scene_cache.clear()           # keep at most one implicit scene alive
+            _scene_cache[key] = scene
+            scene._keepalive = gaussians
+    return scene.render(camera, rows=rows, want_depth=want_depth)
+
+
+def collide(agent_pose, collision, **kw):
+    """``collide(agent_pose, collision) -> hit mask``.
+
+    ``agent_pose``: position(s) [P,3]; ``collision``: :class:`ObstacleGrid` (2-D semantic-map rule)
+    or :class:`CollisionBodies` (ellipsoid-vs-capsule)."""
+    if isinstance(collision, ObstacleGrid):
+        return collision.check(agent_pose, **kw)
+    if isinstance(collision, CollisionBodies):
+        return collision.check(agent_pose, **kw)[0]
+    raise TypeError("collision must be an ObstacleGrid or CollisionBodies")
+
+
+__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "render", "collide", "SageError", "Camera"]

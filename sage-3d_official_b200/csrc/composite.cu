@@ -1,0 +1,162 @@
+// K5: per-pixel front-to-back alpha compositing -> RGB u8 + planar depth f32.
+//
+// Replaces cam.get_rgba() (simple_env.py:1380; generate_images.py:428) and
+// frame['distance_to_image_plane'] (simple_env.py:1425-1432).
+//
+// One CTA = one 16x16 tile, 128 threads, two horizontally adjacent pixels per thread so the
+// blend arithmetic runs on Blackwell's packed binary32 pipe (FFMA2/FMUL2/FADD2: fma.rn.f32x2),
+// which is IEEE per lane and therefore bit-identical to the scalar statement in the oracle.
+// Splat records of the tile's depth-sorted list are gathered (they sit in L2) into shared memory
+// 128 at a time and broadcast to all pixels.  Finished pixels can be stored straight into several
+// frame buffers (peer-mapped, NVLink) — the multi-GPU strip exchange fused into the epilogue.
+#include "sage_internal.cuh"
+
+namespace {
+
+constexpr int C_THREADS = 128;
+constexpr int MAX_PEERS = 8;
+
+struct PeerOut {
+    uint8_t* rgb[MAX_PEERS];
+    float* depth[MAX_PEERS];
+    int n;
+};
+
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// packed deterministic exp2; valid for lanes with x in [-125, 0] (callers mask the others)
+__device__ __forceinline__ float2 sage_exp2_x2(float2 x)
+{
+    const float magic = 12582912.0f;
+    float2 t = __fadd2_rn(x, f2(magic));
+    float2 n = __fadd2_rn(t, f2(-magic));
+    float2 f = __ffma2_rn(n, f2(-1.0f), x);          // x - n, exact product => same rounding
+    float2 p = f2(0x1.5c08e4p-10f);
+    p = __ffma2_rn(p, f, f2(0x1.3d0c52p-7f));
+    p = __ffma2_rn(p, f, f2(0x1.c6b6e4p-5f));
+    p = __ffma2_rn(p, f, f2(0x1.ebf918p-3f));
+    p = __ffma2_rn(p, f, f2(0x1.62e428p-1f));
+    p = __ffma2_rn(p, f, f2(0x1.000002p+0f));
+    float2 r;
+    r.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23));
+    r.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23));
+    return r;
+}
+
+__global__ void __launch_bounds__(C_THREADS)
+k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
+            const float4* __restrict__ rec2, const uint32_t* __restrict__ vals,
+            const uint2* __restrict__ ranges, PeerOut out)
+{
+    __shared__ float4 s0[C_THREADS], s1[C_THREADS], s2[C_THREADS];
+    const int tile = blockIdx.x;
+    const int tx = tile % cam.tiles_x, ty = cam.row0 + tile / cam.tiles_x;
+    const uint2 rg = ranges[tile];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int px = tx * SAGE_TILE + (w & 1) * 8 + (lane & 3) * 2;
+    const int py = ty * SAGE_TILE + (w >> 1) * 8 + (lane >> 2);
+    const float2 pxc = make_float2((float)px + 0.5f, (float)(px + 1) + 0.5f);
+    const float pyc = (float)py + 0.5f;
+    const bool in0 = px < cam.W && py < cam.H, in1 = (px + 1) < cam.W && py < cam.H;
+    bool act0 = in0, act1 = in1;
+    float2 T = f2(1.0f), Cr = f2(0.0f), Cg = f2(0.0f), Cb = f2(0.0f), Dz = f2(0.0f);
+
+    for (uint32_t base = rg.x; base < rg.y; base += C_THREADS) {
+        const int cnt = min((uint32_t)C_THREADS, rg.y - base);
+        if (tid < cnt) {
+            const uint32_t g = __ldg(&vals[base + tid]);
+            s0[tid] = __ldg(&rec0[g]);
+            s1[tid] = __ldg(&rec1[g]);
+            s2[tid] = __ldg(&rec2[g]);
+        }
+        __syncthreads();
+        if (act0 || act1) {
+            for (int j = 0; j < cnt; ++j) {
+                const float4 a = s0[j];   // gx gy qa qb
+                const float4 b = s1[j];   // qc opacity z thr
+                const float dy = pyc - a.y;
+                const float bdy = a.w * dy;
+                const float cdy = b.x * dy;
+                const float cdy2 = cdy * dy;
+                const float2 dx = __fadd2_rn(pxc, f2(-a.x));
+                const float2 wv = __ffma2_rn(f2(a.z), dx, f2(bdy));
+                const float2 pw = __ffma2_rn(dx, wv, f2(cdy2));
+                // b.w is a conservative skip threshold (log2 units): below it alpha < 1/255 for sure
+                bool v0 = act0 && pw.x <= 0.0f && pw.x >= b.w;
+                bool v1 = act1 && pw.y <= 0.0f && pw.y >= b.w;
+                if (!(v0 || v1)) continue;
+                const float2 e = sage_exp2_x2(pw);
+                float2 al = __fmul2_rn(f2(b.y), e);
+                al.x = fminf(SAGE_ALPHA_MAX, al.x);
+                al.y = fminf(SAGE_ALPHA_MAX, al.y);
+                v0 = v0 && al.x >= SAGE_ALPHA_MIN;
+                v1 = v1 && al.y >= SAGE_ALPHA_MIN;
+                al.x = v0 ? al.x : 0.0f;
+                al.y = v1 ? al.y : 0.0f;
+                float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));   // 1 - alpha
+                float2 Tn = __fmul2_rn(T, om);
+                const bool stop0 = v0 && Tn.x < SAGE_T_MIN;
+                const bool stop1 = v1 && Tn.y < SAGE_T_MIN;
+                if (stop0 || stop1) {
+                    if (stop0) { act0 = false; al.x = 0.0f; }
+                    if (stop1) { act1 = false; al.y = 0.0f; }
+                    om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
+                    Tn = __fmul2_rn(T, om);
+                    if (!(act0 || act1)) break;
+                }
+                const float2 wgt = __fmul2_rn(al, T);
+                const float4 c = s2[j];
+                Cr = __ffma2_rn(f2(c.x), wgt, Cr);
+                Cg = __ffma2_rn(f2(c.y), wgt, Cg);
+                Cb = __ffma2_rn(f2(c.z), wgt, Cb);
+                Dz = __ffma2_rn(f2(b.z), wgt, Dz);
+                T = Tn;
+            }
+        }
+        if (__syncthreads_and(!(act0 || act1))) break;
+    }
+
+    // epilogue: quantise and store to every destination frame
+    if (in0 || in1) {
+        const float vals_c[6] = {Cr.x, Cg.x, Cb.x, Cr.y, Cg.y, Cb.y};
+        uint8_t q[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float v = fminf(fmaxf(vals_c[k], 0.0f), 1.0f);
+            q[k] = (uint8_t)(v * 255.0f + 0.5f);
+        }
+        const float cov0 = 1.0f - T.x, cov1 = 1.0f - T.y;
+        const float d0 = cov0 > 1e-6f ? Dz.x / cov0 : 0.0f;
+        const float d1 = cov1 > 1e-6f ? Dz.y / cov1 : 0.0f;
+        const size_t p = (size_t)py * cam.W + px;
+        for (int k = 0; k < out.n; ++k) {
+            uint8_t* rgb = out.rgb[k];
+            float* dep = out.depth[k];
+            if (in0) {
+                rgb[3 * p + 0] = q[0]; rgb[3 * p + 1] = q[1]; rgb[3 * p + 2] = q[2];
+                if (dep) dep[p] = d0;
+            }
+            if (in1) {
+                rgb[3 * p + 3] = q[3]; rgb[3 * p + 4] = q[4]; rgb[3 * p + 5] = q[5];
+                if (dep) dep[p + 1] = d1;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
+                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+                           cudaStream_t st)
+{
+    const int n_tiles = (cam.row1 - cam.row0) * cam.tiles_x;
+    if (n_tiles <= 0) return;
+    PeerOut out;
+    out.n = n_peers < MAX_PEERS ? n_peers : MAX_PEERS;
+    for (int k = 0; k < MAX_PEERS; ++k) {
+        out.rgb[k] = k < out.n ? rgb_peers[k] : nullptr;
+        out.depth[k] = (k < out.n && depth_peers) ? depth_peers[k] : nullptr;
+    }
+    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, out);
+}

@@ -1,0 +1,234 @@
+// K0 precompute (scene upload) and K1 project + cull + SH (per frame).
+//
+// Stands in for the per-Gaussian work hidden inside Isaac's world.step(render=True)
+// (reference call sites simple_env.py:1369, generate_images.py:426).  The arithmetic follows
+// DESIGN.md §2.2-2.3 operation by operation; the CPU oracle restates the same sequence.
+#include "sage_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K0: view-independent terms, computed once per scene: sigmoid(opacity) and the 3-D covariance.
+// SH coefficients are re-laid out as float4 chunks [chunk][gaussian] so that a warp reading one
+// chunk for 32 consecutive Gaussians issues one fully coalesced 512-byte request.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __restrict__ log_scale,
+             const float* __restrict__ quat, const float* __restrict__ opacity,
+             const float* __restrict__ sh)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n) return;
+    float o = 1.0f / (1.0f + sage_exp(-opacity[i]));
+    sc.geo0[i] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], o);
+
+    float sx = sage_exp(log_scale[3 * i + 0]);
+    float sy = sage_exp(log_scale[3 * i + 1]);
+    float sz = sage_exp(log_scale[3 * i + 2]);
+    float qw = quat[4 * i + 0], qx = quat[4 * i + 1], qy = quat[4 * i + 2], qz = quat[4 * i + 3];
+    float qn = sqrtf(fmaf(qz, qz, fmaf(qy, qy, fmaf(qx, qx, qw * qw))));
+    float w = qw / qn, x = qx / qn, y = qy / qn, z = qz / qn;
+    float xx = x * x, yy = y * y, zz = z * z;
+    float xy = x * y, xz = x * z, yz = y * z;
+    float wx = w * x, wy = w * y, wz = w * z;
+    float r00 = 1.0f - 2.0f * (yy + zz), r01 = 2.0f * (xy - wz), r02 = 2.0f * (xz + wy);
+    float r10 = 2.0f * (xy + wz), r11 = 1.0f - 2.0f * (xx + zz), r12 = 2.0f * (yz - wx);
+    float r20 = 2.0f * (xz - wy), r21 = 2.0f * (yz + wx), r22 = 1.0f - 2.0f * (xx + yy);
+    float m00 = r00 * sx, m01 = r01 * sy, m02 = r02 * sz;
+    float m10 = r10 * sx, m11 = r11 * sy, m12 = r12 * sz;
+    float m20 = r20 * sx, m21 = r21 * sy, m22 = r22 * sz;
+    float S00 = fmaf(m02, m02, fmaf(m01, m01, m00 * m00));
+    float S01 = fmaf(m02, m12, fmaf(m01, m11, m00 * m10));
+    float S02 = fmaf(m02, m22, fmaf(m01, m21, m00 * m20));
+    float S11 = fmaf(m12, m12, fmaf(m11, m11, m10 * m10));
+    float S12 = fmaf(m12, m22, fmaf(m11, m21, m10 * m20));
+    float S22 = fmaf(m22, m22, fmaf(m21, m21, m20 * m20));
+    sc.geo1[i] = make_float4(S00, S01, S02, S11);
+    sc.geo2[i] = make_float2(S12, S22);
+
+    const int nf = 3 * (sc.deg + 1) * (sc.deg + 1);
+    const float* src = sh + (size_t)nf * i;
+    for (int c = 0; c < sc.n_chunks; ++c) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (4 * c + k < nf) ? src[4 * c + k] : 0.0f;
+        sc.shc[(size_t)c * sc.n + i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
+                            const float* quat, const float* opacity, const float* sh, cudaStream_t st)
+{
+    if (sc.n <= 0) return;
+    int blocks = (int)((sc.n + 255) / 256);
+    k_precompute<<<blocks, 256, 0, st>>>(sc, xyz, log_scale, quat, opacity, sh);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: project, cull, conic, bounding tile rectangle, SH colour.  One thread per Gaussian;
+// every per-Gaussian stream (geo0/1/2, SH chunks, records) is a 16-byte-per-lane coalesced access.
+// ---------------------------------------------------------------------------------------------
+__device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
+                                            0.31539156525252005f, -1.0925484305920792f,
+                                            0.5462742152960396f};
+__device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
+                                            -0.4570457994644658f, 0.3731763325901154f,
+                                            -0.4570457994644658f, 1.445305721320277f,
+                                            -0.5900435899266435f};
+
+template <int DEG>
+__device__ __forceinline__ void sh_color(const SageSceneDev& sc, int64_t i, float dx, float dy,
+                                         float dz, float& r, float& g, float& b)
+{
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int NF = 3 * NB;
+    constexpr int NC = (NF + 3) / 4;
+    float shv[NC * 4];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float4 v = __ldg(&sc.shc[(size_t)c * sc.n + i]);
+        shv[4 * c + 0] = v.x; shv[4 * c + 1] = v.y; shv[4 * c + 2] = v.z; shv[4 * c + 3] = v.w;
+    }
+    float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    float x = dx / len, y = dy / len, z = dz / len;
+    float basis[NB];
+    basis[0] = 0.28209479177387814f;
+    if constexpr (DEG > 0) {
+        const float C1 = 0.4886025119029199f;
+        basis[1] = -(C1 * y);
+        basis[2] = C1 * z;
+        basis[3] = -(C1 * x);
+    }
+    if constexpr (DEG > 1) {
+        float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        basis[4] = c_SH_C2[0] * xy;
+        basis[5] = c_SH_C2[1] * yz;
+        basis[6] = c_SH_C2[2] * ((2.0f * zz - xx) - yy);
+        basis[7] = c_SH_C2[3] * xz;
+        basis[8] = c_SH_C2[4] * (xx - yy);
+        if constexpr (DEG > 2) {
+            basis[9] = (c_SH_C3[0] * y) * (3.0f * xx - yy);
+            basis[10] = (c_SH_C3[1] * xy) * z;
+            basis[11] = (c_SH_C3[2] * y) * ((4.0f * zz - xx) - yy);
+            basis[12] = (c_SH_C3[3] * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
+            basis[13] = (c_SH_C3[4] * x) * ((4.0f * zz - xx) - yy);
+            basis[14] = (c_SH_C3[5] * z) * (xx - yy);
+            basis[15] = (c_SH_C3[6] * x) * (xx - 3.0f * yy);
+        }
+    }
+    float acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = basis[0] * shv[c];
+#pragma unroll
+        for (int k = 1; k < NB; ++k) a = fmaf(basis[k], shv[3 * k + c], a);
+        acc[c] = fmaxf(a + 0.5f, 0.0f);
+    }
+    r = acc[0]; g = acc[1]; b = acc[2];
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(256)
+k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool vis = false;
+    uint32_t key = SAGE_KEY_CULLED;
+    uint32_t count = 0;
+    if (i < sc.n) {
+        const float4 g0 = __ldg(&sc.geo0[i]);
+        const float mx = g0.x, my = g0.y, mz = g0.z, o = g0.w;
+        const float* R = cam.R;
+        float tx = fmaf(R[2], mz, fmaf(R[1], my, fmaf(R[0], mx, cam.t[0])));
+        float ty = fmaf(R[5], mz, fmaf(R[4], my, fmaf(R[3], mx, cam.t[1])));
+        float tz = fmaf(R[8], mz, fmaf(R[7], my, fmaf(R[6], mx, cam.t[2])));
+        if (tz > cam.near_z && tz < cam.far_z && o >= SAGE_ALPHA_MIN) {
+            const float4 g1 = __ldg(&sc.geo1[i]);
+            const float2 g2 = __ldg(&sc.geo2[i]);
+            const float S00 = g1.x, S01 = g1.y, S02 = g1.z, S11 = g1.w, S12 = g2.x, S22 = g2.y;
+            float txz = tx / tz, tyz = ty / tz;
+            float ctx = fminf(cam.limx, fmaxf(-cam.limx, txz)) * tz;
+            float cty = fminf(cam.limy, fmaxf(-cam.limy, tyz)) * tz;
+            float tz2 = tz * tz;
+            float j00 = cam.fx / tz;
+            float j02 = -(cam.fx * ctx) / tz2;
+            float j11 = cam.fy / tz;
+            float j12 = -(cam.fy * cty) / tz2;
+            float T00 = fmaf(j02, R[6], j00 * R[0]);
+            float T01 = fmaf(j02, R[7], j00 * R[1]);
+            float T02 = fmaf(j02, R[8], j00 * R[2]);
+            float T10 = fmaf(j12, R[6], j11 * R[3]);
+            float T11 = fmaf(j12, R[7], j11 * R[4]);
+            float T12 = fmaf(j12, R[8], j11 * R[5]);
+            float v00 = fmaf(S02, T02, fmaf(S01, T01, S00 * T00));
+            float v01 = fmaf(S12, T02, fmaf(S11, T01, S01 * T00));
+            float v02 = fmaf(S22, T02, fmaf(S12, T01, S02 * T00));
+            float v10 = fmaf(S02, T12, fmaf(S01, T11, S00 * T10));
+            float v11 = fmaf(S12, T12, fmaf(S11, T11, S01 * T10));
+            float v12 = fmaf(S22, T12, fmaf(S12, T11, S02 * T10));
+            float a = fmaf(T02, v02, fmaf(T01, v01, T00 * v00)) + SAGE_BLUR;
+            float b = fmaf(T12, v02, fmaf(T11, v01, T10 * v00));
+            float c = fmaf(T12, v12, fmaf(T11, v11, T10 * v10)) + SAGE_BLUR;
+            float det = fmaf(a, c, -(b * b));
+            if (det > 0.0f && det < INFINITY) {
+                float conic_a = c / det, conic_b = -b / det, conic_c = a / det;
+                float gx = fmaf(cam.fx, txz, cam.cx);
+                float gy = fmaf(cam.fy, tyz, cam.cy);
+                float qa = conic_a * (-0.5f * SAGE_LOG2E);
+                float qb = conic_b * (-SAGE_LOG2E);
+                float qc = conic_c * (-0.5f * SAGE_LOG2E);
+
+                // Conservative bounding rectangle of {alpha >= 1/255}: derived in binary64 from
+                // the *rounded* conic the blend kernel will use, with 0.2 % + 0.02 slack on the
+                // log2 threshold.  Not part of the spec: it only has to be conservative.
+                float l2 = __log2f(255.0f * o);
+                double t2 = (double)l2 * 1.002 + 0.02;
+                double A = -(double)qa, Bq = -0.5 * (double)qb, Cq = -(double)qc;
+                double det2 = A * Cq - Bq * Bq;
+                bool unbounded = !(det2 > 0.0) || !(A > 0.0) || !(Cq > 0.0);
+                double hx = unbounded ? 1e30 : sqrt(t2 * Cq / det2);
+                double hy = unbounded ? 1e30 : sqrt(t2 * A / det2);
+                double xlo = floor((double)gx - hx - 0.5), xhi = ceil((double)gx + hx - 0.5);
+                double ylo = floor((double)gy - hy - 0.5), yhi = ceil((double)gy + hy - 0.5);
+                const double Wm = (double)(cam.W - 1), Hm = (double)(cam.H - 1);
+                if (xhi >= 0.0 && xlo <= Wm && yhi >= 0.0 && ylo <= Hm) {
+                    int ix0 = (int)fmax(xlo, 0.0), ix1 = (int)fmin(xhi, Wm);
+                    int iy0 = (int)fmax(ylo, 0.0), iy1 = (int)fmin(yhi, Hm);
+                    int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
+                    int ty0 = max(iy0 / SAGE_TILE, cam.row0), ty1 = min(iy1 / SAGE_TILE, cam.row1 - 1);
+                    if (ty0 <= ty1 && tx0 <= tx1) {
+                        float cr, cg, cb;
+                        sh_color<DEG>(sc, i, mx - cam.campos[0], my - cam.campos[1],
+                                      mz - cam.campos[2], cr, cg, cb);
+                        float chk = gx + gy + qa + qb + qc + cr + cg + cb;
+                        if (chk - chk == 0.0f) {
+                            vis = true;
+                            key = __float_as_uint(tz);
+                            count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+                            fr.rec0[i] = make_float4(gx, gy, qa, qb);
+                            fr.rec1[i] = make_float4(qc, o, tz, -l2 - 0.01f);
+                            fr.rec2[i] = make_float4(cr, cg, cb, 0.0f);
+                            fr.rect[i] = make_uint2((uint32_t)tx0 | ((uint32_t)tx1 << 16),
+                                                    (uint32_t)ty0 | ((uint32_t)ty1 << 16));
+                        }
+                    }
+                }
+            }
+        }
+        fr.dkey[0][i] = key;
+        fr.ntiles[i] = count;
+    }
+    // one atomic per warp for the visible counter
+    unsigned m = __ballot_sync(0xffffffffu, vis);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], __popc(m));
+}
+
+void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)
+{
+    if (sc.n <= 0) return;
+    int blocks = (int)((sc.n + 255) / 256);
+    switch (sc.deg) {
+        case 0: k_project<0><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 1: k_project<1><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 2: k_project<2><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        default: k_project<3><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+    }
+}

@@ -1,0 +1,118 @@
+// Internal declarations shared by the kernels and the C-ABI layer (sm_100a only).
+//
+// Numerics contract: every float operation on the render/collide path is an
+// IEEE-754 binary32 operation in the order written.  The library is compiled with -fmad=false,
+// so a multiply-add is fused ONLY where fmaf()/__ffma2_rn() is written.  That is what lets the
+// parity tests demand bit-exact agreement with the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sage_splat.h"
+
+#define SAGE_ALPHA_MIN 0.003921569f
+#define SAGE_ALPHA_MAX 0.99f
+#define SAGE_T_MIN 1e-4f
+#define SAGE_BLUR 0.3f
+#define SAGE_LOG2E 1.44269504f
+#define SAGE_KEY_CULLED 0xFFFFFFFFu
+
+// device counters (uint32 each)
+enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_N = 3, CNT_COUNT = 8 };
+
+struct SageCamDev {
+    float R[9];
+    float t[3];
+    float campos[3];
+    float fx, fy, cx, cy;
+    float limx, limy;
+    float near_z, far_z;
+    int W, H;
+    int tiles_x, tiles_y;  // full-frame tile grid
+    int row0, row1;        // tile rows rendered by this call
+};
+
+// ---- deterministic exp2 (mirrors the spec) --------------------------------
+__device__ __forceinline__ float sage_exp2(float x)
+{
+    x = fminf(fmaxf(x, -125.0f), 125.0f);
+    const float magic = 12582912.0f;
+    float t = x + magic;
+    float n = t - magic;
+    float f = x - n;
+    float p = 0x1.5c08e4p-10f;
+    p = fmaf(p, f, 0x1.3d0c52p-7f);
+    p = fmaf(p, f, 0x1.c6b6e4p-5f);
+    p = fmaf(p, f, 0x1.ebf918p-3f);
+    p = fmaf(p, f, 0x1.62e428p-1f);
+    p = fmaf(p, f, 0x1.000002p+0f);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+__device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_LOG2E); }
+
+// ---- frame workspace ---------------------------------------------------------------------
+struct SageFrame {
+    // per-Gaussian (capacity n)
+    float4* rec0;      // gx, gy, qa, qb
+    float4* rec1;      // qc, opacity, z, skip threshold (log2 units)
+    float4* rec2;      // r, g, b, 0
+    uint32_t* dkey[2]; // depth keys, ping-pong
+    uint32_t* dval[2]; // Gaussian ids, ping-pong
+    uint2* rect;       // packed tile rectangle: x = x0 | x1<<16, y = y0 | y1<<16 (inclusive)
+    uint32_t* ntiles;  // tiles touched
+    uint32_t* partial; // block partial sums for the offset scan
+    // per-instance (capacity cap)
+    uint32_t* ikey[2];
+    uint32_t* ival[2];
+    // sort scratch
+    uint32_t* block_hist;   // [R][nb]
+    uint32_t* digit_total;  // [passes][R]
+    // per-tile
+    uint2* ranges;
+    uint32_t* counters;     // CNT_COUNT
+};
+
+// ---- kernel launchers (defined in the .cu files) -------------------------------------------
+struct SageSceneDev {
+    int64_t n;
+    int deg;
+    int n_chunks;       // float4 chunks of SH per Gaussian
+    float4* geo0;       // mu.xyz, sigmoid(opacity)
+    float4* geo1;       // S00 S01 S02 S11
+    float2* geo2;       // S12 S22
+    float4* shc;        // [n_chunks][n]
+};
+
+void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
+                            const float* quat, const float* opacity, const float* sh, cudaStream_t st);
+void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
+
+// radix sort of (key, val) pairs by bits [lo_bit, lo_bit + n_bits); n read from device memory.
+// Result lands in buffer index returned (0 or 1).  digit_total must be zeroed for `passes` rows.
+int sage_radix_sort(uint32_t* keys[2], uint32_t* vals[2], const uint32_t* n_dev, int64_t capacity,
+                    int lo_bit, int n_bits, bool vals_are_iota, uint32_t* block_hist,
+                    uint32_t* digit_total, int* launches, cudaStream_t st);
+int sage_radix_passes(int n_bits);
+size_t sage_radix_block_hist_elems(int64_t capacity);
+#define SAGE_RADIX_MAX_BINS 512
+
+void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order,
+                         int64_t n, int64_t cap, int* launches, cudaStream_t st);
+void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_t cap, int n_tiles,
+                        int* launches, cudaStream_t st);
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
+                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+                           cudaStream_t st);
+
+void sage_launch_collide_grid(const uint8_t* map, int H, int W, double min_x, double max_x,
+                              double min_y, double max_y, double scale, const float* pos_f32,
+                              const double* pos_f64, int P, int np2_promote, uint8_t* hit,
+                              cudaStream_t st);
+void sage_launch_first_hit(const uint8_t* hit, const int32_t* seg_len, int n_segments,
+                           int32_t* first_hit, cudaStream_t st);
+void sage_launch_collide_capsule(int64_t m, const float4* c0, const float4* c1, const float2* c2,
+                                 const float* pos, int P, float radius, float z0, float z1,
+                                 uint32_t* hit_bits, int32_t* first_body, cudaStream_t st);
+void sage_launch_bodies_pack(int64_t m, const float* mu, const float* log_scale, const float* quat,
+                             float4* c0, float4* c1, float2* c2, cudaStream_t st);
+int sage_capsule_max_poses(void);
