@@ -160,6 +160,16 @@ class GaussianScene:
         check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))
         return {k: int(getattr(st, k)) for k, _ in CFrameStats._fields_}
 
+    STAGES = ("project", "depth_sort", "binning", "tile_sort", "tile_ranges", "composite")
+
+    def set_stage_timing(self, n_slots: int):
+        check(_lib.lib().sage_set_stage_timing(self._h, int(n_slots)))
+
+    def stage_times(self, slot: int) -> dict:
+        ms = (C.c_float * len(self.STAGES))()
+        check(_lib.lib().sage_stage_times_get(self._h, int(slot), C.cast(ms, C.c_void_p)))
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
+
     def project(self, cam: Camera, rows=None):
         """Projection kernel only (parity/debug): structured records + visibility mask."""
         rec = (CSplatRecord * max(self.n, 1))()

@@ -59,6 +59,10 @@ struct sage_scene {
     cudaStream_t last_stream = nullptr;
     int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
     bool rendered = false;
+    // optional per-stage timing: n_slots x (SAGE_N_STAGES + 1) events
+    std::vector<cudaEvent_t> events;
+    int n_slots = 0;
+    long frame_index = 0;
 };
 
 struct sage_grid {
@@ -210,6 +214,7 @@ int sage_scene_destroy(sage_scene* s)
     cudaFree(s->fr.digit_total); cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
     cudaFree(s->n_dev);
     if (s->counters_host) cudaFreeHost(s->counters_host);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
     cudaFree(s->frame_rgb); cudaFree(s->frame_depth);
     cudaGetLastError();
     delete s;
@@ -266,20 +271,32 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     int launches = 0;
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, st));
     CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * 256 * (size_t)(dpasses + tpasses), st));
+    cudaEvent_t* ev = s->n_slots > 0
+        ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
+    s->frame_index++;
+#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], st)); } while (0)
     if (n_tiles > 0 && s->sc.n > 0) {
+        STAGE_MARK(0);
         sage_launch_project(s->sc, cd, s->fr, st);
         launches += 1;
+        STAGE_MARK(1);
         int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->sc.n, 0, DEPTH_BITS, true,
                                   s->fr.block_hist, s->fr.digit_total, &launches, st);
         const uint32_t* order = s->fr.dval[res];
+        STAGE_MARK(2);
         sage_launch_binning(cd, s->fr, order, s->sc.n, s->cap, &launches, st);
+        STAGE_MARK(3);
         int ires = sage_radix_sort(s->fr.ikey, s->fr.ival, s->fr.counters + CNT_INSTANCES, s->cap, 0,
                                    tbits, false, s->fr.block_hist,
                                    s->fr.digit_total + (size_t)dpasses * 256, &launches, st);
+        STAGE_MARK(4);
         sage_launch_ranges(s->fr, s->fr.ikey[ires], s->cap, n_tiles, &launches, st);
+        STAGE_MARK(5);
         sage_launch_composite(cd, s->fr, s->fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
         launches += 1;
+        STAGE_MARK(6);
     } else if (n_tiles > 0) {
+        for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
         CK(cudaMemsetAsync(s->fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
         sage_launch_composite(cd, s->fr, s->fr.ival[0], n_peers, rgb_peers, depth_peers, st);
         launches += 1;
@@ -362,6 +379,33 @@ int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out)
     out->algorithmic_bytes = out->n_gaussians * 44 + out->n_visible * 12 * nb + out->n_visible * 32 +
                              out->n_instances * 24 + out->n_instances * 32 +
                              (int64_t)s->last_W * s->last_H * (3 + 4 * s->last_depth);
+    return 0;
+}
+
+int sage_set_stage_timing(sage_scene* s, int n_slots)
+{
+    REQUIRE(s != nullptr, "sage_set_stage_timing: NULL scene");
+    REQUIRE(n_slots >= 0 && n_slots <= 4096, "sage_set_stage_timing: n_slots must be 0..4096");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    s->events.clear();
+    s->n_slots = 0;
+    s->frame_index = 0;
+    s->events.resize((size_t)n_slots * (SAGE_N_STAGES + 1));
+    for (auto& e : s->events) CK(cudaEventCreate(&e));
+    s->n_slots = n_slots;
+    return 0;
+}
+
+int sage_stage_times_get(sage_scene* s, int slot, float ms_out[SAGE_N_STAGES])
+{
+    REQUIRE(s != nullptr && ms_out != nullptr, "sage_stage_times_get: NULL argument");
+    REQUIRE(s->n_slots > 0 && slot >= 0 && slot < s->n_slots, "sage_stage_times_get: bad slot / timing off");
+    CK(cudaSetDevice(s->device));
+    cudaEvent_t* ev = &s->events[(size_t)slot * (SAGE_N_STAGES + 1)];
+    CK(cudaEventSynchronize(ev[SAGE_N_STAGES]));
+    for (int k = 0; k < SAGE_N_STAGES; ++k) CK(cudaEventElapsedTime(&ms_out[k], ev[k], ev[k + 1]));
     return 0;
 }
 

@@ -16,6 +16,21 @@ from dataclasses import dataclass
 import numpy as np
 
 
+def _recycle_large_allocations():
+    """Serve large numpy temporaries from the heap (and keep it) instead of fresh mmap regions:
+    in the sandboxed containers this runs in, first-touch page faults cost ~30 ms/MB."""
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 1 << 30)                    # M_MMAP_THRESHOLD
+        libc.mallopt(-1, ctypes.c_int(2 ** 31 - 1))  # M_TRIM_THRESHOLD
+    except Exception:
+        pass
+
+
+_recycle_large_allocations()
+
+
 @dataclass
 class GaussianCloud:
     """Raw 3DGS attributes, host side (float32, C-contiguous)."""
@@ -77,60 +92,79 @@ def _box_patches(lo, hi, rng, inward: bool, skip_bottom: bool = False):
 
 
 def _matrix_to_quat_wxyz(Rm: np.ndarray) -> np.ndarray:
-    """Batch rotation matrices [N,3,3] -> quaternions [N,4] (w,x,y,z)."""
+    """Batch rotation matrices [N,3,3] -> quaternions [N,4] (w,x,y,z); vectorised, picks the
+    numerically largest component as pivot."""
     m = Rm
-    tr = m[:, 0, 0] + m[:, 1, 1] + m[:, 2, 2]
-    q = np.zeros((m.shape[0], 4))
-    c0 = tr > 0
-    s = np.sqrt(np.maximum(tr[c0] + 1.0, 1e-12)) * 2
-    q[c0] = np.stack([0.25 * s, (m[c0, 2, 1] - m[c0, 1, 2]) / s, (m[c0, 0, 2] - m[c0, 2, 0]) / s,
-                      (m[c0, 1, 0] - m[c0, 0, 1]) / s], 1)
-    rest = ~c0
-    for i in np.nonzero(rest)[0]:
-        a = m[i]
-        k = int(np.argmax([a[0, 0], a[1, 1], a[2, 2]]))
-        j, l = (k + 1) % 3, (k + 2) % 3
-        s = np.sqrt(max(1.0 + a[k, k] - a[j, j] - a[l, l], 1e-12)) * 2
-        v = np.zeros(4)
-        v[0] = (a[l, j] - a[j, l]) / s
-        v[1 + k] = 0.25 * s
-        v[1 + j] = (a[j, k] + a[k, j]) / s
-        v[1 + l] = (a[l, k] + a[k, l]) / s
-        q[i] = v
+    m00, m11, m22 = m[:, 0, 0], m[:, 1, 1], m[:, 2, 2]
+    cand = np.stack([1 + m00 + m11 + m22, 1 + m00 - m11 - m22, 1 - m00 + m11 - m22, 1 - m00 - m11 + m22], 1)
+    k = np.argmax(cand, axis=1)
+    s = 2.0 * np.sqrt(np.maximum(cand[np.arange(m.shape[0]), k], 1e-12))
+    a = (m[:, 2, 1] - m[:, 1, 2]) / s
+    b = (m[:, 0, 2] - m[:, 2, 0]) / s
+    c = (m[:, 1, 0] - m[:, 0, 1]) / s
+    d = (m[:, 0, 1] + m[:, 1, 0]) / s
+    e = (m[:, 0, 2] + m[:, 2, 0]) / s
+    f = (m[:, 1, 2] + m[:, 2, 1]) / s
+    q4 = 0.25 * s
+    q = np.where((k == 0)[:, None], np.stack([q4, a, b, c], 1),
+        np.where((k == 1)[:, None], np.stack([a, q4, d, e], 1),
+        np.where((k == 2)[:, None], np.stack([b, d, q4, f], 1), np.stack([c, e, f, q4], 1))))
     return q
 
 
-def _sample_patches(patches, n: int, rng, sh_degree: int, size_scale: float) -> GaussianCloud:
-    areas = np.array([p.area for p in patches])
-    total = float(areas.sum())
-    spacing = np.sqrt(total / max(n, 1))
-    which = rng.choice(len(patches), size=n, p=areas / total)
-    O = np.stack([p.origin for p in patches])[which]
-    U = np.stack([p.u for p in patches])[which]
-    Vv = np.stack([p.v for p in patches])[which]
-    Nn = np.stack([p.normal for p in patches])[which]
-    col = np.stack([p.color for p in patches])[which]
-    a, b = rng.uniform(size=n), rng.uniform(size=n)
-    thickness = 0.09 * spacing                     # 5 mm at the config-1 density (5.5 cm spacing)
-    xyz = O + a[:, None] * U + b[:, None] * Vv + Nn * rng.normal(0.0, thickness, size=(n, 1))
-    # tangential log-scale U(ln 0.36 s, ln 1.45 s): (0.02, 0.08) m at the config-1 density
-    lo, hi = np.log(0.36 * spacing * size_scale), np.log(1.45 * spacing * size_scale)
-    t1, t2 = rng.uniform(lo, hi, size=n), rng.uniform(lo, hi, size=n)
-    log_scale = np.stack([t1, t2, np.minimum(t1, t2) - np.log(5.0)], 1)
-    uh = U / np.linalg.norm(U, axis=1, keepdims=True)
-    vh = np.cross(Nn, uh)
-    th = rng.uniform(0.0, 2 * np.pi, size=n)
-    c, s = np.cos(th)[:, None], np.sin(th)[:, None]
-    Rm = np.stack([uh * c + vh * s, -uh * s + vh * c, Nn], axis=2)   # columns = local axes
-    quat = _matrix_to_quat_wxyz(Rm) * rng.uniform(0.5, 2.0, size=(n, 1))  # un-normalised on purpose
-    opacity = rng.uniform(0.0, 4.0, size=n)
+def _sample_groups(groups, n: int, rng, sh_degree: int, chunk: int = 262_144) -> GaussianCloud:
+    """Sample n Gaussians over several patch groups.
+
+    groups: list of (patches, fraction_of_n, size_scale).  Patches are drawn from one combined
+    distribution, so the output arrays have no spatial order.  Work proceeds in chunks written into
+    preallocated float32 outputs (first-touch page faults are expensive in the sandboxes this
+    runs in; temporaries stay chunk-sized and are recycled by the allocator).
+    """
+    P_o, P_u, P_v, P_n, P_col, P_w, P_sp, P_ss = [], [], [], [], [], [], [], []
+    for patches, frac, size_scale in groups:
+        areas = np.array([p.area for p in patches])
+        g_n = max(frac * n, 1.0)
+        spacing = np.sqrt(areas.sum() / g_n)
+        for p, ar in zip(patches, areas):
+            P_o.append(p.origin); P_u.append(p.u); P_v.append(p.v); P_n.append(p.normal)
+            P_col.append(p.color); P_w.append(frac * ar / areas.sum()); P_sp.append(spacing); P_ss.append(size_scale)
+    P_o, P_u, P_v, P_n, P_col = (np.stack(x) for x in (P_o, P_u, P_v, P_n, P_col))
+    P_w = np.asarray(P_w); P_w = P_w / P_w.sum()
+    P_sp, P_ss = np.asarray(P_sp), np.asarray(P_ss)
+    P_uh = P_u / np.linalg.norm(P_u, axis=1, keepdims=True)
+    P_vh = np.cross(P_n, P_uh)
     nb = (sh_degree + 1) ** 2
-    sh = np.zeros((n, nb, 3))
-    sh[:, 0, :] = np.clip(col + rng.uniform(-0.35, 0.35, size=(n, 3)), -1.0, 1.0)
-    if nb > 1:
-        sh[:, 1:, :] = rng.normal(0.0, 0.05, size=(n, nb - 1, 3))
-    f32 = lambda x: np.ascontiguousarray(x, dtype=np.float32)
-    return GaussianCloud(f32(xyz), f32(log_scale), f32(quat), f32(opacity), f32(sh))
+    xyz = np.empty((n, 3), np.float32)
+    log_scale = np.empty((n, 3), np.float32)
+    quat = np.empty((n, 4), np.float32)
+    opacity = np.empty(n, np.float32)
+    sh = np.empty((n, nb, 3), np.float32)
+    for s0 in range(0, n, chunk):
+        m = min(chunk, n - s0)
+        which = rng.choice(len(P_w), size=m, p=P_w)
+        spacing = P_sp[which]
+        a, b = rng.uniform(size=m), rng.uniform(size=m)
+        thickness = 0.09 * spacing                 # 5 mm at the config-1 density (5.5 cm spacing)
+        Nn = P_n[which]
+        xyz[s0:s0 + m] = (P_o[which] + a[:, None] * P_u[which] + b[:, None] * P_v[which]
+                          + Nn * (rng.standard_normal(m) * thickness)[:, None])
+        # tangential log-scale U(ln 0.36 s, ln 1.45 s): (0.02, 0.08) m at the config-1 density
+        lo = np.log(0.36 * spacing * P_ss[which])
+        t1 = lo + rng.uniform(size=m) * np.log(1.45 / 0.36)
+        t2 = lo + rng.uniform(size=m) * np.log(1.45 / 0.36)
+        log_scale[s0:s0 + m, 0] = t1
+        log_scale[s0:s0 + m, 1] = t2
+        log_scale[s0:s0 + m, 2] = np.minimum(t1, t2) - np.log(5.0)
+        th = rng.uniform(0.0, 2 * np.pi, size=m)
+        c, sn = np.cos(th)[:, None], np.sin(th)[:, None]
+        uh, vh = P_uh[which], P_vh[which]
+        Rm = np.stack([uh * c + vh * sn, -uh * sn + vh * c, Nn], axis=2)   # columns = local axes
+        quat[s0:s0 + m] = _matrix_to_quat_wxyz(Rm) * rng.uniform(0.5, 2.0, size=(m, 1))  # un-normalised on purpose
+        opacity[s0:s0 + m] = rng.uniform(0.0, 4.0, size=m)
+        sh[s0:s0 + m, 0, :] = np.clip(P_col[which] + rng.uniform(-0.35, 0.35, size=(m, 3)), -1.0, 1.0)
+        if nb > 1:
+            sh[s0:s0 + m, 1:, :] = rng.standard_normal(size=(m, nb - 1, 3), dtype=np.float32) * np.float32(0.05)
+    return GaussianCloud(xyz, log_scale, quat, opacity, sh)
 
 
 def _furniture(rng, count: int, room_lo, room_hi, margin: float = 0.3):
@@ -152,12 +186,8 @@ def synthetic_room(seed: int = 0, n: int = 50_000, sh_degree: int = 3, size=(6.0
     shell = _box_patches(lo, hi, rng, inward=True)
     boxes = _furniture(rng, n_furniture, lo, hi)
     furn = [p for b in boxes for p in _box_patches(b[0], b[1], rng, inward=False, skip_bottom=True)]
-    n_shell = int(round(0.7 * n))
-    a = _sample_patches(shell, n_shell, rng, sh_degree, size_scale)
-    b = _sample_patches(furn, n - n_shell, rng, sh_degree, size_scale * 0.8)
-    cloud = GaussianCloud(*(np.concatenate(p) for p in zip(a.as_tuple(), b.as_tuple())))
-    perm = rng.permutation(cloud.n)           # no spatial order in the input arrays
-    return cloud.subset(perm), {"lo": lo, "hi": hi, "walls": [], "boxes": boxes}
+    cloud = _sample_groups([(shell, 0.7, size_scale), (furn, 0.3, size_scale * 0.8)], n, rng, sh_degree)
+    return cloud, {"lo": lo, "hi": hi, "walls": [], "boxes": boxes}
 
 
 def synthetic_interior(seed: int = 1, n: int = 2_000_000, sh_degree: int = 3, size=(12.0, 10.0, 3.0),
@@ -187,14 +217,9 @@ def synthetic_interior(seed: int = 1, n: int = 2_000_000, sh_degree: int = 3, si
             rhi = np.array([(qx + 1) * mx - th, (qy + 1) * my - th, size[2]])
             boxes += _furniture(rng, per, rlo, rhi)
     furn = [p for b in boxes for p in _box_patches(b[0], b[1], rng, inward=False, skip_bottom=True)]
-    n_shell = int(round(0.55 * n))
-    n_wall = int(round(0.20 * n))
-    parts = [_sample_patches(shell, n_shell, rng, sh_degree, size_scale),
-             _sample_patches(wall_p, n_wall, rng, sh_degree, size_scale),
-             _sample_patches(furn, n - n_shell - n_wall, rng, sh_degree, size_scale * 0.8)]
-    cloud = GaussianCloud(*(np.concatenate(p) for p in zip(*(c.as_tuple() for c in parts))))
-    perm = rng.permutation(cloud.n)
-    return cloud.subset(perm), {"lo": lo, "hi": hi, "walls": walls, "boxes": boxes}
+    cloud = _sample_groups([(shell, 0.55, size_scale), (wall_p, 0.20, size_scale),
+                            (furn, 0.25, size_scale * 0.8)], n, rng, sh_degree)
+    return cloud, {"lo": lo, "hi": hi, "walls": walls, "boxes": boxes}
 
 
 def camera_path(layout, n_poses: int = 256, seed: int = 0, height: float = 1.2):

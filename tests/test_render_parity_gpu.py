@@ -71,13 +71,19 @@ def test_projection_elementwise(sage, oracle):
     assert not np.any(vis & ~o_vis), "GPU kept a Gaussian the spec culls"
     for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b"):
         assert np.array_equal(rec[k][vis].view(np.uint32), o_rec[k][vis].view(np.uint32)), k
-    # Gaussians the GPU dropped beyond the spec's cull must be off-screen by a wide margin
+    # Gaussians the GPU dropped beyond the spec's cull rules: their {alpha >= 1/255} ellipse
+    # (binary64, from the binary32 conic, no slack) must miss every pixel centre of the image.
     extra = o_vis & ~vis
     if extra.any():
         r = o_rec[extra]
-        hx = 3.5 * np.sqrt(r["cov_a"]) + 1.0
-        hy = 3.5 * np.sqrt(r["cov_c"]) + 1.0
-        off = (r["gx"] + hx < 0) | (r["gx"] - hx > cam.width) | (r["gy"] + hy < 0) | (r["gy"] - hy > cam.height)
+        A, B, Cq = -r["qa"].astype(np.float64), -0.5 * r["qb"].astype(np.float64), -r["qc"].astype(np.float64)
+        det = A * Cq - B * B
+        t2 = np.log2(255.0 * r["opacity"].astype(np.float64))
+        ok = det > 0
+        hx = np.where(ok, np.sqrt(np.maximum(t2 * Cq / np.where(ok, det, 1.0), 0.0)), np.inf)
+        hy = np.where(ok, np.sqrt(np.maximum(t2 * A / np.where(ok, det, 1.0), 0.0)), np.inf)
+        gx, gy = r["gx"].astype(np.float64), r["gy"].astype(np.float64)
+        off = (gx + hx < 0.5) | (gx - hx > cam.width - 0.5) | (gy + hy < 0.5) | (gy - hy > cam.height - 0.5)
         assert off.all()
 
 
