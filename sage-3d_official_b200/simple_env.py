@@ -1,0 +1,426 @@
+"""``SimpleVLNEnv`` — drop-in for the reference's Isaac-Sim environment façade
+(Code/benchmark/environment_evaluation/simple_env.py:43), re-backed by the B200 engine.
+
+What ``run_benchmark.py`` / ``measures.py`` touch (SURVEY.md §8b seam 1) is reproduced member for
+member; what Isaac did behind it is replaced:
+
+=====================================  ==========================================================
+reference (file:line)                   here
+=====================================  ==========================================================
+``get_rgb`` :1356 (5 RTX frames)        one ``sage_render_host`` frame, RGB u8 (H,W,3)
+``get_depth`` :1395 (21 RTX frames)     same frame's planar depth, ``clip(0.1, 6.5)`` (:1578)
+``_update_camera_position`` :1196       same pose arithmetic -> ``Camera.from_isaac_pose``
+``apply_cmd_for`` :1987                 same march (20 cm cap, 1 cm steps, 4-way 5 mm exploration,
+ + ``_try_*_movement`` :2116-2234       efficiency thresholds) but all <= 60 candidate positions are
+ + ``_is_position_safe`` :2236          checked in ONE batched grid-collide launch instead of a
+                                        Python call + RTX frame + physics step per sample
+``_init_collision_detector`` :125       :class:`SemanticMap2DCollisionDetector` (GPU lookups),
+                                        ``robot_radius_m=0.08, scale=0.05`` (:136-140)
+=====================================  ==========================================================
+
+Shipped-but-dead behaviour is kept dead on purpose: ``_check_collision`` is never
+called by the motion code, so ``_total_collision_count`` / ``_collision_detected`` only change when a
+caller invokes it explicitly.  Error convention: render returns ``None`` on failure, collide
+``False``; nothing raises out of the hot path.
+
+Candidate positions are generated with the same NumPy expressions as the reference so their dtypes
+(float32 on the straight march, float64 on the exploration directions) and values are identical
+under whichever NumPy runs; the batched kernel honours the per-dtype promotion rules.
+"""
+from __future__ import annotations
+
+import math
+import os
+import time
+from pathlib import Path
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .camera import Camera, USD_GAUSS_MODEL_TO_WORLD
+from .collision_detector import SemanticMap2DCollisionDetector
+
+
+def _debug_print(msg: str) -> None:
+    if not os.environ.get("SILENT_LOGGING_MODE", False):
+        print(msg)
+
+
+class SimpleVLNEnv:
+    """VLN environment with the reference's public surface, rendered and collided on the GPU."""
+
+    CAMERA_HEIGHT = 1.2            # simple_env.py:1204
+    DEPTH_CLIP = (0.1, 6.5)        # simple_env.py:1578
+    AGENT_CENTRE_Z = 0.85          # simple_env.py:238
+    AGENT_RADIUS, AGENT_HEIGHT = 0.1, 0.5   # simple_env.py:754-755
+
+    def __init__(self, scene_usd_path: str, headless: bool = True, hz: int = 30,
+                 agent_prim_path: str = "/World/AgentCamera", resolution: Tuple[int, int] = (640, 480),
+                 map_json_path: str = None, device: int = 0) -> None:
+        self.scene_usd_path = str(Path(scene_usd_path).resolve())
+        self.hz = hz
+        self.agent_prim_path = agent_prim_path
+        self.resolution = resolution
+        self.headless = headless
+        self.is_stop_called = False
+        self.consecutive_collisions = 0
+        self._total_collision_count = 0
+        self._debug_disable_collision = False
+        self._episode_start_time = time.time()
+        self._current_time = time.time()
+        self._collision_detected = False
+        self._log_function = None
+        self._map_json_path = map_json_path
+        self.semantic_map_path = map_json_path
+        self.collision_detector = None
+        self._device = device
+        self._scene = None
+        self._bodies = None
+        self._model_to_world = None
+        self._frame_key = None
+        self._frame = None
+        self.render_calls = 0          # engine frames actually rendered (1 per distinct pose)
+        self.collide_launches = 0      # batched collide launches
+        self._pos = np.array([0.0, 0.0, self.AGENT_CENTRE_Z], dtype=np.float32)
+        self._yaw = 0.0
+        self._init_engine()
+
+    # ---- logging / time (simple_env.py:96-123) -------------------------------------------------
+    def _log(self, msg: str) -> None:
+        _debug_print(msg)
+        if self._log_function:
+            try:
+                self._log_function(msg)
+            except Exception:
+                pass
+
+    def update_time_and_reset_collision(self) -> None:
+        self._current_time = time.time()
+        self._collision_detected = False
+
+    def reset_episode_time(self) -> None:
+        self._episode_start_time = time.time()
+        self._current_time = time.time()
+        self._collision_detected = False
+
+    def set_log_function(self, log_func) -> None:
+        self._log_function = log_func
+        self._init_collision_detector(self._map_json_path)      # the reference re-inits here (:119-123)
+
+    def set_collision_detection(self, enabled: bool) -> None:
+        self._debug_disable_collision = not enabled
+
+    # ---- engine ---------------------------------------------------------------------------------
+    def _init_engine(self) -> None:
+        from .scene_io import load_cloud, resolve_stage_assets
+        from .api import GaussianScene, CollisionBodies
+        self._scene = None
+        self._bodies = None
+        gauss, coll, is_stage = resolve_stage_assets(self.scene_usd_path)
+        # a USDA stage carries rotateXYZ(-90,0,0) on the Gaussian prim (template.usda:120)
+        self._model_to_world = USD_GAUSS_MODEL_TO_WORLD if is_stage else None
+        if gauss is None:
+            self._log(f"[ENV_INIT] no Gaussian payload (.ply/.npz) found for {self.scene_usd_path}; frames will be black")
+            return
+        try:
+            self._scene = GaussianScene(load_cloud(gauss), device=self._device)
+            self._log(f"[ENV_INIT] scene {gauss}: {self._scene.n} Gaussians resident on cuda:{self._device}")
+            if coll is not None:
+                z = np.load(coll)
+                self._bodies = CollisionBodies(z["mu"], z["log_scale"], z["quat"], device=self._device)
+        except Exception as e:
+            self._log(f"[ENV_INIT] failed to load scene: {e}")
+            self._scene = None
+
+    def _init_collision_detector(self, map_json_path: str) -> None:
+        self.collision_detector = None
+        if map_json_path and os.path.exists(map_json_path):
+            try:
+                self.collision_detector = SemanticMap2DCollisionDetector(
+                    map_json_path, robot_radius_m=0.08, scale=0.05, device=self._device)
+                info = self.collision_detector.get_collision_info()
+                self._log(f"[COLLISION_2D] map {map_json_path}: {info['obstacle_pixels']}/{info['total_pixels']} obstacle cells")
+            except Exception as e:
+                self._log(f"[COLLISION_2D] cannot load 2D semantic map collision detector: {e}")
+                self.collision_detector = None
+        else:
+            self._log(f"[COLLISION_2D] no usable 2D semantic map ({map_json_path})")
+
+    def load_scene(self, new_scene_usd_path: str) -> bool:
+        try:
+            self.scene_usd_path = str(Path(new_scene_usd_path).resolve())
+            self._frame_key = None
+            self._init_engine()
+            return self._scene is not None
+        except Exception as e:
+            self._log(f"[SCENE_SWITCH] Scene switch failed: {e}")
+            return False
+
+    def update_map(self, new_map_path: str) -> bool:
+        try:
+            self._map_json_path = new_map_path
+            self.semantic_map_path = new_map_path
+            self._init_collision_detector(new_map_path)
+            return True
+        except Exception as e:
+            self._log(f"[MAP_SWITCH] Map switch failed: {e}")
+            return False
+
+    def close(self) -> None:
+        for h in (self._scene, self._bodies):
+            if h is not None:
+                h.close()
+        self._scene = self._bodies = None
+
+    # ---- pose (simple_env.py:1149-1353) ---------------------------------------------------------
+    def set_start_pose(self, position: List[float], rotation_xyzw: List[float]) -> None:
+        self.is_stop_called = False
+        self.consecutive_collisions = 0
+        self._total_collision_count = 0
+        self._pos = np.array(position, dtype=np.float32)
+        x, y, z, w = rotation_xyzw
+        self._original_quaternion = list(rotation_xyzw).copy()
+        yaw_new = 2 * math.atan2(-x, w)
+        self._yaw = yaw_new - math.pi
+        if self._yaw < -math.pi:
+            self._yaw += 2 * math.pi
+        elif self._yaw > math.pi:
+            self._yaw -= 2 * math.pi
+        self._initial_yaw = self._yaw
+        self._update_camera_position()
+
+    def _update_camera_position(self) -> None:
+        camera_pos = self._pos.copy()
+        camera_pos[2] = self.CAMERA_HEIGHT
+        if hasattr(self, "_original_quaternion"):
+            qx_orig, qy_orig, qz_orig, qw_orig = self._original_quaternion
+            qx_correction = math.sin(math.radians(-45) / 2)
+            base_qx, base_qy, base_qz, base_qw = qx_orig + qx_correction, qy_orig, qz_orig, qw_orig
+            yaw_delta = self._yaw - self._initial_yaw
+            if abs(yaw_delta) > 0.01:
+                qz_d, qw_d = math.sin(yaw_delta / 2.0), math.cos(yaw_delta / 2.0)
+                qx = base_qx * qw_d + base_qw * (-qz_d)
+                qy = base_qy * qw_d
+                qz = base_qz * qw_d
+                qw = base_qw * qw_d - base_qx * (-qz_d)
+            else:
+                qx, qy, qz, qw = base_qx, base_qy, base_qz, base_qw
+        else:
+            qx, qy, qz, qw = -math.sin(self._yaw / 2.0), 0.0, 0.0, math.cos(self._yaw / 2.0)
+        # handed to Isaac as `orientation`, i.e. read scalar-first
+        self._cam_position = camera_pos.astype(np.float32)
+        self._cam_orientation = np.array([qx, qy, qz, qw], dtype=np.float32)
+
+    def _apply_pose(self) -> None:
+        self._update_camera_position()
+
+    def get_agent_pos(self) -> np.ndarray:
+        return self._pos.copy()
+
+    def get_yaw(self) -> float:
+        return self._yaw
+
+    def get_collision_count(self) -> int:
+        return self._total_collision_count
+
+    # ---- render (simple_env.py:1356-1842) -------------------------------------------------------
+    def _camera(self) -> Camera:
+        W, H = int(self.resolution[0]), int(self.resolution[1])
+        return Camera.from_isaac_pose(self._cam_position, self._cam_orientation, W, H,
+                                      model_to_world=self._model_to_world)
+
+    def _render_current(self):
+        self._update_camera_position()
+        key = (self._cam_position.tobytes(), self._cam_orientation.tobytes(), tuple(self.resolution))
+        if self._frame_key != key:
+            rgb, depth = self._scene.render_host(self._camera(), want_depth=True)
+            self._frame = (rgb.copy(), depth.copy())
+            self._frame_key = key
+            self.render_calls += 1
+        return self._frame
+
+    def get_rgb(self) -> Optional[np.ndarray]:
+        W, H = int(self.resolution[0]), int(self.resolution[1])
+        if self._scene is None:
+            return np.zeros((H, W, 3), dtype=np.uint8)
+        try:
+            return self._render_current()[0].astype(np.uint8)
+        except Exception as e:
+            _debug_print(f"[WARN] get_rgb failed: {e}")
+            return None
+
+    def get_depth(self) -> Optional[np.ndarray]:
+        W, H = int(self.resolution[0]), int(self.resolution[1])
+        if self._scene is None:
+            return np.full((H, W), 5.0, dtype=np.float32)
+        try:
+            return np.clip(self._render_current()[1].astype(np.float32), *self.DEPTH_CLIP)
+        except Exception as e:
+            _debug_print(f"[WARN] get_depth failed: {e}")
+            return None
+
+    def get_rgbd(self):
+        return self.get_rgb(), self.get_depth()
+
+    # ---- collide (simple_env.py:1844-2250) ------------------------------------------------------
+    def _is_position_safe(self, pos: np.ndarray) -> bool:
+        try:
+            if self.collision_detector is not None and self.collision_detector.check_collision_3d(pos):
+                return False
+            return True
+        except Exception:
+            return False
+
+    def _check_collision(self, new_pos) -> bool:
+        """Kept for API parity; like the reference it is never called by the motion code."""
+        try:
+            if self._debug_disable_collision:
+                return False
+            if self.collision_detector is not None:
+                if self.collision_detector.check_collision_3d(new_pos):
+                    self._collision_detected = True
+                    self._total_collision_count += 1
+                    return True
+                return False
+            return self.check_capsule(new_pos)
+        except Exception:
+            return False
+
+    def check_capsule(self, pos) -> bool:
+        """3-D agent-capsule test against the scene's collision ellipsoids (K7), when loaded."""
+        if self._bodies is None:
+            return False
+        z0 = self.AGENT_CENTRE_Z - self.AGENT_HEIGHT / 2
+        return bool(self._bodies.check(np.asarray(pos, np.float32)[None, :3], radius=self.AGENT_RADIUS,
+                                       z0=z0, z1=z0 + self.AGENT_HEIGHT)[0][0])
+
+    def _safe_mask(self, candidates: List[np.ndarray]) -> np.ndarray:
+        """safe[k] for every candidate, one launch per dtype group (float32 / float64)."""
+        n = len(candidates)
+        safe = np.ones(n, dtype=bool)
+        det = self.collision_detector
+        if det is None or n == 0:
+            return safe
+        try:
+            groups = {}
+            for k, c in enumerate(candidates):
+                groups.setdefault(np.asarray(c).dtype == np.float32, []).append(k)
+            for is32, idx in groups.items():
+                arr = np.stack([np.asarray(candidates[k]) for k in idx])
+                arr = arr.astype(np.float32) if is32 else arr.astype(np.float64)
+                safe[idx] = ~det.check_many(arr)
+                self.collide_launches += 1
+        except Exception:
+            safe[:] = False
+        return safe
+
+    @staticmethod
+    def _march(start_pos: np.ndarray, direction: np.ndarray, max_distance: float, step_size: float):
+        """Candidate positions and cumulative step lengths of a march (same arithmetic as
+        _try_direct_movement / _try_short_movement)."""
+        total_moved = 0.0
+        current_pos = start_pos.copy()
+        cands, moved = [], []
+        while total_moved < max_distance:
+            step_distance = min(step_size, max_distance - total_moved)
+            next_pos = current_pos + direction * step_distance
+            cands.append(next_pos)
+            current_pos = next_pos
+            total_moved += step_distance
+            moved.append(total_moved)
+        return cands, moved
+
+    def apply_cmd_for(self, vx: float, vy: float, yaw_rate: float, duration_s: float) -> None:
+        cos_yaw, sin_yaw = math.cos(self._yaw), math.sin(self._yaw)
+        world_vx = vx * cos_yaw - vy * sin_yaw
+        world_vy = vx * sin_yaw + vy * cos_yaw
+        total_dx = world_vx * duration_s
+        total_dy = world_vy * duration_s
+        total_dyaw = yaw_rate * duration_s
+        old_pos = self._pos.copy()
+        intended_movement = np.linalg.norm([total_dx, total_dy])
+        if intended_movement > 0.001:
+            target_pos = old_pos.copy()
+            target_pos[0] += total_dx
+            target_pos[1] += total_dy
+            actual_movement = self._safe_gradual_movement(old_pos, target_pos, intended_movement)
+            movement_efficiency = actual_movement / intended_movement if intended_movement > 0 else 1.0
+            if movement_efficiency < 0.3 and intended_movement > 0.05:
+                self.consecutive_collisions += 1
+            elif movement_efficiency > 0.6:
+                self.consecutive_collisions = 0
+        self._yaw += total_dyaw
+        self._yaw = ((self._yaw + math.pi) % (2 * math.pi)) - math.pi
+        self._update_camera_position()
+
+    def _safe_gradual_movement(self, start_pos, target_pos, target_distance) -> float:
+        current_pos = self._pos.copy()
+        direction = target_pos - current_pos
+        direction_norm = np.linalg.norm(direction[:2])
+        if direction_norm < 0.001:
+            return 0.0
+        unit_direction = direction / direction_norm
+        max_distance = min(0.20, target_distance)
+
+        # --- direct march: <= 20 samples, one launch ---
+        cands, _ = self._march(current_pos, unit_direction, max_distance, 0.01)
+        safe = self._safe_mask(cands)
+        n_ok = int(np.argmin(safe)) if not safe.all() else len(cands)
+        reached = cands[n_ok - 1] if n_ok > 0 else current_pos
+        if n_ok > 0:
+            self._pos = reached
+        direct_movement = np.linalg.norm(reached[:2] - current_pos[:2])
+        if direct_movement > 0.01:
+            return direct_movement
+
+        # --- lateral exploration: 4 directions x <= 10 samples of 5 mm, one launch ---
+        blocked = unit_direction
+        perpendicular = np.array([-blocked[1], blocked[0], 0])
+        exploration_directions = [perpendicular, -perpendicular,
+                                  perpendicular * 0.707 + blocked * 0.707,
+                                  -perpendicular * 0.707 + blocked * 0.707]
+        marches = []
+        for d in exploration_directions:
+            dn = np.linalg.norm(d[:2])
+            if dn > 0.001:
+                marches.append(self._march(current_pos, d / dn, 0.05, 0.005))
+        flat = [c for cands_d, _ in marches for c in cands_d]
+        safe = self._safe_mask(flat)
+        best_movement, best_pos, k0 = 0.0, current_pos.copy(), 0
+        for cands_d, moved_d in marches:
+            s = safe[k0:k0 + len(cands_d)]
+            k0 += len(cands_d)
+            n_ok = int(np.argmin(s)) if not s.all() else len(cands_d)
+            if n_ok > 0:
+                self._pos = cands_d[n_ok - 1]          # the probing march leaves the agent there (:2206-2222)
+            movement = moved_d[n_ok - 1] if n_ok > 0 else 0.0
+            if movement > best_movement:
+                best_movement = movement
+                best_pos = self._pos.copy()
+        if best_movement > 0.005:
+            self._pos = best_pos
+            return best_movement
+        return 0.0
+
+    # ---- misc -----------------------------------------------------------------------------------
+    @staticmethod
+    def write_video(frames, path: str, fps: int = 10) -> None:
+        """MP4 (or GIF fallback) of RGB frames; the reference uses imageio (simple_env.py:2716)."""
+        frames = [np.asarray(f, np.uint8) for f in frames if f is not None]
+        if not frames:
+            return
+        try:
+            import imageio
+            imageio.mimsave(path, frames, fps=fps)
+            return
+        except Exception:
+            pass
+        try:
+            import cv2
+            h, w = frames[0].shape[:2]
+            vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
+            for f in frames:
+                vw.write(cv2.cvtColor(f, cv2.COLOR_RGB2BGR))
+            vw.release()
+        except Exception as e:
+            _debug_print(f"[WARN] write_video failed: {e}")
