@@ -165,6 +165,14 @@ static int so_project_one(const so_camera* cam, int deg, const float* xyz, const
                           const float* q, float op_raw, const float* sh, so_splat* out)
 {
     const float* R = cam->R;
+    /* load-time validity rule: every attribute finite, |SH coefficient| < 1e30 */
+    {
+        int nfl = 3 * (deg + 1) * (deg + 1);
+        for (int k = 0; k < nfl; ++k)
+            if (!(fabsf(sh[k]) < 1e30f)) return 0;
+        float chk0 = xyz[0] + xyz[1] + xyz[2] + ls[0] + ls[1] + ls[2] + q[0] + q[1] + q[2] + q[3] + op_raw;
+        if (!(chk0 - chk0 == 0.0f)) return 0;
+    }
     float mx = xyz[0], my = xyz[1], mz = xyz[2];
     float tx = fmaf(R[2], mz, fmaf(R[1], my, fmaf(R[0], mx, cam->t[0])));
     float ty = fmaf(R[5], mz, fmaf(R[4], my, fmaf(R[3], mx, cam->t[1])));

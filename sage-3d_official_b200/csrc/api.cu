@@ -40,7 +40,7 @@ cudaError_t dalloc(T** p, size_t count)
     return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
 }
 
-constexpr int DEPTH_BITS = 32;
+constexpr int DEPTH_BITS = 32;   // upper bound; the per-frame width comes from near/far
 constexpr int MAX_TILE_BITS = 24;
 
 }  // namespace
@@ -132,7 +132,7 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     REQUIRE(out != nullptr, "sage_scene_create: out is NULL");
     *out = nullptr;
     REQUIRE(sage_device_count() > 0, "sage_scene_create: no CUDA device (this library has no CPU fallback)");
-    REQUIRE(n >= 0 && n < (int64_t)0x7FFFFFFF, "sage_scene_create: n out of range");
+    REQUIRE(n >= 0 && n <= (int64_t)SAGE_ID_MASK, "sage_scene_create: n out of range (max 2^28-1 Gaussians)");
     REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sage_scene_create: sh_degree must be 0..3");
     REQUIRE(n == 0 || (xyz && log_scale && quat_wxyz && opacity_raw && sh), "sage_scene_create: NULL attribute pointer");
     CK(cudaSetDevice(device));
@@ -159,7 +159,7 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     CKB(dalloc(&s->fr.ntiles, (size_t)n));
     CKB(dalloc(&s->fr.partial, (size_t)(n / 256 + 2)));
     const int total_passes = sage_radix_passes(DEPTH_BITS) + sage_radix_passes(MAX_TILE_BITS);
-    CKB(dalloc(&s->fr.digit_total, (size_t)total_passes * 256));
+    CKB(dalloc(&s->fr.digit_total, (size_t)total_passes * SAGE_RADIX_MAX_BINS));
     CKB(dalloc(&s->fr.counters, (size_t)CNT_COUNT));
     CKB(dalloc(&s->n_dev, 1));
     CKB(cudaHostAlloc((void**)&s->counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
@@ -267,10 +267,16 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     }
     const int tbits = tile_bits(n_tiles > 1 ? n_tiles : 2);
     REQUIRE(tbits <= MAX_TILE_BITS, "sage_render: too many tiles");
-    const int dpasses = sage_radix_passes(DEPTH_BITS), tpasses = sage_radix_passes(tbits);
+    // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
+    uint32_t bn, bf;
+    memcpy(&bn, &cd.near_z, 4);
+    memcpy(&bf, &cd.far_z, 4);
+    int dbits = 1;
+    while (dbits < 32 && ((uint64_t)1 << dbits) <= (uint64_t)(bf - bn)) ++dbits;
+    const int dpasses = sage_radix_passes(dbits), tpasses = sage_radix_passes(tbits);
     int launches = 0;
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, st));
-    CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * 256 * (size_t)(dpasses + tpasses), st));
+    CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * SAGE_RADIX_MAX_BINS * (size_t)(dpasses + tpasses), st));
     cudaEvent_t* ev = s->n_slots > 0
         ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     s->frame_index++;
@@ -280,15 +286,18 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
         sage_launch_project(s->sc, cd, s->fr, st);
         launches += 1;
         STAGE_MARK(1);
-        int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->sc.n, 0, DEPTH_BITS, true,
-                                  s->fr.block_hist, s->fr.digit_total, &launches, st);
+        int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->fr.counters + CNT_VISIBLE, s->sc.n,
+                                  0, dbits, true, true, s->fr.block_hist, s->fr.digit_total, &launches, st);
         const uint32_t* order = s->fr.dval[res];
         STAGE_MARK(2);
+        sage_launch_sh_color(s->sc, cd, s->fr, order, st);
+        launches += 1;
         sage_launch_binning(cd, s->fr, order, s->sc.n, s->cap, &launches, st);
         STAGE_MARK(3);
-        int ires = sage_radix_sort(s->fr.ikey, s->fr.ival, s->fr.counters + CNT_INSTANCES, s->cap, 0,
-                                   tbits, false, s->fr.block_hist,
-                                   s->fr.digit_total + (size_t)dpasses * 256, &launches, st);
+        int ires = sage_radix_sort(s->fr.ikey, s->fr.ival, s->fr.counters + CNT_INSTANCES,
+                                   s->fr.counters + CNT_INSTANCES, s->cap, 0, tbits, false, false,
+                                   s->fr.block_hist,
+                                   s->fr.digit_total + (size_t)dpasses * SAGE_RADIX_MAX_BINS, &launches, st);
         STAGE_MARK(4);
         sage_launch_ranges(s->fr, s->fr.ikey[ires], s->cap, n_tiles, &launches, st);
         STAGE_MARK(5);
@@ -417,30 +426,36 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     if (make_cam(cam, row0_tiles, row1_tiles, &cd)) return 1;
     CK(cudaSetDevice(s->device));
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, nullptr));
+    CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * SAGE_RADIX_MAX_BINS * (size_t)sage_radix_passes(32), nullptr));
     sage_launch_project(s->sc, cd, s->fr, nullptr);
+    const size_t n = (size_t)s->sc.n;
+    std::vector<uint32_t> key(n);
+    if (n) CK(cudaMemcpy(key.data(), s->fr.dkey[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    {
+        int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->fr.counters + CNT_VISIBLE, s->sc.n, 0, 32,
+                                  true, true, s->fr.block_hist, s->fr.digit_total, nullptr, nullptr);
+        sage_launch_sh_color(s->sc, cd, s->fr, s->fr.dval[res], nullptr);
+    }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    const size_t n = (size_t)s->sc.n;
     std::vector<float4> r0(n), r1(n), r2(n);
     std::vector<uint2> rc(n);
-    std::vector<uint32_t> key(n);
     if (n) {
         CK(cudaMemcpy(r0.data(), s->fr.rec0, n * sizeof(float4), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(r1.data(), s->fr.rec1, n * sizeof(float4), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(r2.data(), s->fr.rec2, n * sizeof(float4), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(rc.data(), s->fr.rect, n * sizeof(uint2), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(key.data(), s->fr.dkey[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     for (size_t i = 0; i < n; ++i) {
         sage_splat_record& o = records_host[i];
         memset(&o, 0, sizeof o);
         visible_host[i] = key[i] != SAGE_KEY_CULLED;
         if (!visible_host[i]) continue;
-        o.gx = r0[i].x; o.gy = r0[i].y; o.qa = r0[i].z; o.qb = r0[i].w;
-        o.qc = r1[i].x; o.opacity = r1[i].y; o.z = r1[i].z;
+        o.gx = r0[i].x; o.gy = r0[i].y; o.qa = r0[i].z;
+        o.qb = r1[i].x; o.qc = r1[i].y; o.opacity = r1[i].z; o.z = r1[i].w;
         o.r = r2[i].x; o.g = r2[i].y; o.b = r2[i].z;
-        o.tile_x0 = rc[i].x & 0xFFFF; o.tile_x1 = rc[i].x >> 16;
-        o.tile_y0 = rc[i].y & 0xFFFF; o.tile_y1 = rc[i].y >> 16;
+        o.tile_x0 = (rc[i].x & 0xFFFF) / SAGE_TILE; o.tile_x1 = (rc[i].x >> 16) / SAGE_TILE;
+        o.tile_y0 = (rc[i].y & 0xFFFF) / SAGE_TILE; o.tile_y1 = (rc[i].y >> 16) / SAGE_TILE;
     }
     return 0;
 }

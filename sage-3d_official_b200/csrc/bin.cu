@@ -92,7 +92,17 @@ k_scan_partials(uint32_t* __restrict__ partial, uint32_t* __restrict__ counters,
     }
 }
 
-// emit (tile, gaussian) pairs in depth order
+// which 8x8 quadrants of tile (tx,ty) the inclusive pixel box [px0,px1]x[py0,py1] overlaps:
+// bit (qy*2 + qx), matching the warp -> quadrant map of the composite kernel
+__device__ __forceinline__ uint32_t quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
+{
+    const int bx = tx * SAGE_TILE, by = ty * SAGE_TILE;
+    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
+    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
+    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
+}
+
+// emit (tile, gaussian | quadrant mask) pairs in depth order
 __global__ void __launch_bounds__(B_THREADS)
 k_emit(SageCamDev cam, const uint32_t* __restrict__ order, const uint32_t* __restrict__ ntiles,
        const uint2* __restrict__ rect, const uint32_t* __restrict__ partial,
@@ -123,20 +133,19 @@ k_emit(SageCamDev cam, const uint32_t* __restrict__ order, const uint32_t* __res
     for (int k = 0; k < B_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0u;
     uint32_t off = partial[blockIdx.x] + woff + (incl - c);
 
-    const int x0 = rc.x & 0xFFFF, x1 = rc.x >> 16, y0 = rc.y & 0xFFFF, y1 = rc.y >> 16;
-    const int wdt = x1 - x0 + 1;
     const int tiles_x = cam.tiles_x, row0 = cam.row0;
     if (c > 32u) {                       // large footprints are spread over the whole block
         uint32_t q = atomicAdd(&big_n, 1u);
         big_q[q] = threadIdx.x;
         big_off[q] = off;
     } else if (c > 0u) {
+        const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
         uint32_t o = off;
-        for (int ty = y0; ty <= y1; ++ty)
-            for (int tx = x0; tx <= x1; ++tx, ++o)
+        for (int ty = py0 / SAGE_TILE; ty <= py1 / SAGE_TILE; ++ty)
+            for (int tx = px0 / SAGE_TILE; tx <= px1 / SAGE_TILE; ++tx, ++o)
                 if (o < cap) {
                     ikey[o] = (uint32_t)((ty - row0) * tiles_x + tx);
-                    ival[o] = g;
+                    ival[o] = g | (quad_mask(px0, px1, py0, py1, tx, ty) << SAGE_ID_BITS);
                 }
     }
     // broadcast the big ones through shared memory
@@ -151,19 +160,19 @@ k_emit(SageCamDev cam, const uint32_t* __restrict__ order, const uint32_t* __res
         const uint32_t bo = big_off[q];
         const uint2 brc = s_rc[t];
         const uint32_t bg = s_g[t];
-        const int bx0 = brc.x & 0xFFFF, bx1 = brc.x >> 16, by0 = brc.y & 0xFFFF, by1 = brc.y >> 16;
-        const int bw = bx1 - bx0 + 1;
-        const uint32_t bc = (uint32_t)bw * (uint32_t)(by1 - by0 + 1);
+        const int px0 = brc.x & 0xFFFF, px1 = brc.x >> 16, py0 = brc.y & 0xFFFF, py1 = brc.y >> 16;
+        const int bx0 = px0 / SAGE_TILE, by0 = py0 / SAGE_TILE;
+        const int bw = px1 / SAGE_TILE - bx0 + 1;
+        const uint32_t bc = (uint32_t)bw * (uint32_t)(py1 / SAGE_TILE - by0 + 1);
         for (uint32_t k = threadIdx.x; k < bc; k += B_THREADS) {
             uint32_t o = bo + k;
             if (o < cap) {
                 int ty = by0 + (int)(k / (uint32_t)bw), tx = bx0 + (int)(k % (uint32_t)bw);
                 ikey[o] = (uint32_t)((ty - row0) * tiles_x + tx);
-                ival[o] = bg;
+                ival[o] = bg | (quad_mask(px0, px1, py0, py1, tx, ty) << SAGE_ID_BITS);
             }
         }
     }
-    (void)wdt;
 }
 
 __global__ void __launch_bounds__(B_THREADS)
@@ -171,11 +180,11 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ co
               uint2* __restrict__ ranges)
 {
     const uint32_t D = counters[CNT_INSTANCES];
-    const uint32_t j = blockIdx.x * B_THREADS + threadIdx.x;
-    if (j >= D) return;
-    const uint32_t k = __ldg(&keys[j]);
-    if (j == 0 || __ldg(&keys[j - 1]) != k) ranges[k].x = j;
-    if (j == D - 1 || __ldg(&keys[j + 1]) != k) ranges[k].y = j + 1;
+    for (uint32_t j = blockIdx.x * B_THREADS + threadIdx.x; j < D; j += gridDim.x * B_THREADS) {
+        const uint32_t k = __ldg(&keys[j]);
+        if (j == 0 || __ldg(&keys[j - 1]) != k) ranges[k].x = j;
+        if (j == D - 1 || __ldg(&keys[j + 1]) != k) ranges[k].y = j + 1;
+    }
 }
 
 }  // namespace
@@ -198,6 +207,7 @@ void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_
     cudaMemsetAsync(fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st);
     int blocks = (int)((cap + B_THREADS - 1) / B_THREADS);
     if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8;      // persistent grid-stride: D is only known on the device
     k_tile_ranges<<<blocks, B_THREADS, 0, st>>>(sorted_keys, fr.counters, fr.ranges);
     if (launches) *launches += 1;
 }

@@ -49,68 +49,86 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
             const uint2* __restrict__ ranges, PeerOut out)
 {
     __shared__ float4 s0[C_THREADS], s1[C_THREADS], s2[C_THREADS];
+    __shared__ uint32_t smask[C_THREADS];
     const int tile = blockIdx.x;
     const int tx = tile % cam.tiles_x, ty = cam.row0 + tile / cam.tiles_x;
     const uint2 rg = ranges[tile];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    // warp w owns the 8x8 quadrant (w&1, w>>1); lane -> row lane>>2, pixel pair lane&3
     const int px = tx * SAGE_TILE + (w & 1) * 8 + (lane & 3) * 2;
     const int py = ty * SAGE_TILE + (w >> 1) * 8 + (lane >> 2);
-    const float2 pxc = make_float2((float)px + 0.5f, (float)(px + 1) + 0.5f);
-    const float pyc = (float)py + 0.5f;
     const bool in0 = px < cam.W && py < cam.H, in1 = (px + 1) < cam.W && py < cam.H;
+    // a finished (or off-image) pixel gets a far-away x so that it fails the cheap skip test
+    const float FAR_X = 3.0e38f;
+    float2 pxc = make_float2(in0 ? (float)px + 0.5f : FAR_X, in1 ? (float)(px + 1) + 0.5f : FAR_X);
+    const float pyc = (float)py + 0.5f;
     bool act0 = in0, act1 = in1;
     float2 T = f2(1.0f), Cr = f2(0.0f), Cg = f2(0.0f), Cb = f2(0.0f), Dz = f2(0.0f);
 
     for (uint32_t base = rg.x; base < rg.y; base += C_THREADS) {
         const int cnt = min((uint32_t)C_THREADS, rg.y - base);
+        uint32_t qm = 0;
         if (tid < cnt) {
-            const uint32_t g = __ldg(&vals[base + tid]);
+            const uint32_t v = __ldg(&vals[base + tid]);
+            const uint32_t g = v & SAGE_ID_MASK;
+            qm = v >> SAGE_ID_BITS;
             s0[tid] = __ldg(&rec0[g]);
             s1[tid] = __ldg(&rec1[g]);
             s2[tid] = __ldg(&rec2[g]);
         }
+        smask[tid] = qm;
         __syncthreads();
-        if (act0 || act1) {
-            for (int j = 0; j < cnt; ++j) {
-                const float4 a = s0[j];   // gx gy qa qb
-                const float4 b = s1[j];   // qc opacity z thr
-                const float dy = pyc - a.y;
-                const float bdy = a.w * dy;
-                const float cdy = b.x * dy;
-                const float cdy2 = cdy * dy;
-                const float2 dx = __fadd2_rn(pxc, f2(-a.x));
-                const float2 wv = __ffma2_rn(f2(a.z), dx, f2(bdy));
-                const float2 pw = __ffma2_rn(dx, wv, f2(cdy2));
-                // b.w is a conservative skip threshold (log2 units): below it alpha < 1/255 for sure
-                bool v0 = act0 && pw.x <= 0.0f && pw.x >= b.w;
-                bool v1 = act1 && pw.y <= 0.0f && pw.y >= b.w;
-                if (!(v0 || v1)) continue;
-                const float2 e = sage_exp2_x2(pw);
-                float2 al = __fmul2_rn(f2(b.y), e);
-                al.x = fminf(SAGE_ALPHA_MAX, al.x);
-                al.y = fminf(SAGE_ALPHA_MAX, al.y);
-                v0 = v0 && al.x >= SAGE_ALPHA_MIN;
-                v1 = v1 && al.y >= SAGE_ALPHA_MIN;
-                al.x = v0 ? al.x : 0.0f;
-                al.y = v1 ? al.y : 0.0f;
-                float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));   // 1 - alpha
-                float2 Tn = __fmul2_rn(T, om);
-                const bool stop0 = v0 && Tn.x < SAGE_T_MIN;
-                const bool stop1 = v1 && Tn.y < SAGE_T_MIN;
-                if (stop0 || stop1) {
-                    if (stop0) { act0 = false; al.x = 0.0f; }
-                    if (stop1) { act1 = false; al.y = 0.0f; }
-                    om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
-                    Tn = __fmul2_rn(T, om);
-                    if (!(act0 || act1)) break;
+        // warp-uniform liveness: every lane takes part in the ballots below
+        if (__any_sync(0xffffffffu, act0 || act1)) {
+#pragma unroll 1
+            for (int k = 0; k < C_THREADS / 32; ++k) {
+                if (k * 32 >= cnt) break;
+                // entries of this 32-chunk whose bounding box reaches this warp's quadrant
+                unsigned m = __ballot_sync(0xffffffffu, (smask[k * 32 + lane] >> w) & 1u);
+                while (m) {
+                    const int j = k * 32 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 a = s0[j];                                   // gx gy qa thr
+                    const float2 bq = *reinterpret_cast<const float2*>(&s1[j]);   // qb qc
+                    const float dy = pyc - a.y;
+                    const float2 t2 = __fmul2_rn(bq, f2(dy));                 // bdy, cdy
+                    const float cdy2 = t2.y * dy;
+                    const float2 dx = __fadd2_rn(pxc, f2(-a.x));
+                    const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
+                    const float2 pw = __ffma2_rn(dx, wv, f2(cdy2));
+                    // a.w: conservative skip threshold (log2 units): below it alpha < 1/255 for sure
+                    if (!(pw.x >= a.w || pw.y >= a.w)) continue;
+                    bool v0 = act0 && pw.x <= 0.0f && pw.x >= a.w;
+                    bool v1 = act1 && pw.y <= 0.0f && pw.y >= a.w;
+                    if (!(v0 || v1)) continue;
+                    const float2 oz = *reinterpret_cast<const float2*>(&s1[j].z);   // opacity, z
+                    const float2 e = sage_exp2_x2(pw);
+                    float2 al = __fmul2_rn(f2(oz.x), e);
+                    al.x = fminf(SAGE_ALPHA_MAX, al.x);
+                    al.y = fminf(SAGE_ALPHA_MAX, al.y);
+                    v0 = v0 && al.x >= SAGE_ALPHA_MIN;
+                    v1 = v1 && al.y >= SAGE_ALPHA_MIN;
+                    al.x = v0 ? al.x : 0.0f;
+                    al.y = v1 ? al.y : 0.0f;
+                    float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));   // 1 - alpha
+                    float2 Tn = __fmul2_rn(T, om);
+                    const bool stop0 = v0 && Tn.x < SAGE_T_MIN;
+                    const bool stop1 = v1 && Tn.y < SAGE_T_MIN;
+                    if (stop0 || stop1) {
+                        if (stop0) { act0 = false; al.x = 0.0f; pxc.x = FAR_X; }
+                        if (stop1) { act1 = false; al.y = 0.0f; pxc.y = FAR_X; }
+                        om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
+                        Tn = __fmul2_rn(T, om);
+                    }
+                    const float2 wgt = __fmul2_rn(al, T);
+                    const float4 c = s2[j];
+                    Cr = __ffma2_rn(f2(c.x), wgt, Cr);
+                    Cg = __ffma2_rn(f2(c.y), wgt, Cg);
+                    Cb = __ffma2_rn(f2(c.z), wgt, Cb);
+                    Dz = __ffma2_rn(f2(oz.y), wgt, Dz);
+                    T = Tn;
                 }
-                const float2 wgt = __fmul2_rn(al, T);
-                const float4 c = s2[j];
-                Cr = __ffma2_rn(f2(c.x), wgt, Cr);
-                Cg = __ffma2_rn(f2(c.y), wgt, Cg);
-                Cb = __ffma2_rn(f2(c.z), wgt, Cb);
-                Dz = __ffma2_rn(f2(b.z), wgt, Dz);
-                T = Tn;
+                if (!__any_sync(0xffffffffu, act0 || act1)) break;
             }
         }
         if (__syncthreads_and(!(act0 || act1))) break;

@@ -1,4 +1,4 @@
-// K0 precompute (scene upload) and K1 project + cull + SH (per frame).
+// K0 precompute (scene upload), K1a project + cull (per frame), K1b SH colour (per frame).
 //
 // Stands in for the per-Gaussian work hidden inside Isaac's world.step(render=True)
 // (reference call sites simple_env.py:1369, generate_images.py:426).  The arithmetic follows
@@ -6,9 +6,11 @@
 #include "sage_internal.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// K0: view-independent terms, computed once per scene: sigmoid(opacity) and the 3-D covariance.
-// SH coefficients are re-laid out as float4 chunks [chunk][gaussian] so that a warp reading one
-// chunk for 32 consecutive Gaussians issues one fully coalesced 512-byte request.
+// K0: view-independent terms, computed once per scene: sigmoid(opacity), the 3-D covariance, and
+// the SH coefficients repacked as 16-byte chunks, contiguous per Gaussian (a visible Gaussian's
+// 192 B are six whole 32-byte sectors, so a scattered visible set wastes no DRAM traffic).
+// Gaussians with a non-finite attribute or an SH coefficient >= 1e30 in magnitude are dropped at
+// load (spec rule): their opacity is stored as 0, which the per-frame cull rejects.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __restrict__ log_scale,
@@ -17,7 +19,23 @@ k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __rest
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sc.n) return;
-    float o = 1.0f / (1.0f + sage_exp(-opacity[i]));
+    const int nf = 3 * (sc.deg + 1) * (sc.deg + 1);
+    const float* src = sh + (size_t)nf * i;
+    bool ok = true;
+    for (int c = 0; c < sc.n_chunks; ++c) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = (4 * c + k < nf) ? src[4 * c + k] : 0.0f;
+            ok = ok && (fabsf(v[k]) < 1e30f);          // false for NaN / inf as well
+        }
+        sc.shc[(size_t)i * sc.n_chunks + c] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    float chk = xyz[3 * i + 0] + xyz[3 * i + 1] + xyz[3 * i + 2] + log_scale[3 * i + 0] +
+                log_scale[3 * i + 1] + log_scale[3 * i + 2] + quat[4 * i + 0] + quat[4 * i + 1] +
+                quat[4 * i + 2] + quat[4 * i + 3] + opacity[i];
+    ok = ok && (chk - chk == 0.0f);
+    float o = ok ? 1.0f / (1.0f + sage_exp(-opacity[i])) : 0.0f;
     sc.geo0[i] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], o);
 
     float sx = sage_exp(log_scale[3 * i + 0]);
@@ -43,15 +61,6 @@ k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __rest
     float S22 = fmaf(m22, m22, fmaf(m21, m21, m20 * m20));
     sc.geo1[i] = make_float4(S00, S01, S02, S11);
     sc.geo2[i] = make_float2(S12, S22);
-
-    const int nf = 3 * (sc.deg + 1) * (sc.deg + 1);
-    const float* src = sh + (size_t)nf * i;
-    for (int c = 0; c < sc.n_chunks; ++c) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (4 * c + k < nf) ? src[4 * c + k] : 0.0f;
-        sc.shc[(size_t)c * sc.n + i] = make_float4(v[0], v[1], v[2], v[3]);
-    }
 }
 
 void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
@@ -63,69 +72,10 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: project, cull, conic, bounding tile rectangle, SH colour.  One thread per Gaussian;
-// every per-Gaussian stream (geo0/1/2, SH chunks, records) is a 16-byte-per-lane coalesced access.
+// K1a: project, cull, conic, conservative pixel bounding box.  One thread per Gaussian; every
+// per-Gaussian stream is a 16-byte-per-lane coalesced access.  Emits the depth key
+// (bits(z) - bits(near), or CULLED) that the first radix pass compacts and sorts in one go.
 // ---------------------------------------------------------------------------------------------
-__device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
-                                            0.31539156525252005f, -1.0925484305920792f,
-                                            0.5462742152960396f};
-__device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
-                                            -0.4570457994644658f, 0.3731763325901154f,
-                                            -0.4570457994644658f, 1.445305721320277f,
-                                            -0.5900435899266435f};
-
-template <int DEG>
-__device__ __forceinline__ void sh_color(const SageSceneDev& sc, int64_t i, float dx, float dy,
-                                         float dz, float& r, float& g, float& b)
-{
-    constexpr int NB = (DEG + 1) * (DEG + 1);
-    constexpr int NF = 3 * NB;
-    constexpr int NC = (NF + 3) / 4;
-    float shv[NC * 4];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        float4 v = __ldg(&sc.shc[(size_t)c * sc.n + i]);
-        shv[4 * c + 0] = v.x; shv[4 * c + 1] = v.y; shv[4 * c + 2] = v.z; shv[4 * c + 3] = v.w;
-    }
-    float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-    float x = dx / len, y = dy / len, z = dz / len;
-    float basis[NB];
-    basis[0] = 0.28209479177387814f;
-    if constexpr (DEG > 0) {
-        const float C1 = 0.4886025119029199f;
-        basis[1] = -(C1 * y);
-        basis[2] = C1 * z;
-        basis[3] = -(C1 * x);
-    }
-    if constexpr (DEG > 1) {
-        float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        basis[4] = c_SH_C2[0] * xy;
-        basis[5] = c_SH_C2[1] * yz;
-        basis[6] = c_SH_C2[2] * ((2.0f * zz - xx) - yy);
-        basis[7] = c_SH_C2[3] * xz;
-        basis[8] = c_SH_C2[4] * (xx - yy);
-        if constexpr (DEG > 2) {
-            basis[9] = (c_SH_C3[0] * y) * (3.0f * xx - yy);
-            basis[10] = (c_SH_C3[1] * xy) * z;
-            basis[11] = (c_SH_C3[2] * y) * ((4.0f * zz - xx) - yy);
-            basis[12] = (c_SH_C3[3] * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
-            basis[13] = (c_SH_C3[4] * x) * ((4.0f * zz - xx) - yy);
-            basis[14] = (c_SH_C3[5] * z) * (xx - yy);
-            basis[15] = (c_SH_C3[6] * x) * (xx - 3.0f * yy);
-        }
-    }
-    float acc[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float a = basis[0] * shv[c];
-#pragma unroll
-        for (int k = 1; k < NB; ++k) a = fmaf(basis[k], shv[3 * k + c], a);
-        acc[c] = fmaxf(a + 0.5f, 0.0f);
-    }
-    r = acc[0]; g = acc[1]; b = acc[2];
-}
-
-template <int DEG>
 __global__ void __launch_bounds__(256)
 k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 {
@@ -175,6 +125,7 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 float qa = conic_a * (-0.5f * SAGE_LOG2E);
                 float qb = conic_b * (-SAGE_LOG2E);
                 float qc = conic_c * (-0.5f * SAGE_LOG2E);
+                float chk = gx + gy + qa + qb + qc;
 
                 // Conservative bounding rectangle of {alpha >= 1/255}: derived in binary64 from
                 // the *rounded* conic the blend kernel will use, with 0.2 % + 0.02 slack on the
@@ -189,26 +140,23 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 double xlo = floor((double)gx - hx - 0.5), xhi = ceil((double)gx + hx - 0.5);
                 double ylo = floor((double)gy - hy - 0.5), yhi = ceil((double)gy + hy - 0.5);
                 const double Wm = (double)(cam.W - 1), Hm = (double)(cam.H - 1);
-                if (xhi >= 0.0 && xlo <= Wm && yhi >= 0.0 && ylo <= Hm) {
+                if ((chk - chk == 0.0f) && xhi >= 0.0 && xlo <= Wm && yhi >= 0.0 && ylo <= Hm) {
                     int ix0 = (int)fmax(xlo, 0.0), ix1 = (int)fmin(xhi, Wm);
                     int iy0 = (int)fmax(ylo, 0.0), iy1 = (int)fmin(yhi, Hm);
-                    int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
-                    int ty0 = max(iy0 / SAGE_TILE, cam.row0), ty1 = min(iy1 / SAGE_TILE, cam.row1 - 1);
-                    if (ty0 <= ty1 && tx0 <= tx1) {
-                        float cr, cg, cb;
-                        sh_color<DEG>(sc, i, mx - cam.campos[0], my - cam.campos[1],
-                                      mz - cam.campos[2], cr, cg, cb);
-                        float chk = gx + gy + qa + qb + qc + cr + cg + cb;
-                        if (chk - chk == 0.0f) {
-                            vis = true;
-                            key = __float_as_uint(tz);
-                            count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-                            fr.rec0[i] = make_float4(gx, gy, qa, qb);
-                            fr.rec1[i] = make_float4(qc, o, tz, -l2 - 0.01f);
-                            fr.rec2[i] = make_float4(cr, cg, cb, 0.0f);
-                            fr.rect[i] = make_uint2((uint32_t)tx0 | ((uint32_t)tx1 << 16),
-                                                    (uint32_t)ty0 | ((uint32_t)ty1 << 16));
-                        }
+                    // clip to the tile rows this call renders (multi-GPU row sharding)
+                    iy0 = max(iy0, cam.row0 * SAGE_TILE);
+                    iy1 = min(iy1, min(cam.row1 * SAGE_TILE, cam.H) - 1);
+                    if (iy0 <= iy1 && ix0 <= ix1) {
+                        const int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
+                        const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
+                        vis = true;
+                        key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
+                        count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+                        fr.rec0[i] = make_float4(gx, gy, qa, -l2 - 0.01f);
+                        fr.rec1[i] = make_float4(qb, qc, o, tz);
+                        // inclusive pixel bounding box (u16 each)
+                        fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
+                                                (uint32_t)iy0 | ((uint32_t)iy1 << 16));
                     }
                 }
             }
@@ -221,14 +169,92 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], __popc(m));
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1b: view-dependent SH colour for the V visible Gaussians (any order; uses the depth-sorted id
+// list).  Separate from K1a so that neither kernel carries the other's registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
+                                            0.31539156525252005f, -1.0925484305920792f,
+                                            0.5462742152960396f};
+__device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
+                                            -0.4570457994644658f, 0.3731763325901154f,
+                                            -0.4570457994644658f, 1.445305721320277f,
+                                            -0.5900435899266435f};
+
+template <int DEG>
+__global__ void __launch_bounds__(256)
+k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order)
+{
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    constexpr int NF = 3 * NB;
+    constexpr int NC = (NF + 3) / 4;
+    const uint32_t V = fr.counters[CNT_VISIBLE];
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= V) return;
+    const uint32_t i = __ldg(&order[r]);
+    const float4 g0 = __ldg(&sc.geo0[i]);
+    float shv[NC * 4];
+    const float4* sp = sc.shc + (size_t)i * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        float4 v = __ldg(&sp[c]);
+        shv[4 * c + 0] = v.x; shv[4 * c + 1] = v.y; shv[4 * c + 2] = v.z; shv[4 * c + 3] = v.w;
+    }
+    const float dx = g0.x - cam.campos[0], dy = g0.y - cam.campos[1], dz = g0.z - cam.campos[2];
+    float len = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    float x = dx / len, y = dy / len, z = dz / len;
+    float basis[NB];
+    basis[0] = 0.28209479177387814f;
+    if constexpr (DEG > 0) {
+        const float C1 = 0.4886025119029199f;
+        basis[1] = -(C1 * y);
+        basis[2] = C1 * z;
+        basis[3] = -(C1 * x);
+    }
+    if constexpr (DEG > 1) {
+        float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        basis[4] = c_SH_C2[0] * xy;
+        basis[5] = c_SH_C2[1] * yz;
+        basis[6] = c_SH_C2[2] * ((2.0f * zz - xx) - yy);
+        basis[7] = c_SH_C2[3] * xz;
+        basis[8] = c_SH_C2[4] * (xx - yy);
+        if constexpr (DEG > 2) {
+            basis[9] = (c_SH_C3[0] * y) * (3.0f * xx - yy);
+            basis[10] = (c_SH_C3[1] * xy) * z;
+            basis[11] = (c_SH_C3[2] * y) * ((4.0f * zz - xx) - yy);
+            basis[12] = (c_SH_C3[3] * z) * ((2.0f * zz - 3.0f * xx) - 3.0f * yy);
+            basis[13] = (c_SH_C3[4] * x) * ((4.0f * zz - xx) - yy);
+            basis[14] = (c_SH_C3[5] * z) * (xx - yy);
+            basis[15] = (c_SH_C3[6] * x) * (xx - 3.0f * yy);
+        }
+    }
+    float acc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float a = basis[0] * shv[c];
+#pragma unroll
+        for (int k = 1; k < NB; ++k) a = fmaf(basis[k], shv[3 * k + c], a);
+        acc[c] = fmaxf(a + 0.5f, 0.0f);
+    }
+    fr.rec2[i] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+}
+
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
+    k_project<<<blocks, 256, 0, st>>>(sc, cam, fr);
+}
+
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
+                          const uint32_t* order, cudaStream_t st)
+{
+    if (sc.n <= 0) return;
+    int blocks = (int)((sc.n + 255) / 256);
     switch (sc.deg) {
-        case 0: k_project<0><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        case 1: k_project<1><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        case 2: k_project<2><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        default: k_project<3><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
     }
 }

@@ -16,6 +16,9 @@
 #define SAGE_BLUR 0.3f
 #define SAGE_LOG2E 1.44269504f
 #define SAGE_KEY_CULLED 0xFFFFFFFFu
+// instance value = Gaussian id (28 bits) | 8x8-quadrant overlap mask of the tile (4 bits)
+#define SAGE_ID_BITS 28
+#define SAGE_ID_MASK 0x0FFFFFFFu
 
 // device counters (uint32 each)
 enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_N = 3, CNT_COUNT = 8 };
@@ -53,12 +56,12 @@ __device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_L
 // ---- frame workspace ---------------------------------------------------------------------
 struct SageFrame {
     // per-Gaussian (capacity n)
-    float4* rec0;      // gx, gy, qa, qb
-    float4* rec1;      // qc, opacity, z, skip threshold (log2 units)
+    float4* rec0;      // gx, gy, qa, skip threshold (log2 units)
+    float4* rec1;      // qb, qc, opacity, z
     float4* rec2;      // r, g, b, 0
     uint32_t* dkey[2]; // depth keys, ping-pong
     uint32_t* dval[2]; // Gaussian ids, ping-pong
-    uint2* rect;       // packed tile rectangle: x = x0 | x1<<16, y = y0 | y1<<16 (inclusive)
+    uint2* rect;       // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     uint32_t* ntiles;  // tiles touched
     uint32_t* partial; // block partial sums for the offset scan
     // per-instance (capacity cap)
@@ -80,17 +83,23 @@ struct SageSceneDev {
     float4* geo0;       // mu.xyz, sigmoid(opacity)
     float4* geo1;       // S00 S01 S02 S11
     float2* geo2;       // S12 S22
-    float4* shc;        // [n_chunks][n]
+    float4* shc;        // [n][n_chunks]: SH coefficients, contiguous per Gaussian
 };
 
 void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
                             const float* quat, const float* opacity, const float* sh, cudaStream_t st);
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
+                          const uint32_t* order, cudaStream_t st);
 
-// radix sort of (key, val) pairs by bits [lo_bit, lo_bit + n_bits); n read from device memory.
-// Result lands in buffer index returned (0 or 1).  digit_total must be zeroed for `passes` rows.
-int sage_radix_sort(uint32_t* keys[2], uint32_t* vals[2], const uint32_t* n_dev, int64_t capacity,
-                    int lo_bit, int n_bits, bool vals_are_iota, uint32_t* block_hist,
+// Stable LSD radix sort of (key, val) pairs by bits [lo_bit, lo_bit + n_bits); element counts are read
+// from device memory: n_first for pass 0, n_rest for the later passes.  With compact_first, pass 0
+// drops keys equal to SAGE_KEY_CULLED (compaction fused into the first scatter), so n_rest must
+// point at the survivor count.  Returns the index (0/1) of the buffer pair holding the result.
+// digit_total must be zeroed: SAGE_RADIX_MAX_BINS words per pass.
+int sage_radix_sort(uint32_t* keys[2], uint32_t* vals[2], const uint32_t* n_first_dev,
+                    const uint32_t* n_rest_dev, int64_t capacity, int lo_bit, int n_bits,
+                    bool vals_are_iota, bool compact_first, uint32_t* block_hist,
                     uint32_t* digit_total, int* launches, cudaStream_t st);
 int sage_radix_passes(int n_bits);
 size_t sage_radix_block_hist_elems(int64_t capacity);

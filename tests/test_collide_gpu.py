@@ -86,8 +86,8 @@ def test_device_resident_grid_query(sage, oracle):
 def test_capsule_matches_oracle(sage, oracle, seed):
     from sage3d_official_b200.scenes import collision_ellipsoids
     _, layout = sage.synthetic_interior(1, 10)
-    mu, ls, q = collision_ellipsoids(layout, seed=seed, per_m2=60.0)
-    assert mu.shape[0] > 10_000
+    mu, ls, q = collision_ellipsoids(layout, seed=seed, per_m2=200.0)
+    assert mu.shape[0] > 10_000, mu.shape
     bodies = sage.CollisionBodies(mu, ls, q)
     rng = np.random.default_rng(seed)
     P = 300
