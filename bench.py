@@ -309,11 +309,10 @@ def run_native(args):
         nb = 16
         px = W * H if world == 1 else W * (min(rows[1] * 16, H) - rows[0] * 16)
         alg = {   # algorithmic bytes per launch of each stage
-            "project": args.n * 44 + V * 12 * nb + V * 32,
-            "depth_sort": args.n * 8 * 2,
-            "binning": V * 16 + D * 8,
-            "tile_sort": D * 8 * 2,
-            "tile_ranges": D * 4,
+            "project": args.n * 44 + V * 32,
+            "sh_color": V * (12 * nb + 16 + 16),
+            "binning": 2 * V * 16 + D * 8,
+            "tile_sort": D * (8 + 4),
             "composite": D * 36 + px * 7,
         }
         dom_ms = stage[dom]

@@ -40,8 +40,6 @@ cudaError_t dalloc(T** p, size_t count)
     return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
 }
 
-constexpr int DEPTH_BITS = 32;   // upper bound; the per-frame width comes from near/far
-constexpr int MAX_TILE_BITS = 24;
 
 }  // namespace
 
@@ -93,22 +91,17 @@ struct sage_bodies {
 
 static void free_instances(sage_scene* s)
 {
-    for (int k = 0; k < 2; ++k) {
-        cudaFree(s->fr.ikey[k]); s->fr.ikey[k] = nullptr;
-        cudaFree(s->fr.ival[k]); s->fr.ival[k] = nullptr;
-    }
-    cudaFree(s->fr.block_hist); s->fr.block_hist = nullptr;
+    cudaFree(s->fr.inst_key); s->fr.inst_key = nullptr;
+    cudaFree(s->fr.inst_key_alt); s->fr.inst_key_alt = nullptr;
+    cudaFree(s->fr.inst_val); s->fr.inst_val = nullptr;
 }
 
 static int alloc_instances(sage_scene* s, int64_t cap)
 {
     free_instances(s);
-    for (int k = 0; k < 2; ++k) {
-        CK(dalloc(&s->fr.ikey[k], (size_t)cap));
-        CK(dalloc(&s->fr.ival[k], (size_t)cap));
-    }
-    int64_t mx = cap > s->sc.n ? cap : s->sc.n;
-    CK(dalloc(&s->fr.block_hist, sage_radix_block_hist_elems(mx)));
+    CK(dalloc(&s->fr.inst_key, (size_t)cap));
+    CK(dalloc(&s->fr.inst_key_alt, (size_t)cap));
+    CK(dalloc(&s->fr.inst_val, (size_t)cap));
     s->cap = cap;
     return 0;
 }
@@ -151,15 +144,10 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     CKB(dalloc(&s->fr.rec0, (size_t)n));
     CKB(dalloc(&s->fr.rec1, (size_t)n));
     CKB(dalloc(&s->fr.rec2, (size_t)n));
-    for (int k = 0; k < 2; ++k) {
-        CKB(dalloc(&s->fr.dkey[k], (size_t)n));
-        CKB(dalloc(&s->fr.dval[k], (size_t)n));
-    }
+    CKB(dalloc(&s->fr.dkey, (size_t)n));
+    CKB(dalloc(&s->fr.vis_list, (size_t)n));
     CKB(dalloc(&s->fr.rect, (size_t)n));
     CKB(dalloc(&s->fr.ntiles, (size_t)n));
-    CKB(dalloc(&s->fr.partial, (size_t)(n / 256 + 2)));
-    const int total_passes = sage_radix_passes(DEPTH_BITS) + sage_radix_passes(MAX_TILE_BITS);
-    CKB(dalloc(&s->fr.digit_total, (size_t)total_passes * SAGE_RADIX_MAX_BINS));
     CKB(dalloc(&s->fr.counters, (size_t)CNT_COUNT));
     CKB(dalloc(&s->n_dev, 1));
     CKB(cudaHostAlloc((void**)&s->counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
@@ -208,10 +196,10 @@ int sage_scene_destroy(sage_scene* s)
     cudaDeviceSynchronize();
     cudaFree(s->sc.geo0); cudaFree(s->sc.geo1); cudaFree(s->sc.geo2); cudaFree(s->sc.shc);
     cudaFree(s->fr.rec0); cudaFree(s->fr.rec1); cudaFree(s->fr.rec2);
-    for (int k = 0; k < 2; ++k) { cudaFree(s->fr.dkey[k]); cudaFree(s->fr.dval[k]); }
-    cudaFree(s->fr.rect); cudaFree(s->fr.ntiles); cudaFree(s->fr.partial);
+    cudaFree(s->fr.dkey); cudaFree(s->fr.vis_list);
+    cudaFree(s->fr.rect); cudaFree(s->fr.ntiles);
     free_instances(s);
-    cudaFree(s->fr.digit_total); cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
+    cudaFree(s->fr.tile_count); cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
     cudaFree(s->n_dev);
     if (s->counters_host) cudaFreeHost(s->counters_host);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
@@ -242,13 +230,6 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     return 0;
 }
 
-static int tile_bits(int n_tiles)
-{
-    int b = 1;
-    while ((1 << b) < n_tiles) ++b;
-    return b;
-}
-
 static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1, int n_peers,
                        uint8_t* const* rgb_peers, float* const* depth_peers, cudaStream_t st)
 {
@@ -262,21 +243,22 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     if (n_tiles > s->max_tiles) {   // resolution-dependent scratch grows on first use
         CK(cudaStreamSynchronize(st));
         cudaFree(s->fr.ranges);
+        cudaFree(s->fr.tile_count);
+        s->fr.ranges = nullptr; s->fr.tile_count = nullptr; s->max_tiles = 0;
         CK(dalloc(&s->fr.ranges, (size_t)n_tiles));
+        CK(dalloc(&s->fr.tile_count, (size_t)2 * n_tiles));
         s->max_tiles = n_tiles;
     }
-    const int tbits = tile_bits(n_tiles > 1 ? n_tiles : 2);
-    REQUIRE(tbits <= MAX_TILE_BITS, "sage_render: too many tiles");
+    s->fr.tile_cursor = s->fr.tile_count + s->max_tiles;
     // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
     uint32_t bn, bf;
     memcpy(&bn, &cd.near_z, 4);
     memcpy(&bf, &cd.far_z, 4);
     int dbits = 1;
     while (dbits < 32 && ((uint64_t)1 << dbits) <= (uint64_t)(bf - bn)) ++dbits;
-    const int dpasses = sage_radix_passes(dbits), tpasses = sage_radix_passes(tbits);
     int launches = 0;
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, st));
-    CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * SAGE_RADIX_MAX_BINS * (size_t)(dpasses + tpasses), st));
+    if (n_tiles > 0) CK(cudaMemsetAsync(s->fr.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)s->max_tiles, st));
     cudaEvent_t* ev = s->n_slots > 0
         ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     s->frame_index++;
@@ -284,30 +266,20 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     if (n_tiles > 0 && s->sc.n > 0) {
         STAGE_MARK(0);
         sage_launch_project(s->sc, cd, s->fr, st);
-        launches += 1;
         STAGE_MARK(1);
-        int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->fr.counters + CNT_VISIBLE, s->sc.n,
-                                  0, dbits, true, true, s->fr.block_hist, s->fr.digit_total, &launches, st);
-        const uint32_t* order = s->fr.dval[res];
+        sage_launch_sh_color(s->sc, cd, s->fr, st);
         STAGE_MARK(2);
-        sage_launch_sh_color(s->sc, cd, s->fr, order, st);
-        launches += 1;
-        sage_launch_binning(cd, s->fr, order, s->sc.n, s->cap, &launches, st);
+        sage_launch_binning(cd, s->fr, s->sc.n, s->cap, n_tiles, &launches, st);
         STAGE_MARK(3);
-        int ires = sage_radix_sort(s->fr.ikey, s->fr.ival, s->fr.counters + CNT_INSTANCES,
-                                   s->fr.counters + CNT_INSTANCES, s->cap, 0, tbits, false, false,
-                                   s->fr.block_hist,
-                                   s->fr.digit_total + (size_t)dpasses * SAGE_RADIX_MAX_BINS, &launches, st);
+        sage_launch_tile_sort(s->fr, n_tiles, dbits, st);
         STAGE_MARK(4);
-        sage_launch_ranges(s->fr, s->fr.ikey[ires], s->cap, n_tiles, &launches, st);
+        sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
+        launches += 4;
         STAGE_MARK(5);
-        sage_launch_composite(cd, s->fr, s->fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
-        launches += 1;
-        STAGE_MARK(6);
     } else if (n_tiles > 0) {
         for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
         CK(cudaMemsetAsync(s->fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
-        sage_launch_composite(cd, s->fr, s->fr.ival[0], n_peers, rgb_peers, depth_peers, st);
+        sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
         launches += 1;
     }
     CK(cudaGetLastError());
@@ -426,18 +398,17 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     if (make_cam(cam, row0_tiles, row1_tiles, &cd)) return 1;
     CK(cudaSetDevice(s->device));
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, nullptr));
-    CK(cudaMemsetAsync(s->fr.digit_total, 0, sizeof(uint32_t) * SAGE_RADIX_MAX_BINS * (size_t)sage_radix_passes(32), nullptr));
     sage_launch_project(s->sc, cd, s->fr, nullptr);
-    const size_t n = (size_t)s->sc.n;
-    std::vector<uint32_t> key(n);
-    if (n) CK(cudaMemcpy(key.data(), s->fr.dkey[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    {
-        int res = sage_radix_sort(s->fr.dkey, s->fr.dval, s->n_dev, s->fr.counters + CNT_VISIBLE, s->sc.n, 0, 32,
-                                  true, true, s->fr.block_hist, s->fr.digit_total, nullptr, nullptr);
-        sage_launch_sh_color(s->sc, cd, s->fr, s->fr.dval[res], nullptr);
-    }
+    sage_launch_sh_color(s->sc, cd, s->fr, nullptr);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
+    const size_t n = (size_t)s->sc.n;
+    uint32_t V = 0;
+    CK(cudaMemcpy(&V, s->fr.counters + CNT_VISIBLE, sizeof V, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> vlist(V);
+    if (V) CK(cudaMemcpy(vlist.data(), s->fr.vis_list, V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> visv(n, 0);
+    for (uint32_t g : vlist) visv[g] = 1;
     std::vector<float4> r0(n), r1(n), r2(n);
     std::vector<uint2> rc(n);
     if (n) {
@@ -449,7 +420,7 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     for (size_t i = 0; i < n; ++i) {
         sage_splat_record& o = records_host[i];
         memset(&o, 0, sizeof o);
-        visible_host[i] = key[i] != SAGE_KEY_CULLED;
+        visible_host[i] = visv[i];
         if (!visible_host[i]) continue;
         o.gx = r0[i].x; o.gy = r0[i].y; o.qa = r0[i].z;
         o.qb = r1[i].x; o.qc = r1[i].y; o.opacity = r1[i].z; o.z = r1[i].w;

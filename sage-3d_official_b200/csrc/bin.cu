@@ -1,7 +1,14 @@
-// K2 (offset scan + instance emission) and K4 (tile ranges).
+// K2-K4: tile binning and the per-tile depth sort.
 //
-// Instances are emitted in depth order (the order[] produced by the depth sort), so the stable
-// by-tile radix sort that follows leaves each tile's list depth-sorted.
+//   k_expand<COUNT>   every visible Gaussian adds 1 to the counter of each tile it touches
+//   k_scan_tiles      exclusive scan of the T tile counters -> per-tile ranges, D = total
+//   k_expand<FILL>    every (tile, Gaussian) instance claims a slot in its tile's range (atomic
+//                     cursor) and writes a 64-bit key  depth(27) << 32 | id(28) << 4 | quadrants(4)
+//   k_tile_sort       one CTA per tile sorts its range by (depth, id) in shared memory
+//
+// The slot order produced by the atomics is arbitrary; the per-tile sort on the full (depth, id)
+// key makes the final order — and with it every output bit — deterministic.  No global sort, no
+// 64-bit global keys shuffled through HBM passes: each instance key is written once and read once.
 #include "sage_internal.cuh"
 
 namespace {
@@ -19,43 +26,93 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
     return v;
 }
 
-// partial[b] = sum of tiles touched by sorted Gaussians [256 b, 256 b + 256)
-__global__ void __launch_bounds__(B_THREADS)
-k_tiles_partial(const uint32_t* __restrict__ order, const uint32_t* __restrict__ ntiles,
-                const uint32_t* __restrict__ counters, uint32_t* __restrict__ partial)
+// which 8x8 quadrants of tile (tx,ty) the inclusive pixel box [px0,px1]x[py0,py1] overlaps:
+// bit (qy*2 + qx), matching the warp -> quadrant map of the composite kernel
+__device__ __forceinline__ uint32_t quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
 {
-    const uint32_t V = counters[CNT_VISIBLE];
-    const uint32_t r = blockIdx.x * B_THREADS + threadIdx.x;
+    const int bx = tx * SAGE_TILE, by = ty * SAGE_TILE;
+    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
+    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
+    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
+}
+
+// Load-balanced expansion: a block takes 256 visible Gaussians, scans their tile counts and lets
+// its threads walk the concatenated instance list (binary search for the owner), so a splat
+// covering thousands of tiles costs the same per instance as one covering four.
+template <bool FILL>
+__global__ void __launch_bounds__(B_THREADS)
+k_expand(SageCamDev cam, SageFrame fr, uint32_t cap)
+{
+    const uint32_t V = fr.counters[CNT_VISIBLE];
     if (blockIdx.x * B_THREADS >= V) return;
-    uint32_t c = r < V ? __ldg(&ntiles[__ldg(&order[r])]) : 0u;
-    __shared__ uint32_t sm[B_THREADS / 32];
-    uint32_t s = c;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    const uint32_t r = blockIdx.x * B_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __shared__ uint32_t s_off[B_THREADS + 1];
+    __shared__ uint32_t s_g[B_THREADS];
+    __shared__ uint2 s_rc[B_THREADS];
+    __shared__ uint32_t wsum[B_THREADS / 32];
+    uint32_t g = 0, c = 0;
+    uint2 rc = make_uint2(0, 0);
+    if (r < V) {
+        g = __ldg(&fr.vis_list[r]);
+        c = __ldg(&fr.ntiles[g]);
+        rc = __ldg(&fr.rect[g]);
+    }
+    uint32_t incl = warp_incl_scan_u32(c);
+    if (lane == 31) wsum[w] = incl;
+    s_g[threadIdx.x] = g;
+    s_rc[threadIdx.x] = rc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
+    uint32_t woff = 0;
 #pragma unroll
-        for (int k = 0; k < B_THREADS / 32; ++k) t += sm[k];
-        partial[blockIdx.x] = t;
+    for (int k = 0; k < B_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0u;
+    s_off[threadIdx.x] = woff + incl - c;
+    if (threadIdx.x == B_THREADS - 1) s_off[B_THREADS] = woff + incl;
+    __syncthreads();
+    const uint32_t total = s_off[B_THREADS];
+    const int tiles_x = cam.tiles_x, row0 = cam.row0;
+    for (uint32_t k = threadIdx.x; k < total; k += B_THREADS) {
+        // owner = last o with s_off[o] <= k
+        int lo = 0, hi = B_THREADS - 1;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+        }
+        const uint2 b = s_rc[lo];
+        const int px0 = b.x & 0xFFFF, px1 = b.x >> 16, py0 = b.y & 0xFFFF, py1 = b.y >> 16;
+        const int bx0 = px0 / SAGE_TILE, by0 = py0 / SAGE_TILE;
+        const uint32_t bw = (uint32_t)(px1 / SAGE_TILE - bx0 + 1);
+        const uint32_t local = k - s_off[lo];
+        const int ty = by0 + (int)(local / bw), tx = bx0 + (int)(local % bw);
+        const uint32_t tile = (uint32_t)((ty - row0) * tiles_x + tx);
+        if (!FILL) {
+            atomicAdd(&fr.tile_count[tile], 1u);
+        } else {
+            const uint32_t gid = s_g[lo];
+            const uint32_t slot = fr.ranges[tile].x + atomicAdd(&fr.tile_cursor[tile], 1u);
+            if (slot < cap) {
+                const unsigned long long key = ((unsigned long long)__ldg(&fr.dkey[gid]) << 32) |
+                                               ((unsigned long long)gid << 4) |
+                                               quad_mask(px0, px1, py0, py1, tx, ty);
+                fr.inst_key[slot] = key;
+            }
+        }
     }
 }
 
-// single block: exclusive scan of partial[0..nbv); total instance count -> counters
+// single block: exclusive scan of the tile counters -> ranges[t] = (begin, end), D -> counters
 __global__ void __launch_bounds__(1024)
-k_scan_partials(uint32_t* __restrict__ partial, uint32_t* __restrict__ counters, uint32_t cap)
+k_scan_tiles(SageFrame fr, int n_tiles, uint32_t cap)
 {
-    const uint32_t V = counters[CNT_VISIBLE];
-    const uint32_t nbv = (V + B_THREADS - 1) / B_THREADS;
     __shared__ unsigned long long wsum[32];
     __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (uint32_t start = 0; start < nbv; start += 1024) {
-        uint32_t idx = start + threadIdx.x;
-        unsigned long long v = idx < nbv ? (unsigned long long)partial[idx] : 0ull;
+    for (int start = 0; start < n_tiles; start += 1024) {
+        const int idx = start + threadIdx.x;
+        unsigned long long v = idx < n_tiles ? (unsigned long long)fr.tile_count[idx] : 0ull;
         unsigned long long incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -75,139 +132,161 @@ k_scan_partials(uint32_t* __restrict__ partial, uint32_t* __restrict__ counters,
             wsum[lane] = ti - t;
         }
         __syncthreads();
-        unsigned long long carry = carry_s;
-        unsigned long long ex = carry + wsum[w] + (incl - v);
-        if (idx < nbv) partial[idx] = (uint32_t)(ex > 0xFFFFFFFFull ? 0xFFFFFFFFull : ex);
+        const unsigned long long ex = carry_s + wsum[w] + (incl - v);
+        if (idx < n_tiles) {
+            unsigned long long b = ex > cap ? cap : ex, e = ex + v > cap ? cap : ex + v;
+            fr.ranges[idx] = make_uint2((uint32_t)b, (uint32_t)e);
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = ex + v;   // last thread's inclusive prefix == running total
+        if (threadIdx.x == 1023) carry_s = ex + v;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         unsigned long long total = carry_s;
         if (total > (unsigned long long)cap) {
-            counters[CNT_OVERFLOW] = 1u;
+            fr.counters[CNT_OVERFLOW] = 1u;
             total = cap;
         }
-        counters[CNT_INSTANCES] = (uint32_t)total;
+        fr.counters[CNT_INSTANCES] = (uint32_t)total;
     }
 }
 
-// which 8x8 quadrants of tile (tx,ty) the inclusive pixel box [px0,px1]x[py0,py1] overlaps:
-// bit (qy*2 + qx), matching the warp -> quadrant map of the composite kernel
-__device__ __forceinline__ uint32_t quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
+// ---------------------------------------------------------------------------------------------
+// Per-tile sort.  LSD radix on the 27 depth bits (4 stable passes of 7 bits, 128 bins = one bin
+// per thread), then equal-depth runs — rare: exact binary32 ties — are put in id order by
+// odd-even transposition.  Lists up to TS_CAP keys are sorted in shared memory; longer ones
+// ping-pong between the two global key buffers (they stay in L2).
+// ---------------------------------------------------------------------------------------------
+constexpr int TS_THREADS = 128;
+constexpr int TS_WARPS = TS_THREADS / 32;
+constexpr int TS_CAP = 2048;
+constexpr int TS_BINS = 128;
+constexpr int TS_DIGIT_BITS = 7;
+
+__device__ __forceinline__ uint32_t ts_digit(unsigned long long k, int shift)
 {
-    const int bx = tx * SAGE_TILE, by = ty * SAGE_TILE;
-    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
-    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
-    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
+    return (uint32_t)(k >> shift) & (TS_BINS - 1);
 }
 
-// emit (tile, gaussian | quadrant mask) pairs in depth order
-__global__ void __launch_bounds__(B_THREADS)
-k_emit(SageCamDev cam, const uint32_t* __restrict__ order, const uint32_t* __restrict__ ntiles,
-       const uint2* __restrict__ rect, const uint32_t* __restrict__ partial,
-       const uint32_t* __restrict__ counters, uint32_t* __restrict__ ikey,
-       uint32_t* __restrict__ ival, uint32_t cap)
+// one stable pass src -> dst; returns false (and leaves dst untouched) when every key has the
+// same digit.  whist: [TS_WARPS][TS_BINS] shared counters.
+__device__ bool ts_pass(const unsigned long long* src, unsigned long long* dst, uint32_t n, int shift,
+                        uint32_t (*whist)[TS_BINS])
 {
-    const uint32_t V = counters[CNT_VISIBLE];
-    if (blockIdx.x * B_THREADS >= V) return;
-    const uint32_t r = blockIdx.x * B_THREADS + threadIdx.x;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t g = 0, c = 0;
-    uint2 rc = make_uint2(0, 0);
-    if (r < V) {
-        g = __ldg(&order[r]);
-        c = __ldg(&ntiles[g]);
-        rc = __ldg(&rect[g]);
-    }
-    __shared__ uint32_t wsum[B_THREADS / 32];
-    __shared__ uint32_t big_q[B_THREADS];
-    __shared__ uint32_t big_off[B_THREADS];
-    __shared__ uint32_t big_n;
-    if (threadIdx.x == 0) big_n = 0;
-    uint32_t incl = warp_incl_scan_u32(c);
-    if (lane == 31) wsum[w] = incl;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < TS_WARPS * TS_BINS; i += TS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
-    uint32_t woff = 0;
+    // warp w owns the contiguous segment [seg0, seg1) so that (warp, position) order == list order
+    const uint32_t per = (n + TS_WARPS - 1) / TS_WARPS;
+    const uint32_t seg0 = min(n, w * per), seg1 = min(n, seg0 + per);
+    for (uint32_t e = seg0 + lane; e < seg1; e += 32) atomicAdd(&whist[w][ts_digit(src[e], shift)], 1u);
+    __syncthreads();
+    // thread d: totals over warps, then exclusive scan over the 128 digits
+    uint32_t cnt[TS_WARPS], tot = 0;
 #pragma unroll
-    for (int k = 0; k < B_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0u;
-    uint32_t off = partial[blockIdx.x] + woff + (incl - c);
-
-    const int tiles_x = cam.tiles_x, row0 = cam.row0;
-    if (c > 32u) {                       // large footprints are spread over the whole block
-        uint32_t q = atomicAdd(&big_n, 1u);
-        big_q[q] = threadIdx.x;
-        big_off[q] = off;
-    } else if (c > 0u) {
-        const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
-        uint32_t o = off;
-        for (int ty = py0 / SAGE_TILE; ty <= py1 / SAGE_TILE; ++ty)
-            for (int tx = px0 / SAGE_TILE; tx <= px1 / SAGE_TILE; ++tx, ++o)
-                if (o < cap) {
-                    ikey[o] = (uint32_t)((ty - row0) * tiles_x + tx);
-                    ival[o] = g | (quad_mask(px0, px1, py0, py1, tx, ty) << SAGE_ID_BITS);
-                }
-    }
-    // broadcast the big ones through shared memory
-    __shared__ uint32_t s_g[B_THREADS];
-    __shared__ uint2 s_rc[B_THREADS];
-    s_g[threadIdx.x] = g;
-    s_rc[threadIdx.x] = rc;
+    for (int ww = 0; ww < TS_WARPS; ++ww) { cnt[ww] = whist[ww][tid]; tot += cnt[ww]; }
+    const int uniform = __syncthreads_or(tot == n);
+    if (uniform) return false;
+    __shared__ uint32_t wtot[TS_WARPS];
+    uint32_t incl = warp_incl_scan_u32(tot);
+    if (lane == 31) wtot[w] = incl;
     __syncthreads();
-    const uint32_t nbig = big_n;
-    for (uint32_t q = 0; q < nbig; ++q) {
-        const uint32_t t = big_q[q];
-        const uint32_t bo = big_off[q];
-        const uint2 brc = s_rc[t];
-        const uint32_t bg = s_g[t];
-        const int px0 = brc.x & 0xFFFF, px1 = brc.x >> 16, py0 = brc.y & 0xFFFF, py1 = brc.y >> 16;
-        const int bx0 = px0 / SAGE_TILE, by0 = py0 / SAGE_TILE;
-        const int bw = px1 / SAGE_TILE - bx0 + 1;
-        const uint32_t bc = (uint32_t)bw * (uint32_t)(py1 / SAGE_TILE - by0 + 1);
-        for (uint32_t k = threadIdx.x; k < bc; k += B_THREADS) {
-            uint32_t o = bo + k;
-            if (o < cap) {
-                int ty = by0 + (int)(k / (uint32_t)bw), tx = bx0 + (int)(k % (uint32_t)bw);
-                ikey[o] = (uint32_t)((ty - row0) * tiles_x + tx);
-                ival[o] = bg | (quad_mask(px0, px1, py0, py1, tx, ty) << SAGE_ID_BITS);
+    uint32_t base = incl - tot;
+#pragma unroll
+    for (int ww = 0; ww < TS_WARPS; ++ww) base += (ww < w) ? wtot[ww] : 0u;
+#pragma unroll
+    for (int ww = 0; ww < TS_WARPS; ++ww) { whist[ww][tid] = base; base += cnt[ww]; }
+    __syncthreads();
+    // ranked scatter of each warp's segment, 32 keys at a time
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (uint32_t e0 = seg0; e0 < seg1; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const bool valid = e < seg1;
+        const unsigned long long k = valid ? src[e] : 0ull;
+        const uint32_t d = valid ? ts_digit(k, shift) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (valid && lane == leader) {
+            prev = whist[w][d];
+            whist[w][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        if (valid) dst[prev + __popc(peers & lt_mask)] = k;
+        __syncwarp();
+    }
+    __syncthreads();
+    return true;
+}
+
+__global__ void __launch_bounds__(TS_THREADS)
+k_tile_sort(SageFrame fr, int depth_bits)
+{
+    __shared__ unsigned long long sbuf[2][TS_CAP];
+    __shared__ uint32_t whist[TS_WARPS][TS_BINS];
+    const uint2 rg = fr.ranges[blockIdx.x];
+    const uint32_t n = rg.y - rg.x;
+    if (n == 0) return;
+    const int tid = threadIdx.x;
+    unsigned long long* g0 = fr.inst_key + rg.x;
+    unsigned long long* g1 = fr.inst_key_alt + rg.x;
+    uint32_t* out = fr.inst_val + rg.x;
+    if (n == 1) {
+        if (tid == 0) out[0] = (uint32_t)g0[0];
+        return;
+    }
+    unsigned long long* buf[2];
+    const bool in_smem = n <= TS_CAP;
+    if (in_smem) {
+        buf[0] = sbuf[0]; buf[1] = sbuf[1];
+        for (uint32_t e = tid; e < n; e += TS_THREADS) sbuf[0][e] = g0[e];
+        __syncthreads();
+    } else {
+        buf[0] = g0; buf[1] = g1;
+        __threadfence_block();
+    }
+    int cur = 0;
+    for (int shift = 32; shift < 32 + depth_bits; shift += TS_DIGIT_BITS)
+        if (ts_pass(buf[cur], buf[cur ^ 1], n, shift, whist)) cur ^= 1;
+    unsigned long long* a = buf[cur];
+    // equal-depth runs -> ascending id (odd-even transposition restricted to equal depths)
+    {
+        int unordered = 0;
+        for (uint32_t e = tid; e + 1 < n; e += TS_THREADS) {
+            const unsigned long long x = a[e], y = a[e + 1];
+            unordered |= ((x >> 32) == (y >> 32)) && (x > y);
+        }
+        unordered = __syncthreads_or(unordered);
+        while (unordered) {
+            int swapped = 0;
+            for (int phase = 0; phase < 2; ++phase) {
+                for (uint32_t e = 2 * tid + phase; e + 1 < n; e += 2 * TS_THREADS) {
+                    const unsigned long long x = a[e], y = a[e + 1];
+                    if ((x >> 32) == (y >> 32) && x > y) { a[e] = y; a[e + 1] = x; swapped = 1; }
+                }
+                __syncthreads();
             }
+            unordered = __syncthreads_or(swapped);
         }
     }
-}
-
-__global__ void __launch_bounds__(B_THREADS)
-k_tile_ranges(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ counters,
-              uint2* __restrict__ ranges)
-{
-    const uint32_t D = counters[CNT_INSTANCES];
-    for (uint32_t j = blockIdx.x * B_THREADS + threadIdx.x; j < D; j += gridDim.x * B_THREADS) {
-        const uint32_t k = __ldg(&keys[j]);
-        if (j == 0 || __ldg(&keys[j - 1]) != k) ranges[k].x = j;
-        if (j == D - 1 || __ldg(&keys[j + 1]) != k) ranges[k].y = j + 1;
-    }
+    for (uint32_t e = tid; e < n; e += TS_THREADS) out[e] = (uint32_t)a[e];   // id << 4 | quadrants
 }
 
 }  // namespace
 
-void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order,
-                         int64_t n, int64_t cap, int* launches, cudaStream_t st)
+void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, int64_t n, int64_t cap,
+                         int n_tiles, int* launches, cudaStream_t st)
 {
-    if (n <= 0) return;
-    int blocks = (int)((n + B_THREADS - 1) / B_THREADS);
-    k_tiles_partial<<<blocks, B_THREADS, 0, st>>>(order, fr.ntiles, fr.counters, fr.partial);
-    k_scan_partials<<<1, 1024, 0, st>>>(fr.partial, fr.counters, (uint32_t)cap);
-    k_emit<<<blocks, B_THREADS, 0, st>>>(cam, order, fr.ntiles, fr.rect, fr.partial, fr.counters,
-                                         fr.ikey[0], fr.ival[0], (uint32_t)cap);
+    if (n <= 0 || n_tiles <= 0) return;
+    const int blocks = (int)((n + B_THREADS - 1) / B_THREADS);
+    k_expand<false><<<blocks, B_THREADS, 0, st>>>(cam, fr, (uint32_t)cap);
+    k_scan_tiles<<<1, 1024, 0, st>>>(fr, n_tiles, (uint32_t)cap);
+    k_expand<true><<<blocks, B_THREADS, 0, st>>>(cam, fr, (uint32_t)cap);
     if (launches) *launches += 3;
 }
 
-void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_t cap, int n_tiles,
-                        int* launches, cudaStream_t st)
+void sage_launch_tile_sort(const SageFrame& fr, int n_tiles, int depth_bits, cudaStream_t st)
 {
-    cudaMemsetAsync(fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st);
-    int blocks = (int)((cap + B_THREADS - 1) / B_THREADS);
-    if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8;      // persistent grid-stride: D is only known on the device
-    k_tile_ranges<<<blocks, B_THREADS, 0, st>>>(sorted_keys, fr.counters, fr.ranges);
-    if (launches) *launches += 1;
+    if (n_tiles <= 0) return;
+    k_tile_sort<<<n_tiles, TS_THREADS, 0, st>>>(fr, depth_bits);
 }

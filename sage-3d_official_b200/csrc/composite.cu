@@ -70,8 +70,8 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
         uint32_t qm = 0;
         if (tid < cnt) {
             const uint32_t v = __ldg(&vals[base + tid]);
-            const uint32_t g = v & SAGE_ID_MASK;
-            qm = v >> SAGE_ID_BITS;
+            const uint32_t g = v >> 4;
+            qm = v & 15u;
             s0[tid] = __ldg(&rec0[g]);
             s1[tid] = __ldg(&rec1[g]);
             s2[tid] = __ldg(&rec2[g]);
@@ -164,8 +164,7 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
 
 }  // namespace
 
-void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
-                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
                            cudaStream_t st)
 {
     const int n_tiles = (cam.row1 - cam.row0) * cam.tiles_x;
@@ -176,5 +175,5 @@ void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uin
         out.rgb[k] = k < out.n ? rgb_peers[k] : nullptr;
         out.depth[k] = (k < out.n && depth_peers) ? depth_peers[k] : nullptr;
     }
-    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, out);
+    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, fr.inst_val, fr.ranges, out);
 }

@@ -73,16 +73,14 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 
 // ---------------------------------------------------------------------------------------------
 // K1a: project, cull, conic, conservative pixel bounding box.  One thread per Gaussian; every
-// per-Gaussian stream is a 16-byte-per-lane coalesced access.  Emits the depth key
-// (bits(z) - bits(near), or CULLED) that the first radix pass compacts and sorts in one go.
+// per-Gaussian stream is a 16-byte-per-lane coalesced access.  Survivors get a depth key
+// bits(z) - bits(near) and are appended to the visible list (warp-aggregated atomic).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
-    uint32_t key = SAGE_KEY_CULLED;
-    uint32_t count = 0;
     if (i < sc.n) {
         const float4 g0 = __ldg(&sc.geo0[i]);
         const float mx = g0.x, my = g0.y, mz = g0.z, o = g0.w;
@@ -150,8 +148,8 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                         const int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
                         const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
                         vis = true;
-                        key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                        count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+                        fr.dkey[i] = __float_as_uint(tz) - __float_as_uint(cam.near_z);
+                        fr.ntiles[i] = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
                         fr.rec0[i] = make_float4(gx, gy, qa, -l2 - 0.01f);
                         fr.rec1[i] = make_float4(qb, qc, o, tz);
                         // inclusive pixel bounding box (u16 each)
@@ -161,17 +159,18 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 }
             }
         }
-        fr.dkey[0][i] = key;
-        fr.ntiles[i] = count;
     }
-    // one atomic per warp for the visible counter
-    unsigned m = __ballot_sync(0xffffffffu, vis);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], __popc(m));
+    // append the survivors to the visible list: one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, vis);
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0 && m) base = atomicAdd(&fr.counters[CNT_VISIBLE], (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (vis) fr.vis_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1b: view-dependent SH colour for the V visible Gaussians (any order; uses the depth-sorted id
-// list).  Separate from K1a so that neither kernel carries the other's registers.
+// K1b: view-dependent SH colour for the V visible Gaussians (walks the visible list).  Separate from K1a so that neither kernel carries the other's registers.
 // ---------------------------------------------------------------------------------------------
 __device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
                                             0.31539156525252005f, -1.0925484305920792f,
@@ -183,7 +182,7 @@ __device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 
 template <int DEG>
 __global__ void __launch_bounds__(256)
-k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order)
+k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     constexpr int NF = 3 * NB;
@@ -191,7 +190,7 @@ k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __rest
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= V) return;
-    const uint32_t i = __ldg(&order[r]);
+    const uint32_t i = __ldg(&fr.vis_list[r]);
     const float4 g0 = __ldg(&sc.geo0[i]);
     float shv[NC * 4];
     const float4* sp = sc.shc + (size_t)i * NC;
@@ -246,15 +245,14 @@ void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const Sa
     k_project<<<blocks, 256, 0, st>>>(sc, cam, fr);
 }
 
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
-                          const uint32_t* order, cudaStream_t st)
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
     switch (sc.deg) {
-        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
     }
 }

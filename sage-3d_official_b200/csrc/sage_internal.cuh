@@ -16,8 +16,7 @@
 #define SAGE_BLUR 0.3f
 #define SAGE_LOG2E 1.44269504f
 #define SAGE_KEY_CULLED 0xFFFFFFFFu
-// instance value = Gaussian id (28 bits) | 8x8-quadrant overlap mask of the tile (4 bits)
-#define SAGE_ID_BITS 28
+// instance value = Gaussian id (28 bits) << 4 | 8x8-quadrant overlap mask of the tile (4 bits)
 #define SAGE_ID_MASK 0x0FFFFFFFu
 
 // device counters (uint32 each)
@@ -56,21 +55,20 @@ __device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_L
 // ---- frame workspace ---------------------------------------------------------------------
 struct SageFrame {
     // per-Gaussian (capacity n)
-    float4* rec0;      // gx, gy, qa, skip threshold (log2 units)
-    float4* rec1;      // qb, qc, opacity, z
-    float4* rec2;      // r, g, b, 0
-    uint32_t* dkey[2]; // depth keys, ping-pong
-    uint32_t* dval[2]; // Gaussian ids, ping-pong
-    uint2* rect;       // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
-    uint32_t* ntiles;  // tiles touched
-    uint32_t* partial; // block partial sums for the offset scan
+    float4* rec0;        // gx, gy, qa, skip threshold (log2 units)
+    float4* rec1;        // qb, qc, opacity, z
+    float4* rec2;        // r, g, b, 0
+    uint32_t* dkey;      // depth key bits(z) - bits(near) of visible Gaussians
+    uint32_t* vis_list;  // ids of the V visible Gaussians (arbitrary order)
+    uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
+    uint32_t* ntiles;    // tiles touched
     // per-instance (capacity cap)
-    uint32_t* ikey[2];
-    uint32_t* ival[2];
-    // sort scratch
-    uint32_t* block_hist;   // [R][nb]
-    uint32_t* digit_total;  // [passes][R]
+    unsigned long long* inst_key;      // depth << 32 | id << 4 | quadrant mask
+    unsigned long long* inst_key_alt;  // ping-pong partner for tile lists too long for shared memory
+    uint32_t* inst_val;                // per-tile depth-sorted (id << 4 | quadrant mask)
     // per-tile
+    uint32_t* tile_count;   // [max_tiles]
+    uint32_t* tile_cursor;  // [max_tiles], directly after tile_count (one memset clears both)
     uint2* ranges;
     uint32_t* counters;     // CNT_COUNT
 };
@@ -89,28 +87,12 @@ struct SageSceneDev {
 void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
                             const float* quat, const float* opacity, const float* sh, cudaStream_t st);
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
-                          const uint32_t* order, cudaStream_t st);
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
 
-// Stable LSD radix sort of (key, val) pairs by bits [lo_bit, lo_bit + n_bits); element counts are read
-// from device memory: n_first for pass 0, n_rest for the later passes.  With compact_first, pass 0
-// drops keys equal to SAGE_KEY_CULLED (compaction fused into the first scatter), so n_rest must
-// point at the survivor count.  Returns the index (0/1) of the buffer pair holding the result.
-// digit_total must be zeroed: SAGE_RADIX_MAX_BINS words per pass.
-int sage_radix_sort(uint32_t* keys[2], uint32_t* vals[2], const uint32_t* n_first_dev,
-                    const uint32_t* n_rest_dev, int64_t capacity, int lo_bit, int n_bits,
-                    bool vals_are_iota, bool compact_first, uint32_t* block_hist,
-                    uint32_t* digit_total, int* launches, cudaStream_t st);
-int sage_radix_passes(int n_bits);
-size_t sage_radix_block_hist_elems(int64_t capacity);
-#define SAGE_RADIX_MAX_BINS 512
-
-void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order,
-                         int64_t n, int64_t cap, int* launches, cudaStream_t st);
-void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_t cap, int n_tiles,
-                        int* launches, cudaStream_t st);
-void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
-                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, int64_t n, int64_t cap,
+                         int n_tiles, int* launches, cudaStream_t st);
+void sage_launch_tile_sort(const SageFrame& fr, int n_tiles, int depth_bits, cudaStream_t st);
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
                            cudaStream_t st);
 
 void sage_launch_collide_grid(const uint8_t* map, int H, int W, double min_x, double max_x,
