@@ -101,7 +101,9 @@ k_expand(SageCamDev cam, SageFrame fr, uint32_t cap)
     }
 }
 
-// single block: exclusive scan of the tile counters -> ranges[t] = (begin, end), D -> counters
+// single block: exclusive scan of the tile counters -> ranges[t] = (begin, end), D -> counters.
+// Each thread scans SCAN_IPT consecutive tiles in registers, so 8192 tiles take one block pass.
+constexpr int SCAN_IPT = 8;
 __global__ void __launch_bounds__(1024)
 k_scan_tiles(SageFrame fr, int n_tiles, uint32_t cap)
 {
@@ -110,9 +112,15 @@ k_scan_tiles(SageFrame fr, int n_tiles, uint32_t cap)
     if (threadIdx.x == 0) carry_s = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int start = 0; start < n_tiles; start += 1024) {
-        const int idx = start + threadIdx.x;
-        unsigned long long v = idx < n_tiles ? (unsigned long long)fr.tile_count[idx] : 0ull;
+    for (int start = 0; start < n_tiles; start += 1024 * SCAN_IPT) {
+        const int idx0 = start + threadIdx.x * SCAN_IPT;
+        uint32_t c[SCAN_IPT];
+        unsigned long long v = 0ull;
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; ++k) {
+            c[k] = (idx0 + k < n_tiles) ? fr.tile_count[idx0 + k] : 0u;
+            v += c[k];
+        }
         unsigned long long incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -132,13 +140,17 @@ k_scan_tiles(SageFrame fr, int n_tiles, uint32_t cap)
             wsum[lane] = ti - t;
         }
         __syncthreads();
-        const unsigned long long ex = carry_s + wsum[w] + (incl - v);
-        if (idx < n_tiles) {
-            unsigned long long b = ex > cap ? cap : ex, e = ex + v > cap ? cap : ex + v;
-            fr.ranges[idx] = make_uint2((uint32_t)b, (uint32_t)e);
+        unsigned long long run = carry_s + wsum[w] + (incl - v);
+#pragma unroll
+        for (int k = 0; k < SCAN_IPT; ++k) {
+            if (idx0 + k < n_tiles) {
+                unsigned long long b = run > cap ? cap : run, e = run + c[k] > cap ? cap : run + c[k];
+                fr.ranges[idx0 + k] = make_uint2((uint32_t)b, (uint32_t)e);
+            }
+            run += c[k];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = ex + v;
+        if (threadIdx.x == 1023) carry_s = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -157,6 +169,114 @@ k_scan_tiles(SageFrame fr, int n_tiles, uint32_t cap)
 // odd-even transposition.  Lists up to TS_CAP keys are sorted in shared memory; longer ones
 // ping-pong between the two global key buffers (they stay in L2).
 // ---------------------------------------------------------------------------------------------
+// Lists of up to WS_CAP keys (the common case) are sorted by ONE WARP each, warp-synchronously: no
+// block barriers, keys ping-pong in the warp's slice of shared memory.  The key range of the list
+// (max - min depth) decides how many 8-bit passes are needed (usually 3).
+constexpr int WS_CAP = 512;
+constexpr int WS_WARPS = 4;
+constexpr int WS_BINS = 256;
+
+__global__ void __launch_bounds__(WS_WARPS * 32)
+k_tile_sort_warp(SageFrame fr, int n_tiles)
+{
+    __shared__ unsigned long long skeys[WS_WARPS][2][WS_CAP];
+    __shared__ uint32_t shist[WS_WARPS][WS_BINS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int tile = blockIdx.x * WS_WARPS + w;
+    if (tile >= n_tiles) return;
+    const uint2 rg = fr.ranges[tile];
+    const uint32_t n = rg.y - rg.x;
+    if (n == 0 || n > WS_CAP) return;
+    const unsigned long long* src = fr.inst_key + rg.x;
+    uint32_t* out = fr.inst_val + rg.x;
+    unsigned long long* buf0 = skeys[w][0];
+    unsigned long long* buf1 = skeys[w][1];
+    uint32_t* hist = shist[w];
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t dmin = 0xFFFFFFFFu, dmax = 0u;
+    for (uint32_t e = lane; e < n; e += 32) {
+        const unsigned long long k = src[e];
+        buf0[e] = k;
+        const uint32_t d = (uint32_t)(k >> 32);
+        dmin = min(dmin, d);
+        dmax = max(dmax, d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dmin = min(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    __syncwarp();
+    const uint32_t span = dmax - dmin;
+    const uint32_t nchunk = (n + 31) / 32;
+    int cur = 0;
+    for (int shift = 0; shift < 32 && (span >> shift) != 0u; shift += 8) {
+        unsigned long long* a = cur ? buf1 : buf0;
+        unsigned long long* b = cur ? buf0 : buf1;
+#pragma unroll
+        for (int k = 0; k < WS_BINS / 32; ++k) hist[k * 32 + lane] = 0;
+        __syncwarp();
+        for (uint32_t c = 0; c < nchunk; ++c) {
+            const uint32_t e = c * 32 + lane;
+            const bool valid = e < n;
+            const uint32_t d = valid ? ((((uint32_t)(a[e] >> 32) - dmin) >> shift) & 255u) : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (valid && lane == __ffs(peers) - 1) hist[d] += __popc(peers);
+            __syncwarp();
+        }
+        // exclusive scan of 256 bins: 8 consecutive bins per lane
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { loc[k] = hist[lane * 8 + k]; sum += loc[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hist[lane * 8 + k] = run; run += loc[k]; }
+        __syncwarp();
+        for (uint32_t c = 0; c < nchunk; ++c) {
+            const uint32_t e = c * 32 + lane;
+            const bool valid = e < n;
+            const unsigned long long key = valid ? a[e] : 0ull;
+            const uint32_t d = valid ? ((((uint32_t)(key >> 32) - dmin) >> shift) & 255u) : 0xFFFFFFFFu;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            uint32_t prev = 0;
+            if (valid && lane == leader) { prev = hist[d]; hist[d] = prev + __popc(peers); }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            if (valid) b[prev + __popc(peers & lt_mask)] = key;
+            __syncwarp();
+        }
+        cur ^= 1;
+    }
+    unsigned long long* a = cur ? buf1 : buf0;
+    // equal-depth runs -> ascending id (exact binary32 depth ties are rare)
+    {
+        int bad = 0;
+        for (uint32_t e = lane; e + 1 < n; e += 32) {
+            const unsigned long long x = a[e], y = a[e + 1];
+            bad |= ((x >> 32) == (y >> 32)) && (x > y);
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        while (bad) {
+            int swapped = 0;
+            for (int phase = 0; phase < 2; ++phase) {
+                for (uint32_t e = 2 * lane + phase; e + 1 < n; e += 64) {
+                    const unsigned long long x = a[e], y = a[e + 1];
+                    if ((x >> 32) == (y >> 32) && x > y) { a[e] = y; a[e + 1] = x; swapped = 1; }
+                }
+                __syncwarp();
+            }
+            bad = __any_sync(0xffffffffu, swapped);
+        }
+    }
+    for (uint32_t e = lane; e < n; e += 32) out[e] = (uint32_t)a[e];   // id << 4 | quadrants
+}
+
 constexpr int TS_THREADS = 128;
 constexpr int TS_WARPS = TS_THREADS / 32;
 constexpr int TS_CAP = 2048;
@@ -226,15 +346,11 @@ k_tile_sort(SageFrame fr, int depth_bits)
     __shared__ uint32_t whist[TS_WARPS][TS_BINS];
     const uint2 rg = fr.ranges[blockIdx.x];
     const uint32_t n = rg.y - rg.x;
-    if (n == 0) return;
+    if (n <= WS_CAP) return;                 // short lists belong to k_tile_sort_warp
     const int tid = threadIdx.x;
     unsigned long long* g0 = fr.inst_key + rg.x;
     unsigned long long* g1 = fr.inst_key_alt + rg.x;
     uint32_t* out = fr.inst_val + rg.x;
-    if (n == 1) {
-        if (tid == 0) out[0] = (uint32_t)g0[0];
-        return;
-    }
     unsigned long long* buf[2];
     const bool in_smem = n <= TS_CAP;
     if (in_smem) {
@@ -288,5 +404,6 @@ void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, int64_t n, 
 void sage_launch_tile_sort(const SageFrame& fr, int n_tiles, int depth_bits, cudaStream_t st)
 {
     if (n_tiles <= 0) return;
+    k_tile_sort_warp<<<(n_tiles + WS_WARPS - 1) / WS_WARPS, WS_WARPS * 32, 0, st>>>(fr, n_tiles);
     k_tile_sort<<<n_tiles, TS_THREADS, 0, st>>>(fr, depth_bits);
 }

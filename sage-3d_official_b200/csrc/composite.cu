@@ -58,12 +58,13 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
     const int px = tx * SAGE_TILE + (w & 1) * 8 + (lane & 3) * 2;
     const int py = ty * SAGE_TILE + (w >> 1) * 8 + (lane >> 2);
     const bool in0 = px < cam.W && py < cam.H, in1 = (px + 1) < cam.W && py < cam.H;
-    // a finished (or off-image) pixel gets a far-away x so that it fails the cheap skip test
-    const float FAR_X = 3.0e38f;
-    float2 pxc = make_float2(in0 ? (float)px + 0.5f : FAR_X, in1 ? (float)(px + 1) + 0.5f : FAR_X);
+    // A finished (or off-image) pixel gets x = NaN: its power2 is NaN, every comparison on it is
+    // false, so it drops out of the blend without carrying an "active" flag through the loop.
+    const float NAN_X = __int_as_float(0x7fc00000);
+    float2 pxc = make_float2(in0 ? (float)px + 0.5f : NAN_X, in1 ? (float)(px + 1) + 0.5f : NAN_X);
     const float pyc = (float)py + 0.5f;
-    bool act0 = in0, act1 = in1;
     float2 T = f2(1.0f), Cr = f2(0.0f), Cg = f2(0.0f), Cb = f2(0.0f), Dz = f2(0.0f);
+#define SAGE_LIVE() (pxc.x == pxc.x || pxc.y == pxc.y)
 
     for (uint32_t base = rg.x; base < rg.y; base += C_THREADS) {
         const int cnt = min((uint32_t)C_THREADS, rg.y - base);
@@ -79,7 +80,7 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
         smask[tid] = qm;
         __syncthreads();
         // warp-uniform liveness: every lane takes part in the ballots below
-        if (__any_sync(0xffffffffu, act0 || act1)) {
+        if (__any_sync(0xffffffffu, SAGE_LIVE())) {
 #pragma unroll 1
             for (int k = 0; k < C_THREADS / 32; ++k) {
                 if (k * 32 >= cnt) break;
@@ -98,8 +99,8 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
                     const float2 pw = __ffma2_rn(dx, wv, f2(cdy2));
                     // a.w: conservative skip threshold (log2 units): below it alpha < 1/255 for sure
                     if (!(pw.x >= a.w || pw.y >= a.w)) continue;
-                    bool v0 = act0 && pw.x <= 0.0f && pw.x >= a.w;
-                    bool v1 = act1 && pw.y <= 0.0f && pw.y >= a.w;
+                    bool v0 = pw.x >= a.w && pw.x <= 0.0f;
+                    bool v1 = pw.y >= a.w && pw.y <= 0.0f;
                     if (!(v0 || v1)) continue;
                     const float2 oz = *reinterpret_cast<const float2*>(&s1[j].z);   // opacity, z
                     const float2 e = sage_exp2_x2(pw);
@@ -108,31 +109,30 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
                     al.y = fminf(SAGE_ALPHA_MAX, al.y);
                     v0 = v0 && al.x >= SAGE_ALPHA_MIN;
                     v1 = v1 && al.y >= SAGE_ALPHA_MIN;
-                    al.x = v0 ? al.x : 0.0f;
-                    al.y = v1 ? al.y : 0.0f;
-                    float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));   // 1 - alpha
-                    float2 Tn = __fmul2_rn(T, om);
-                    const bool stop0 = v0 && Tn.x < SAGE_T_MIN;
-                    const bool stop1 = v1 && Tn.y < SAGE_T_MIN;
-                    if (stop0 || stop1) {
-                        if (stop0) { act0 = false; al.x = 0.0f; pxc.x = FAR_X; }
-                        if (stop1) { act1 = false; al.y = 0.0f; pxc.y = FAR_X; }
-                        om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
-                        Tn = __fmul2_rn(T, om);
-                    }
-                    const float2 wgt = __fmul2_rn(al, T);
+                    const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));   // 1 - alpha
+                    const float2 Tn = __fmul2_rn(T, om);
+                    // keep: the splat is blended; stop: it would push T below 1e-4 -> pixel done
+                    const bool keep0 = v0 && !(Tn.x < SAGE_T_MIN);
+                    const bool keep1 = v1 && !(Tn.y < SAGE_T_MIN);
+                    pxc.x = (v0 && !keep0) ? NAN_X : pxc.x;
+                    pxc.y = (v1 && !keep1) ? NAN_X : pxc.y;
+                    float2 wgt = __fmul2_rn(al, T);
+                    wgt.x = keep0 ? wgt.x : 0.0f;     // a zero weight leaves C, Dz bit-identical
+                    wgt.y = keep1 ? wgt.y : 0.0f;
+                    T.x = keep0 ? Tn.x : T.x;
+                    T.y = keep1 ? Tn.y : T.y;
                     const float4 c = s2[j];
                     Cr = __ffma2_rn(f2(c.x), wgt, Cr);
                     Cg = __ffma2_rn(f2(c.y), wgt, Cg);
                     Cb = __ffma2_rn(f2(c.z), wgt, Cb);
                     Dz = __ffma2_rn(f2(oz.y), wgt, Dz);
-                    T = Tn;
                 }
-                if (!__any_sync(0xffffffffu, act0 || act1)) break;
+                if (!__any_sync(0xffffffffu, SAGE_LIVE())) break;
             }
         }
-        if (__syncthreads_and(!(act0 || act1))) break;
+        if (__syncthreads_and(!SAGE_LIVE())) break;
     }
+#undef SAGE_LIVE
 
     // epilogue: quantise and store to every destination frame
     if (in0 || in1) {
