@@ -61,9 +61,6 @@ struct sage_scene {
     std::vector<cudaEvent_t> events;
     int n_slots = 0;
     long frame_index = 0;
-    // K1b (SH colour) runs on a side stream, concurrently with binning and the per-tile sort
-    cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct sage_grid {
@@ -149,13 +146,11 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     CKB(dalloc(&s->fr.rec2, (size_t)n));
     CKB(dalloc(&s->fr.dkey, (size_t)n));
     CKB(dalloc(&s->fr.vis_list, (size_t)n));
+    CKB(dalloc(&s->fr.big_list, (size_t)n));
     CKB(dalloc(&s->fr.rect, (size_t)n));
     CKB(dalloc(&s->fr.ntiles, (size_t)n));
     CKB(dalloc(&s->fr.counters, (size_t)CNT_COUNT));
     CKB(dalloc(&s->n_dev, 1));
-    CKB(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
-    CKB(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-    CKB(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     CKB(cudaHostAlloc((void**)&s->counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
     memset(s->counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
     uint32_t n32 = (uint32_t)n;
@@ -202,16 +197,13 @@ int sage_scene_destroy(sage_scene* s)
     cudaDeviceSynchronize();
     cudaFree(s->sc.geo0); cudaFree(s->sc.geo1); cudaFree(s->sc.geo2); cudaFree(s->sc.shc);
     cudaFree(s->fr.rec0); cudaFree(s->fr.rec1); cudaFree(s->fr.rec2);
-    cudaFree(s->fr.dkey); cudaFree(s->fr.vis_list);
+    cudaFree(s->fr.dkey); cudaFree(s->fr.vis_list); cudaFree(s->fr.big_list);
     cudaFree(s->fr.rect); cudaFree(s->fr.ntiles);
     free_instances(s);
     cudaFree(s->fr.tile_count); cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
     cudaFree(s->n_dev);
     if (s->counters_host) cudaFreeHost(s->counters_host);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->ev_join) cudaEventDestroy(s->ev_join);
-    if (s->aux) cudaStreamDestroy(s->aux);
     cudaFree(s->frame_rgb); cudaFree(s->frame_depth);
     cudaGetLastError();
     delete s;
@@ -269,31 +261,24 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, st));
     if (n_tiles > 0) CK(cudaMemsetAsync(s->fr.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)s->max_tiles, st));
     cudaEvent_t* ev = s->n_slots > 0
-        ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 3)] : nullptr;
+        ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     s->frame_index++;
 #define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], st)); } while (0)
     if (n_tiles > 0 && s->sc.n > 0) {
         STAGE_MARK(0);
-        sage_launch_project(s->sc, cd, s->fr, st);
+        sage_launch_project(s->sc, cd, s->fr, st);      // + per-tile counts of small footprints
         STAGE_MARK(1);
-        // fork: SH colour only needs the visible list; it overlaps binning + tile sort
-        CK(cudaEventRecord(s->ev_fork, st));
-        CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
-        if (ev) CK(cudaEventRecord(ev[SAGE_N_STAGES + 1], s->aux));
-        sage_launch_sh_color(s->sc, cd, s->fr, s->aux);
-        if (ev) CK(cudaEventRecord(ev[SAGE_N_STAGES + 2], s->aux));
-        CK(cudaEventRecord(s->ev_join, s->aux));
-        sage_launch_binning(cd, s->fr, s->sc.n, s->cap, n_tiles, &launches, st);
+        sage_launch_sh_color(s->sc, cd, s->fr, st);
         STAGE_MARK(2);
-        sage_launch_tile_sort(s->fr, n_tiles, dbits, st);
+        sage_launch_binning(cd, s->fr, s->sc.n, s->cap, n_tiles, &launches, st);
         STAGE_MARK(3);
-        CK(cudaStreamWaitEvent(st, s->ev_join, 0));      // join before the blend reads colours
+        sage_launch_tile_sort(s->fr, n_tiles, dbits, st);
         STAGE_MARK(4);
         sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
         launches += 5;
         STAGE_MARK(5);
     } else if (n_tiles > 0) {
-        for (int k = 0; k <= SAGE_N_STAGES + 2; ++k) STAGE_MARK(k);
+        for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
         CK(cudaMemsetAsync(s->fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
         sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
         launches += 1;
@@ -389,7 +374,7 @@ int sage_set_stage_timing(sage_scene* s, int n_slots)
     s->events.clear();
     s->n_slots = 0;
     s->frame_index = 0;
-    s->events.resize((size_t)n_slots * (SAGE_N_STAGES + 3));
+    s->events.resize((size_t)n_slots * (SAGE_N_STAGES + 1));
     for (auto& e : s->events) CK(cudaEventCreate(&e));
     s->n_slots = n_slots;
     return 0;
@@ -400,16 +385,9 @@ int sage_stage_times_get(sage_scene* s, int slot, float ms_out[SAGE_N_STAGES])
     REQUIRE(s != nullptr && ms_out != nullptr, "sage_stage_times_get: NULL argument");
     REQUIRE(s->n_slots > 0 && slot >= 0 && slot < s->n_slots, "sage_stage_times_get: bad slot / timing off");
     CK(cudaSetDevice(s->device));
-    cudaEvent_t* ev = &s->events[(size_t)slot * (SAGE_N_STAGES + 3)];
-    CK(cudaEventSynchronize(ev[5]));
-    CK(cudaEventSynchronize(ev[SAGE_N_STAGES + 2]));
-    // main stream: project [0,1], binning [1,2], tile sort [2,3], (join wait [3,4]), composite [4,5];
-    // side stream: SH colour [N+1, N+2]
-    CK(cudaEventElapsedTime(&ms_out[0], ev[0], ev[1]));
-    CK(cudaEventElapsedTime(&ms_out[1], ev[SAGE_N_STAGES + 1], ev[SAGE_N_STAGES + 2]));
-    CK(cudaEventElapsedTime(&ms_out[2], ev[1], ev[2]));
-    CK(cudaEventElapsedTime(&ms_out[3], ev[2], ev[3]));
-    CK(cudaEventElapsedTime(&ms_out[4], ev[4], ev[5]));
+    cudaEvent_t* ev = &s->events[(size_t)slot * (SAGE_N_STAGES + 1)];
+    CK(cudaEventSynchronize(ev[SAGE_N_STAGES]));
+    for (int k = 0; k < SAGE_N_STAGES; ++k) CK(cudaEventElapsedTime(&ms_out[k], ev[k], ev[k + 1]));
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // K2-K4: tile binning and the per-tile depth sort.
 //
-//   k_expand<COUNT>   every visible Gaussian adds 1 to the counter of each tile it touches
+//   (k_project)       small footprints add 1 to the counter of each tile they touch
+//   k_count_big       the same for footprints of more than SAGE_SMALL_FOOTPRINT tiles
 //   k_scan_tiles      exclusive scan of the T tile counters -> per-tile ranges, D = total
 //   k_expand<FILL>    every (tile, Gaussian) instance claims a slot in its tile's range (atomic
 //                     cursor) and writes a 64-bit key  depth(27) << 32 | id(28) << 4 | quadrants(4)
@@ -98,6 +99,23 @@ k_expand(SageCamDev cam, SageFrame fr, uint32_t cap)
                 fr.inst_key[slot] = key;
             }
         }
+    }
+}
+
+// Tile counts of the large footprints (K1a counted the small ones): a block per Gaussian, its
+// threads striding over the tile rectangle.
+__global__ void __launch_bounds__(B_THREADS)
+k_count_big(SageCamDev cam, SageFrame fr)
+{
+    const uint32_t nbig = fr.counters[CNT_BIG];
+    for (uint32_t q = blockIdx.x; q < nbig; q += gridDim.x) {
+        const uint32_t g = fr.big_list[q];
+        const uint2 b = fr.rect[g];
+        const int bx0 = (b.x & 0xFFFF) / SAGE_TILE, by0 = (b.y & 0xFFFF) / SAGE_TILE;
+        const uint32_t bw = (uint32_t)((b.x >> 16) / SAGE_TILE - bx0 + 1);
+        const uint32_t bc = bw * (uint32_t)((b.y >> 16) / SAGE_TILE - by0 + 1);
+        for (uint32_t k = threadIdx.x; k < bc; k += B_THREADS)
+            atomicAdd(&fr.tile_count[(by0 + (int)(k / bw) - cam.row0) * cam.tiles_x + bx0 + (int)(k % bw)], 1u);
     }
 }
 
@@ -395,7 +413,7 @@ void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, int64_t n, 
 {
     if (n <= 0 || n_tiles <= 0) return;
     const int blocks = (int)((n + B_THREADS - 1) / B_THREADS);
-    k_expand<false><<<blocks, B_THREADS, 0, st>>>(cam, fr, (uint32_t)cap);
+    k_count_big<<<148 * 4, B_THREADS, 0, st>>>(cam, fr);
     k_scan_tiles<<<1, 1024, 0, st>>>(fr, n_tiles, (uint32_t)cap);
     k_expand<true><<<blocks, B_THREADS, 0, st>>>(cam, fr, (uint32_t)cap);
     if (launches) *launches += 3;

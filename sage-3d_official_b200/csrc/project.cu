@@ -149,7 +149,17 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                         const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
                         vis = true;
                         fr.dkey[i] = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                        fr.ntiles[i] = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+                        const uint32_t nt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
+                        fr.ntiles[i] = nt;
+                        // per-tile instance counts: small footprints are counted right here
+                        // (fire-and-forget reductions); large ones are left to k_count_big
+                        if (nt <= SAGE_SMALL_FOOTPRINT) {
+                            for (int tyy = ty0; tyy <= ty1; ++tyy)
+                                for (int txx = tx0; txx <= tx1; ++txx)
+                                    atomicAdd(&fr.tile_count[(tyy - cam.row0) * cam.tiles_x + txx], 1u);
+                        } else {
+                            fr.big_list[atomicAdd(&fr.counters[CNT_BIG], 1u)] = (uint32_t)i;
+                        }
                         fr.rec0[i] = make_float4(gx, gy, qa, -l2 - 0.01f);
                         fr.rec1[i] = make_float4(qb, qc, o, tz);
                         // inclusive pixel bounding box (u16 each)

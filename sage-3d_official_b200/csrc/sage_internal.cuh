@@ -20,7 +20,9 @@
 #define SAGE_ID_MASK 0x0FFFFFFFu
 
 // device counters (uint32 each)
-enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_N = 3, CNT_COUNT = 8 };
+enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_BIG = 3, CNT_COUNT = 8 };
+// footprints of at most this many tiles are counted inside the projection kernel
+#define SAGE_SMALL_FOOTPRINT 16u
 
 struct SageCamDev {
     float R[9];
@@ -60,6 +62,7 @@ struct SageFrame {
     float4* rec2;        // r, g, b, 0
     uint32_t* dkey;      // depth key bits(z) - bits(near) of visible Gaussians
     uint32_t* vis_list;  // ids of the V visible Gaussians (arbitrary order)
+    uint32_t* big_list;  // ids of visible Gaussians touching more than SAGE_SMALL_FOOTPRINT tiles
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     uint32_t* ntiles;    // tiles touched
     // per-instance (capacity cap)
