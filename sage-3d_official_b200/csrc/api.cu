@@ -231,6 +231,22 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     return 0;
 }
 
+// resolution-dependent scratch (tile counters, cursors, ranges) grows on first use
+static int ensure_tiles(sage_scene* s, int n_tiles, cudaStream_t st)
+{
+    if (n_tiles > s->max_tiles) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(s->fr.ranges);
+        cudaFree(s->fr.tile_count);
+        s->fr.ranges = nullptr; s->fr.tile_count = nullptr; s->max_tiles = 0;
+        CK(dalloc(&s->fr.ranges, (size_t)n_tiles));
+        CK(dalloc(&s->fr.tile_count, (size_t)2 * n_tiles));
+        s->max_tiles = n_tiles;
+    }
+    s->fr.tile_cursor = s->fr.tile_count + s->max_tiles;
+    return 0;
+}
+
 static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1, int n_peers,
                        uint8_t* const* rgb_peers, float* const* depth_peers, cudaStream_t st)
 {
@@ -241,16 +257,7 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     if (make_cam(cam, row0, row1, &cd)) return 1;
     CK(cudaSetDevice(s->device));
     const int n_tiles = (row1 - row0) * cd.tiles_x;
-    if (n_tiles > s->max_tiles) {   // resolution-dependent scratch grows on first use
-        CK(cudaStreamSynchronize(st));
-        cudaFree(s->fr.ranges);
-        cudaFree(s->fr.tile_count);
-        s->fr.ranges = nullptr; s->fr.tile_count = nullptr; s->max_tiles = 0;
-        CK(dalloc(&s->fr.ranges, (size_t)n_tiles));
-        CK(dalloc(&s->fr.tile_count, (size_t)2 * n_tiles));
-        s->max_tiles = n_tiles;
-    }
-    s->fr.tile_cursor = s->fr.tile_count + s->max_tiles;
+    if (ensure_tiles(s, n_tiles, st)) return 1;
     // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
     uint32_t bn, bf;
     memcpy(&bn, &cd.near_z, 4);
@@ -398,7 +405,9 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     SageCamDev cd;
     if (make_cam(cam, row0_tiles, row1_tiles, &cd)) return 1;
     CK(cudaSetDevice(s->device));
+    if (ensure_tiles(s, (row1_tiles - row0_tiles) * cd.tiles_x, nullptr)) return 1;
     CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, nullptr));
+    CK(cudaMemsetAsync(s->fr.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)(s->max_tiles ? s->max_tiles : 1), nullptr));
     sage_launch_project(s->sc, cd, s->fr, nullptr);
     sage_launch_sh_color(s->sc, cd, s->fr, nullptr);
     CK(cudaGetLastError());
