@@ -203,22 +203,17 @@ def run_native(args):
     W, H = args.width, args.height
     scene = sage.GaussianScene(cloud, device=local)
     dev = torch.device("cuda", local)
-    ty = (H + 15) // 16
-    # tile-row blocks (68 rows at 1080p -> e.g. 9,9,9,9,8,8,8,8 for 8 ranks)
-    base, rem = divmod(ty, world)
-    cuts = [0]
-    for r in range(world):
-        cuts.append(cuts[-1] + base + (1 if r < rem else 0))
-    rows = (cuts[rank], cuts[rank + 1])
+    from sage3d_official_b200.multigpu import rows_of
+    rows = rows_of(rank, H, world)      # tile-row blocks: 68 rows at 1080p -> 9,9,9,9,8,8,8,8 for 8 ranks
 
     nbuf = 2
     rgb = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dep = [torch.zeros((H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
 
-    peer_rgb = peer_dep = None
+    peers = None
     if world > 1:
-        from sage3d_official_b200.multigpu import exchange_peer_pointers
-        peer_rgb, peer_dep = exchange_peer_pointers(rgb, dep, rank, world)
+        from sage3d_official_b200.multigpu import PeerFrames
+        peers = PeerFrames(rgb, dep, rank, world)
 
     def step(i):
         cam = cams[i % len(cams)]
@@ -226,8 +221,8 @@ def run_native(args):
         if world == 1:
             scene.render(cam, out=(rgb[b], dep[b]))
         else:
-            scene.render_peers(cam, rows, peer_rgb[b], peer_dep[b])
-            dist.barrier()      # closes the frame: every rank's strips have landed everywhere
+            scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
+            peers.close_frame()      # device-side: every rank's strips have landed everywhere
 
     def sync_all():
         torch.cuda.synchronize()

@@ -118,10 +118,13 @@ int sage_stage_times_get(sage_scene* s, int slot, float ms_out[SAGE_N_STAGES]);
 int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
                  sage_splat_record* records_host, uint8_t* visible_host);
 
-/* CUDA IPC plumbing for sage_render_peers (64-byte handles exchanged by the host program). */
-int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64]);
-int sage_ipc_open(const uint8_t handle[64], void** dev_ptr_out);
-int sage_ipc_close(void* dev_ptr);
+/* CUDA IPC plumbing for sage_render_peers.  A frame buffer may live inside a larger allocation
+ * (e.g. a torch caching-allocator segment): export returns the 64-byte handle of the enclosing
+ * allocation plus the byte offset of dev_ptr inside it; open maps the allocation in the calling
+ * process and returns base + offset.  close takes the pointer returned by open and its offset. */
+int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64], uint64_t* offset_out);
+int sage_ipc_open(const uint8_t handle[64], uint64_t offset, void** dev_ptr_out);
+int sage_ipc_close(void* dev_ptr, uint64_t offset);
 
 /* ---- 2-D grid collide -------------------------------------------------------------------
  * Obstacle grid of SemanticMap2DCollisionDetector (collision_detector.py:95-132), uploaded once.

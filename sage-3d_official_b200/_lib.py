@@ -80,9 +80,9 @@ def lib():
     L.sage_set_stage_timing.argtypes = [vp, i32]
     L.sage_stage_times_get.argtypes = [vp, i32, vp]
     L.sage_project.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp]
-    L.sage_ipc_export.argtypes = [vp, vp]
-    L.sage_ipc_open.argtypes = [vp, C.POINTER(vp)]
-    L.sage_ipc_close.argtypes = [vp]
+    L.sage_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.sage_ipc_open.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.sage_ipc_close.argtypes = [vp, C.c_uint64]
     dbl = C.c_double
     L.sage_grid_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, dbl, dbl, dbl, dbl, dbl]
     L.sage_grid_destroy.argtypes = [vp]

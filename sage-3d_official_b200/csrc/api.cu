@@ -441,29 +441,41 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     return 0;
 }
 
-int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64])
+int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64], uint64_t* offset_out)
 {
-    REQUIRE(dev_ptr && handle_out, "sage_ipc_export: NULL argument");
+    REQUIRE(dev_ptr && handle_out && offset_out, "sage_ipc_export: NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    // base of the enclosing allocation (driver entry point fetched at run time: no link-time libcuda)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    REQUIRE(fn != nullptr && qr == cudaDriverEntryPointSuccess, "sage_ipc_export: cuMemGetAddressRange unavailable");
+    unsigned long long base = 0;
+    size_t size = 0;
+    REQUIRE(((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) == 0, "sage_ipc_export: cuMemGetAddressRange failed");
     cudaIpcMemHandle_t h;
-    CK(cudaIpcGetMemHandle(&h, dev_ptr));
+    CK(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
     memcpy(handle_out, &h, 64);
+    *offset_out = (uint64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
     return 0;
 }
 
-int sage_ipc_open(const uint8_t handle[64], void** dev_ptr_out)
+int sage_ipc_open(const uint8_t handle[64], uint64_t offset, void** dev_ptr_out)
 {
     REQUIRE(handle && dev_ptr_out, "sage_ipc_open: NULL argument");
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, 64);
-    CK(cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr_out = (void*)((uint8_t*)base + offset);
     return 0;
 }
 
-int sage_ipc_close(void* dev_ptr)
+int sage_ipc_close(void* dev_ptr, uint64_t offset)
 {
     if (!dev_ptr) return 0;
-    CK(cudaIpcCloseMemHandle(dev_ptr));
+    CK(cudaIpcCloseMemHandle((void*)((uint8_t*)dev_ptr - offset)));
     return 0;
 }
 

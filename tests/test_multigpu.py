@@ -1,0 +1,107 @@
+"""Multi-process paths: tile-row partition + strip gather on CPU (gloo, world_size 2), and the
+peer-store composite epilogue between two processes sharing the one GPU of the test box."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_frame(h, w):
+    y, x = np.mgrid[0:h, 0:w]
+    return np.stack([(x * 7 + y * 3) % 256, (x + y * 11) % 256, (x * y) % 256], -1).astype(np.uint8)
+
+
+def _cpu_worker(rank, world, port, h, w, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    from sage3d_official_b200.multigpu import gather_strips, pixel_rows, rows_of
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.from_numpy(_fake_frame(h, w))
+    a, b = pixel_rows(rows_of(rank, h, world), h)
+    frame = gather_strips(full[a:b].clone(), h, w, rank, world)
+    depth = gather_strips(full[a:b, :, 0].float().clone(), h, w, rank, world)
+    q.put((rank, bool(torch.equal(frame, full)), bool(torch.equal(depth, full[:, :, 0].float()))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (100, 64)])
+def test_strip_gather_gloo_world2(h, w):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cpu_worker, args=(r, 2, port, h, w, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, True), (1, True, True)]
+
+
+def test_tile_row_cuts():
+    from sage3d_official_b200.multigpu import tile_row_cuts, rows_of, pixel_rows
+    assert tile_row_cuts(1080, 8) == [0, 9, 18, 27, 36, 44, 52, 60, 68]
+    assert tile_row_cuts(1080, 1) == [0, 68]
+    assert tile_row_cuts(480, 4) == [0, 8, 16, 23, 30]
+    for world in (1, 2, 3, 8):
+        rows = [rows_of(r, 1080, world) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 68
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+    assert pixel_rows((60, 68), 1080) == (960, 1080)
+
+
+def _gpu_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    import sage3d_official_b200 as sage
+    from sage3d_official_b200.multigpu import PeerFrames, rows_of
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)     # both ranks share cuda:0 here
+    cloud, _ = sage.synthetic_room(0, 20_000)
+    cam = sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 640, 480)
+    scene = sage.GaussianScene(cloud)
+    ref_rgb, ref_dep = (t.clone() for t in scene.render(cam))
+    rgb = [torch.zeros_like(ref_rgb)]
+    dep = [torch.zeros_like(ref_dep)]
+    peers = PeerFrames(rgb, dep, rank, world)
+    scene.render_peers(cam, rows_of(rank, cam.height, world), peers.rgb[0], peers.depth[0])
+    torch.cuda.synchronize()
+    dist.barrier()
+    ok = bool(torch.equal(rgb[0], ref_rgb)) and bool(torch.equal(dep[0], ref_dep))
+    dist.barrier()
+    peers.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_store_composite_two_processes_one_gpu():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
