@@ -311,9 +311,10 @@ def run_native(args):
         px = W * H if world == 1 else W * (min(rows[1] * 16, H) - rows[0] * 16)
         alg = {   # algorithmic bytes per launch of each stage
             "project": args.n * 44 + V * 32,
+            "depth_sort": args.n * 4 + V * 8 * 2 * 3,
             "sh_color": V * (12 * nb + 16 + 16),
-            "binning": 2 * V * 16 + D * 8,
-            "tile_sort": D * (8 + 4),
+            "emit": V * 16 + D * 8,
+            "tile_sort": D * 8 * 2 * 2 + D * 4,
             "composite": D * 36 + px * 7,
         }
         dom_ms = stage[dom]

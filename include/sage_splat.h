@@ -110,7 +110,7 @@ int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out);
 /* Per-stage device timing (bench/roofline): with n_slots > 0 every frame records CUDA events
  * between its stages on the caller's stream into slot (frame_index % n_slots); n_slots = 0 turns
  * it off.  sage_stage_times_get waits for that frame and returns milliseconds per stage. */
-#define SAGE_N_STAGES 5 /* project, sh_color, binning (count+scan+fill), tile_sort, composite */
+#define SAGE_N_STAGES 6 /* project, depth_sort, sh_color, emit, tile_sort (+ranges), composite */
 int sage_set_stage_timing(sage_scene* s, int n_slots);
 int sage_stage_times_get(sage_scene* s, int slot, float ms_out[SAGE_N_STAGES]);
 

@@ -160,7 +160,7 @@ class GaussianScene:
         check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))
         return {k: int(getattr(st, k)) for k, _ in CFrameStats._fields_}
 
-    STAGES = ("project", "sh_color", "binning", "tile_sort", "composite")
+    STAGES = ("project", "depth_sort", "sh_color", "emit", "tile_sort", "composite")
 
     def set_stage_timing(self, n_slots: int):
         check(_lib.lib().sage_set_stage_timing(self._h, int(n_slots)))

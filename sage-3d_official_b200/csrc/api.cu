@@ -57,6 +57,7 @@ struct sage_scene {
     cudaStream_t last_stream = nullptr;
     int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
     bool rendered = false;
+    uint32_t epoch = 8;        // look-back epochs: 8 fresh values per frame
     // optional per-stage timing: n_slots x (SAGE_N_STAGES + 1) events
     std::vector<cudaEvent_t> events;
     int n_slots = 0;
@@ -91,17 +92,24 @@ struct sage_bodies {
 
 static void free_instances(sage_scene* s)
 {
-    cudaFree(s->fr.inst_key); s->fr.inst_key = nullptr;
-    cudaFree(s->fr.inst_key_alt); s->fr.inst_key_alt = nullptr;
-    cudaFree(s->fr.inst_val); s->fr.inst_val = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(s->fr.ikey[k]); s->fr.ikey[k] = nullptr;
+        cudaFree(s->fr.ival[k]); s->fr.ival[k] = nullptr;
+    }
+    cudaFree(s->fr.lookback); s->fr.lookback = nullptr;
 }
 
 static int alloc_instances(sage_scene* s, int64_t cap)
 {
     free_instances(s);
-    CK(dalloc(&s->fr.inst_key, (size_t)cap));
-    CK(dalloc(&s->fr.inst_key_alt, (size_t)cap));
-    CK(dalloc(&s->fr.inst_val, (size_t)cap));
+    for (int k = 0; k < 2; ++k) {
+        CK(dalloc(&s->fr.ikey[k], (size_t)cap));
+        CK(dalloc(&s->fr.ival[k], (size_t)cap));
+    }
+    const int64_t mx = cap > s->sc.n ? cap : s->sc.n;
+    const size_t words = sage_sort_lookback_words(mx);
+    CK(dalloc(&s->fr.lookback, words));
+    CK(cudaMemset(s->fr.lookback, 0, words * sizeof(unsigned long long)));   // epoch 0 = never published
     s->cap = cap;
     return 0;
 }
@@ -144,12 +152,18 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     CKB(dalloc(&s->fr.rec0, (size_t)n));
     CKB(dalloc(&s->fr.rec1, (size_t)n));
     CKB(dalloc(&s->fr.rec2, (size_t)n));
-    CKB(dalloc(&s->fr.dkey, (size_t)n));
-    CKB(dalloc(&s->fr.vis_list, (size_t)n));
-    CKB(dalloc(&s->fr.big_list, (size_t)n));
+    for (int k = 0; k < 2; ++k) {
+        CKB(dalloc(&s->fr.dkey[k], (size_t)n));
+        CKB(dalloc(&s->fr.dval[k], (size_t)n));
+    }
+    CKB(dalloc(&s->fr.chain, (size_t)(n / 256 + 2)));
+    CKB(cudaMemset(s->fr.chain, 0, (size_t)(n / 256 + 2) * sizeof(unsigned long long)));
     CKB(dalloc(&s->fr.rect, (size_t)n));
     CKB(dalloc(&s->fr.ntiles, (size_t)n));
-    CKB(dalloc(&s->fr.counters, (size_t)CNT_COUNT));
+    CKB(dalloc(&s->fr.counters, (size_t)SAGE_ZERO_WORDS));
+    s->fr.tickets = s->fr.counters + CNT_COUNT;
+    s->fr.depth_hist = s->fr.tickets + SAGE_TICKET_COUNT;
+    s->fr.tile_hist = s->fr.depth_hist + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS;
     CKB(dalloc(&s->n_dev, 1));
     CKB(cudaHostAlloc((void**)&s->counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
     memset(s->counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
@@ -197,10 +211,11 @@ int sage_scene_destroy(sage_scene* s)
     cudaDeviceSynchronize();
     cudaFree(s->sc.geo0); cudaFree(s->sc.geo1); cudaFree(s->sc.geo2); cudaFree(s->sc.shc);
     cudaFree(s->fr.rec0); cudaFree(s->fr.rec1); cudaFree(s->fr.rec2);
-    cudaFree(s->fr.dkey); cudaFree(s->fr.vis_list); cudaFree(s->fr.big_list);
+    for (int k = 0; k < 2; ++k) { cudaFree(s->fr.dkey[k]); cudaFree(s->fr.dval[k]); }
+    cudaFree(s->fr.chain);
     cudaFree(s->fr.rect); cudaFree(s->fr.ntiles);
     free_instances(s);
-    cudaFree(s->fr.tile_count); cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
+    cudaFree(s->fr.ranges); cudaFree(s->fr.counters);
     cudaFree(s->n_dev);
     if (s->counters_host) cudaFreeHost(s->counters_host);
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
@@ -231,19 +246,52 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     return 0;
 }
 
-// resolution-dependent scratch (tile counters, cursors, ranges) grows on first use
+// resolution-dependent scratch (tile ranges) grows on first use
 static int ensure_tiles(sage_scene* s, int n_tiles, cudaStream_t st)
 {
     if (n_tiles > s->max_tiles) {
         CK(cudaStreamSynchronize(st));
         cudaFree(s->fr.ranges);
-        cudaFree(s->fr.tile_count);
-        s->fr.ranges = nullptr; s->fr.tile_count = nullptr; s->max_tiles = 0;
+        s->fr.ranges = nullptr; s->max_tiles = 0;
         CK(dalloc(&s->fr.ranges, (size_t)n_tiles));
-        CK(dalloc(&s->fr.tile_count, (size_t)2 * n_tiles));
         s->max_tiles = n_tiles;
     }
-    s->fr.tile_cursor = s->fr.tile_count + s->max_tiles;
+    return 0;
+}
+
+static int depth_key_bits(const SageCamDev& cd)
+{
+    // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
+    uint32_t bn, bf;
+    memcpy(&bn, &cd.near_z, 4);
+    memcpy(&bf, &cd.far_z, 4);
+    int dbits = 1;
+    while (dbits < 32 && ((uint64_t)1 << dbits) <= (uint64_t)(bf - bn)) ++dbits;
+    return dbits;
+}
+
+// project -> depth sort (+compaction) -> SH colour; *order_buf = buffer index holding order[]
+static int front_half(sage_scene* s, const SageCamDev& cd, int* launches, cudaEvent_t* ev, cudaStream_t st, int* order_buf)
+{
+    if (ev) CK(cudaEventRecord(ev[0], st));
+    sage_launch_project(s->sc, cd, s->fr, st);
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    SageSortPlan dp{};
+    dp.keys[0] = s->fr.dkey[0]; dp.keys[1] = s->fr.dkey[1];
+    dp.vals[0] = s->fr.dval[0]; dp.vals[1] = s->fr.dval[1];
+    dp.n_first = s->n_dev; dp.n_rest = s->fr.counters + CNT_VISIBLE;
+    dp.capacity = s->sc.n; dp.lo_bit = 0; dp.n_bits = depth_key_bits(cd);
+    sage_sort_shape(dp.n_bits, &dp.digit_bits, &dp.passes);
+    dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false;
+    dp.hist = s->fr.depth_hist; dp.total_out = nullptr;
+    dp.lookback = s->fr.lookback; dp.tickets = s->fr.tickets + SAGE_TICKET_DEPTH; dp.epoch0 = s->epoch;
+    const int res = sage_radix_sort(dp, launches, st);
+    REQUIRE(res >= 0, "depth sort: unsupported key width");
+    if (ev) CK(cudaEventRecord(ev[2], st));
+    sage_launch_sh_color(s->sc, cd, s->fr, s->fr.dval[res], st);
+    if (ev) CK(cudaEventRecord(ev[3], st));
+    *launches += 2;
+    *order_buf = res;
     return 0;
 }
 
@@ -258,36 +306,43 @@ static int render_impl(sage_scene* s, const sage_camera* cam, int row0, int row1
     CK(cudaSetDevice(s->device));
     const int n_tiles = (row1 - row0) * cd.tiles_x;
     if (ensure_tiles(s, n_tiles, st)) return 1;
-    // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
-    uint32_t bn, bf;
-    memcpy(&bn, &cd.near_z, 4);
-    memcpy(&bf, &cd.far_z, 4);
-    int dbits = 1;
-    while (dbits < 32 && ((uint64_t)1 << dbits) <= (uint64_t)(bf - bn)) ++dbits;
+    int tbits = 1;
+    while ((1 << tbits) < n_tiles) ++tbits;
+    REQUIRE(tbits <= 24, "sage_render: too many tiles");
+    const int tpasses = (tbits + 7) / 8;
     int launches = 0;
-    CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, st));
-    if (n_tiles > 0) CK(cudaMemsetAsync(s->fr.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)s->max_tiles, st));
+    CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, st));
+    s->epoch += 8;
+    if (s->epoch > (1u << 30) - 16) s->epoch = 8;
     cudaEvent_t* ev = s->n_slots > 0
         ? &s->events[(size_t)(s->frame_index % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     s->frame_index++;
 #define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], st)); } while (0)
     if (n_tiles > 0 && s->sc.n > 0) {
-        STAGE_MARK(0);
-        sage_launch_project(s->sc, cd, s->fr, st);      // + per-tile counts of small footprints
-        STAGE_MARK(1);
-        sage_launch_sh_color(s->sc, cd, s->fr, st);
-        STAGE_MARK(2);
-        sage_launch_binning(cd, s->fr, s->sc.n, s->cap, n_tiles, &launches, st);
-        STAGE_MARK(3);
-        sage_launch_tile_sort(s->fr, n_tiles, dbits, st);
+        int ob = 0;
+        if (front_half(s, cd, &launches, ev, st, &ob)) return 1;     // stages 0..2
+        const uint32_t* order = s->fr.dval[ob];
+        sage_launch_emit(cd, s->fr, order, s->sc.n, s->cap, tpasses, s->epoch + 3, st);
         STAGE_MARK(4);
-        sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
-        launches += 5;
+        SageSortPlan tp{};
+        tp.keys[0] = s->fr.ikey[0]; tp.keys[1] = s->fr.ikey[1];
+        tp.vals[0] = s->fr.ival[0]; tp.vals[1] = s->fr.ival[1];
+        tp.n_first = tp.n_rest = s->fr.counters + CNT_INSTANCES;
+        tp.capacity = s->cap; tp.lo_bit = 0; tp.n_bits = tbits; tp.digit_bits = 8; tp.passes = tpasses;
+        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true;
+        tp.hist = s->fr.tile_hist; tp.total_out = nullptr;
+        tp.lookback = s->fr.lookback; tp.tickets = s->fr.tickets + SAGE_TICKET_TILE; tp.epoch0 = s->epoch + 4;
+        const int ires = sage_radix_sort(tp, &launches, st);
+        REQUIRE(ires >= 0, "tile sort: unsupported key width");
+        sage_launch_ranges(s->fr, s->fr.ikey[ires], s->cap, n_tiles, st);
         STAGE_MARK(5);
+        sage_launch_composite(cd, s->fr, s->fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
+        launches += 3;
+        STAGE_MARK(6);
     } else if (n_tiles > 0) {
         for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
         CK(cudaMemsetAsync(s->fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
-        sage_launch_composite(cd, s->fr, n_peers, rgb_peers, depth_peers, st);
+        sage_launch_composite(cd, s->fr, s->fr.ival[0], n_peers, rgb_peers, depth_peers, st);
         launches += 1;
     }
     CK(cudaGetLastError());
@@ -405,18 +460,17 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     SageCamDev cd;
     if (make_cam(cam, row0_tiles, row1_tiles, &cd)) return 1;
     CK(cudaSetDevice(s->device));
-    if (ensure_tiles(s, (row1_tiles - row0_tiles) * cd.tiles_x, nullptr)) return 1;
-    CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * CNT_COUNT, nullptr));
-    CK(cudaMemsetAsync(s->fr.tile_count, 0, sizeof(uint32_t) * 2 * (size_t)(s->max_tiles ? s->max_tiles : 1), nullptr));
-    sage_launch_project(s->sc, cd, s->fr, nullptr);
-    sage_launch_sh_color(s->sc, cd, s->fr, nullptr);
+    CK(cudaMemsetAsync(s->fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, nullptr));
+    s->epoch += 8;
+    int launches = 0, ob = 0;
+    if (front_half(s, cd, &launches, nullptr, nullptr, &ob)) return 1;
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     const size_t n = (size_t)s->sc.n;
     uint32_t V = 0;
     CK(cudaMemcpy(&V, s->fr.counters + CNT_VISIBLE, sizeof V, cudaMemcpyDeviceToHost));
     std::vector<uint32_t> vlist(V);
-    if (V) CK(cudaMemcpy(vlist.data(), s->fr.vis_list, V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (V) CK(cudaMemcpy(vlist.data(), s->fr.dval[ob], V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     std::vector<uint8_t> visv(n, 0);
     for (uint32_t g : vlist) visv[g] = 1;
     std::vector<float4> r0(n), r1(n), r2(n);

@@ -164,7 +164,8 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
 
 }  // namespace
 
-void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
+                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
                            cudaStream_t st)
 {
     const int n_tiles = (cam.row1 - cam.row0) * cam.tiles_x;
@@ -175,5 +176,5 @@ void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, int n_pee
         out.rgb[k] = k < out.n ? rgb_peers[k] : nullptr;
         out.depth[k] = (k < out.n && depth_peers) ? depth_peers[k] : nullptr;
     }
-    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, fr.inst_val, fr.ranges, out);
+    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, out);
 }

@@ -73,14 +73,15 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 
 // ---------------------------------------------------------------------------------------------
 // K1a: project, cull, conic, conservative pixel bounding box.  One thread per Gaussian; every
-// per-Gaussian stream is a 16-byte-per-lane coalesced access.  Survivors get a depth key
-// bits(z) - bits(near) and are appended to the visible list (warp-aggregated atomic).
+// per-Gaussian stream is a 16-byte-per-lane coalesced access.  Emits the depth key
+// (bits(z) - bits(near), or CULLED) that the first radix pass compacts and sorts in one go.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
+    uint32_t key = SAGE_KEY_CULLED, count = 0;
     if (i < sc.n) {
         const float4 g0 = __ldg(&sc.geo0[i]);
         const float mx = g0.x, my = g0.y, mz = g0.z, o = g0.w;
@@ -148,18 +149,8 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                         const int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
                         const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
                         vis = true;
-                        fr.dkey[i] = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                        const uint32_t nt = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-                        fr.ntiles[i] = nt;
-                        // per-tile instance counts: small footprints are counted right here
-                        // (fire-and-forget reductions); large ones are left to k_count_big
-                        if (nt <= SAGE_SMALL_FOOTPRINT) {
-                            for (int tyy = ty0; tyy <= ty1; ++tyy)
-                                for (int txx = tx0; txx <= tx1; ++txx)
-                                    atomicAdd(&fr.tile_count[(tyy - cam.row0) * cam.tiles_x + txx], 1u);
-                        } else {
-                            fr.big_list[atomicAdd(&fr.counters[CNT_BIG], 1u)] = (uint32_t)i;
-                        }
+                        key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
+                        count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
                         fr.rec0[i] = make_float4(gx, gy, qa, -l2 - 0.01f);
                         fr.rec1[i] = make_float4(qb, qc, o, tz);
                         // inclusive pixel bounding box (u16 each)
@@ -169,18 +160,17 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 }
             }
         }
+        fr.dkey[0][i] = key;
+        fr.ntiles[i] = count;
     }
-    // append the survivors to the visible list: one atomic per warp
+    // one atomic per warp for the visible counter
     const unsigned m = __ballot_sync(0xffffffffu, vis);
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0 && m) base = atomicAdd(&fr.counters[CNT_VISIBLE], (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (vis) fr.vis_list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], (uint32_t)__popc(m));
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1b: view-dependent SH colour for the V visible Gaussians (walks the visible list).  Separate from K1a so that neither kernel carries the other's registers.
+// K1b: view-dependent SH colour for the V visible Gaussians (walks the depth-sorted id list).
+// Separate from K1a so that neither kernel carries the other's registers.
 // ---------------------------------------------------------------------------------------------
 __device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
                                             0.31539156525252005f, -1.0925484305920792f,
@@ -192,7 +182,7 @@ __device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 
 template <int DEG>
 __global__ void __launch_bounds__(256)
-k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr)
+k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order)
 {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     constexpr int NF = 3 * NB;
@@ -200,7 +190,7 @@ k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr)
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= V) return;
-    const uint32_t i = __ldg(&fr.vis_list[r]);
+    const uint32_t i = __ldg(&order[r]);
     const float4 g0 = __ldg(&sc.geo0[i]);
     float shv[NC * 4];
     const float4* sp = sc.shc + (size_t)i * NC;
@@ -255,14 +245,15 @@ void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const Sa
     k_project<<<blocks, 256, 0, st>>>(sc, cam, fr);
 }
 
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
+                          const uint32_t* order, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
     switch (sc.deg) {
-        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
-        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr); break;
+        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
     }
 }

@@ -20,9 +20,7 @@
 #define SAGE_ID_MASK 0x0FFFFFFFu
 
 // device counters (uint32 each)
-enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_BIG = 3, CNT_COUNT = 8 };
-// footprints of at most this many tiles are counted inside the projection kernel
-#define SAGE_SMALL_FOOTPRINT 16u
+enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_COUNT = 8 };
 
 struct SageCamDev {
     float R[9];
@@ -55,25 +53,49 @@ __device__ __forceinline__ float sage_exp2(float x)
 __device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_LOG2E); }
 
 // ---- frame workspace ---------------------------------------------------------------------
+#define SAGE_RADIX_MAX_BINS 512
+#define SAGE_MAX_PASSES 4
+enum { SAGE_TICKET_DEPTH = 0, SAGE_TICKET_EMIT = 4, SAGE_TICKET_TILE = 5, SAGE_TICKET_COUNT = 12 };
+
 struct SageFrame {
     // per-Gaussian (capacity n)
     float4* rec0;        // gx, gy, qa, skip threshold (log2 units)
     float4* rec1;        // qb, qc, opacity, z
     float4* rec2;        // r, g, b, 0
-    uint32_t* dkey;      // depth key bits(z) - bits(near) of visible Gaussians
-    uint32_t* vis_list;  // ids of the V visible Gaussians (arbitrary order)
-    uint32_t* big_list;  // ids of visible Gaussians touching more than SAGE_SMALL_FOOTPRINT tiles
+    uint32_t* dkey[2];   // depth keys bits(z) - bits(near) (or CULLED), ping-pong
+    uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     uint32_t* ntiles;    // tiles touched
     // per-instance (capacity cap)
-    unsigned long long* inst_key;      // depth << 32 | id << 4 | quadrant mask
-    unsigned long long* inst_key_alt;  // ping-pong partner for tile lists too long for shared memory
-    uint32_t* inst_val;                // per-tile depth-sorted (id << 4 | quadrant mask)
-    // per-tile
-    uint32_t* tile_count;   // [max_tiles]
-    uint32_t* tile_cursor;  // [max_tiles], directly after tile_count (one memset clears both)
-    uint2* ranges;
+    uint32_t* ikey[2];   // tile id, ping-pong
+    uint32_t* ival[2];   // id << 4 | quadrant mask, ping-pong
+    // sort / scan state
+    unsigned long long* lookback;  // [blocks][SAGE_RADIX_MAX_BINS] epoch|state|value words (never cleared)
+    unsigned long long* chain;     // [n/256 + 1] chained-scan words of the emission kernel
+    // one block cleared per frame: counters | tickets | depth_hist | tile_hist
     uint32_t* counters;     // CNT_COUNT
+    uint32_t* tickets;      // SAGE_TICKET_COUNT
+    uint32_t* depth_hist;   // [SAGE_MAX_PASSES][SAGE_RADIX_MAX_BINS]
+    uint32_t* tile_hist;    // [SAGE_MAX_PASSES][256]
+    // per-tile
+    uint2* ranges;
+};
+#define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS + SAGE_MAX_PASSES * 256)
+
+struct SageSortPlan {
+    uint32_t* keys[2];
+    uint32_t* vals[2];
+    const uint32_t* n_first;   // element count of pass 0 (device)
+    const uint32_t* n_rest;    // element count of the later passes (device)
+    int64_t capacity;
+    int lo_bit, n_bits;
+    int digit_bits, passes;    // from sage_sort_shape, or forced by the caller
+    bool vals_are_iota, compact_first, hist_ready;
+    uint32_t* hist;            // [passes][1 << digit_bits], zeroed (or pre-accumulated if hist_ready)
+    uint32_t* total_out;       // optional: total of pass 0's histogram
+    unsigned long long* lookback;
+    uint32_t* tickets;         // [passes], zeroed
+    uint32_t epoch0;           // epochs epoch0 .. epoch0 + passes - 1 must be fresh
 };
 
 // ---- kernel launchers (defined in the .cu files) -------------------------------------------
@@ -90,12 +112,20 @@ struct SageSceneDev {
 void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
                             const float* quat, const float* opacity, const float* sh, cudaStream_t st);
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
+void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
+                          const uint32_t* order, cudaStream_t st);
 
-void sage_launch_binning(const SageCamDev& cam, const SageFrame& fr, int64_t n, int64_t cap,
-                         int n_tiles, int* launches, cudaStream_t st);
-void sage_launch_tile_sort(const SageFrame& fr, int n_tiles, int depth_bits, cudaStream_t st);
-void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+// Stable LSD radix sort, one kernel per pass (decoupled look-back).  Returns the index (0/1) of the
+// buffer pair that holds the result, or -1 for an unsupported shape.
+int sage_radix_sort(const SageSortPlan& plan, int* launches, cudaStream_t st);
+void sage_sort_shape(int n_bits, int* digit_bits, int* passes);
+size_t sage_sort_lookback_words(int64_t capacity);
+
+void sage_launch_emit(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order, int64_t n,
+                      int64_t cap, int tile_passes, uint32_t epoch, cudaStream_t st);
+void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_t cap, int n_tiles, cudaStream_t st);
+void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
+                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
                            cudaStream_t st);
 
 void sage_launch_collide_grid(const uint8_t* map, int H, int W, double min_x, double max_x,

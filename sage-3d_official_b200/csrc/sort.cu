@@ -1,0 +1,256 @@
+// K3: stable LSD radix sort of (key32, val32) pairs — ONE kernel per pass ("onesweep" form):
+// every block ranks its 4096 items locally, publishes its per-digit counts, and obtains the counts
+// of all earlier blocks by decoupled look-back instead of a separate histogram + scan launch.
+//
+// Used twice per frame (no host round trip: element counts are read from device memory):
+//  (a) depth sort of the Gaussians: key = bits(z) - bits(near) (<= 27 significant bits, 3 passes of
+//      9 bits); pass 0 also compacts (drops SAGE_KEY_CULLED).  The sort is stable and its input
+//      is in index order, so equal depths stay in Gaussian-index order — the spec's tie-break.
+//  (b) stable binning of the depth-ordered (tile, Gaussian) instances by tile id (13 bits at
+//      1080p, 2 passes of 8): every tile's list comes out depth-sorted, no 64-bit keys anywhere.
+//
+// Look-back state is one 64-bit word per (block, digit): epoch(30) | state(2) | value(32).  The
+// epoch changes every pass of every frame, so the state array is never cleared.  Blocks take their
+// tile index from an atomic ticket, which guarantees that every predecessor a block waits for is
+// already resident (forward progress); the spin is bounded and traps instead of hanging.
+#include "sage_internal.cuh"
+
+namespace {
+
+constexpr int S_THREADS = 256;
+constexpr int S_IPT = 16;
+constexpr int S_TILE = S_THREADS * S_IPT;
+constexpr int S_WARPS = S_THREADS / 32;
+
+constexpr unsigned long long ST_AGG = 1ull, ST_PREFIX = 2ull;
+
+__device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, unsigned long long state, uint32_t v)
+{
+    return ((unsigned long long)epoch << 34) | (state << 32) | (unsigned long long)v;
+}
+
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- global digit histograms for all passes of a sort, in one read of the keys ----------------
+template <int RB, int NP, bool COMPACT>
+__global__ void __launch_bounds__(S_THREADS)
+k_radix_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_ptr, int lo_bit,
+             uint32_t* __restrict__ hist /*[NP][1<<RB]*/)
+{
+    constexpr int RADIX = 1 << RB;
+    __shared__ uint32_t h[NP][RADIX];
+    for (int i = threadIdx.x; i < NP * RADIX; i += S_THREADS) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t n = *n_ptr;
+    for (uint32_t idx = blockIdx.x * S_THREADS + threadIdx.x; idx < n; idx += gridDim.x * S_THREADS) {
+        const uint32_t k = __ldg(&keys[idx]);
+        if (COMPACT && k == SAGE_KEY_CULLED) continue;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) atomicAdd(&h[p][(k >> (lo_bit + RB * p)) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NP * RADIX; i += S_THREADS) {
+        const uint32_t c = (&h[0][0])[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// ---- exclusive scan of each pass's histogram (one block per pass) -------------------------------
+template <int RB>
+__global__ void __launch_bounds__(S_THREADS)
+k_radix_offsets(uint32_t* __restrict__ hist, uint32_t* __restrict__ total_out)
+{
+    constexpr int RADIX = 1 << RB;
+    constexpr int PER = RADIX / S_THREADS;     // 1 (RB=8) or 2 (RB=9)
+    uint32_t* h = hist + (size_t)blockIdx.x * RADIX;
+    __shared__ uint32_t wsum[S_WARPS];
+    uint32_t v[PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { v[k] = h[threadIdx.x * PER + k]; s += v[k]; }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t base = incl - s;
+#pragma unroll
+    for (int k = 0; k < S_WARPS; ++k) base += (k < w) ? wsum[k] : 0u;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { h[threadIdx.x * PER + k] = base; base += v[k]; }
+    if (blockIdx.x == 0 && threadIdx.x == S_THREADS - 1 && total_out) *total_out = base;
+}
+
+// ---- one sort pass ------------------------------------------------------------------------------
+template <int RB, bool COMPACT>
+__global__ void __launch_bounds__(S_THREADS)
+k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+           uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+           const uint32_t* __restrict__ n_ptr, int shift, const uint32_t* __restrict__ digit_base,
+           unsigned long long* __restrict__ lookback, uint32_t* __restrict__ ticket, uint32_t epoch,
+           int vals_are_iota)
+{
+    constexpr int RADIX = 1 << RB;
+    constexpr int PER = RADIX / S_THREADS;
+    const uint32_t n = *n_ptr;
+    const uint32_t nb = (n + S_TILE - 1) / S_TILE;
+    __shared__ uint32_t wh[S_WARPS][RADIX];
+    __shared__ uint32_t s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < S_WARPS * RADIX; i += S_THREADS) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t b = s_tile;
+    if (b >= nb) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    // warp-striped ownership: warp w holds items [w*512, (w+1)*512) of the tile, item (i, lane) at
+    // offset i*32 + lane, so (warp, i, lane) order == input order (stability).  All loads first.
+    const uint32_t wbase = b * S_TILE + w * (32 * S_IPT);
+    uint32_t key[S_IPT], val[S_IPT];
+#pragma unroll
+    for (int i = 0; i < S_IPT; ++i) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        key[i] = idx < n ? __ldg(&keys_in[idx]) : SAGE_KEY_CULLED;
+    }
+#pragma unroll
+    for (int i = 0; i < S_IPT; ++i) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        val[i] = vals_are_iota ? idx : (idx < n ? __ldg(&vals_in[idx]) : 0u);
+    }
+    // local ranks: warp-private digit counters, peers found with match.any
+    uint32_t rank[S_IPT];
+    const unsigned lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < S_IPT; ++i) {
+        const uint32_t idx = wbase + i * 32 + lane;
+        const bool valid = idx < n && (!COMPACT || key[i] != SAGE_KEY_CULLED);
+        const uint32_t d = valid ? ((key[i] >> shift) & (RADIX - 1)) : 0xFFFFFFFFu;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t prev = 0;
+        if (valid && lane == leader) {
+            prev = wh[w][d];
+            wh[w][d] = prev + __popc(peers);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[i] = valid ? prev + __popc(peers & lt_mask) : 0xFFFFFFFFu;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: block count -> publish -> look back -> publish inclusive -> per-warp bases
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = threadIdx.x * PER + k;
+        uint32_t cnt[S_WARPS], tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < S_WARPS; ++ww) { cnt[ww] = wh[ww][d]; tot += cnt[ww]; }
+        unsigned long long* mine = lookback + (size_t)b * RADIX + d;
+        uint32_t excl = 0;
+        if (b == 0) {
+            lb_store(mine, lb_pack(epoch, ST_PREFIX, tot));
+        } else {
+            lb_store(mine, lb_pack(epoch, ST_AGG, tot));
+            int t = (int)b - 1;
+            uint32_t spins = 0;
+            while (true) {
+                const unsigned long long s = lb_load(lookback + (size_t)t * RADIX + d);
+                if ((uint32_t)(s >> 34) != epoch) {           // predecessor has not published yet
+                    if (++spins > (1u << 26)) __trap();       // never hang the GPU
+                    __nanosleep(20);
+                    continue;
+                }
+                excl += (uint32_t)s;
+                if (((s >> 32) & 3ull) == ST_PREFIX) break;
+                --t;
+            }
+            lb_store(mine, lb_pack(epoch, ST_PREFIX, excl + tot));
+        }
+        uint32_t run = digit_base[d] + excl;
+#pragma unroll
+        for (int ww = 0; ww < S_WARPS; ++ww) { wh[ww][d] = run; run += cnt[ww]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < S_IPT; ++i) {
+        if (rank[i] != 0xFFFFFFFFu) {
+            const uint32_t d = (key[i] >> shift) & (RADIX - 1);
+            const uint32_t pos = wh[w][d] + rank[i];
+            keys_out[pos] = key[i];
+            vals_out[pos] = val[i];
+        }
+    }
+}
+
+template <int RB, int NP, bool COMPACT>
+void sort_impl(const SageSortPlan& pl, cudaStream_t st)
+{
+    constexpr int RADIX = 1 << RB;
+    int grid = (int)((pl.capacity + S_TILE - 1) / S_TILE);
+    if (grid < 1) grid = 1;
+    if (!pl.hist_ready) {
+        int hgrid = grid < 148 * 8 ? grid : 148 * 8;
+        k_radix_hist<RB, NP, COMPACT><<<hgrid, S_THREADS, 0, st>>>(pl.keys[0], pl.n_first, pl.lo_bit, pl.hist);
+    }
+    k_radix_offsets<RB><<<NP, S_THREADS, 0, st>>>(pl.hist, pl.total_out);
+    int cur = 0;
+    for (int p = 0; p < NP; ++p) {
+        const uint32_t* n_dev = p == 0 ? pl.n_first : pl.n_rest;
+        if (COMPACT && p == 0)
+            k_onesweep<RB, true><<<grid, S_THREADS, 0, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+                                                            n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
+                                                            pl.lookback, pl.tickets + p, pl.epoch0 + p, pl.vals_are_iota ? 1 : 0);
+        else
+            k_onesweep<RB, false><<<grid, S_THREADS, 0, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+                                                             n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
+                                                             pl.lookback, pl.tickets + p, pl.epoch0 + p,
+                                                             (pl.vals_are_iota && p == 0) ? 1 : 0);
+        cur ^= 1;
+    }
+}
+
+}  // namespace
+
+void sage_sort_shape(int n_bits, int* digit_bits, int* passes)
+{
+    // 9-bit digits when that saves a pass (27-bit depth keys: 3 passes), else 8
+    const int rb = ((n_bits + 8) / 9 < (n_bits + 7) / 8) ? 9 : 8;
+    *digit_bits = rb;
+    *passes = (n_bits + rb - 1) / rb;
+}
+
+size_t sage_sort_lookback_words(int64_t capacity)
+{
+    size_t nb = (size_t)((capacity + S_TILE - 1) / S_TILE) + 1;
+    return nb * SAGE_RADIX_MAX_BINS;
+}
+
+int sage_radix_sort(const SageSortPlan& pl, int* launches, cudaStream_t st)
+{
+    int rb, np;
+    sage_sort_shape(pl.n_bits, &rb, &np);
+    const bool c = pl.compact_first;
+#define SAGE_SORT_CASE(RB_, NP_)                                                     \
+    if (rb == RB_ && np == NP_) {                                                    \
+        if (c) sort_impl<RB_, NP_, true>(pl, st); else sort_impl<RB_, NP_, false>(pl, st); \
+        if (launches) *launches += NP_ + 1 + (pl.hist_ready ? 0 : 1);                \
+        return np & 1;                                                               \
+    }
+    SAGE_SORT_CASE(8, 1) SAGE_SORT_CASE(8, 2) SAGE_SORT_CASE(8, 3) SAGE_SORT_CASE(8, 4)
+    SAGE_SORT_CASE(9, 1) SAGE_SORT_CASE(9, 2) SAGE_SORT_CASE(9, 3)
+#undef SAGE_SORT_CASE
+    return -1;
+}
