@@ -240,8 +240,7 @@ size_t sage_sort_lookback_words(int64_t capacity)
 
 int sage_radix_sort(const SageSortPlan& pl, int* launches, cudaStream_t st)
 {
-    int rb, np;
-    sage_sort_shape(pl.n_bits, &rb, &np);
+    const int rb = pl.digit_bits, np = pl.passes;     // chosen by the caller (sage_sort_shape or forced)
     const bool c = pl.compact_first;
 #define SAGE_SORT_CASE(RB_, NP_)                                                     \
     if (rb == RB_ && np == NP_) {                                                    \
