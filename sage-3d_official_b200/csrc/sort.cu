@@ -17,8 +17,8 @@
 
 namespace {
 
-constexpr int S_THREADS = 256;
-constexpr int S_IPT = 16;
+constexpr int S_THREADS = 512;
+constexpr int S_IPT = 8;
 constexpr int S_TILE = S_THREADS * S_IPT;
 constexpr int S_WARPS = S_THREADS / 32;
 
@@ -71,14 +71,12 @@ __global__ void __launch_bounds__(S_THREADS)
 k_radix_offsets(uint32_t* __restrict__ hist, uint32_t* __restrict__ total_out)
 {
     constexpr int RADIX = 1 << RB;
-    constexpr int PER = RADIX / S_THREADS;     // 1 (RB=8) or 2 (RB=9)
+    static_assert(RADIX <= S_THREADS, "one digit per thread");
     uint32_t* h = hist + (size_t)blockIdx.x * RADIX;
     __shared__ uint32_t wsum[S_WARPS];
-    uint32_t v[PER], s = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { v[k] = h[threadIdx.x * PER + k]; s += v[k]; }
+    const uint32_t v = threadIdx.x < RADIX ? h[threadIdx.x] : 0u;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t incl = s;
+    uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -86,12 +84,10 @@ k_radix_offsets(uint32_t* __restrict__ hist, uint32_t* __restrict__ total_out)
     }
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
-    uint32_t base = incl - s;
-#pragma unroll
-    for (int k = 0; k < S_WARPS; ++k) base += (k < w) ? wsum[k] : 0u;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { h[threadIdx.x * PER + k] = base; base += v[k]; }
-    if (blockIdx.x == 0 && threadIdx.x == S_THREADS - 1 && total_out) *total_out = base;
+    uint32_t base = incl - v;
+    for (int k = 0; k < w; ++k) base += wsum[k];
+    if (threadIdx.x < RADIX) h[threadIdx.x] = base;
+    if (blockIdx.x == 0 && threadIdx.x == RADIX - 1 && total_out) *total_out = base + v;
 }
 
 // ---- one sort pass ------------------------------------------------------------------------------
@@ -104,7 +100,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
            int vals_are_iota)
 {
     constexpr int RADIX = 1 << RB;
-    constexpr int PER = RADIX / S_THREADS;
+    static_assert(RADIX <= S_THREADS, "one digit per thread");
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
     __shared__ uint32_t wh[S_WARPS][RADIX];
@@ -152,9 +148,8 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     __syncthreads();
 
     // per digit: block count -> publish -> look back -> publish inclusive -> per-warp bases
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int d = threadIdx.x * PER + k;
+    if (threadIdx.x < RADIX) {
+        const int d = threadIdx.x;
         uint32_t cnt[S_WARPS], tot = 0;
 #pragma unroll
         for (int ww = 0; ww < S_WARPS; ++ww) { cnt[ww] = wh[ww][d]; tot += cnt[ww]; }
