@@ -97,16 +97,25 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
             cs_store(chain + b, ((unsigned long long)epoch << 34) | (1ull << 32) | total);
             int t = (int)b - 1;
             uint32_t spins = 0;
-            while (true) {
-                const unsigned long long s = cs_load(chain + t);
-                if ((uint32_t)(s >> 34) != epoch) {
-                    if (++spins > (1u << 26)) __trap();
-                    __nanosleep(20);
-                    continue;
+            bool done = false;
+            while (!done) {                                    // batched look-back, as in sort.cu
+                unsigned long long s[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s[j] = (t - j >= 0) ? cs_load(chain + (t - j)) : 0ull;
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!done && used == j && t - j >= 0 && (uint32_t)(s[j] >> 34) == epoch) {
+                        excl += (uint32_t)s[j];
+                        used = j + 1;
+                        done = ((s[j] >> 32) & 3ull) == 2ull;
+                    }
                 }
-                excl += (uint32_t)s;
-                if (((s >> 32) & 3ull) == 2ull) break;
-                --t;
+                t -= used;
+                if (!done && used == 0) {
+                    if (++spins > (1u << 24)) __trap();
+                    __nanosleep(32);
+                }
             }
             cs_store(chain + b, ((unsigned long long)epoch << 34) | (2ull << 32) | (excl + total));
         }

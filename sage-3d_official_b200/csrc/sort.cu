@@ -23,6 +23,7 @@ constexpr int S_TILE = S_THREADS * S_IPT;
 constexpr int S_WARPS = S_THREADS / 32;
 
 constexpr unsigned long long ST_AGG = 1ull, ST_PREFIX = 2ull;
+constexpr int LB_BATCH = 8;
 
 __device__ __forceinline__ unsigned long long lb_pack(uint32_t epoch, unsigned long long state, uint32_t v)
 {
@@ -159,18 +160,31 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             lb_store(mine, lb_pack(epoch, ST_PREFIX, tot));
         } else {
             lb_store(mine, lb_pack(epoch, ST_AGG, tot));
+            // Look back over the earlier tiles, LB_BATCH of them per round trip: the loads of a
+            // batch are independent (memory-level parallelism), then consumed in order up to the
+            // first tile that already holds an inclusive prefix or has not published yet.
             int t = (int)b - 1;
             uint32_t spins = 0;
-            while (true) {
-                const unsigned long long s = lb_load(lookback + (size_t)t * RADIX + d);
-                if ((uint32_t)(s >> 34) != epoch) {           // predecessor has not published yet
-                    if (++spins > (1u << 26)) __trap();       // never hang the GPU
-                    __nanosleep(20);
-                    continue;
+            bool done = false;
+            while (!done) {
+                unsigned long long s[LB_BATCH];
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; ++j)
+                    s[j] = (t - j >= 0) ? lb_load(lookback + (size_t)(t - j) * RADIX + d) : 0ull;
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB_BATCH; ++j) {
+                    if (!done && used == j && t - j >= 0 && (uint32_t)(s[j] >> 34) == epoch) {
+                        excl += (uint32_t)s[j];
+                        used = j + 1;
+                        done = ((s[j] >> 32) & 3ull) == ST_PREFIX;
+                    }
                 }
-                excl += (uint32_t)s;
-                if (((s >> 32) & 3ull) == ST_PREFIX) break;
-                --t;
+                t -= used;
+                if (!done && used == 0) {                      // predecessor has not published yet
+                    if (++spins > (1u << 24)) __trap();        // never hang the GPU
+                    __nanosleep(32);
+                }
             }
             lb_store(mine, lb_pack(epoch, ST_PREFIX, excl + tot));
         }
