@@ -104,8 +104,13 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     static_assert(RADIX <= S_THREADS, "one digit per thread");
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
-    __shared__ uint32_t wh[S_WARPS][RADIX];
-    __shared__ uint32_t s_tile;
+    // dynamic shared memory: warp-private digit counters, then the staging area of the scatter
+    extern __shared__ uint32_t smem_dyn[];
+    uint32_t (*wh)[RADIX] = reinterpret_cast<uint32_t (*)[RADIX]>(smem_dyn);      // [S_WARPS][RADIX]
+    uint32_t* gdelta = smem_dyn + S_WARPS * RADIX;                                // [RADIX]
+    uint32_t* skey = gdelta + RADIX;                                              // [S_TILE]
+    uint32_t* sval = skey + S_TILE;                                               // [S_TILE]
+    __shared__ uint32_t s_tile, s_wtot[S_WARPS];
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < S_WARPS * RADIX; i += S_THREADS) (&wh[0][0])[i] = 0;
     __syncthreads();
@@ -149,13 +154,12 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     __syncthreads();
 
     // per digit: block count -> publish -> look back -> publish inclusive -> per-warp bases
+    uint32_t cnt[S_WARPS], tot = 0, excl = 0;
     if (threadIdx.x < RADIX) {
         const int d = threadIdx.x;
-        uint32_t cnt[S_WARPS], tot = 0;
 #pragma unroll
         for (int ww = 0; ww < S_WARPS; ++ww) { cnt[ww] = wh[ww][d]; tot += cnt[ww]; }
         unsigned long long* mine = lookback + (size_t)b * RADIX + d;
-        uint32_t excl = 0;
         if (b == 0) {
             lb_store(mine, lb_pack(epoch, ST_PREFIX, tot));
         } else {
@@ -188,19 +192,49 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
             }
             lb_store(mine, lb_pack(epoch, ST_PREFIX, excl + tot));
         }
-        uint32_t run = digit_base[d] + excl;
-#pragma unroll
-        for (int ww = 0; ww < S_WARPS; ++ww) { wh[ww][d] = run; run += cnt[ww]; }
     }
+    // block-local exclusive scan of the digit totals -> where each digit's run starts in the staging
+    // area; gdelta[d] = (global start of this block's run of digit d) - (its local start)
+    {
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wtot[w] = incl;
+        __syncthreads();
+        uint32_t lstart = incl - tot;
+        for (int k = 0; k < w; ++k) lstart += s_wtot[k];
+        if (threadIdx.x < RADIX) {
+            const int d = threadIdx.x;
+            gdelta[d] = digit_base[d] + excl - lstart;
+            uint32_t run = lstart;
+#pragma unroll
+            for (int ww = 0; ww < S_WARPS; ++ww) { wh[ww][d] = run; run += cnt[ww]; }
+        }
+    }
+    uint32_t n_valid = 0;
+#pragma unroll
+    for (int k = 0; k < S_WARPS; ++k) n_valid += s_wtot[k];       // s_wtot is final after the barrier above
     __syncthreads();
+    // stage in digit order ...
 #pragma unroll
     for (int i = 0; i < S_IPT; ++i) {
         if (rank[i] != 0xFFFFFFFFu) {
             const uint32_t d = (key[i] >> shift) & (RADIX - 1);
-            const uint32_t pos = wh[w][d] + rank[i];
-            keys_out[pos] = key[i];
-            vals_out[pos] = val[i];
+            const uint32_t lp = wh[w][d] + rank[i];
+            skey[lp] = key[i];
+            sval[lp] = val[i];
         }
+    }
+    __syncthreads();
+    // ... and write out: consecutive threads -> consecutive addresses inside every digit run
+    for (uint32_t j = threadIdx.x; j < n_valid; j += S_THREADS) {
+        const uint32_t k = skey[j];
+        const uint32_t pos = j + gdelta[(k >> shift) & (RADIX - 1)];
+        keys_out[pos] = k;
+        vals_out[pos] = sval[j];
     }
 }
 
@@ -208,6 +242,13 @@ template <int RB, int NP, bool COMPACT>
 void sort_impl(const SageSortPlan& pl, cudaStream_t st)
 {
     constexpr int RADIX = 1 << RB;
+    constexpr size_t SMEM = sizeof(uint32_t) * (S_WARPS * RADIX + RADIX + 2 * S_TILE);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_onesweep<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        cudaFuncSetAttribute(k_onesweep<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        configured = true;
+    }
     int grid = (int)((pl.capacity + S_TILE - 1) / S_TILE);
     if (grid < 1) grid = 1;
     if (!pl.hist_ready) {
@@ -219,11 +260,11 @@ void sort_impl(const SageSortPlan& pl, cudaStream_t st)
     for (int p = 0; p < NP; ++p) {
         const uint32_t* n_dev = p == 0 ? pl.n_first : pl.n_rest;
         if (COMPACT && p == 0)
-            k_onesweep<RB, true><<<grid, S_THREADS, 0, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+            k_onesweep<RB, true><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
                                                             n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
                                                             pl.lookback, pl.tickets + p, pl.epoch0 + p, pl.vals_are_iota ? 1 : 0);
         else
-            k_onesweep<RB, false><<<grid, S_THREADS, 0, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+            k_onesweep<RB, false><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
                                                              n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
                                                              pl.lookback, pl.tickets + p, pl.epoch0 + p,
                                                              (pl.vals_are_iota && p == 0) ? 1 : 0);

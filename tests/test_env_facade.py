@@ -125,3 +125,60 @@ def test_ply_roundtrip_and_usda_stage_resolution(sage, tmp_path):
     assert env._model_to_world is not None          # rotateXYZ(-90,0,0) folded into the view
     assert env.get_rgb().shape == (64, 96, 3)
     env.close()
+
+
+@pytest.mark.gpu
+def test_isaac_shim_serves_generate_images_call_sequence(sage, oracle, tmp_path):
+    """The calls generate_images.py makes (lines 320-350, 417-428), against the stand-ins."""
+    import sys
+    from conftest import oracle_camera
+    from sage3d_official_b200.scene_io import save_ply
+    from sage3d_official_b200.camera import USD_GAUSS_MODEL_TO_WORLD as M
+    import sage3d_official_b200.isaac_shim as shim
+    shim.install()
+    import omni.usd
+    from omni.isaac.kit import SimulationApp
+    from omni.isaac.core import World
+    from omni.isaac.core.utils.stage import open_stage
+    from omni.isaac.sensor import Camera
+    from pxr import Gf, UsdGeom, UsdLux
+
+    cloud, _ = sage.synthetic_room(2, 20_000)
+    model = sage.GaussianCloud(*(a.copy() for a in cloud.as_tuple()))
+    model.xyz[:] = (cloud.xyz.astype(np.float64) @ M).astype(np.float32)    # PLY (model) space
+    save_ply(tmp_path / "0007.ply", model)
+    usda = tmp_path / "0007.usda"
+    usda.write_text('#usda 1.0\ndef Xform "World" { def "gauss" ( prepend references = @./0007.usdz@</World/gauss> ) {} }\n')
+
+    app = SimulationApp({"headless": True})
+    omni.usd.get_context().close_stage()
+    assert not open_stage(usd_path=str(tmp_path / "missing.usda"))
+    assert open_stage(usd_path=str(usda))
+    stage = omni.usd.get_context().get_stage()
+    if not stage.GetPrimAtPath("/World/EnvLight"):
+        dome = UsdLux.DomeLight.Define(stage, "/World/EnvLight")
+        dome.CreateIntensityAttr(30000.0)
+        dome.CreateColorAttr(Gf.Vec3f(1.0, 1.0, 1.0))
+    assert stage.GetPrimAtPath("/World/EnvLight")
+    world = World()
+    world.reset()
+    for _ in range(5):
+        world.step(render=True)
+    cam = Camera(prim_path="/World/NaVILACamera", frequency=30, resolution=(256, 192))
+    cam.initialize()
+    UsdGeom.Camera(stage.GetPrimAtPath("/World/NaVILACamera")).GetFocalLengthAttr().Set(8.0)
+    position = np.array([1.5, 1.0, 0.3], dtype=np.float32)
+    position[2] = 1.2
+    rotation = [-0.2588, 0.0, 0.0, 0.9659]                                   # trajectory [qx,qy,qz,qw] passed verbatim
+    cam.set_world_pose(position=position, orientation=np.array(rotation, dtype=np.float32))
+    for _ in range(3):
+        world.step(render=True)
+    img = cam.get_rgba()
+    assert img.shape == (192, 256, 4) and img.dtype == np.uint8 and (img[..., 3] == 255).all()
+    ref_cam = sage.Camera.from_isaac_pose(position, rotation, 256, 192, model_to_world=M)
+    o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, ref_cam), *model.as_tuple())
+    assert np.array_equal(img[:, :, :3], o_rgb)
+    assert np.array_equal(cam.get_current_frame()["distance_to_image_plane"], o_dep)
+    world.clear()
+    omni.usd.get_context().close_stage()
+    app.close()

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Run the reference's entry points UNMODIFIED on top of this engine.
+
+    python tools/launch_sage_bench.py /path/to/run_benchmark.py  [its own arguments ...]
+    python tools/launch_sage_bench.py /path/to/generate_images.py [its own arguments ...]
+
+`run_benchmark.py` finds the drop-in `simple_env` / `collision_detector` modules in sys.modules
+(it force-inserts its own directory at sys.path[0], so only pre-registration wins);
+`generate_images.py` finds the Isaac stand-ins of `isaac_shim`.
+"""
+import runpy
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    if len(sys.argv) < 2:
+        raise SystemExit(__doc__)
+    script = sys.argv[1]
+    import sage3d_official_b200.simple_env as fast_env
+    import sage3d_official_b200.collision_detector as fast_det
+    import sage3d_official_b200.isaac_shim as shim
+    shim.install()
+    sys.modules["simple_env"] = fast_env
+    sys.modules["collision_detector"] = fast_det
+    sys.argv = [script] + sys.argv[2:]
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
