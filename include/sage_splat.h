@@ -97,6 +97,15 @@ int sage_render(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_
 int sage_render_host(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
                      uint8_t* rgb_host, float* depth_host, sage_stream_t stream);
 
+/* Pipelined host path: two frames can be in flight (slot 0 / 1, each with its own frame context and
+ * internal stream).  sage_render_host_async returns at once; sage_host_wait(slot) blocks until that
+ * slot's RGB/depth have landed in the host buffers passed to it (keep them alive and distinct per
+ * slot).  Submitting frame i+1 on the other slot before waiting for frame i overlaps frame i's
+ * device->host copy and compositing with frame i+1's projection and sorts. */
+int sage_render_host_async(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                           uint8_t* rgb_host, float* depth_host, int slot);
+int sage_host_wait(sage_scene* s, int slot);
+
 /* Multi-GPU fused composite+gather: like sage_render, but every finished pixel is stored
  * straight into each of n_peers frame buffers (peer-mapped device pointers, e.g. opened with
  * sage_ipc_open) over NVLink, so the strip exchange needs no separate collective copy. */

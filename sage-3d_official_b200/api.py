@@ -155,6 +155,25 @@ class GaussianScene:
                                               _ptr(dep_t) if want_depth else C.c_void_p(0), _stream_ptr(stream)))
         return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
 
+    def render_host_async(self, cam: Camera, slot: int, rows=None, want_depth: bool = True):
+        """Submit a frame on pipeline slot 0/1; returns the slot's pinned host arrays (valid after
+        :meth:`host_wait`).  Alternate slots to keep two frames in flight."""
+        torch = _torch()
+        key = (cam.height, cam.width, "async", int(slot))
+        if key not in self._pinned:
+            self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+                                 torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
+        rgb_t, dep_t = self._pinned[key]
+        r0, r1 = self._rows(cam, rows)
+        cc = _ccam(cam)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_render_host_async(self._h, C.byref(cc), r0, r1, _ptr(rgb_t),
+                                                    _ptr(dep_t) if want_depth else C.c_void_p(0), int(slot)))
+        return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
+
+    def host_wait(self, slot: int):
+        check(_lib.lib().sage_host_wait(self._h, int(slot)))
+
     def stats(self) -> dict:
         st = CFrameStats()
         check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))

@@ -1,0 +1,509 @@
+// C-ABI of libsage_splat.so, part 2: scene upload and rendering.
+//
+// A scene owns SAGE_N_CTX frame contexts (all per-frame device state, double-buffered).  Consecutive
+// frames alternate contexts, so a caller that alternates two streams gets frame N+1's projection /
+// sorts running while frame N is still compositing — the issue-bound blend kernel and the
+// latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host.
+#include <cstring>
+#include <vector>
+
+#include "api_common.cuh"
+
+#define SAGE_N_CTX 2
+
+namespace {
+
+struct FrameCtx {
+    SageFrame fr{};
+    int64_t cap = 0;                 // instance capacity of this context
+    int max_tiles = 0;               // capacity of fr.ranges
+    uint32_t epoch = 8;              // look-back epochs: 8 fresh values per frame
+    uint32_t* counters_host = nullptr;   // pinned copy of the counters
+    cudaEvent_t done = nullptr;      // end of the last frame that used this context
+    cudaStream_t stream = nullptr;   // internal stream of the asynchronous host path
+    uint8_t* out_rgb = nullptr;      // internal device frame (host paths)
+    float* out_depth = nullptr;
+    size_t out_px = 0;
+    cudaStream_t last_stream = nullptr;
+    int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
+    bool used = false;
+};
+
+}  // namespace
+
+struct sage_scene {
+    int device = 0;
+    SageSceneDev sc{};
+    FrameCtx ctx[SAGE_N_CTX];
+    uint32_t* n_dev = nullptr;       // device copy of n (element count of the first depth-sort pass)
+    long frame_index = 0;
+    int last_ctx = -1;
+    // optional per-stage timing: n_slots x (SAGE_N_STAGES + 1) events
+    std::vector<cudaEvent_t> events;
+    int n_slots = 0;
+    long timed_frames = 0;
+};
+
+static void free_instances(FrameCtx& c)
+{
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c.fr.ikey[k]); c.fr.ikey[k] = nullptr;
+        cudaFree(c.fr.ival[k]); c.fr.ival[k] = nullptr;
+    }
+    cudaFree(c.fr.lookback); c.fr.lookback = nullptr;
+}
+
+static int alloc_instances(sage_scene* s, FrameCtx& c, int64_t cap)
+{
+    free_instances(c);
+    for (int k = 0; k < 2; ++k) {
+        CK(dalloc(&c.fr.ikey[k], (size_t)cap));
+        CK(dalloc(&c.fr.ival[k], (size_t)cap));
+    }
+    const int64_t mx = cap > s->sc.n ? cap : s->sc.n;
+    const size_t words = sage_sort_lookback_words(mx);
+    CK(dalloc(&c.fr.lookback, words));
+    CK(cudaMemset(c.fr.lookback, 0, words * sizeof(unsigned long long)));   // epoch 0 = never published
+    c.cap = cap;
+    return 0;
+}
+
+static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
+{
+    const size_t n = (size_t)s->sc.n;
+    CK(dalloc(&c.fr.rec0, n));
+    CK(dalloc(&c.fr.rec1, n));
+    CK(dalloc(&c.fr.rec2, n));
+    for (int k = 0; k < 2; ++k) {
+        CK(dalloc(&c.fr.dkey[k], n));
+        CK(dalloc(&c.fr.dval[k], n));
+    }
+    CK(dalloc(&c.fr.rect, n));
+    CK(dalloc(&c.fr.ntiles, n));
+    CK(dalloc(&c.fr.chain, n / 256 + 2));
+    CK(cudaMemset(c.fr.chain, 0, (n / 256 + 2) * sizeof(unsigned long long)));
+    CK(dalloc(&c.fr.counters, (size_t)SAGE_ZERO_WORDS));
+    c.fr.tickets = c.fr.counters + CNT_COUNT;
+    c.fr.depth_hist = c.fr.tickets + SAGE_TICKET_COUNT;
+    c.fr.tile_hist = c.fr.depth_hist + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS;
+    CK(cudaHostAlloc((void**)&c.counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
+    memset(c.counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
+    CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    return alloc_instances(s, c, cap);
+}
+
+static void free_ctx(FrameCtx& c)
+{
+    cudaFree(c.fr.rec0); cudaFree(c.fr.rec1); cudaFree(c.fr.rec2);
+    for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
+    cudaFree(c.fr.rect); cudaFree(c.fr.ntiles); cudaFree(c.fr.chain);
+    free_instances(c);
+    cudaFree(c.fr.ranges); cudaFree(c.fr.counters);
+    if (c.counters_host) cudaFreeHost(c.counters_host);
+    if (c.done) cudaEventDestroy(c.done);
+    if (c.stream) cudaStreamDestroy(c.stream);
+    cudaFree(c.out_rgb); cudaFree(c.out_depth);
+    c = FrameCtx{};
+}
+
+static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
+{
+    REQUIRE(cam != nullptr, "camera is NULL");
+    REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 16384 && cam->height <= 16384, "camera: bad resolution");
+    REQUIRE(cam->fx > 0.0f && cam->fy > 0.0f, "camera: focal length must be positive");
+    REQUIRE(cam->near_z > 0.0f && cam->far_z > cam->near_z, "camera: need 0 < near < far");
+    memcpy(d->R, cam->R, sizeof d->R);
+    memcpy(d->t, cam->t, sizeof d->t);
+    memcpy(d->campos, cam->campos, sizeof d->campos);
+    d->fx = cam->fx; d->fy = cam->fy; d->cx = cam->cx; d->cy = cam->cy;
+    d->limx = 1.3f * ((0.5f * (float)cam->width) / cam->fx);
+    d->limy = 1.3f * ((0.5f * (float)cam->height) / cam->fy);
+    d->near_z = cam->near_z; d->far_z = cam->far_z;
+    d->W = cam->width; d->H = cam->height;
+    d->tiles_x = (cam->width + SAGE_TILE - 1) / SAGE_TILE;
+    d->tiles_y = (cam->height + SAGE_TILE - 1) / SAGE_TILE;
+    REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= d->tiles_y, "tile-row range out of bounds");
+    d->row0 = row0; d->row1 = row1;
+    return 0;
+}
+
+// resolution-dependent scratch (tile ranges) grows on first use
+static int ensure_tiles(FrameCtx& c, int n_tiles, cudaStream_t st)
+{
+    if (n_tiles > c.max_tiles) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c.fr.ranges);
+        c.fr.ranges = nullptr; c.max_tiles = 0;
+        CK(dalloc(&c.fr.ranges, (size_t)n_tiles));
+        c.max_tiles = n_tiles;
+    }
+    return 0;
+}
+
+static int ensure_out(FrameCtx& c, size_t px, cudaStream_t st)
+{
+    if (px > c.out_px) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c.out_rgb); cudaFree(c.out_depth);
+        c.out_rgb = nullptr; c.out_depth = nullptr; c.out_px = 0;
+        CK(dalloc(&c.out_rgb, px * 3));
+        CK(dalloc(&c.out_depth, px));
+        c.out_px = px;
+    }
+    return 0;
+}
+
+static int depth_key_bits(const SageCamDev& cd)
+{
+    // depth keys are bits(z) - bits(near) with near < z < far: only this many bits are significant
+    uint32_t bn, bf;
+    memcpy(&bn, &cd.near_z, 4);
+    memcpy(&bf, &cd.far_z, 4);
+    int dbits = 1;
+    while (dbits < 32 && ((uint64_t)1 << dbits) <= (uint64_t)(bf - bn)) ++dbits;
+    return dbits;
+}
+
+// project -> depth sort (+compaction) -> SH colour; *order_buf = buffer index holding order[]
+static int front_half(sage_scene* s, FrameCtx& c, const SageCamDev& cd, int* launches, cudaEvent_t* ev,
+                      cudaStream_t st, int* order_buf)
+{
+    if (ev) CK(cudaEventRecord(ev[0], st));
+    sage_launch_project(s->sc, cd, c.fr, st);
+    if (ev) CK(cudaEventRecord(ev[1], st));
+    SageSortPlan dp{};
+    dp.keys[0] = c.fr.dkey[0]; dp.keys[1] = c.fr.dkey[1];
+    dp.vals[0] = c.fr.dval[0]; dp.vals[1] = c.fr.dval[1];
+    dp.n_first = s->n_dev; dp.n_rest = c.fr.counters + CNT_VISIBLE;
+    dp.capacity = s->sc.n; dp.lo_bit = 0; dp.n_bits = depth_key_bits(cd);
+    sage_sort_shape(dp.n_bits, &dp.digit_bits, &dp.passes);
+    dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false;
+    dp.hist = c.fr.depth_hist; dp.total_out = nullptr;
+    dp.lookback = c.fr.lookback; dp.tickets = c.fr.tickets + SAGE_TICKET_DEPTH; dp.epoch0 = c.epoch;
+    const int res = sage_radix_sort(dp, launches, st);
+    REQUIRE(res >= 0, "depth sort: unsupported key width");
+    if (ev) CK(cudaEventRecord(ev[2], st));
+    sage_launch_sh_color(s->sc, cd, c.fr, c.fr.dval[res], st);
+    if (ev) CK(cudaEventRecord(ev[3], st));
+    *launches += 2;
+    *order_buf = res;
+    return 0;
+}
+
+static void next_epoch(FrameCtx& c)
+{
+    c.epoch += 8;
+    if (c.epoch > (1u << 30) - 16) c.epoch = 8;
+}
+
+// One frame on context `ci` (or the next context in rotation when ci < 0), on stream `st`.
+static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, int row1, int n_peers,
+                       uint8_t* const* rgb_peers, float* const* depth_peers, cudaStream_t st)
+{
+    REQUIRE(s != nullptr, "sage_render: NULL scene");
+    REQUIRE(n_peers >= 1 && n_peers <= 8, "sage_render: n_peers must be 1..8");
+    for (int k = 0; k < n_peers; ++k) REQUIRE(rgb_peers[k] != nullptr, "sage_render: NULL rgb buffer");
+    SageCamDev cd;
+    if (make_cam(cam, row0, row1, &cd)) return 1;
+    CK(cudaSetDevice(s->device));
+    if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
+    FrameCtx& c = s->ctx[ci];
+    const int n_tiles = (row1 - row0) * cd.tiles_x;
+    if (ensure_tiles(c, n_tiles, st)) return 1;
+    int tbits = 1;
+    while ((1 << tbits) < n_tiles) ++tbits;
+    REQUIRE(tbits <= 24, "sage_render: too many tiles");
+    const int tpasses = (tbits + 7) / 8;
+    int launches = 0;
+    if (c.used) CK(cudaStreamWaitEvent(st, c.done, 0));     // previous frame on this context has drained
+    CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, st));
+    next_epoch(c);
+    cudaEvent_t* ev = s->n_slots > 0
+        ? &s->events[(size_t)(s->timed_frames % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
+    if (ev) s->timed_frames++;
+    s->frame_index++;
+#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], st)); } while (0)
+    if (n_tiles > 0 && s->sc.n > 0) {
+        int ob = 0;
+        if (front_half(s, c, cd, &launches, ev, st, &ob)) return 1;     // stages 0..2
+        const uint32_t* order = c.fr.dval[ob];
+        sage_launch_emit(cd, c.fr, order, s->sc.n, c.cap, tpasses, c.epoch + 3, st);
+        STAGE_MARK(4);
+        SageSortPlan tp{};
+        tp.keys[0] = c.fr.ikey[0]; tp.keys[1] = c.fr.ikey[1];
+        tp.vals[0] = c.fr.ival[0]; tp.vals[1] = c.fr.ival[1];
+        tp.n_first = tp.n_rest = c.fr.counters + CNT_INSTANCES;
+        tp.capacity = c.cap; tp.lo_bit = 0; tp.n_bits = tbits; tp.digit_bits = 8; tp.passes = tpasses;
+        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true;
+        tp.hist = c.fr.tile_hist; tp.total_out = nullptr;
+        tp.lookback = c.fr.lookback; tp.tickets = c.fr.tickets + SAGE_TICKET_TILE; tp.epoch0 = c.epoch + 4;
+        const int ires = sage_radix_sort(tp, &launches, st);
+        REQUIRE(ires >= 0, "tile sort: unsupported key width");
+        sage_launch_ranges(c.fr, c.fr.ikey[ires], c.cap, n_tiles, st);
+        STAGE_MARK(5);
+        sage_launch_composite(cd, c.fr, c.fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
+        launches += 3;
+        STAGE_MARK(6);
+    } else if (n_tiles > 0) {
+        for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
+        CK(cudaMemsetAsync(c.fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
+        sage_launch_composite(cd, c.fr, c.fr.ival[0], n_peers, rgb_peers, depth_peers, st);
+        launches += 1;
+    }
+#undef STAGE_MARK
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c.counters_host, c.fr.counters, sizeof(uint32_t) * CNT_COUNT, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.done, st));
+    c.used = true;
+    c.last_stream = st;
+    c.last_W = cd.W; c.last_H = cd.H;
+    c.last_depth = (depth_peers && depth_peers[0]) ? 1 : 0;
+    c.last_launches = launches;
+    s->last_ctx = ci;
+    return 0;
+}
+
+extern "C" {
+
+int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, const float* xyz,
+                      const float* log_scale, const float* quat_wxyz, const float* opacity_raw,
+                      const float* sh, int64_t max_instances)
+{
+    REQUIRE(out != nullptr, "sage_scene_create: out is NULL");
+    *out = nullptr;
+    REQUIRE(sage_device_count() > 0, "sage_scene_create: no CUDA device (this library has no CPU fallback)");
+    REQUIRE(n >= 0 && n <= (int64_t)SAGE_ID_MASK, "sage_scene_create: n out of range (max 2^28-1 Gaussians)");
+    REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sage_scene_create: sh_degree must be 0..3");
+    REQUIRE(n == 0 || (xyz && log_scale && quat_wxyz && opacity_raw && sh), "sage_scene_create: NULL attribute pointer");
+    CK(cudaSetDevice(device));
+    sage_scene* s = new sage_scene();
+    s->device = device;
+    s->sc.n = n;
+    s->sc.deg = sh_degree;
+    const int nf = 3 * (sh_degree + 1) * (sh_degree + 1);
+    s->sc.n_chunks = (nf + 3) / 4;
+    auto bail = [&](int rc) { sage_scene_destroy(s); return rc; };
+#define CKB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(sage_fail(#call, __FILE__, __LINE__, e__)); } while (0)
+    CKB(dalloc(&s->sc.geo0, (size_t)n));
+    CKB(dalloc(&s->sc.geo1, (size_t)n));
+    CKB(dalloc(&s->sc.geo2, (size_t)n));
+    CKB(dalloc(&s->sc.shc, (size_t)n * s->sc.n_chunks));
+    CKB(dalloc(&s->n_dev, 1));
+    uint32_t n32 = (uint32_t)n;
+    CKB(cudaMemcpy(s->n_dev, &n32, sizeof n32, cudaMemcpyHostToDevice));
+    const int64_t cap = max_instances > 0 ? max_instances : (8 * n > (1 << 24) ? 8 * n : (1 << 24));
+    for (int k = 0; k < SAGE_N_CTX; ++k)
+        if (alloc_ctx(s, s->ctx[k], cap)) return bail(1);
+
+    if (n > 0) {
+        // inputs may be host or device pointers: stage through device copies (UVA resolves the kind)
+        float *d_xyz, *d_ls, *d_q, *d_op, *d_sh;
+        CKB(dalloc(&d_xyz, (size_t)3 * n));
+        CKB(dalloc(&d_ls, (size_t)3 * n));
+        CKB(dalloc(&d_q, (size_t)4 * n));
+        CKB(dalloc(&d_op, (size_t)n));
+        CKB(dalloc(&d_sh, (size_t)nf * n));
+        CKB(cudaMemcpy(d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyDefault));
+        CKB(cudaMemcpy(d_ls, log_scale, sizeof(float) * 3 * n, cudaMemcpyDefault));
+        CKB(cudaMemcpy(d_q, quat_wxyz, sizeof(float) * 4 * n, cudaMemcpyDefault));
+        CKB(cudaMemcpy(d_op, opacity_raw, sizeof(float) * n, cudaMemcpyDefault));
+        CKB(cudaMemcpy(d_sh, sh, sizeof(float) * (size_t)nf * n, cudaMemcpyDefault));
+        sage_launch_precompute(s->sc, d_xyz, d_ls, d_q, d_op, d_sh, nullptr);
+        CKB(cudaGetLastError());
+        CKB(cudaDeviceSynchronize());
+        cudaFree(d_xyz); cudaFree(d_ls); cudaFree(d_q); cudaFree(d_op); cudaFree(d_sh);
+    }
+#undef CKB
+    *out = s;
+    return 0;
+}
+
+int sage_scene_reserve(sage_scene* s, int64_t max_instances)
+{
+    REQUIRE(s != nullptr, "sage_scene_reserve: NULL scene");
+    REQUIRE(max_instances > 0 && max_instances < (int64_t)0xFFFFFFFF, "sage_scene_reserve: bad capacity");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < SAGE_N_CTX; ++k)
+        if (alloc_instances(s, s->ctx[k], max_instances)) return 1;
+    return 0;
+}
+
+int sage_scene_destroy(sage_scene* s)
+{
+    if (!s) return 0;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    cudaFree(s->sc.geo0); cudaFree(s->sc.geo1); cudaFree(s->sc.geo2); cudaFree(s->sc.shc);
+    for (int k = 0; k < SAGE_N_CTX; ++k) free_ctx(s->ctx[k]);
+    cudaFree(s->n_dev);
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    cudaGetLastError();
+    delete s;
+    return 0;
+}
+
+int sage_render(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                uint8_t* rgb_dev, float* depth_dev, sage_stream_t stream)
+{
+    uint8_t* rgbs[1] = {rgb_dev};
+    float* deps[1] = {depth_dev};
+    return render_impl(s, -1, cam, row0_tiles, row1_tiles, 1, rgbs, depth_dev ? deps : nullptr,
+                       (cudaStream_t)stream);
+}
+
+int sage_render_peers(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                      int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
+                      sage_stream_t stream)
+{
+    REQUIRE(rgb_peers != nullptr, "sage_render_peers: NULL peer table");
+    return render_impl(s, -1, cam, row0_tiles, row1_tiles, n_peers, rgb_peers, depth_peers,
+                       (cudaStream_t)stream);
+}
+
+// render on context ci / stream st into the context's device frame, then copy the rows to the host
+static int render_to_host(sage_scene* s, int ci, const sage_camera* cam, int row0, int row1,
+                          uint8_t* rgb_host, float* depth_host, cudaStream_t st)
+{
+    REQUIRE(s != nullptr, "sage_render_host: NULL scene");
+    REQUIRE(cam != nullptr && rgb_host != nullptr, "sage_render_host: NULL camera or rgb buffer");
+    CK(cudaSetDevice(s->device));
+    if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
+    FrameCtx& c = s->ctx[ci];
+    if (ensure_out(c, (size_t)cam->width * (size_t)cam->height, st)) return 1;
+    uint8_t* rgbs[1] = {c.out_rgb};
+    float* deps[1] = {c.out_depth};
+    if (render_impl(s, ci, cam, row0, row1, 1, rgbs, depth_host ? deps : nullptr, st)) return 1;
+    const int y0 = row0 * SAGE_TILE;
+    int y1 = row1 * SAGE_TILE;
+    if (y1 > cam->height) y1 = cam->height;
+    if (y1 > y0) {
+        const size_t off = (size_t)y0 * cam->width, cnt = (size_t)(y1 - y0) * cam->width;
+        CK(cudaMemcpyAsync(rgb_host + off * 3, c.out_rgb + off * 3, cnt * 3, cudaMemcpyDeviceToHost, st));
+        if (depth_host)
+            CK(cudaMemcpyAsync(depth_host + off, c.out_depth + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(c.done, st));     // the context is busy until its copies have drained
+    return 0;
+}
+
+int sage_render_host(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                     uint8_t* rgb_host, float* depth_host, sage_stream_t stream)
+{
+    if (render_to_host(s, -1, cam, row0_tiles, row1_tiles, rgb_host, depth_host, (cudaStream_t)stream)) return 1;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+int sage_render_host_async(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                           uint8_t* rgb_host, float* depth_host, int slot)
+{
+    REQUIRE(s != nullptr, "sage_render_host_async: NULL scene");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_host_async: slot must be 0 or 1");
+    return render_to_host(s, slot, cam, row0_tiles, row1_tiles, rgb_host, depth_host, s->ctx[slot].stream);
+}
+
+int sage_host_wait(sage_scene* s, int slot)
+{
+    REQUIRE(s != nullptr, "sage_host_wait: NULL scene");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_host_wait: slot must be 0 or 1");
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->ctx[slot].stream));
+    return 0;
+}
+
+int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out)
+{
+    REQUIRE(s != nullptr && out != nullptr, "sage_frame_stats_get: NULL argument");
+    REQUIRE(s->last_ctx >= 0, "sage_frame_stats_get: no frame rendered yet");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[s->last_ctx];
+    CK(cudaEventSynchronize(c.done));
+    const uint32_t* cn = c.counters_host;
+    memset(out, 0, sizeof *out);
+    out->n_gaussians = s->sc.n;
+    out->n_visible = cn[CNT_VISIBLE];
+    out->n_instances = cn[CNT_INSTANCES];
+    out->instance_capacity = c.cap;
+    out->overflow = (int32_t)cn[CNT_OVERFLOW];
+    out->kernel_launches = c.last_launches;
+    const int64_t nb = (int64_t)(s->sc.deg + 1) * (s->sc.deg + 1);
+    out->algorithmic_bytes = out->n_gaussians * 44 + out->n_visible * 12 * nb + out->n_visible * 32 +
+                             out->n_instances * 24 + out->n_instances * 32 +
+                             (int64_t)c.last_W * c.last_H * (3 + 4 * c.last_depth);
+    return 0;
+}
+
+int sage_set_stage_timing(sage_scene* s, int n_slots)
+{
+    REQUIRE(s != nullptr, "sage_set_stage_timing: NULL scene");
+    REQUIRE(n_slots >= 0 && n_slots <= 4096, "sage_set_stage_timing: n_slots must be 0..4096");
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    s->events.clear();
+    s->n_slots = 0;
+    s->timed_frames = 0;
+    s->events.resize((size_t)n_slots * (SAGE_N_STAGES + 1));
+    for (auto& e : s->events) CK(cudaEventCreate(&e));
+    s->n_slots = n_slots;
+    return 0;
+}
+
+int sage_stage_times_get(sage_scene* s, int slot, float ms_out[SAGE_N_STAGES])
+{
+    REQUIRE(s != nullptr && ms_out != nullptr, "sage_stage_times_get: NULL argument");
+    REQUIRE(s->n_slots > 0 && slot >= 0 && slot < s->n_slots, "sage_stage_times_get: bad slot / timing off");
+    CK(cudaSetDevice(s->device));
+    cudaEvent_t* ev = &s->events[(size_t)slot * (SAGE_N_STAGES + 1)];
+    CK(cudaEventSynchronize(ev[SAGE_N_STAGES]));
+    for (int k = 0; k < SAGE_N_STAGES; ++k) CK(cudaEventElapsedTime(&ms_out[k], ev[k], ev[k + 1]));
+    return 0;
+}
+
+int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
+                 sage_splat_record* records_host, uint8_t* visible_host)
+{
+    REQUIRE(s != nullptr && records_host != nullptr && visible_host != nullptr, "sage_project: NULL argument");
+    SageCamDev cd;
+    if (make_cam(cam, row0_tiles, row1_tiles, &cd)) return 1;
+    CK(cudaSetDevice(s->device));
+    CK(cudaDeviceSynchronize());
+    FrameCtx& c = s->ctx[0];
+    CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, nullptr));
+    next_epoch(c);
+    int launches = 0, ob = 0;
+    if (front_half(s, c, cd, &launches, nullptr, nullptr, &ob)) return 1;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    const size_t n = (size_t)s->sc.n;
+    uint32_t V = 0;
+    CK(cudaMemcpy(&V, c.fr.counters + CNT_VISIBLE, sizeof V, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> vlist(V);
+    if (V) CK(cudaMemcpy(vlist.data(), c.fr.dval[ob], V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> visv(n, 0);
+    for (uint32_t g : vlist) visv[g] = 1;
+    std::vector<float4> r0(n), r1(n), r2(n);
+    std::vector<uint2> rc(n);
+    if (n) {
+        CK(cudaMemcpy(r0.data(), c.fr.rec0, n * sizeof(float4), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(r1.data(), c.fr.rec1, n * sizeof(float4), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(r2.data(), c.fr.rec2, n * sizeof(float4), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rc.data(), c.fr.rect, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    }
+    for (size_t i = 0; i < n; ++i) {
+        sage_splat_record& o = records_host[i];
+        memset(&o, 0, sizeof o);
+        visible_host[i] = visv[i];
+        if (!visible_host[i]) continue;
+        o.gx = r0[i].x; o.gy = r0[i].y; o.qa = r0[i].z;
+        o.qb = r1[i].x; o.qc = r1[i].y; o.opacity = r1[i].z; o.z = r1[i].w;
+        o.r = r2[i].x; o.g = r2[i].y; o.b = r2[i].z;
+        o.tile_x0 = (rc[i].x & 0xFFFF) / SAGE_TILE; o.tile_x1 = (rc[i].x >> 16) / SAGE_TILE;
+        o.tile_y0 = (rc[i].y & 0xFFFF) / SAGE_TILE; o.tile_y1 = (rc[i].y >> 16) / SAGE_TILE;
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -56,7 +56,7 @@ class SimpleVLNEnv:
 
     def __init__(self, scene_usd_path: str, headless: bool = True, hz: int = 30,
                  agent_prim_path: str = "/World/AgentCamera", resolution: Tuple[int, int] = (640, 480),
-                 map_json_path: str = None, device: int = 0) -> None:
+                 map_json_path: str = None, device: int = 0, gaussians=None, collision_bodies=None) -> None:
         self.scene_usd_path = str(Path(scene_usd_path).resolve())
         self.hz = hz
         self.agent_prim_path = agent_prim_path
@@ -74,6 +74,7 @@ class SimpleVLNEnv:
         self.semantic_map_path = map_json_path
         self.collision_detector = None
         self._device = device
+        self._preloaded = (gaussians, collision_bodies)     # optional in-memory assets (not in the reference)
         self._scene = None
         self._bodies = None
         self._model_to_world = None
@@ -116,6 +117,12 @@ class SimpleVLNEnv:
         from .api import GaussianScene, CollisionBodies
         self._scene = None
         self._bodies = None
+        if self._preloaded[0] is not None:
+            self._model_to_world = None
+            self._scene = GaussianScene(self._preloaded[0], device=self._device)
+            if self._preloaded[1] is not None:
+                self._bodies = CollisionBodies(*self._preloaded[1], device=self._device)
+            return
         gauss, coll, is_stage = resolve_stage_assets(self.scene_usd_path)
         # a USDA stage carries rotateXYZ(-90,0,0) on the Gaussian prim (template.usda:120)
         self._model_to_world = USD_GAUSS_MODEL_TO_WORLD if is_stage else None

@@ -175,7 +175,7 @@ def test_isaac_shim_serves_generate_images_call_sequence(sage, oracle, tmp_path)
         world.step(render=True)
     img = cam.get_rgba()
     assert img.shape == (192, 256, 4) and img.dtype == np.uint8 and (img[..., 3] == 255).all()
-    ref_cam = sage.Camera.from_isaac_pose(position, rotation, 256, 192, model_to_world=M)
+    ref_cam = sage.Camera.from_isaac_pose(position, np.array(rotation, dtype=np.float32), 256, 192, model_to_world=M)
     o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, ref_cam), *model.as_tuple())
     assert np.array_equal(img[:, :, :3], o_rgb)
     assert np.array_equal(cam.get_current_frame()["distance_to_image_plane"], o_dep)

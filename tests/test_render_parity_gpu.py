@@ -154,3 +154,35 @@ def test_long_tile_lists_use_the_global_sort_path(sage, oracle):
     # duplicate depths inside long lists too
     cloud.xyz[: n // 2, 0] = 3.0
     _check_frame(sage, oracle, cloud, cam)
+
+
+def test_two_frames_in_flight_match_serial_frames(sage, oracle):
+    import torch
+    cloud, layout = sage.synthetic_room(0, 30_000)
+    cams = [sage.Camera.look_heading(p, h, 320, 240) for p, h in sage.camera_path(layout, 6, seed=1)]
+    scene = sage.GaussianScene(cloud)
+    serial = [tuple(a.copy() for a in scene.render_host(c)) for c in cams]
+    # pipelined host path: wait for frame i-2, submit frame i
+    got = [None] * len(cams)
+    bufs = {}
+    for i, c in enumerate(cams):
+        if i >= 2:
+            scene.host_wait(i % 2)
+            got[i - 2] = tuple(a.copy() for a in bufs[i % 2])
+        bufs[i % 2] = scene.render_host_async(c, i % 2)
+    for i in (len(cams) - 2, len(cams) - 1):
+        scene.host_wait(i % 2)
+        got[i] = tuple(a.copy() for a in bufs[i % 2])
+    for (r0, d0), (r1, d1) in zip(serial, got):
+        assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
+    # device path on two alternating streams
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i, c in enumerate(cams):
+        with torch.cuda.stream(streams[i % 2]):
+            outs.append(scene.render(c))
+    torch.cuda.synchronize()
+    for (r0, d0), (rt, dt) in zip(serial, outs):
+        assert np.array_equal(r0, rt.cpu().numpy()) and np.array_equal(d0, dt.cpu().numpy())
+    o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, cams[3]), *cloud.as_tuple())
+    assert np.array_equal(serial[3][0], o_rgb) and np.array_equal(serial[3][1], o_dep)

@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Configs 3 and 5 of BASELINE.json: an agent-step loop through the SimpleVLNEnv drop-in —
+render (RGB + depth) + batched collide march per step — with a scripted action source in place of
+the VLM (0 ms think time).  Prints one JSON line: steps/s and the per-step latency split.
+
+    python tools/episode_bench.py [--steps 500] [--n 2000000] [--width 1920 --height 1080]
+
+The reference's own loop for the same step issues 5 + 21 RTX frames for get_rgb/get_depth and up
+to 60 more inside apply_cmd_for, plus <= 60 sequential Python collision lookups
+(simple_env.py:1356-1589, 2116-2234); here it is one engine frame and <= 2 collide launches.
+"""
+import argparse
+import json
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--n", type=int, default=2_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--capsule", action="store_true", help="also run the ellipsoid-vs-capsule test per step")
+    args = ap.parse_args()
+    import sage3d_official_b200 as sage
+    from sage3d_official_b200.simple_env import SimpleVLNEnv
+    from sage3d_official_b200.scenes import write_semantic_map, collision_ellipsoids, layout_semantic_map
+    from sage3d_official_b200.scene_io import morton_order
+
+    cloud, layout = sage.synthetic_interior(1, args.n)
+    cloud = cloud.subset(morton_order(cloud.xyz))
+    tmp = Path(tempfile.mkdtemp())
+    map_path = write_semantic_map(layout, tmp / "map.json")
+    env = SimpleVLNEnv(str(tmp / "scene_in_memory.npz"), resolution=(args.width, args.height),
+                       map_json_path=str(map_path), gaussians=cloud)
+    env.set_log_function(lambda m: None)
+    bodies = None
+    if args.capsule:
+        mu, ls, q = collision_ellipsoids(layout, per_m2=400.0)
+        bodies = sage.CollisionBodies(mu, ls, q)
+    # start pose: free space, trajectory-frame coordinates (x3 = x2 - (min+max), trajectory_2d_to_3d.py:56-63)
+    det = env.collision_detector
+    p0, h0 = sage.camera_path(layout, 1, seed=3)[0]
+    sx, sy = det.min_x + det.max_x, det.min_y + det.max_y
+    psi = (h0 + np.pi + np.pi) % (2 * np.pi) - np.pi
+    env.set_start_pose([float(p0[0] - sx), float(p0[1] - sy), 0.85], [-float(np.sin(psi / 2)), 0.0, 0.0, float(np.cos(psi / 2))])
+    rng = np.random.default_rng(0)
+    t_render = t_collide = t_capsule = 0.0
+    moved = 0
+    env.get_rgb()                                                   # warm-up frame
+    t0 = time.perf_counter()
+    for step in range(args.steps):
+        a = time.perf_counter()
+        rgb = env.get_rgb()
+        depth = env.get_depth()
+        b = time.perf_counter()
+        r = rng.uniform()
+        if r < 0.6:
+            cmd = (0.25, 0.0, 0.0, 1.0)
+        elif r < 0.8:
+            cmd = (0.0, 0.0, np.radians(15.0), 1.0)
+        else:
+            cmd = (0.0, 0.0, -np.radians(15.0), 1.0)
+        before = env.get_agent_pos()
+        env.apply_cmd_for(*cmd)
+        c = time.perf_counter()
+        if bodies is not None:
+            pos = env.get_agent_pos().astype(np.float32)[None, :]
+            bodies.check(pos)
+        d = time.perf_counter()
+        moved += int(np.linalg.norm(env.get_agent_pos()[:2] - before[:2]) > 1e-6)
+        t_render += b - a; t_collide += c - b; t_capsule += d - c
+    total = time.perf_counter() - t0
+    out = {
+        "workload": f"{args.steps}-step episode, {args.width}x{args.height} RGB+depth, N={args.n}, grid collide march"
+                    + (" + capsule vs %d ellipsoids" % bodies.m if bodies is not None else ""),
+        "steps_per_s": args.steps / total,
+        "ms_per_step": 1000 * total / args.steps,
+        "render_ms": 1000 * t_render / args.steps,
+        "collide_ms": 1000 * t_collide / args.steps,
+        "capsule_ms": 1000 * t_capsule / args.steps if bodies is not None else None,
+        "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule) / args.steps,
+        "engine_frames": env.render_calls, "collide_launches": env.collide_launches, "steps_that_moved": moved,
+        "frame_shape": list(rgb.shape), "depth_range": [float(depth.min()), float(depth.max())],
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
