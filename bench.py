@@ -269,6 +269,14 @@ def run_native(args):
         for k, v in scene.stage_times(s).items():
             stage[k] += v / nslots
     st = scene.stats()
+    # the same breakdown without inter-frame overlap (one stream): what each stage costs alone
+    scene.set_stage_timing(64)
+    for i in range(64):
+        scene.render(cams[(args.warmup + i) % len(cams)], rows=rows if world > 1 else None, out=(rgb[0], dep[0]))
+    stage_serial = {k: 0.0 for k in scene.STAGES}
+    for s_ in range(64):
+        for k, v in scene.stage_times(s_).items():
+            stage_serial[k] += v / 64
     scene.set_stage_timing(0)
 
     # frame-averaged counters over a sample of the walk (V, D vary per pose)
@@ -320,7 +328,9 @@ def run_native(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        dom = max(stage, key=stage.get)
+        # dominant kernel = longest stage when frames do not overlap (under the two-stream overlap a
+        # stage's event bracket also contains time spent waiting behind the other frame's kernels)
+        dom = max(stage_serial, key=stage_serial.get)
         nb = 16
         px = W * H if world == 1 else W * (min(rows[1] * 16, H) - rows[0] * 16)
         alg = {   # algorithmic bytes per launch of each stage
@@ -331,7 +341,17 @@ def run_native(args):
             "tile_sort": D * 8 * 2 * 2 + D * 4,
             "composite": D * 36 + px * 7,
         }
-        dom_ms = stage[dom]
+        dom_ms = stage_serial[dom]
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                tj = json.loads(tp.read_text())
+                if dom in tj:
+                    traffic, traffic_src = float(tj[dom]["dram_bytes"]), tj[dom].get("source")
+            except Exception:
+                pass
         achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         frame_ms = ms / args.steps          # whole frame, device-timed (stages overlap: SH colour runs on a side stream)
         line = {
@@ -348,9 +368,11 @@ def run_native(args):
                     "note": "sage_render_host_async/sage_host_wait: host camera in, RGB+depth copied to pinned host for every frame, two frames in flight"},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg[dom],
-                         "frame": {"algorithmic_bytes": B, "stage_ms": stage, "frame_ms": frame_ms,
+                         "traffic_source": traffic_src,
+                         "frame": {"algorithmic_bytes": B, "stage_ms": stage, "stage_ms_serial": stage_serial,
+                                   "serial_frame_ms": sum(stage_serial.values()), "frame_ms": frame_ms,
                                    "achieved_gbs": B / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0}},
         }
         if not args.no_cpu_baseline:

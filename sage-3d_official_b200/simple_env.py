@@ -240,8 +240,8 @@ class SimpleVLNEnv:
         self._update_camera_position()
         key = (self._cam_position.tobytes(), self._cam_orientation.tobytes(), tuple(self.resolution))
         if self._frame_key != key:
-            rgb, depth = self._scene.render_host(self._camera(), want_depth=True)
-            self._frame = (rgb.copy(), depth.copy())
+            # views of the engine's pinned buffers; every getter hands out its own copy
+            self._frame = self._scene.render_host(self._camera(), want_depth=True)
             self._frame_key = key
             self.render_calls += 1
         return self._frame
@@ -251,7 +251,7 @@ class SimpleVLNEnv:
         if self._scene is None:
             return np.zeros((H, W, 3), dtype=np.uint8)
         try:
-            return self._render_current()[0].astype(np.uint8)
+            return np.array(self._render_current()[0], dtype=np.uint8, copy=True)
         except Exception as e:
             _debug_print(f"[WARN] get_rgb failed: {e}")
             return None
@@ -261,7 +261,7 @@ class SimpleVLNEnv:
         if self._scene is None:
             return np.full((H, W), 5.0, dtype=np.float32)
         try:
-            return np.clip(self._render_current()[1].astype(np.float32), *self.DEPTH_CLIP)
+            return np.clip(self._render_current()[1], *self.DEPTH_CLIP)
         except Exception as e:
             _debug_print(f"[WARN] get_depth failed: {e}")
             return None
