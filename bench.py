@@ -204,8 +204,19 @@ def run_native(args):
     W, H = args.width, args.height
     scene = sage.GaussianScene(cloud, device=local)
     dev = torch.device("cuda", local)
-    from sage3d_official_b200.multigpu import rows_of
+    from sage3d_official_b200.multigpu import rows_of, balanced_cuts
     rows = rows_of(rank, H, world)      # tile-row blocks: 68 rows at 1080p -> 9,9,9,9,8,8,8,8 for 8 ranks
+    if world > 1:
+        # load-balance the split once, from the per-row instance counts of calibration frames
+        # (identical on every rank: same scene, same poses): cost = instances + 0.35 x pixels/16
+        ty_all = (H + 15) // 16
+        cost = np.zeros(ty_all)
+        for ci in np.linspace(0, len(cams) - 1, 8).astype(int):
+            scene.render(cams[ci])
+            cost += scene.row_instances(ty_all)
+        cost = cost / 8 + 0.35 * (W * 16 / 16.0)
+        cuts = balanced_cuts(cost, world)
+        rows = (cuts[rank], cuts[rank + 1])
 
     nbuf = 2
     rgb = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]

@@ -116,6 +116,9 @@ int sage_render_peers(sage_scene* s, const sage_camera* cam, int row0_tiles, int
 /* Synchronises with the last frame on the scene and returns its counters. */
 int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out);
 
+/* (tile, Gaussian) instances per tile row of the last frame (load-balancing the multi-GPU row split). */
+int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows);
+
 /* Per-stage device timing (bench/roofline): with n_slots > 0 every frame records CUDA events
  * between its stages on the caller's stream into slot (frame_index % n_slots); n_slots = 0 turns
  * it off.  sage_stage_times_get waits for that frame and returns milliseconds per stage. */

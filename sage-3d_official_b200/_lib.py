@@ -15,7 +15,7 @@ EXPORTS = [
     "sage_last_error", "sage_abi_version", "sage_device_count",
     "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy",
     "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_render_peers", "sage_frame_stats_get", "sage_project",
-    "sage_set_stage_timing", "sage_stage_times_get",
+    "sage_frame_row_instances", "sage_set_stage_timing", "sage_stage_times_get",
     "sage_ipc_export", "sage_ipc_open", "sage_ipc_close",
     "sage_grid_create", "sage_grid_destroy", "sage_collide_grid", "sage_collide_grid_f64",
     "sage_collide_grid_dev",
@@ -79,6 +79,7 @@ def lib():
     L.sage_host_wait.argtypes = [vp, i32]
     L.sage_render_peers.argtypes = [vp, C.POINTER(CCamera), i32, i32, i32, C.POINTER(vp), C.POINTER(vp), vp]
     L.sage_frame_stats_get.argtypes = [vp, C.POINTER(CFrameStats)]
+    L.sage_frame_row_instances.argtypes = [vp, vp, i32]
     L.sage_set_stage_timing.argtypes = [vp, i32]
     L.sage_stage_times_get.argtypes = [vp, i32, vp]
     L.sage_project.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp]

@@ -179,6 +179,12 @@ class GaussianScene:
         check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))
         return {k: int(getattr(st, k)) for k, _ in CFrameStats._fields_}
 
+    def row_instances(self, n_rows: int) -> np.ndarray:
+        """(tile, Gaussian) instances per tile row of the last frame."""
+        out = np.zeros(int(n_rows), np.int64)
+        check(_lib.lib().sage_frame_row_instances(self._h, _ptr(out), int(n_rows)))
+        return out
+
     STAGES = ("project", "depth_sort", "sh_color", "emit", "tile_sort", "composite")
 
     def set_stage_timing(self, n_slots: int):

@@ -20,6 +20,7 @@ struct PeerOut {
     uint8_t* rgb[MAX_PEERS];
     float* depth[MAX_PEERS];
     int n;
+    int wide;     // 8-byte stores allowed: W % 8 == 0 and every buffer 8-byte aligned
 };
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
@@ -134,19 +135,44 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
     }
 #undef SAGE_LIVE
 
-    // epilogue: quantise and store to every destination frame
-    if (in0 || in1) {
+    // epilogue: quantise and store to every destination frame.  Wide path (frame width a multiple of
+    // 8, 8-byte aligned buffers): the 24 RGB bytes of a quadrant row (4 lanes x 2 px) leave as three
+    // 8-byte words assembled with shuffles, depth as one float2 per lane — 8x fewer store
+    // instructions, which matters most when the destinations are peer GPUs behind NVLink.
+    uint8_t q[6];
+    {
         const float vals_c[6] = {Cr.x, Cg.x, Cb.x, Cr.y, Cg.y, Cb.y};
-        uint8_t q[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             float v = fminf(fmaxf(vals_c[k], 0.0f), 1.0f);
             q[k] = (uint8_t)(v * 255.0f + 0.5f);
         }
-        const float cov0 = 1.0f - T.x, cov1 = 1.0f - T.y;
-        const float d0 = cov0 > 1e-6f ? Dz.x / cov0 : 0.0f;
-        const float d1 = cov1 > 1e-6f ? Dz.y / cov1 : 0.0f;
-        const size_t p = (size_t)py * cam.W + px;
+    }
+    const float cov0 = 1.0f - T.x, cov1 = 1.0f - T.y;
+    const float d0 = cov0 > 1e-6f ? Dz.x / cov0 : 0.0f;
+    const float d1 = cov1 > 1e-6f ? Dz.y / cov1 : 0.0f;
+    const size_t p = (size_t)py * cam.W + px;
+    // whole-warp decision: the quadrant lies fully inside the image and the layout is aligned
+    const int qx0 = tx * SAGE_TILE + (w & 1) * 8, qy0 = ty * SAGE_TILE + (w >> 1) * 8;
+    const bool wide = out.wide && (qx0 + 8 <= cam.W) && (qy0 + 8 <= cam.H);
+    if (wide) {
+        // this lane's 6 bytes as a 64-bit value; lanes 4r..4r+3 form one row
+        const unsigned long long mine = (unsigned long long)q[0] | ((unsigned long long)q[1] << 8) |
+                                        ((unsigned long long)q[2] << 16) | ((unsigned long long)q[3] << 24) |
+                                        ((unsigned long long)q[4] << 32) | ((unsigned long long)q[5] << 40);
+        const int sub = lane & 3;
+        const unsigned long long nxt = __shfl_down_sync(0xffffffffu, mine, 1);
+        // word k of the row (k = 0,1,2) starts at byte 8k = lane k's byte (8k - 6k) = 2k
+        unsigned long long word = 0;
+        if (sub == 0) word = mine | (nxt << 48);                       // b0..5 of lane0 + b0..1 of lane1
+        else if (sub == 1) word = (mine >> 16) | (nxt << 32);          // b2..5 of lane1 + b0..3 of lane2
+        else if (sub == 2) word = (mine >> 32) | (nxt << 16);          // b4..5 of lane2 + b0..5 of lane3
+        const size_t row_byte = ((size_t)py * cam.W + qx0) * 3;
+        for (int k = 0; k < out.n; ++k) {
+            if (sub < 3) *reinterpret_cast<unsigned long long*>(out.rgb[k] + row_byte + 8 * sub) = word;
+            if (out.depth[k]) *reinterpret_cast<float2*>(out.depth[k] + p) = make_float2(d0, d1);
+        }
+    } else if (in0 || in1) {
         for (int k = 0; k < out.n; ++k) {
             uint8_t* rgb = out.rgb[k];
             float* dep = out.depth[k];
@@ -171,10 +197,13 @@ void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uin
     const int n_tiles = (cam.row1 - cam.row0) * cam.tiles_x;
     if (n_tiles <= 0) return;
     PeerOut out;
+    bool aligned = (cam.W % 8) == 0;
     out.n = n_peers < MAX_PEERS ? n_peers : MAX_PEERS;
     for (int k = 0; k < MAX_PEERS; ++k) {
         out.rgb[k] = k < out.n ? rgb_peers[k] : nullptr;
         out.depth[k] = (k < out.n && depth_peers) ? depth_peers[k] : nullptr;
+        if (k < out.n && (((uintptr_t)out.rgb[k] & 7u) || ((uintptr_t)out.depth[k] & 7u))) aligned = false;
     }
+    out.wide = aligned ? 1 : 0;
     k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, out);
 }

@@ -26,6 +26,7 @@ struct FrameCtx {
     size_t out_px = 0;
     cudaStream_t last_stream = nullptr;
     int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
+    int last_row0 = 0, last_row1 = 0, last_tiles_x = 0;
     bool used = false;
 };
 
@@ -260,6 +261,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     c.last_W = cd.W; c.last_H = cd.H;
     c.last_depth = (depth_peers && depth_peers[0]) ? 1 : 0;
     c.last_launches = launches;
+    c.last_row0 = row0; c.last_row1 = row1; c.last_tiles_x = cd.tiles_x;
     s->last_ctx = ci;
     return 0;
 }
@@ -432,6 +434,28 @@ int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out)
     out->algorithmic_bytes = out->n_gaussians * 44 + out->n_visible * 12 * nb + out->n_visible * 32 +
                              out->n_instances * 24 + out->n_instances * 32 +
                              (int64_t)c.last_W * c.last_H * (3 + 4 * c.last_depth);
+    return 0;
+}
+
+int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows)
+{
+    REQUIRE(s != nullptr && rows_out_host != nullptr, "sage_frame_row_instances: NULL argument");
+    REQUIRE(s->last_ctx >= 0, "sage_frame_row_instances: no frame rendered yet");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[s->last_ctx];
+    CK(cudaEventSynchronize(c.done));
+    const int rows = c.last_row1 - c.last_row0;
+    REQUIRE(n_rows == rows, "sage_frame_row_instances: n_rows must equal the rows of the last frame");
+    std::vector<uint2> rg((size_t)rows * c.last_tiles_x);
+    if (!rg.empty()) CK(cudaMemcpy(rg.data(), c.fr.ranges, rg.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < rows; ++r) {
+        int64_t acc = 0;
+        for (int x = 0; x < c.last_tiles_x; ++x) {
+            const uint2 v = rg[(size_t)r * c.last_tiles_x + x];
+            acc += (int64_t)v.y - (int64_t)v.x;
+        }
+        rows_out_host[r] = acc;
+    }
     return 0;
 }
 

@@ -34,6 +34,26 @@ def tile_row_cuts(height: int, world: int) -> List[int]:
     return cuts
 
 
+def balanced_cuts(row_cost: Sequence[float], world: int) -> List[int]:
+    """Tile-row boundaries that equalise a per-row cost (e.g. instances per row of a calibration
+    frame plus a per-pixel term) instead of the row count; every rank keeps at least one row."""
+    cost = np.asarray(row_cost, dtype=np.float64)
+    n = len(cost)
+    if world >= n:
+        return list(range(n)) + [n] * (world - n + 1)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        k = int(np.searchsorted(cum, target))
+        k = min(max(k, cuts[-1] + 1), n - (world - r))
+        if k - 1 > cuts[-1] and abs(cum[k - 1] - target) < abs(cum[k] - target):
+            k -= 1
+        cuts.append(k)
+    cuts.append(n)
+    return cuts
+
+
 def rows_of(rank: int, height: int, world: int) -> Tuple[int, int]:
     cuts = tile_row_cuts(height, world)
     return cuts[rank], cuts[rank + 1]
