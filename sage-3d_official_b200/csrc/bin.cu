@@ -170,6 +170,33 @@ k_tile_ranges(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ co
     }
 }
 
+// Heaviest tiles first: a tile is blended by one CTA however long its list is, so the longest lists
+// must start early or they become the tail of the composite kernel.  One block orders the tiles by
+// descending power-of-two length class (order inside a class is irrelevant to the result).
+__global__ void __launch_bounds__(1024)
+k_tile_order(const uint2* __restrict__ ranges, int n_tiles, uint32_t* __restrict__ order)
+{
+    __shared__ uint32_t cls_count[33], cls_base[33];
+    if (threadIdx.x < 33) cls_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t n = r.y - r.x;
+        atomicAdd(&cls_count[n ? 32 - __clz(n) : 0], 1u);      // class 0: empty, k: 2^(k-1) <= n < 2^k
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int c = 32; c >= 0; --c) { cls_base[c] = run; run += cls_count[c]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        const uint2 r = ranges[t];
+        const uint32_t n = r.y - r.x;
+        order[atomicAdd(&cls_base[n ? 32 - __clz(n) : 0], 1u)] = (uint32_t)t;
+    }
+}
+
 }  // namespace
 
 void sage_launch_emit(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order, int64_t n,
@@ -192,4 +219,5 @@ void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8) blocks = 148 * 8;      // persistent grid-stride: D is only known on the device
     k_tile_ranges<<<blocks, B_THREADS, 0, st>>>(sorted_keys, fr.counters, fr.ranges);
+    k_tile_order<<<1, 1024, 0, st>>>(fr.ranges, n_tiles, fr.tile_order);
 }

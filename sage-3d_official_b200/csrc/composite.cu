@@ -47,11 +47,11 @@ __device__ __forceinline__ float2 sage_exp2_x2(float2 x)
 __global__ void __launch_bounds__(C_THREADS)
 k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
             const float4* __restrict__ rec2, const uint32_t* __restrict__ vals,
-            const uint2* __restrict__ ranges, PeerOut out)
+            const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, PeerOut out)
 {
     __shared__ float4 s0[C_THREADS], s1[C_THREADS], s2[C_THREADS];
     __shared__ uint32_t smask[C_THREADS];
-    const int tile = blockIdx.x;
+    const int tile = (int)tile_order[blockIdx.x];
     const int tx = tile % cam.tiles_x, ty = cam.row0 + tile / cam.tiles_x;
     const uint2 rg = ranges[tile];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
@@ -205,5 +205,5 @@ void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uin
         if (k < out.n && (((uintptr_t)out.rgb[k] & 7u) || ((uintptr_t)out.depth[k] & 7u))) aligned = false;
     }
     out.wide = aligned ? 1 : 0;
-    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, out);
+    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, fr.tile_order, out);
 }

@@ -79,6 +79,7 @@ struct SageFrame {
     uint32_t* tile_hist;    // [SAGE_MAX_PASSES][256]
     // per-tile
     uint2* ranges;
+    uint32_t* tile_order;   // tiles by descending list length: CTA b of the composite takes tile_order[b]
 };
 #define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS + SAGE_MAX_PASSES * 256)
 

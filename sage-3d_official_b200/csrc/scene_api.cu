@@ -100,7 +100,7 @@ static void free_ctx(FrameCtx& c)
     for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
     cudaFree(c.fr.rect); cudaFree(c.fr.ntiles); cudaFree(c.fr.chain);
     free_instances(c);
-    cudaFree(c.fr.ranges); cudaFree(c.fr.counters);
+    cudaFree(c.fr.ranges); cudaFree(c.fr.tile_order); cudaFree(c.fr.counters);
     if (c.counters_host) cudaFreeHost(c.counters_host);
     if (c.done) cudaEventDestroy(c.done);
     if (c.stream) cudaStreamDestroy(c.stream);
@@ -134,9 +134,10 @@ static int ensure_tiles(FrameCtx& c, int n_tiles, cudaStream_t st)
 {
     if (n_tiles > c.max_tiles) {
         CK(cudaStreamSynchronize(st));
-        cudaFree(c.fr.ranges);
-        c.fr.ranges = nullptr; c.max_tiles = 0;
+        cudaFree(c.fr.ranges); cudaFree(c.fr.tile_order);
+        c.fr.ranges = nullptr; c.fr.tile_order = nullptr; c.max_tiles = 0;
         CK(dalloc(&c.fr.ranges, (size_t)n_tiles));
+        CK(dalloc(&c.fr.tile_order, (size_t)n_tiles));
         c.max_tiles = n_tiles;
     }
     return 0;
@@ -248,7 +249,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
         STAGE_MARK(6);
     } else if (n_tiles > 0) {
         for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
-        CK(cudaMemsetAsync(c.fr.ranges, 0, sizeof(uint2) * (size_t)n_tiles, st));
+        sage_launch_ranges(c.fr, c.fr.ikey[0], c.cap, n_tiles, st);        // D = 0: all ranges empty
         sage_launch_composite(cd, c.fr, c.fr.ival[0], n_peers, rgb_peers, depth_peers, st);
         launches += 1;
     }
