@@ -387,7 +387,7 @@ def run_native(args):
                                    "serial_frame_ms": sum(stage_serial.values()), "frame_ms": frame_ms,
                                    "achieved_gbs": B / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0}},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N=1 only
             import oracle
             oracle.build()
             cores = os.cpu_count() or 1

@@ -105,3 +105,29 @@ def test_peer_store_composite_two_processes_one_gpu():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_balanced_cuts_equalise_cost():
+    from sage3d_official_b200.multigpu import balanced_cuts
+    cost = np.array([10.0] * 20 + [100.0] * 30 + [40.0] * 18)
+    for world in (1, 2, 4, 8):
+        cuts = balanced_cuts(cost, world)
+        assert cuts[0] == 0 and cuts[-1] == len(cost) and len(cuts) == world + 1
+        assert all(b > a for a, b in zip(cuts[:-1], cuts[1:]))
+        shares = [cost[a:b].sum() for a, b in zip(cuts[:-1], cuts[1:])]
+        assert max(shares) <= 1.35 * cost.sum() / world
+    assert balanced_cuts([1.0, 1.0, 1.0], 5)[-1] == 3
+
+
+@pytest.mark.gpu
+def test_row_instances_sum_to_frame_total():
+    import sage3d_official_b200 as sage
+    cloud, _ = sage.synthetic_room(0, 20_000)
+    cam = sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 640, 480)
+    scene = sage.GaussianScene(cloud)
+    scene.render(cam)
+    rows = scene.row_instances(30)
+    assert rows.sum() == scene.stats()["n_instances"] and (rows >= 0).all() and rows.max() > 0
+    scene.render(cam, rows=(10, 20))
+    part = scene.row_instances(10)
+    assert part.sum() == scene.stats()["n_instances"]
