@@ -181,7 +181,7 @@ __device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
                                             -0.5900435899266435f};
 
 template <int DEG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order)
 {
     constexpr int NB = (DEG + 1) * (DEG + 1);
