@@ -18,8 +18,7 @@
 namespace {
 
 constexpr int S_THREADS = 512;
-constexpr int S_IPT = 8;
-constexpr int S_TILE = S_THREADS * S_IPT;
+constexpr int S_IPT_MIN = 8;                       // smallest items/thread used (sizes the look-back array)
 constexpr int S_WARPS = S_THREADS / 32;
 
 constexpr unsigned long long ST_AGG = 1ull, ST_PREFIX = 2ull;
@@ -92,7 +91,7 @@ k_radix_offsets(uint32_t* __restrict__ hist, uint32_t* __restrict__ total_out)
 }
 
 // ---- one sort pass ------------------------------------------------------------------------------
-template <int RB, bool COMPACT>
+template <int RB, bool COMPACT, int S_IPT>
 __global__ void __launch_bounds__(S_THREADS)
 k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
@@ -101,6 +100,7 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
            int vals_are_iota)
 {
     constexpr int RADIX = 1 << RB;
+    constexpr int S_TILE = S_THREADS * S_IPT;
     static_assert(RADIX <= S_THREADS, "one digit per thread");
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
@@ -238,15 +238,16 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     }
 }
 
-template <int RB, int NP, bool COMPACT>
+template <int RB, int NP, bool COMPACT, int S_IPT>
 void sort_impl(const SageSortPlan& pl, cudaStream_t st)
 {
     constexpr int RADIX = 1 << RB;
+    constexpr int S_TILE = S_THREADS * S_IPT;
     constexpr size_t SMEM = sizeof(uint32_t) * (S_WARPS * RADIX + RADIX + 2 * S_TILE);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_onesweep<RB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-        cudaFuncSetAttribute(k_onesweep<RB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        cudaFuncSetAttribute(k_onesweep<RB, true, S_IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        cudaFuncSetAttribute(k_onesweep<RB, false, S_IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         configured = true;
     }
     int grid = (int)((pl.capacity + S_TILE - 1) / S_TILE);
@@ -260,11 +261,11 @@ void sort_impl(const SageSortPlan& pl, cudaStream_t st)
     for (int p = 0; p < NP; ++p) {
         const uint32_t* n_dev = p == 0 ? pl.n_first : pl.n_rest;
         if (COMPACT && p == 0)
-            k_onesweep<RB, true><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+            k_onesweep<RB, true, S_IPT><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
                                                             n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
                                                             pl.lookback, pl.tickets + p, pl.epoch0 + p, pl.vals_are_iota ? 1 : 0);
         else
-            k_onesweep<RB, false><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
+            k_onesweep<RB, false, S_IPT><<<grid, S_THREADS, SMEM, st>>>(pl.keys[cur], pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1],
                                                              n_dev, pl.lo_bit + RB * p, pl.hist + (size_t)p * RADIX,
                                                              pl.lookback, pl.tickets + p, pl.epoch0 + p,
                                                              (pl.vals_are_iota && p == 0) ? 1 : 0);
@@ -284,7 +285,8 @@ void sage_sort_shape(int n_bits, int* digit_bits, int* passes)
 
 size_t sage_sort_lookback_words(int64_t capacity)
 {
-    size_t nb = (size_t)((capacity + S_TILE - 1) / S_TILE) + 1;
+    const int tile_min = S_THREADS * S_IPT_MIN;
+    size_t nb = (size_t)((capacity + tile_min - 1) / tile_min) + 1;
     return nb * SAGE_RADIX_MAX_BINS;
 }
 
@@ -294,7 +296,11 @@ int sage_radix_sort(const SageSortPlan& pl, int* launches, cudaStream_t st)
     const bool c = pl.compact_first;
 #define SAGE_SORT_CASE(RB_, NP_)                                                     \
     if (rb == RB_ && np == NP_) {                                                    \
-        if (c) sort_impl<RB_, NP_, true>(pl, st); else sort_impl<RB_, NP_, false>(pl, st); \
+        if (pl.items_per_thread == 16) {                                             \
+            if (c) sort_impl<RB_, NP_, true, 16>(pl, st); else sort_impl<RB_, NP_, false, 16>(pl, st); \
+        } else {                                                                     \
+            if (c) sort_impl<RB_, NP_, true, 8>(pl, st); else sort_impl<RB_, NP_, false, 8>(pl, st);   \
+        }                                                                            \
         if (launches) *launches += NP_ + 1 + (pl.hist_ready ? 0 : 1);                \
         return np & 1;                                                               \
     }
