@@ -91,7 +91,7 @@ struct SageSortPlan {
     int64_t capacity;
     int lo_bit, n_bits;
     int digit_bits, passes;    // from sage_sort_shape, or forced by the caller
-    int items_per_thread;      // 8 or 16 (x 512 threads = items per block; fewer blocks = shorter look-back chains)
+    int items_per_thread;      // 8, 16 or 32 (x 512 threads = items per block; fewer blocks = shorter look-back chains)
     bool vals_are_iota, compact_first, hist_ready;
     uint32_t* hist;            // [passes][1 << digit_bits], zeroed (or pre-accumulated if hist_ready)
     uint32_t* total_out;       // optional: total of pass 0's histogram

@@ -121,16 +121,11 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     // warp-striped ownership: warp w holds items [w*512, (w+1)*512) of the tile, item (i, lane) at
     // offset i*32 + lane, so (warp, i, lane) order == input order (stability).  All loads first.
     const uint32_t wbase = b * S_TILE + w * (32 * S_IPT);
-    uint32_t key[S_IPT], val[S_IPT];
+    uint32_t key[S_IPT];
 #pragma unroll
     for (int i = 0; i < S_IPT; ++i) {
         const uint32_t idx = wbase + i * 32 + lane;
         key[i] = idx < n ? __ldg(&keys_in[idx]) : SAGE_KEY_CULLED;
-    }
-#pragma unroll
-    for (int i = 0; i < S_IPT; ++i) {
-        const uint32_t idx = wbase + i * 32 + lane;
-        val[i] = vals_are_iota ? idx : (idx < n ? __ldg(&vals_in[idx]) : 0u);
     }
     // local ranks: warp-private digit counters, peers found with match.any
     uint32_t rank[S_IPT];
@@ -224,8 +219,9 @@ k_onesweep(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
         if (rank[i] != 0xFFFFFFFFu) {
             const uint32_t d = (key[i] >> shift) & (RADIX - 1);
             const uint32_t lp = wh[w][d] + rank[i];
+            const uint32_t idx = wbase + i * 32 + lane;
             skey[lp] = key[i];
-            sval[lp] = val[i];
+            sval[lp] = vals_are_iota ? idx : __ldg(&vals_in[idx]);     // values are only read here
         }
     }
     __syncthreads();
@@ -296,7 +292,9 @@ int sage_radix_sort(const SageSortPlan& pl, int* launches, cudaStream_t st)
     const bool c = pl.compact_first;
 #define SAGE_SORT_CASE(RB_, NP_)                                                     \
     if (rb == RB_ && np == NP_) {                                                    \
-        if (pl.items_per_thread == 16) {                                             \
+        if (pl.items_per_thread == 32) {                                             \
+            if (c) sort_impl<RB_, NP_, true, 32>(pl, st); else sort_impl<RB_, NP_, false, 32>(pl, st); \
+        } else if (pl.items_per_thread == 16) {                                      \
             if (c) sort_impl<RB_, NP_, true, 16>(pl, st); else sort_impl<RB_, NP_, false, 16>(pl, st); \
         } else {                                                                     \
             if (c) sort_impl<RB_, NP_, true, 8>(pl, st); else sort_impl<RB_, NP_, false, 8>(pl, st);   \
