@@ -180,7 +180,7 @@ static int front_half(sage_scene* s, FrameCtx& c, const SageCamDev& cd, int* lau
     dp.n_first = s->n_dev; dp.n_rest = c.fr.counters + CNT_VISIBLE;
     dp.capacity = s->sc.n; dp.lo_bit = 0; dp.n_bits = depth_key_bits(cd);
     sage_sort_shape(dp.n_bits, &dp.digit_bits, &dp.passes);
-    dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false; dp.items_per_thread = 16;
+    dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false; dp.items_per_thread = 8;    // measured: 8 beats 16 here
     dp.hist = c.fr.depth_hist; dp.total_out = nullptr;
     dp.lookback = c.fr.lookback; dp.tickets = c.fr.tickets + SAGE_TICKET_DEPTH; dp.epoch0 = c.epoch;
     const int res = sage_radix_sort(dp, launches, st);
@@ -237,7 +237,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
         tp.vals[0] = c.fr.ival[0]; tp.vals[1] = c.fr.ival[1];
         tp.n_first = tp.n_rest = c.fr.counters + CNT_INSTANCES;
         tp.capacity = c.cap; tp.lo_bit = 0; tp.n_bits = tbits; tp.digit_bits = 8; tp.passes = tpasses;
-        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true; tp.items_per_thread = 32;
+        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true; tp.items_per_thread = 16;   // measured: 16 beats 8 and 32
         tp.hist = c.fr.tile_hist; tp.total_out = nullptr;
         tp.lookback = c.fr.lookback; tp.tickets = c.fr.tickets + SAGE_TICKET_TILE; tp.epoch0 = c.epoch + 4;
         const int ires = sage_radix_sort(tp, &launches, st);
