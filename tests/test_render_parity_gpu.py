@@ -186,3 +186,41 @@ def test_two_frames_in_flight_match_serial_frames(sage, oracle):
         assert np.array_equal(r0, rt.cpu().numpy()) and np.array_equal(d0, dt.cpu().numpy())
     o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, cams[3]), *cloud.as_tuple())
     assert np.array_equal(serial[3][0], o_rgb) and np.array_equal(serial[3][1], o_dep)
+
+
+def test_config2_full_size_parity_1080p_2m(sage, oracle):
+    """BASELINE configs[1] at full size: 2 M Gaussians, 1920x1080, bit-exact against the oracle
+    (needs the GPU box's host cores: ~1 s of OpenMP oracle per frame)."""
+    from sage3d_official_b200.scene_io import morton_order
+    cloud, layout = sage.synthetic_interior(1, 2_000_000)
+    cloud = cloud.subset(morton_order(cloud.xyz))
+    poses = sage.camera_path(layout, 256, seed=0)
+    scene = sage.GaussianScene(cloud)
+    for pi in (0, 171):
+        cam = sage.Camera.look_heading(poses[pi][0], poses[pi][1], 1920, 1080)
+        st = _check_frame(sage, oracle, cloud, cam, scene=scene)
+        assert st["n_visible"] > 200_000 and st["n_instances"] > 1_000_000
+
+
+def test_size_independent_properties(sage):
+    import torch
+    cloud, layout = sage.synthetic_interior(2, 300_000)
+    cam = sage.Camera.look_heading(*sage.camera_path(layout, 4, seed=5)[2], 1280, 720)
+    scene = sage.GaussianScene(cloud)
+    a = tuple(t.clone() for t in scene.render(cam))
+    b = tuple(t.clone() for t in scene.render(cam))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "not deterministic"
+    # Gaussians that cannot contribute (opacity below 1/255 after the sigmoid, or behind the camera)
+    # leave every bit unchanged, wherever they sit in the index order
+    rng = np.random.default_rng(0)
+    extra = cloud.subset(rng.integers(0, cloud.n, 50_000))
+    extra.opacity[:25_000] = -9.0
+    extra.xyz[25_000:] += (np.array([np.cos(cam.meta.get("h", 0.0)), 0, 0]) * 0).astype(np.float32)
+    extra.xyz[25_000:, :] = (cam.campos - 5.0 * cam.R[2]).astype(np.float32) + rng.normal(0, 0.2, (25_000, 3)).astype(np.float32)
+    mixed = sage.GaussianCloud(*(np.concatenate([x, y]) for x, y in zip(extra.as_tuple(), cloud.as_tuple())))
+    c = sage.GaussianScene(mixed).render(cam)
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    # depth lies inside the clipping range wherever something was hit; colours are saturating u8
+    d = a[1]
+    assert float(d.min()) >= 0.0 and float(d.max()) < cam.far
+    assert float(d[d > 0].min()) > cam.near * 0.99
