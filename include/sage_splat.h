@@ -51,7 +51,8 @@ typedef struct sage_camera {
 typedef struct sage_frame_stats {
     int64_t n_gaussians;      /* N */
     int64_t n_visible;        /* V: survivors of the cull */
-    int64_t n_instances;      /* D: (tile, Gaussian) pairs */
+    int64_t n_instances;      /* D: (tile, Gaussian) pairs (clamped to the capacity) */
+    int64_t n_instances_wanted; /* D before clamping: what sage_scene_reserve needs after an overflow */
     int64_t instance_capacity;
     int64_t algorithmic_bytes;/* N*44 + V*12*(deg+1)^2 + V*32 + D*24 + D*32 + W*H*(3+4*depth) */
     int32_t overflow;         /* 1: D exceeded instance_capacity; the frame is incomplete */

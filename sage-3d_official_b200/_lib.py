@@ -34,7 +34,7 @@ class CCamera(C.Structure):
 
 
 class CFrameStats(C.Structure):
-    _fields_ = [("n_gaussians", C.c_int64), ("n_visible", C.c_int64), ("n_instances", C.c_int64),
+    _fields_ = [("n_gaussians", C.c_int64), ("n_visible", C.c_int64), ("n_instances", C.c_int64), ("n_instances_wanted", C.c_int64),
                 ("instance_capacity", C.c_int64), ("algorithmic_bytes", C.c_int64),
                 ("overflow", C.c_int32), ("kernel_launches", C.c_int32)]
 

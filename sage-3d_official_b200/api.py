@@ -151,8 +151,14 @@ class GaussianScene:
         r0, r1 = self._rows(cam, rows)
         cc = _ccam(cam)
         with torch.cuda.device(self.device):
-            check(_lib.lib().sage_render_host(self._h, C.byref(cc), r0, r1, _ptr(rgb_t),
-                                              _ptr(dep_t) if want_depth else C.c_void_p(0), _stream_ptr(stream)))
+            for attempt in range(2):
+                check(_lib.lib().sage_render_host(self._h, C.byref(cc), r0, r1, _ptr(rgb_t),
+                                                  _ptr(dep_t) if want_depth else C.c_void_p(0), _stream_ptr(stream)))
+                st = self.stats()                  # the call above synchronised: no extra wait
+                if not st["overflow"]:
+                    break
+                # the (tile, Gaussian) lists did not fit (camera inside geometry): grow and redo
+                self.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)
         return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
 
     def render_host_async(self, cam: Camera, slot: int, rows=None, want_depth: bool = True):

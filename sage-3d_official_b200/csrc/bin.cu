@@ -122,6 +122,7 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
         s_base = excl;
         if (b == nblk - 1) {                       // grand total D (clamped to the capacity)
             unsigned long long D = (unsigned long long)excl + total;
+            fr.counters[CNT_WANTED] = (uint32_t)D;
             if (D > cap) { fr.counters[CNT_OVERFLOW] = 1u; D = cap; }
             fr.counters[CNT_INSTANCES] = (uint32_t)D;
         }

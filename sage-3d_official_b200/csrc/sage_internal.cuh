@@ -20,7 +20,7 @@
 #define SAGE_ID_MASK 0x0FFFFFFFu
 
 // device counters (uint32 each)
-enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_COUNT = 8 };
+enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_WANTED = 3, CNT_COUNT = 8 };
 
 struct SageCamDev {
     float R[9];

@@ -428,6 +428,7 @@ int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out)
     out->n_gaussians = s->sc.n;
     out->n_visible = cn[CNT_VISIBLE];
     out->n_instances = cn[CNT_INSTANCES];
+    out->n_instances_wanted = cn[CNT_WANTED];
     out->instance_capacity = c.cap;
     out->overflow = (int32_t)cn[CNT_OVERFLOW];
     out->kernel_launches = c.last_launches;

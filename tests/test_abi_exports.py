@@ -30,7 +30,7 @@ def test_header_symbols_all_exported(sage):
 def test_struct_layouts_match_header(sage):
     from sage3d_official_b200 import _lib
     assert C.sizeof(_lib.CCamera) == 4 * (9 + 3 + 3 + 4) + 4 * 2 + 4 * 2
-    assert C.sizeof(_lib.CFrameStats) == 8 * 5 + 4 * 2
+    assert C.sizeof(_lib.CFrameStats) == 8 * 6 + 4 * 2
     assert C.sizeof(_lib.CSplatRecord) == 4 * 14
 
 

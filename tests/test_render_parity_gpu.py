@@ -224,3 +224,14 @@ def test_size_independent_properties(sage):
     d = a[1]
     assert float(d.min()) >= 0.0 and float(d.max()) < cam.far
     assert float(d[d > 0].min()) > cam.near * 0.99
+
+
+def test_host_path_grows_capacity_on_overflow(sage, oracle):
+    cloud, _ = sage.synthetic_room(0, 20_000)
+    cam = sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 640, 480)
+    scene = sage.GaussianScene(cloud, max_instances=2000)
+    rgb, dep = scene.render_host(cam)                      # overflows, reserves, renders again
+    st = scene.stats()
+    assert st["overflow"] == 0 and st["instance_capacity"] > 2000 and st["n_instances"] == st["n_instances_wanted"]
+    o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, cam), *cloud.as_tuple())
+    assert np.array_equal(rgb, o_rgb) and np.array_equal(dep, o_dep)

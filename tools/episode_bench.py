@@ -55,6 +55,7 @@ def main():
     rng = np.random.default_rng(0)
     t_render = t_collide = t_capsule = 0.0
     moved = 0
+    frame_ms, inst = [], []
     env.get_rgb()                                                   # warm-up frame
     t0 = time.perf_counter()
     for step in range(args.steps):
@@ -62,6 +63,8 @@ def main():
         rgb = env.get_rgb()
         depth = env.get_depth()
         b = time.perf_counter()
+        frame_ms.append(1000 * (b - a))
+        inst.append(env._scene.stats()["n_instances_wanted"])
         r = rng.uniform()
         if r < 0.6:
             cmd = (0.25, 0.0, 0.0, 1.0)
@@ -88,6 +91,8 @@ def main():
         "collide_ms": 1000 * t_collide / args.steps,
         "capsule_ms": 1000 * t_capsule / args.steps if bodies is not None else None,
         "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule) / args.steps,
+        "render_ms_p50_p90_max": [float(np.percentile(frame_ms, 50)), float(np.percentile(frame_ms, 90)), float(np.max(frame_ms))],
+        "instances_p50_p90_max": [int(np.percentile(inst, 50)), int(np.percentile(inst, 90)), int(np.max(inst))],
         "engine_frames": env.render_calls, "collide_launches": env.collide_launches, "steps_that_moved": moved,
         "frame_shape": list(rgb.shape), "depth_range": [float(depth.min()), float(depth.max())],
     }
