@@ -57,14 +57,22 @@ def main():
     moved = 0
     frame_ms, inst = [], []
     env.get_rgb()                                                   # warm-up frame
+    env._scene.set_stage_timing(1)
+    stage_acc = {k: 0.0 for k in env._scene.STAGES}
     t0 = time.perf_counter()
+    timed = 0
     for step in range(args.steps):
+        calls0 = env.render_calls
         a = time.perf_counter()
         rgb = env.get_rgb()
         depth = env.get_depth()
         b = time.perf_counter()
         frame_ms.append(1000 * (b - a))
         inst.append(env._scene.stats()["n_instances_wanted"])
+        if env.render_calls > calls0:
+            timed += 1
+            for k_, v_ in env._scene.stage_times(0).items():
+                stage_acc[k_] += v_
         r = rng.uniform()
         if r < 0.6:
             cmd = (0.25, 0.0, 0.0, 1.0)
@@ -93,6 +101,7 @@ def main():
         "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule) / args.steps,
         "render_ms_p50_p90_max": [float(np.percentile(frame_ms, 50)), float(np.percentile(frame_ms, 90)), float(np.max(frame_ms))],
         "instances_p50_p90_max": [int(np.percentile(inst, 50)), int(np.percentile(inst, 90)), int(np.max(inst))],
+        "stage_ms_mean": {k_: v_ / max(timed, 1) for k_, v_ in stage_acc.items()},
         "engine_frames": env.render_calls, "collide_launches": env.collide_launches, "steps_that_moved": moved,
         "frame_shape": list(rgb.shape), "depth_range": [float(depth.min()), float(depth.max())],
     }
