@@ -177,6 +177,23 @@ class GaussianScene:
                                                     _ptr(dep_t) if want_depth else C.c_void_p(0), int(slot)))
         return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
 
+    def render_batch_host(self, cams, want_depth: bool = True):
+        """Render a sequence of camera poses (e.g. every sampled waypoint of a trajectory, as
+        generate_images.py does one by one) keeping two frames in flight.  Yields
+        ``(index, rgb, depth)`` in order; the arrays are views of pinned buffers that are reused two
+        frames later — copy or encode them before advancing the generator twice."""
+        cams = list(cams)
+        bufs = {}
+        for i, cam in enumerate(cams):
+            slot = i % 2
+            if i >= 2:
+                self.host_wait(slot)
+                yield (i - 2,) + bufs[slot]
+            bufs[slot] = self.render_host_async(cam, slot, want_depth=want_depth)
+        for i in range(max(0, len(cams) - 2), len(cams)):
+            self.host_wait(i % 2)
+            yield (i,) + bufs[i % 2]
+
     def host_wait(self, slot: int):
         check(_lib.lib().sage_host_wait(self._h, int(slot)))
 

@@ -175,6 +175,10 @@ def test_two_frames_in_flight_match_serial_frames(sage, oracle):
         got[i] = tuple(a.copy() for a in bufs[i % 2])
     for (r0, d0), (r1, d1) in zip(serial, got):
         assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
+    batch = [(i, r.copy(), d.copy()) for i, r, d in scene.render_batch_host(cams)]
+    assert [b[0] for b in batch] == list(range(len(cams)))
+    for (r0, d0), (_, r1, d1) in zip(serial, batch):
+        assert np.array_equal(r0, r1) and np.array_equal(d0, d1)
     # device path on two alternating streams
     streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     outs = []
@@ -235,3 +239,31 @@ def test_host_path_grows_capacity_on_overflow(sage, oracle):
     assert st["overflow"] == 0 and st["instance_capacity"] > 2000 and st["n_instances"] == st["n_instances_wanted"]
     o_rgb, o_dep, _ = oracle.render(oracle_camera(oracle, cam), *cloud.as_tuple())
     assert np.array_equal(rgb, o_rgb) and np.array_equal(dep, o_dep)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_stress_parity(sage, oracle, seed):
+    """Random small scenes with hostile parameters: huge and tiny splats, extreme anisotropy,
+    near-plane crossings, degenerate / non-finite attributes, odd resolutions and intrinsics."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 3000))
+    deg = int(rng.integers(0, 4))
+    W, H = int(rng.integers(17, 400)), int(rng.integers(17, 300))
+    cloud, _ = sage.synthetic_room(seed, n, sh_degree=deg)
+    cloud.log_scale[:] = rng.uniform(-9.0, 1.5, size=(n, 3)).astype(np.float32)       # 0.1 mm .. 4.5 m
+    cloud.opacity[:] = rng.uniform(-8.0, 8.0, size=n).astype(np.float32)
+    cloud.quat[:] = rng.normal(size=(n, 4)).astype(np.float32)
+    cloud.sh[:] = rng.normal(0, 0.6, size=cloud.sh.shape).astype(np.float32)
+    k = max(1, n // 50)
+    bad = rng.integers(0, n, size=6 * k)
+    cloud.quat[bad[:k]] = 0.0                                  # degenerate rotation -> NaN covariance
+    cloud.xyz[bad[k:2 * k], 0] = np.nan
+    cloud.log_scale[bad[2 * k:3 * k], 1] = np.inf
+    cloud.opacity[bad[3 * k:4 * k]] = -np.inf
+    cloud.sh[bad[4 * k:5 * k], 0, 1] = 1e31                    # beyond the load rule's 1e30
+    cloud.sh[bad[5 * k:6 * k], -1, 2] = np.nan
+    pos = rng.uniform([0.2, 0.2, 0.3], [5.8, 3.8, 2.7])
+    q = rng.normal(size=4)
+    cam = sage.Camera.from_isaac_pose(pos, q, W, H, focal_mm=float(rng.uniform(3.0, 30.0)),
+                                      near=float(rng.uniform(0.01, 0.5)), far=float(rng.uniform(3.0, 80.0)))
+    _check_frame(sage, oracle, cloud, cam)
