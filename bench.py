@@ -218,7 +218,7 @@ def run_native(args):
         cuts = balanced_cuts(cost, world)
         rows = (cuts[rank], cuts[rank + 1])
 
-    nbuf = 2
+    nbuf = int(os.environ.get("SAGE_BENCH_STREAMS", "2"))
     rgb = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     dep = [torch.zeros((H, W), dtype=torch.float32, device=dev) for _ in range(nbuf)]
 
@@ -229,7 +229,7 @@ def run_native(args):
 
     # single GPU: consecutive frames alternate two streams (and the scene's two frame contexts), so
     # frame i+1's projection/sorts overlap frame i's compositing
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)]
 
     def step(i):
         cam = cams[i % len(cams)]

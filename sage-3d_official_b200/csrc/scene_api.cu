@@ -9,7 +9,9 @@
 
 #include "api_common.cuh"
 
+#ifndef SAGE_N_CTX
 #define SAGE_N_CTX 2
+#endif
 
 namespace {
 
