@@ -114,6 +114,11 @@ int sage_render_peers(sage_scene* s, const sage_camera* cam, int row0_tiles, int
                       int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
                       sage_stream_t stream);
 
+/* Optional clamp applied to the depth output in the composite epilogue (the reference's
+ * np.clip(depth, 0.1, 6.5), simple_env.py:1578, without a second pass over the frame on the host).
+ * lo > hi disables it (default). */
+int sage_scene_set_depth_clip(sage_scene* s, float lo, float hi);
+
 /* Synchronises with the last frame on the scene and returns its counters. */
 int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out);
 

@@ -13,7 +13,7 @@ LIB_PATH = _HERE / "libsage_splat.so"
 #: every symbol declared in include/sage_splat.h (tests check the .so exports all of them)
 EXPORTS = [
     "sage_last_error", "sage_abi_version", "sage_device_count",
-    "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy",
+    "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy", "sage_scene_set_depth_clip",
     "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_render_peers", "sage_frame_stats_get", "sage_project",
     "sage_frame_row_instances", "sage_set_stage_timing", "sage_stage_times_get",
     "sage_ipc_export", "sage_ipc_open", "sage_ipc_close",
@@ -73,6 +73,7 @@ def lib():
     L.sage_scene_create.argtypes = [C.POINTER(vp), i32, i64, i32, vp, vp, vp, vp, vp, i64]
     L.sage_scene_reserve.argtypes = [vp, i64]
     L.sage_scene_destroy.argtypes = [vp]
+    L.sage_scene_set_depth_clip.argtypes = [vp, C.c_float, C.c_float]
     L.sage_render.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
     L.sage_render_host.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
     L.sage_render_host_async.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, i32]

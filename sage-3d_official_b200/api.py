@@ -98,6 +98,10 @@ class GaussianScene:
         except Exception:
             pass
 
+    def set_depth_clip(self, lo: float = 1.0, hi: float = 0.0):
+        """Clamp the depth output on the device (lo > hi switches it off)."""
+        check(_lib.lib().sage_scene_set_depth_clip(self._h, float(lo), float(hi)))
+
     def reserve(self, max_instances: int):
         check(_lib.lib().sage_scene_reserve(self._h, int(max_instances)))
 

@@ -149,8 +149,12 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
         }
     }
     const float cov0 = 1.0f - T.x, cov1 = 1.0f - T.y;
-    const float d0 = cov0 > 1e-6f ? Dz.x / cov0 : 0.0f;
-    const float d1 = cov1 > 1e-6f ? Dz.y / cov1 : 0.0f;
+    float d0 = cov0 > 1e-6f ? Dz.x / cov0 : 0.0f;
+    float d1 = cov1 > 1e-6f ? Dz.y / cov1 : 0.0f;
+    if (cam.depth_lo <= cam.depth_hi) {                 // optional output clamp (façade: clip(0.1, 6.5))
+        d0 = fminf(fmaxf(d0, cam.depth_lo), cam.depth_hi);
+        d1 = fminf(fmaxf(d1, cam.depth_lo), cam.depth_hi);
+    }
     const size_t p = (size_t)py * cam.W + px;
     // whole-warp decision: the quadrant lies fully inside the image and the layout is aligned
     const int qx0 = tx * SAGE_TILE + (w & 1) * 8, qy0 = ty * SAGE_TILE + (w >> 1) * 8;

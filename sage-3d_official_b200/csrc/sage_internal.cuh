@@ -32,6 +32,7 @@ struct SageCamDev {
     int W, H;
     int tiles_x, tiles_y;  // full-frame tile grid
     int row0, row1;        // tile rows rendered by this call
+    float depth_lo, depth_hi;  // output clamp of the depth map (lo > hi: off)
 };
 
 // ---- deterministic exp2 (mirrors the spec) --------------------------------

@@ -45,6 +45,7 @@ struct sage_scene {
     std::vector<cudaEvent_t> events;
     int n_slots = 0;
     long timed_frames = 0;
+    float depth_lo = 1.0f, depth_hi = 0.0f;   // depth output clamp (off while lo > hi)
 };
 
 static void free_instances(FrameCtx& c)
@@ -128,6 +129,7 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     d->tiles_y = (cam->height + SAGE_TILE - 1) / SAGE_TILE;
     REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= d->tiles_y, "tile-row range out of bounds");
     d->row0 = row0; d->row1 = row1;
+    d->depth_lo = 1.0f; d->depth_hi = 0.0f;
     return 0;
 }
 
@@ -210,6 +212,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     for (int k = 0; k < n_peers; ++k) REQUIRE(rgb_peers[k] != nullptr, "sage_render: NULL rgb buffer");
     SageCamDev cd;
     if (make_cam(cam, row0, row1, &cd)) return 1;
+    cd.depth_lo = s->depth_lo; cd.depth_hi = s->depth_hi;
     CK(cudaSetDevice(s->device));
     if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
     FrameCtx& c = s->ctx[ci];
@@ -415,6 +418,13 @@ int sage_host_wait(sage_scene* s, int slot)
     REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_host_wait: slot must be 0 or 1");
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->ctx[slot].stream));
+    return 0;
+}
+
+int sage_scene_set_depth_clip(sage_scene* s, float lo, float hi)
+{
+    REQUIRE(s != nullptr, "sage_scene_set_depth_clip: NULL scene");
+    s->depth_lo = lo; s->depth_hi = hi;
     return 0;
 }
 

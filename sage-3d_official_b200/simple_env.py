@@ -120,6 +120,7 @@ class SimpleVLNEnv:
         if self._preloaded[0] is not None:
             self._model_to_world = None
             self._scene = GaussianScene(self._preloaded[0], device=self._device)
+            self._scene.set_depth_clip(*self.DEPTH_CLIP)
             if self._preloaded[1] is not None:
                 self._bodies = CollisionBodies(*self._preloaded[1], device=self._device)
             return
@@ -131,6 +132,7 @@ class SimpleVLNEnv:
             return
         try:
             self._scene = GaussianScene(load_cloud(gauss), device=self._device)
+            self._scene.set_depth_clip(*self.DEPTH_CLIP)      # clip(0.1, 6.5) applied in the kernel epilogue
             self._log(f"[ENV_INIT] scene {gauss}: {self._scene.n} Gaussians resident on cuda:{self._device}")
             if coll is not None:
                 z = np.load(coll)
@@ -261,7 +263,7 @@ class SimpleVLNEnv:
         if self._scene is None:
             return np.full((H, W), 5.0, dtype=np.float32)
         try:
-            return np.clip(self._render_current()[1], *self.DEPTH_CLIP)
+            return np.array(self._render_current()[1], dtype=np.float32, copy=True)   # already clipped on the device
         except Exception as e:
             _debug_print(f"[WARN] get_depth failed: {e}")
             return None
