@@ -6,9 +6,12 @@
 // One CTA = one 16x16 tile, 128 threads, two horizontally adjacent pixels per thread so the
 // blend arithmetic runs on Blackwell's packed binary32 pipe (FFMA2/FMUL2/FADD2: fma.rn.f32x2),
 // which is IEEE per lane and therefore bit-identical to the scalar statement in the oracle.
-// Splat records of the tile's depth-sorted list are gathered (they sit in L2) into shared memory
-// 128 at a time and broadcast to all pixels.  Finished pixels can be stored straight into several
-// frame buffers (peer-mapped, NVLink) — the multi-GPU strip exchange fused into the epilogue.
+// Splat records (one 48-byte block per Gaussian, L2-resident) of the tile's depth-sorted list are
+// staged into shared memory 128 at a time by the TMA engine: every thread issues one
+// cp.async.bulk (global -> shared, 48 B) that completes on an mbarrier; two stages, so the
+// gather of batch b+1 is in flight while batch b is blended.  Finished pixels can be stored
+// straight into several frame buffers (peer-mapped, NVLink) — the multi-GPU strip exchange
+// fused into the epilogue.
 #include "sage_internal.cuh"
 
 namespace {
@@ -24,6 +27,32 @@ struct PeerOut {
 };
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
+// ---- mbarrier + bulk-copy (TMA) primitives --------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 22)) __trap();      // never hang the GPU
+    }
+}
 
 // packed deterministic exp2; valid for lanes with x in [-125, 0] (callers mask the others)
 __device__ __forceinline__ float2 sage_exp2_x2(float2 x)
@@ -45,12 +74,12 @@ __device__ __forceinline__ float2 sage_exp2_x2(float2 x)
 }
 
 __global__ void __launch_bounds__(C_THREADS)
-k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __restrict__ rec1,
-            const float4* __restrict__ rec2, const uint32_t* __restrict__ vals,
+k_composite(SageCamDev cam, const float4* __restrict__ rec, const uint32_t* __restrict__ vals,
             const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, PeerOut out)
 {
-    __shared__ float4 s0[C_THREADS], s1[C_THREADS], s2[C_THREADS];
-    __shared__ uint32_t smask[C_THREADS];
+    __shared__ __align__(16) float4 srec[2][C_THREADS * 3];   // two stages of 128 x 48-byte records
+    __shared__ uint32_t smask_s[2][C_THREADS];
+    __shared__ __align__(8) unsigned long long sbar[2];
     const int tile = (int)tile_order[blockIdx.x];
     const int tx = tile % cam.tiles_x, ty = cam.row0 + tile / cam.tiles_x;
     const uint2 rg = ranges[tile];
@@ -67,19 +96,44 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
     float2 T = f2(1.0f), Cr = f2(0.0f), Cg = f2(0.0f), Cb = f2(0.0f), Dz = f2(0.0f);
 #define SAGE_LIVE() (pxc.x == pxc.x || pxc.y == pxc.y)
 
-    for (uint32_t base = rg.x; base < rg.y; base += C_THREADS) {
+    if (tid == 0) {
+        mbar_init(&sbar[0], 1);
+        mbar_init(&sbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // issue the TMA gather of one batch into `stage`; v = this thread's instance value of the batch
+    auto issue = [&](int stage, uint32_t batch_base, uint32_t v) {
+        const uint32_t c = min((uint32_t)C_THREADS, rg.y - batch_base);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of the stage
+        if (tid == 0) mbar_expect_tx(&sbar[stage], c * 48u);
+        smask_s[stage][tid] = (uint32_t)tid < c ? (v & 15u) : 0u;
+        if ((uint32_t)tid < c) bulk_g2s(&srec[stage][tid * 3], rec + (size_t)(v >> 4) * 3, 48u, &sbar[stage]);
+    };
+    uint32_t v_pref = (rg.x + tid < rg.y) ? __ldg(&vals[rg.x + tid]) : 0u;
+    bool pending[2] = {false, false};
+    uint32_t parity[2] = {0u, 0u};
+    if (rg.x < rg.y) {
+        issue(0, rg.x, v_pref);
+        pending[0] = true;
+        v_pref = (rg.x + C_THREADS + tid < rg.y) ? __ldg(&vals[rg.x + C_THREADS + tid]) : 0u;
+    }
+    __syncthreads();                                   // stage-0 masks visible to every warp
+
+    int b = 0;
+    for (uint32_t base = rg.x; base < rg.y; base += C_THREADS, ++b) {
         const int cnt = min((uint32_t)C_THREADS, rg.y - base);
-        uint32_t qm = 0;
-        if (tid < cnt) {
-            const uint32_t v = __ldg(&vals[base + tid]);
-            const uint32_t g = v >> 4;
-            qm = v & 15u;
-            s0[tid] = __ldg(&rec0[g]);
-            s1[tid] = __ldg(&rec1[g]);
-            s2[tid] = __ldg(&rec2[g]);
+        const int st = b & 1;
+        if (base + C_THREADS < rg.y) {                 // next batch: gather in flight while this one is blended
+            issue(st ^ 1, base + C_THREADS, v_pref);
+            pending[st ^ 1] = true;
+            v_pref = (base + 2 * C_THREADS + tid < rg.y) ? __ldg(&vals[base + 2 * C_THREADS + tid]) : 0u;
         }
-        smask[tid] = qm;
-        __syncthreads();
+        mbar_wait(&sbar[st], parity[st]);
+        parity[st] ^= 1u;
+        pending[st] = false;
+        const float4* s_rec = srec[st];
+        const uint32_t* smask = smask_s[st];
         // warp-uniform liveness: every lane takes part in the ballots below
         if (__any_sync(0xffffffffu, SAGE_LIVE())) {
 #pragma unroll 1
@@ -90,8 +144,8 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
                 while (m) {
                     const int j = k * 32 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float4 a = s0[j];                                   // gx gy qa thr
-                    const float2 bq = *reinterpret_cast<const float2*>(&s1[j]);   // qb qc
+                    const float4 a = s_rec[3 * j];                            // gx gy qa thr
+                    const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1]);   // qb qc
                     const float dy = pyc - a.y;
                     const float2 t2 = __fmul2_rn(bq, f2(dy));                 // bdy, cdy
                     const float cdy2 = t2.y * dy;
@@ -103,7 +157,7 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
                     bool v0 = pw.x >= a.w && pw.x <= 0.0f;
                     bool v1 = pw.y >= a.w && pw.y <= 0.0f;
                     if (!(v0 || v1)) continue;
-                    const float2 oz = *reinterpret_cast<const float2*>(&s1[j].z);   // opacity, z
+                    const float2 oz = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1].z);   // opacity, z
                     const float2 e = sage_exp2_x2(pw);
                     float2 al = __fmul2_rn(f2(oz.x), e);
                     al.x = fminf(SAGE_ALPHA_MAX, al.x);
@@ -122,7 +176,7 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
                     wgt.y = keep1 ? wgt.y : 0.0f;
                     T.x = keep0 ? Tn.x : T.x;
                     T.y = keep1 ? Tn.y : T.y;
-                    const float4 c = s2[j];
+                    const float4 c = s_rec[3 * j + 2];
                     Cr = __ffma2_rn(f2(c.x), wgt, Cr);
                     Cg = __ffma2_rn(f2(c.y), wgt, Cg);
                     Cb = __ffma2_rn(f2(c.z), wgt, Cb);
@@ -133,6 +187,9 @@ k_composite(SageCamDev cam, const float4* __restrict__ rec0, const float4* __res
         }
         if (__syncthreads_and(!SAGE_LIVE())) break;
     }
+    // a gather issued for a batch nobody will read must still land before the CTA retires
+    if (pending[0]) mbar_wait(&sbar[0], parity[0]);
+    if (pending[1]) mbar_wait(&sbar[1], parity[1]);
 #undef SAGE_LIVE
 
     // epilogue: quantise and store to every destination frame.  Wide path (frame width a multiple of
@@ -209,5 +266,5 @@ void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uin
         if (k < out.n && (((uintptr_t)out.rgb[k] & 7u) || ((uintptr_t)out.depth[k] & 7u))) aligned = false;
     }
     out.wide = aligned ? 1 : 0;
-    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec0, fr.rec1, fr.rec2, sorted_vals, fr.ranges, fr.tile_order, out);
+    k_composite<<<n_tiles, C_THREADS, 0, st>>>(cam, fr.rec, sorted_vals, fr.ranges, fr.tile_order, out);
 }

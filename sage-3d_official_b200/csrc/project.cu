@@ -151,8 +151,8 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                         vis = true;
                         key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
                         count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-                        fr.rec0[i] = make_float4(gx, gy, qa, -l2 - 0.01f);
-                        fr.rec1[i] = make_float4(qb, qc, o, tz);
+                        fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
+                        fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
                         // inclusive pixel bounding box (u16 each)
                         fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
                                                 (uint32_t)iy0 | ((uint32_t)iy1 << 16));
@@ -235,7 +235,7 @@ k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __rest
         for (int k = 1; k < NB; ++k) a = fmaf(basis[k], shv[3 * k + c], a);
         acc[c] = fmaxf(a + 0.5f, 0.0f);
     }
-    fr.rec2[i] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+    fr.rec[3 * (size_t)i + 2] = make_float4(acc[0], acc[1], acc[2], 0.0f);
 }
 
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)

@@ -60,9 +60,7 @@ enum { SAGE_TICKET_DEPTH = 0, SAGE_TICKET_EMIT = 4, SAGE_TICKET_TILE = 5, SAGE_T
 
 struct SageFrame {
     // per-Gaussian (capacity n)
-    float4* rec0;        // gx, gy, qa, skip threshold (log2 units)
-    float4* rec1;        // qb, qc, opacity, z
-    float4* rec2;        // r, g, b, 0
+    float4* rec;         // 3 float4 per Gaussian (one 48-byte TMA block): gx gy qa thr | qb qc o z | r g b 0
     uint32_t* dkey[2];   // depth keys bits(z) - bits(near) (or CULLED), ping-pong
     uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16

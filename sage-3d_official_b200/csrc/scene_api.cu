@@ -75,9 +75,7 @@ static int alloc_instances(sage_scene* s, FrameCtx& c, int64_t cap)
 static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
 {
     const size_t n = (size_t)s->sc.n;
-    CK(dalloc(&c.fr.rec0, n));
-    CK(dalloc(&c.fr.rec1, n));
-    CK(dalloc(&c.fr.rec2, n));
+    CK(dalloc(&c.fr.rec, 3 * n));
     for (int k = 0; k < 2; ++k) {
         CK(dalloc(&c.fr.dkey[k], n));
         CK(dalloc(&c.fr.dval[k], n));
@@ -99,7 +97,7 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
 
 static void free_ctx(FrameCtx& c)
 {
-    cudaFree(c.fr.rec0); cudaFree(c.fr.rec1); cudaFree(c.fr.rec2);
+    cudaFree(c.fr.rec);
     for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
     cudaFree(c.fr.rect); cudaFree(c.fr.ntiles); cudaFree(c.fr.chain);
     free_instances(c);
@@ -522,12 +520,10 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     if (V) CK(cudaMemcpy(vlist.data(), c.fr.dval[ob], V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     std::vector<uint8_t> visv(n, 0);
     for (uint32_t g : vlist) visv[g] = 1;
-    std::vector<float4> r0(n), r1(n), r2(n);
+    std::vector<float4> rr(3 * n);
     std::vector<uint2> rc(n);
     if (n) {
-        CK(cudaMemcpy(r0.data(), c.fr.rec0, n * sizeof(float4), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(r1.data(), c.fr.rec1, n * sizeof(float4), cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(r2.data(), c.fr.rec2, n * sizeof(float4), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rr.data(), c.fr.rec, 3 * n * sizeof(float4), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(rc.data(), c.fr.rect, n * sizeof(uint2), cudaMemcpyDeviceToHost));
     }
     for (size_t i = 0; i < n; ++i) {
@@ -535,9 +531,10 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
         memset(&o, 0, sizeof o);
         visible_host[i] = visv[i];
         if (!visible_host[i]) continue;
-        o.gx = r0[i].x; o.gy = r0[i].y; o.qa = r0[i].z;
-        o.qb = r1[i].x; o.qc = r1[i].y; o.opacity = r1[i].z; o.z = r1[i].w;
-        o.r = r2[i].x; o.g = r2[i].y; o.b = r2[i].z;
+        const float4 r0 = rr[3 * i], r1 = rr[3 * i + 1], r2 = rr[3 * i + 2];
+        o.gx = r0.x; o.gy = r0.y; o.qa = r0.z;
+        o.qb = r1.x; o.qc = r1.y; o.opacity = r1.z; o.z = r1.w;
+        o.r = r2.x; o.g = r2.y; o.b = r2.z;
         o.tile_x0 = (rc[i].x & 0xFFFF) / SAGE_TILE; o.tile_x1 = (rc[i].x >> 16) / SAGE_TILE;
         o.tile_y0 = (rc[i].y & 0xFFFF) / SAGE_TILE; o.tile_y1 = (rc[i].y >> 16) / SAGE_TILE;
     }
