@@ -49,8 +49,8 @@ WORKLOAD = "synthetic 12x10x3 m multi-room interior (seed 1), N=2,000,000, SH de
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=2_000_000)
     ap.add_argument("--width", type=int, default=1920)
