@@ -179,6 +179,47 @@ int sage_collide_capsule(sage_bodies* b, const float* pos_host, int P, float rad
                          float z1, uint8_t* hit_host, int32_t* first_body_host,
                          sage_stream_t stream);
 
+/* ---- frame hand-off: JPEG on the GPU --------------------------------
+ * The reference turns every frame into a JPEG on the host with Pillow's defaults —
+ *   Image.fromarray(img_array).save(traj_dir / filename)
+ *       (data_pipeline/training_data_construction/generate_images.py:431-432)
+ *   pil_image.save(buffer, format='JPEG')   (vlm_client_modular.py:351,402,453)
+ * — after a 6.2 MB device->host copy of the 1080p frame.  sage_jpeg_* encode on the device;
+ * the byte stream is IDENTICAL to Pillow/libjpeg-turbo's Image.save(format='JPEG',
+ * quality=quality) of the same pixels (baseline, 4:2:0, Annex-K Huffman tables), so only the
+ * encoded bytes need to cross PCIe.
+ * max_batch: frames one call can encode (and the number of independent scratch slots);
+ * max_bytes_per_frame <= 0 picks W*H*3/2 + 4096. */
+typedef struct sage_jpeg sage_jpeg;
+int sage_jpeg_create(sage_jpeg** out, int device, int width, int height, int quality,
+                     int max_batch, int64_t max_bytes_per_frame);
+int sage_jpeg_destroy(sage_jpeg* j);
+int sage_jpeg_max_bytes(sage_jpeg* j, int64_t* out);
+/* rgb_dev u8 [batch][H][W][3] -> out_dev[f * out_stride ...], sizes_dev[f] = bytes written, or
+ * -(bytes needed) when out_stride is too small, or -1 when the scan exceeds the encoder's
+ * max_bytes_per_frame.  Asynchronous on `stream`; all pointers are device pointers. */
+int sage_jpeg_encode(sage_jpeg* j, const uint8_t* rgb_dev, int batch, uint8_t* out_dev,
+                     int64_t out_stride, int64_t* sizes_dev, sage_stream_t stream);
+/* Same, encoded bytes and sizes delivered to HOST memory; synchronises `stream`. */
+int sage_jpeg_encode_host(sage_jpeg* j, const uint8_t* rgb_dev, int batch, uint8_t* out_host,
+                          int64_t out_stride, int64_t* sizes_host, sage_stream_t stream);
+/* Debug/parity: quantised coefficients (int16 [blocks][64], zig-zag, scan order), MCU bit
+ * offsets and total scan bits of frame slot `frame` of the last encode. */
+int sage_jpeg_debug(sage_jpeg* j, int frame, int16_t* coef_host, uint32_t* mcu_bitoff_host,
+                    uint32_t* total_bits_host);
+
+/* Fused hand-off behind env.get_rgb() -> VLM client / generate_images' save loop: render on
+ * slot's frame context (as sage_render_host_async), encode on the same stream, and move only
+ * what the caller asks for across PCIe.  rgb_host / depth_host may be NULL (then the raw
+ * frame / depth never leave the device).  The encoder must match the camera's resolution and
+ * have max_batch >= 2 (slot = scratch slot).  sage_render_jpeg_wait blocks until slot's frame
+ * is done, copies exactly the encoded bytes into jpeg_host (capacity cap) and returns their
+ * count in *size_out. */
+int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
+                           uint8_t* rgb_host, float* depth_host);
+int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host,
+                          int64_t cap, int64_t* size_out);
+
 #ifdef __cplusplus
 }
 #endif

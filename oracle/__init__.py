@@ -24,8 +24,8 @@ _lib = None
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with gcc (seconds).  Rebuilds when the source is newer."""
-    src = _HERE / "sage_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    newest = max(p.stat().st_mtime for p in _HERE.glob("*.c"))
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < newest:
         subprocess.run(["make", "-C", str(_HERE), "-B", "libsage_oracle.so"], check=True,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return _LIB_PATH
@@ -151,3 +151,26 @@ def collide_capsule(mu, log_scale, quat, pos, radius=0.1, z0=0.6, z1=1.1):
                              C.c_float(radius), C.c_float(z0), C.c_float(z1), _p(hit, C.c_uint8),
                              _p(first, C.c_int32))
     return hit.astype(bool), first
+
+
+def jpeg_encode(rgb, quality: int = 75, want_coefs: bool = False):
+    """Restatement of Pillow's ``Image.fromarray(rgb).save(buf, format='JPEG', quality=quality)``
+    (jpeg_oracle.c).  rgb u8 [H,W,3] -> bytes (and, optionally, the quantised coefficients
+    int16 [blocks,64] in zig-zag / scan order)."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    H, W, ch = rgb.shape
+    assert ch == 3
+    cap = W * H * 4 + 8192
+    out = np.zeros(cap, np.uint8)
+    n = C.c_int64(0)
+    nblk = ((W + 15) // 16) * ((H + 15) // 16) * 6
+    coefs = np.zeros((nblk, 64), np.int16) if want_coefs else None
+    L = lib()
+    L.so_jpeg_encode_coefs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                       C.POINTER(C.c_int64), C.c_void_p]
+    rc = L.so_jpeg_encode_coefs(rgb.ctypes.data, W, H, int(quality), out.ctypes.data, cap, C.byref(n),
+                                coefs.ctypes.data if want_coefs else None)
+    if rc != 0:
+        raise RuntimeError(f"so_jpeg_encode failed rc={rc}")
+    data = out[:n.value].tobytes()
+    return (data, coefs) if want_coefs else data

@@ -20,6 +20,8 @@ EXPORTS = [
     "sage_grid_create", "sage_grid_destroy", "sage_collide_grid", "sage_collide_grid_f64",
     "sage_collide_grid_dev",
     "sage_bodies_create", "sage_bodies_destroy", "sage_collide_capsule",
+    "sage_jpeg_create", "sage_jpeg_destroy", "sage_jpeg_max_bytes", "sage_jpeg_encode", "sage_jpeg_encode_host",
+    "sage_jpeg_debug", "sage_render_jpeg_async", "sage_render_jpeg_wait",
 ]
 
 
@@ -96,6 +98,14 @@ def lib():
     L.sage_bodies_create.argtypes = [C.POINTER(vp), i32, i64, vp, vp, vp]
     L.sage_bodies_destroy.argtypes = [vp]
     L.sage_collide_capsule.argtypes = [vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    L.sage_jpeg_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i64]
+    L.sage_jpeg_destroy.argtypes = [vp]
+    L.sage_jpeg_max_bytes.argtypes = [vp, C.POINTER(i64)]
+    L.sage_jpeg_encode.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    L.sage_jpeg_encode_host.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    L.sage_jpeg_debug.argtypes = [vp, i32, vp, vp, vp]
+    L.sage_render_jpeg_async.argtypes = [vp, C.POINTER(CCamera), vp, i32, vp, vp]
+    L.sage_render_jpeg_wait.argtypes = [vp, vp, i32, vp, i64, C.POINTER(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name != "sage_last_error":

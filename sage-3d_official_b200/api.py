@@ -201,6 +201,46 @@ class GaussianScene:
     def host_wait(self, slot: int):
         check(_lib.lib().sage_host_wait(self._h, int(slot)))
 
+    # -- frame hand-off: render -> JPEG on the device --
+    def render_jpeg_async(self, cam: Camera, encoder: "JpegEncoder", slot: int, want_rgb: bool = False,
+                          want_depth: bool = False):
+        """Submit render + JPEG encode on pipeline slot 0/1.  Only what is asked for crosses PCIe:
+        the encoded bytes (always, fetched by :meth:`jpeg_wait`), the raw RGB frame and/or depth
+        (optional; returned as pinned host arrays valid after :meth:`jpeg_wait`)."""
+        torch = _torch()
+        rgb_t = dep_t = None
+        if want_rgb or want_depth:
+            key = (cam.height, cam.width, "async", int(slot))
+            if key not in self._pinned:
+                self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+                                     torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
+            rgb_t, dep_t = self._pinned[key]
+        cc = _ccam(cam)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_render_jpeg_async(self._h, C.byref(cc), encoder._h, int(slot),
+                                                    _ptr(rgb_t) if want_rgb else C.c_void_p(0),
+                                                    _ptr(dep_t) if want_depth else C.c_void_p(0)))
+        return (rgb_t.numpy() if want_rgb else None), (dep_t.numpy() if want_depth else None)
+
+    def jpeg_wait(self, encoder: "JpegEncoder", slot: int) -> bytes:
+        """Block until slot's frame is rendered and encoded; returns the JPEG file bytes."""
+        buf = encoder._host_buf(slot)
+        n = C.c_int64(0)
+        check(_lib.lib().sage_render_jpeg_wait(self._h, encoder._h, int(slot), _ptr(buf), int(buf.numel()), C.byref(n)))
+        return buf.numpy()[:n.value].tobytes()
+
+    def render_batch_jpeg(self, cams, encoder: "JpegEncoder"):
+        """Every pose of a trajectory -> JPEG bytes, two frames in flight (what
+        generate_images.py:408-456 does one waypoint at a time with 3 RTX frames, a 3 MB
+        read-back and a host-side Pillow encode each).  Yields ``(index, jpeg_bytes)`` in order."""
+        cams = list(cams)
+        for i, cam in enumerate(cams):
+            if i >= 2:
+                yield i - 2, self.jpeg_wait(encoder, i % 2)
+            self.render_jpeg_async(cam, encoder, i % 2)
+        for i in range(max(0, len(cams) - 2), len(cams)):
+            yield i, self.jpeg_wait(encoder, i % 2)
+
     def stats(self) -> dict:
         st = CFrameStats()
         check(_lib.lib().sage_frame_stats_get(self._h, C.byref(st)))
@@ -340,6 +380,90 @@ class CollisionBodies:
         return hit.astype(bool), first
 
 
+class JpegEncoder:
+    """Baseline JPEG encoder on the GPU (handle of ``sage_jpeg``).  Output bytes are identical to
+    Pillow's ``Image.fromarray(rgb).save(buf, format='JPEG', quality=quality)`` — the call the
+    reference makes on the host for every frame (generate_images.py:431-432,
+    vlm_client_modular.py:351,402,453)."""
+
+    def __init__(self, width: int, height: int, quality: int = 75, max_batch: int = 2, device: int = 0,
+                 max_bytes_per_frame: int = 0):
+        _lib.require_gpu()
+        self.width, self.height, self.quality = int(width), int(height), int(quality)
+        self.max_batch, self.device = int(max_batch), int(device)
+        self._h = C.c_void_p()
+        check(_lib.lib().sage_jpeg_create(C.byref(self._h), self.device, self.width, self.height, self.quality,
+                                          self.max_batch, int(max_bytes_per_frame)))
+        mb = C.c_int64(0)
+        check(_lib.lib().sage_jpeg_max_bytes(self._h, C.byref(mb)))
+        self.max_bytes = int(mb.value)
+        self._bufs = {}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().sage_jpeg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _host_buf(self, slot):
+        torch = _torch()
+        if slot not in self._bufs:
+            self._bufs[slot] = torch.zeros(self.max_bytes, dtype=torch.uint8).pin_memory()
+        return self._bufs[slot]
+
+    def encode(self, rgb, stream=None):
+        """rgb: CUDA uint8 tensor [H,W,3] or [B,H,W,3] -> list of ``bytes`` (one JPEG file each)."""
+        torch = _torch()
+        if rgb.dim() == 3:
+            rgb = rgb.unsqueeze(0)
+        if tuple(rgb.shape[1:]) != (self.height, self.width, 3) or rgb.dtype != torch.uint8 or not rgb.is_cuda:
+            raise ValueError(f"expected a CUDA uint8 tensor [B,{self.height},{self.width},3]")
+        rgb = rgb.contiguous()
+        B = int(rgb.shape[0])
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        key = ("batch", B)
+        if key not in self._bufs:
+            self._bufs[key] = (torch.zeros((B, self.max_bytes), dtype=torch.uint8).pin_memory(),
+                               torch.zeros(B, dtype=torch.int64).pin_memory())
+        out, sizes = self._bufs[key]
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_jpeg_encode_host(self._h, _ptr(rgb), B, _ptr(out), self.max_bytes, _ptr(sizes),
+                                                   _stream_ptr(stream)))
+        o = out.numpy()
+        return [o[f, :int(sizes[f])].tobytes() for f in range(B)]
+
+    def encode_device(self, rgb, out=None, sizes=None, stream=None):
+        """Asynchronous, device to device: returns (out u8 [B,max_bytes], sizes i64 [B]) CUDA tensors."""
+        torch = _torch()
+        if rgb.dim() == 3:
+            rgb = rgb.unsqueeze(0)
+        rgb = rgb.contiguous()
+        B = int(rgb.shape[0])
+        if out is None:
+            out = torch.empty((B, self.max_bytes), dtype=torch.uint8, device=rgb.device)
+        if sizes is None:
+            sizes = torch.empty(B, dtype=torch.int64, device=rgb.device)
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_jpeg_encode(self._h, _ptr(rgb), B, _ptr(out), int(out.shape[1]), _ptr(sizes),
+                                              _stream_ptr(stream)))
+        return out, sizes
+
+    def debug(self, frame: int = 0):
+        """Stage-level parity: (coefficients int16 [blocks,64], MCU bit offsets u32, total bits)."""
+        nmcu = ((self.width + 15) // 16) * ((self.height + 15) // 16)
+        coef = np.zeros((nmcu * 6, 64), np.int16)
+        off = np.zeros(nmcu, np.uint32)
+        tot = np.zeros(1, np.uint32)
+        check(_lib.lib().sage_jpeg_debug(self._h, int(frame), _ptr(coef), _ptr(off), _ptr(tot)))
+        return coef, off, int(tot[0])
+
+
 # ---- functional surface (north_star) ---------------------------------------------------------
 
 _scene_cache: dict = {}
@@ -376,4 +500,4 @@ def collide(agent_pose, collision, **kw):
     raise TypeError("collision must be an ObstacleGrid or CollisionBodies")
 
 
-__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "render", "collide", "SageError", "Camera"]
+__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "JpegEncoder", "render", "collide", "SageError", "Camera"]

@@ -5,7 +5,12 @@
 // so a multiply-add is fused ONLY where fmaf()/__ffma2_rn() is written.  That is what lets the
 // parity tests demand bit-exact agreement with the CPU oracle.
 #pragma once
+#ifdef SAGE_CUDA_EMU            /* development-only lock-step emulator (tools/cuda_emu/), never shipped */
+#include "../../tools/cuda_emu/cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#define SAGE_KLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#endif
 #include <stdint.h>
 
 #include "../../include/sage_splat.h"
@@ -141,3 +146,16 @@ void sage_launch_collide_capsule(int64_t m, const float4* c0, const float4* c1, 
 void sage_launch_bodies_pack(int64_t m, const float* mu, const float* log_scale, const float* quat,
                              float4* c0, float4* c1, float2* c2, cudaStream_t st);
 int sage_capsule_max_poses(void);
+
+// ---- JPEG encoder internals shared with scene_api.cu (jpeg.cu) -------------------------------
+struct sage_jpeg;
+int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int batch, int slot0, uint8_t* out_dev, int64_t out_stride,
+                      long long* sizes_dev, cudaStream_t st);
+uint8_t* sage_jpeg_stage_out(sage_jpeg* j);
+long long* sage_jpeg_stage_sizes_dev(sage_jpeg* j);
+long long* sage_jpeg_stage_sizes_host(sage_jpeg* j);
+int64_t sage_jpeg_stage_stride(const sage_jpeg* j);
+int sage_jpeg_width(const sage_jpeg* j);
+int sage_jpeg_height(const sage_jpeg* j);
+int sage_jpeg_device(const sage_jpeg* j);
+int sage_jpeg_max_batch(const sage_jpeg* j);

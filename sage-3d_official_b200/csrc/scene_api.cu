@@ -419,6 +419,52 @@ int sage_host_wait(sage_scene* s, int slot)
     return 0;
 }
 
+int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
+                           uint8_t* rgb_host, float* depth_host)
+{
+    REQUIRE(s != nullptr && cam != nullptr && j != nullptr, "sage_render_jpeg_async: NULL argument");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_async: slot must be 0 or 1");
+    REQUIRE(sage_jpeg_device(j) == s->device, "sage_render_jpeg_async: encoder lives on another device");
+    REQUIRE(sage_jpeg_width(j) == cam->width && sage_jpeg_height(j) == cam->height,
+            "sage_render_jpeg_async: encoder resolution differs from the camera's");
+    REQUIRE(sage_jpeg_max_batch(j) >= SAGE_N_CTX, "sage_render_jpeg_async: encoder needs max_batch >= 2");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[slot];
+    cudaStream_t st = c.stream;
+    const size_t px = (size_t)cam->width * (size_t)cam->height;
+    if (ensure_out(c, px, st)) return 1;
+    uint8_t* rgbs[1] = {c.out_rgb};
+    float* deps[1] = {c.out_depth};
+    const int rows = (cam->height + SAGE_TILE - 1) / SAGE_TILE;
+    if (render_impl(s, slot, cam, 0, rows, 1, rgbs, depth_host ? deps : nullptr, st)) return 1;
+    const int64_t stride = sage_jpeg_stage_stride(j);
+    if (sage_jpeg_enqueue(j, c.out_rgb, 1, slot, sage_jpeg_stage_out(j) + (size_t)slot * stride, stride,
+                          sage_jpeg_stage_sizes_dev(j) + slot, st)) return 1;
+    CK(cudaMemcpyAsync(sage_jpeg_stage_sizes_host(j) + slot, sage_jpeg_stage_sizes_dev(j) + slot, sizeof(long long),
+                       cudaMemcpyDeviceToHost, st));
+    if (rgb_host) CK(cudaMemcpyAsync(rgb_host, c.out_rgb, px * 3, cudaMemcpyDeviceToHost, st));
+    if (depth_host) CK(cudaMemcpyAsync(depth_host, c.out_depth, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.done, st));
+    return 0;
+}
+
+int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host, int64_t cap, int64_t* size_out)
+{
+    REQUIRE(s != nullptr && j != nullptr && jpeg_host != nullptr && size_out != nullptr, "sage_render_jpeg_wait: NULL argument");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_wait: slot must be 0 or 1");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[slot];
+    CK(cudaStreamSynchronize(c.stream));
+    const long long sz = sage_jpeg_stage_sizes_host(j)[slot];
+    *size_out = sz;
+    REQUIRE(sz > 0, "sage_render_jpeg_wait: the encoded frame exceeds the encoder's max_bytes_per_frame");
+    REQUIRE(sz <= cap, "sage_render_jpeg_wait: jpeg_host is too small (*size_out holds the size needed)");
+    CK(cudaMemcpyAsync(jpeg_host, sage_jpeg_stage_out(j) + (size_t)slot * sage_jpeg_stage_stride(j), (size_t)sz,
+                       cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
 int sage_scene_set_depth_clip(sage_scene* s, float lo, float hi)
 {
     REQUIRE(s != nullptr, "sage_scene_set_depth_clip: NULL scene");
