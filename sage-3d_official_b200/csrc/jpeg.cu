@@ -234,7 +234,8 @@ struct __align__(16) J1Warp {
 __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __restrict__ jd,
                                                             const uint8_t* __restrict__ rgb_all,
                                                             int16_t* __restrict__ coef_all,
-                                                            uint16_t* __restrict__ acbits_all)
+                                                            uint16_t* __restrict__ acbits_all,
+                                                            int16_t* __restrict__ dcs_all)
 {
     __shared__ J1Warp s_warp[J1_WARPS];
     __shared__ uint16_t s_qdiv[2][64];
@@ -360,6 +361,8 @@ __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __res
         const uint4* sv = reinterpret_cast<const uint4*>(s.zz);
         dst[lane] = sv[lane];
         if (lane < 16) dst[32 + lane] = sv[32 + lane];
+        // the six DC values again, densely packed: J2 reads nothing else of the coefficients
+        if (lane < 6) dcs_all[(size_t)f * jd->nblk + (size_t)m * 6 + lane] = s.zz[lane * 64];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -383,18 +386,11 @@ __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __res
 }
 
 // ---- J2: bit offsets ---------------------------------------------------------------------------
-__device__ __forceinline__ int dc_code_len(const int16_t* __restrict__ coef, int b, const uint32_t (*dc_tab)[12])
-{
-    const int m = b / 6, k = b - m * 6;
-    const int pb = dc_pred_block(m, k);
-    const int pred = pb >= 0 ? (int)coef[(size_t)pb * 64] : 0;
-    const int d = (int)coef[(size_t)b * 64] - pred;
-    const int nb = size_category(d < 0 ? -d : d);
-    return (int)(dc_tab[k >> 2][nb] >> 16) + nb;
-}
-
+// One CTA per frame.  Phase A (thread per MCU, coalesced): bits of the MCU = its six AC lengths +
+// the six DC-difference code lengths (predictors: the previous block of the same component,
+// jchuff.c last_dc_val).  Phase B: exclusive scan, every thread owning a contiguous run.
 __global__ void __launch_bounds__(1024) k_jpeg_scan(const JpegDev* __restrict__ jd,
-                                                    const int16_t* __restrict__ coef_all,
+                                                    const int16_t* __restrict__ dcs_all,
                                                     const uint16_t* __restrict__ acbits_all,
                                                     uint32_t* __restrict__ mcu_bitoff_all,
                                                     uint32_t* __restrict__ raw_all, JpegFrameInfo* __restrict__ info_all)
@@ -406,16 +402,26 @@ __global__ void __launch_bounds__(1024) k_jpeg_scan(const JpegDev* __restrict__ 
     __syncthreads();
     const int f = blockIdx.x;
     const int nmcu = jd->nmcu;
-    const int16_t* coef = coef_all + (size_t)f * jd->nblk * 64;
+    const int16_t* dcs = dcs_all + (size_t)f * jd->nblk;
     const uint16_t* acbits = acbits_all + (size_t)f * jd->nblk;
     uint32_t* mcu_bitoff = mcu_bitoff_all + (size_t)f * nmcu;
-    // every thread owns a contiguous run of MCUs
+    for (int m = tid; m < nmcu; m += 1024) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int pb = dc_pred_block(m, k);
+            const int pred = pb >= 0 ? (int)dcs[pb] : 0;
+            const int d = (int)dcs[m * 6 + k] - pred;
+            const int nb = size_category(d < 0 ? -d : d);
+            bits += (uint32_t)acbits[m * 6 + k] + (s_dc[k >> 2][nb] >> 16) + (uint32_t)nb;
+        }
+        mcu_bitoff[m] = bits;
+    }
+    __syncthreads();
     const int per = (nmcu + 1023) / 1024;
     const int m0 = min(tid * per, nmcu), m1 = min(m0 + per, nmcu);
     uint32_t sum = 0;
-    for (int m = m0; m < m1; ++m)
-        for (int k = 0; k < 6; ++k) sum += (uint32_t)acbits[m * 6 + k] + (uint32_t)dc_code_len(coef, m * 6 + k, s_dc);
-    // exclusive scan over the 1024 threads
+    for (int m = m0; m < m1; ++m) sum += mcu_bitoff[m];
     uint32_t incl = (uint32_t)warp_incl_scan((int)sum, lane);
     if (lane == 31) s_wsum[wid] = incl;
     __syncthreads();
@@ -443,8 +449,9 @@ __global__ void __launch_bounds__(1024) k_jpeg_scan(const JpegDev* __restrict__ 
     __syncthreads();
     uint32_t run = s_wsum[wid] + incl - sum;
     for (int m = m0; m < m1; ++m) {
+        const uint32_t b = mcu_bitoff[m];
         mcu_bitoff[m] = run;
-        for (int k = 0; k < 6; ++k) run += (uint32_t)acbits[m * 6 + k] + (uint32_t)dc_code_len(coef, m * 6 + k, s_dc);
+        run += b;
     }
 }
 
@@ -713,6 +720,7 @@ struct sage_jpeg {
     JpegDev* dev = nullptr;
     int16_t* coef = nullptr;
     uint16_t* acbits = nullptr;
+    int16_t* dcs = nullptr;
     uint32_t* mcu_bitoff = nullptr;
     uint32_t* raw = nullptr;
     uint32_t* ffcnt = nullptr;
@@ -736,13 +744,14 @@ int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int batch, int slot0
     const size_t z = (size_t)slot0;
     int16_t* coef = j->coef + z * h.nblk * 64;
     uint16_t* acbits = j->acbits + z * h.nblk;
+    int16_t* dcs = j->dcs + z * h.nblk;
     uint32_t* bitoff = j->mcu_bitoff + z * h.nmcu;
     uint32_t* raw = j->raw + z * h.raw_words;
     uint32_t* ffcnt = j->ffcnt + z * h.n_chunks;
     JpegFrameInfo* info = j->info + z;
     CK(cudaMemsetAsync(raw, 0, (size_t)batch * h.raw_words * 4, st));
-    SAGE_KLAUNCH(k_jpeg_dct, dim3((h.nmcu + J1_WARPS - 1) / J1_WARPS, batch), J1_WARPS * 32, st, j->dev, rgb_dev, coef, acbits);
-    SAGE_KLAUNCH(k_jpeg_scan, batch, 1024, st, j->dev, coef, acbits, bitoff, raw, info);
+    SAGE_KLAUNCH(k_jpeg_dct, dim3((h.nmcu + J1_WARPS - 1) / J1_WARPS, batch), J1_WARPS * 32, st, j->dev, rgb_dev, coef, acbits, dcs);
+    SAGE_KLAUNCH(k_jpeg_scan, batch, 1024, st, j->dev, dcs, acbits, bitoff, raw, info);
     SAGE_KLAUNCH(k_jpeg_huff, dim3((h.nmcu + J3_WARPS - 1) / J3_WARPS, batch), J3_WARPS * 32, st, j->dev, coef, bitoff, info, raw);
     SAGE_KLAUNCH(k_jpeg_ffcount, dim3(h.n_chunks, batch), 256, st, j->dev, info, raw, ffcnt);
     SAGE_KLAUNCH(k_jpeg_ffscan, batch, 256, st, j->dev, info, ffcnt, out_dev, (long long)out_stride, sizes_dev);
@@ -768,7 +777,7 @@ int sage_jpeg_destroy(sage_jpeg* j)
     if (!j) return 0;
     cudaSetDevice(j->device);
     cudaDeviceSynchronize();
-    cudaFree(j->dev); cudaFree(j->coef); cudaFree(j->acbits); cudaFree(j->mcu_bitoff); cudaFree(j->raw);
+    cudaFree(j->dev); cudaFree(j->coef); cudaFree(j->acbits); cudaFree(j->dcs); cudaFree(j->mcu_bitoff); cudaFree(j->raw);
     cudaFree(j->ffcnt); cudaFree(j->info); cudaFree(j->out_dev); cudaFree(j->sizes_dev);
     if (j->sizes_pinned) cudaFreeHost(j->sizes_pinned);
     cudaGetLastError();
@@ -858,6 +867,7 @@ int sage_jpeg_create(sage_jpeg** out, int device, int width, int height, int qua
     CKB(cudaMemcpy(j->dev, &h, sizeof h, cudaMemcpyHostToDevice));
     CKB(dalloc(&j->coef, B * h.nblk * 64));
     CKB(dalloc(&j->acbits, B * h.nblk));
+    CKB(dalloc(&j->dcs, B * h.nblk));
     CKB(dalloc(&j->mcu_bitoff, B * h.nmcu));
     CKB(dalloc(&j->raw, B * h.raw_words + 4));
     CKB(dalloc(&j->ffcnt, B * h.n_chunks));
