@@ -26,7 +26,7 @@ import numpy as np
 
 from ..camera import Camera as _RasterCamera, FOCAL_LENGTH_MM, USD_GAUSS_MODEL_TO_WORLD
 
-_state = {"stage": None}
+_state = {"stage": None, "jpeg_handoff": False}
 
 
 class _Attr:
@@ -185,7 +185,20 @@ class Camera:
                                                 self.resolution[1], model_to_world=st.model_to_world,
                                                 focal_mm=self.focal_length, near=self.clipping_range[0],
                                                 far=self.clipping_range[1])
-            rgb, depth = st.scene.render_host(cam, want_depth=True)
+            self._jpeg = None
+            if _state["jpeg_handoff"]:
+                # frame hand-off: the JPEG generate_images.py:431-432 is about to make, made on the device
+                from ..api import JpegEncoder
+                enc = getattr(st, "_encoder", None)
+                if enc is None or (enc.width, enc.height) != self.resolution:
+                    enc = st._encoder = JpegEncoder(self.resolution[0], self.resolution[1], max_batch=2)
+                rgb, depth = st.scene.render_jpeg_async(cam, enc, 0, want_rgb=True, want_depth=True)
+                self._jpeg = st.scene.jpeg_wait(enc, 0)
+                if st.scene.stats()["overflow"]:
+                    self._jpeg = None
+                    rgb, depth = st.scene.render_host(cam, want_depth=True)
+            else:
+                rgb, depth = st.scene.render_host(cam, want_depth=True)
             self._frame = (rgb.copy(), depth.copy())
             self._frame_key = key
         return self._frame
@@ -195,7 +208,11 @@ class Camera:
         if f is None:
             return None
         rgb = f[0]
-        return np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        rgba = np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        if getattr(self, "_jpeg", None) is not None:
+            from ..handoff import DeviceFrame
+            return DeviceFrame(rgba, self._jpeg, rgb, lambda: True)     # rgb is this frame's private copy
+        return rgba
 
     def get_current_frame(self):
         f = self._render()
@@ -240,8 +257,17 @@ class Vec3f(tuple):
         return super().__new__(cls, a[0] if len(a) == 1 else a)
 
 
-def install():
-    """Register the stand-in modules under the names the reference imports."""
+def install(jpeg_handoff=None):
+    """Register the stand-in modules under the names the reference imports.
+
+    jpeg_handoff (default: the SAGE_JPEG_HANDOFF environment variable): frames come back as
+    handoff.DeviceFrame and ``Image.fromarray(frame[:, :, :3].copy()).save('x.jpg')``
+    (generate_images.py:431-432) writes the JPEG the device already encoded."""
+    from ..handoff import handoff_requested, install_pillow_hook
+    _state["jpeg_handoff"] = handoff_requested() if jpeg_handoff is None else bool(jpeg_handoff)
+    if _state["jpeg_handoff"]:
+        install_pillow_hook()
+
     def mod(name, **attrs):
         m = types.ModuleType(name)
         m.__dict__.update(attrs)

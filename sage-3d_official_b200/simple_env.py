@@ -56,7 +56,8 @@ class SimpleVLNEnv:
 
     def __init__(self, scene_usd_path: str, headless: bool = True, hz: int = 30,
                  agent_prim_path: str = "/World/AgentCamera", resolution: Tuple[int, int] = (640, 480),
-                 map_json_path: str = None, device: int = 0, gaussians=None, collision_bodies=None) -> None:
+                 map_json_path: str = None, device: int = 0, gaussians=None, collision_bodies=None,
+                 jpeg_handoff: Optional[bool] = None) -> None:
         self.scene_usd_path = str(Path(scene_usd_path).resolve())
         self.hz = hz
         self.agent_prim_path = agent_prim_path
@@ -80,6 +81,14 @@ class SimpleVLNEnv:
         self._model_to_world = None
         self._frame_key = None
         self._frame = None
+        # frame hand-off (handoff.py): also encode every frame to JPEG on the device so an unmodified
+        # caller's Image.fromarray(rgb).save(..., 'JPEG') costs a memcpy instead of a 13 ms encode
+        from .handoff import handoff_requested, install_pillow_hook
+        self._jpeg_handoff = handoff_requested() if jpeg_handoff is None else bool(jpeg_handoff)
+        if self._jpeg_handoff:
+            install_pillow_hook()
+        self._jpeg = None
+        self._encoder = None
         self.render_calls = 0          # engine frames actually rendered (1 per distinct pose)
         self.collide_launches = 0      # batched collide launches
         self._pos = np.array([0.0, 0.0, self.AGENT_CENTRE_Z], dtype=np.float32)
@@ -243,17 +252,39 @@ class SimpleVLNEnv:
         key = (self._cam_position.tobytes(), self._cam_orientation.tobytes(), tuple(self.resolution))
         if self._frame_key != key:
             # views of the engine's pinned buffers; every getter hands out its own copy
-            self._frame = self._scene.render_host(self._camera(), want_depth=True)
+            if self._jpeg_handoff:
+                self._frame, self._jpeg = self._render_with_jpeg(self._camera())
+            else:
+                self._frame = self._scene.render_host(self._camera(), want_depth=True)
             self._frame_key = key
             self.render_calls += 1
         return self._frame
+
+    def _render_with_jpeg(self, cam: Camera):
+        from .api import JpegEncoder
+        if self._encoder is None or (self._encoder.width, self._encoder.height) != (cam.width, cam.height):
+            self._encoder = JpegEncoder(cam.width, cam.height, quality=75, max_batch=2, device=self._device)
+        for _ in range(2):
+            frame = self._scene.render_jpeg_async(cam, self._encoder, 0, want_rgb=True, want_depth=True)
+            jpeg = self._scene.jpeg_wait(self._encoder, 0)
+            st = self._scene.stats()
+            if not st["overflow"]:
+                break
+            self._scene.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)    # as render_host does
+        return frame, jpeg
 
     def get_rgb(self) -> Optional[np.ndarray]:
         W, H = int(self.resolution[0]), int(self.resolution[1])
         if self._scene is None:
             return np.zeros((H, W, 3), dtype=np.uint8)
         try:
-            return np.array(self._render_current()[0], dtype=np.uint8, copy=True)
+            frame = self._render_current()
+            rgb = np.array(frame[0], dtype=np.uint8, copy=True)
+            if self._jpeg_handoff and self._jpeg is not None:
+                from .handoff import DeviceFrame
+                # frame[0] is the engine's pinned copy: pristine until the next render replaces it
+                return DeviceFrame(rgb, self._jpeg, frame[0], lambda f=frame: self._frame is f)
+            return rgb
         except Exception as e:
             _debug_print(f"[WARN] get_rgb failed: {e}")
             return None

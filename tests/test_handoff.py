@@ -1,0 +1,118 @@
+"""CPU: the Pillow hook of handoff.py — pre-encoded bytes are used iff the pixels being saved are
+bit-identical to the encoded frame and the caller asked for a default JPEG; everything else falls
+through to Pillow.  (The "device" bytes here are made by Pillow itself; byte-equality of the real
+device encoder with Pillow is tests/test_jpeg_gpu.py.)"""
+import io
+
+import numpy as np
+import pytest
+from PIL import Image
+
+
+def _pillow(a, **kw):
+    b = io.BytesIO()
+    Image.fromarray(np.asarray(a)).save(b, format="JPEG", **kw)
+    return b.getvalue()
+
+
+@pytest.fixture()
+def hook(sage):
+    from sage3d_official_b200 import handoff
+    handoff.install_pillow_hook()
+    h0 = handoff.hook_stats()
+    yield handoff, h0
+    handoff.uninstall_pillow_hook()
+
+
+def _frame(handoff, H=48, W=64, seed=0, valid=lambda: True):
+    rng = np.random.default_rng(seed)
+    pristine = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    marker = b"\xff\xd8SAGE-PRECODED" + bytes([seed]) + b"\xff\xd9"     # recognisable stand-in for device bytes
+    return handoff.DeviceFrame(pristine.copy(), marker, pristine, valid), pristine, marker
+
+
+def test_untouched_frame_uses_precoded_bytes(hook):
+    handoff, h0 = hook
+    fr, pristine, marker = _frame(handoff)
+    im = Image.fromarray(fr)
+    assert np.array_equal(np.asarray(im), pristine)        # a real image, pixels intact
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == marker
+    b = io.BytesIO(); im.convert("RGB").save(b, format="jpeg")        # vlm_client_modular.py:448-453
+    assert b.getvalue() == marker
+    assert handoff.hook_stats()["hits"] == h0["hits"] + 2
+
+
+def test_path_save_by_extension(hook, tmp_path):
+    handoff, _ = hook
+    fr, pristine, marker = _frame(handoff, seed=1)
+    rgba = handoff.DeviceFrame(np.concatenate([pristine, np.full((48, 64, 1), 255, np.uint8)], 2), marker, pristine, lambda: True)
+    Image.fromarray(rgba[:, :, :3].copy()).save(tmp_path / "a_001.jpg")       # generate_images.py:431-432
+    assert (tmp_path / "a_001.jpg").read_bytes() == marker
+    Image.fromarray(fr).save(tmp_path / "a.png")                               # other formats: Pillow
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "a.png")), pristine)
+
+
+def test_any_difference_falls_back_to_pillow(hook):
+    handoff, _ = hook
+    fr, pristine, marker = _frame(handoff, seed=2)
+    # options
+    b = io.BytesIO(); Image.fromarray(fr).save(b, format="JPEG", quality=90)
+    assert b.getvalue() == _pillow(pristine, quality=90)
+    # the array was modified after get_rgb()
+    fr2 = fr.copy(); fr2[3, 4, 1] ^= 1
+    b = io.BytesIO(); Image.fromarray(fr2).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(fr2)
+    # a different channel slice of an RGBA frame has the right shape but the wrong pixels
+    rgba = handoff.DeviceFrame(np.concatenate([pristine, np.full((48, 64, 1), 255, np.uint8)], 2), marker, pristine, lambda: True)
+    gba = rgba[:, :, 1:4].copy()
+    b = io.BytesIO(); Image.fromarray(gba).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(gba)
+    # the image was drawn on after fromarray (copy-on-write of the read-only core image)
+    im = Image.fromarray(fr)
+    im.putpixel((0, 0), (1, 2, 3))
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() != marker and b.getvalue() == _pillow(np.asarray(im))
+    from PIL import ImageDraw
+    im = Image.fromarray(fr)
+    ImageDraw.Draw(im).line((0, 0, 10, 10), fill=(255, 0, 0))
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == _pillow(np.asarray(im))
+    # resized / converted images are new objects
+    b = io.BytesIO(); Image.fromarray(fr).resize((32, 24)).save(b, format="JPEG")
+    assert b.getvalue()[:2] == b"\xff\xd8" and b.getvalue() != marker
+    b = io.BytesIO(); Image.fromarray(fr).convert("L").save(b, format="JPEG")
+    assert b.getvalue() != marker
+    # the engine has rendered another frame since (pinned copy no longer this frame)
+    stale, _, _ = _frame(handoff, seed=3, valid=lambda: False)
+    b = io.BytesIO(); Image.fromarray(stale).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(stale)
+    # plain arrays are untouched by the hook
+    b = io.BytesIO(); Image.fromarray(pristine).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(pristine)
+
+
+def test_history_of_converted_images_shares_pixels(hook):
+    handoff, _ = hook
+    fr, pristine, marker = _frame(handoff, seed=4)
+    im = Image.fromarray(fr)
+    hist = [im.convert("RGB") for _ in range(8)]
+    hist[3].putpixel((5, 5), (9, 9, 9))                 # mutating one copy must not leak into the others
+    for k, h in enumerate(hist):
+        b = io.BytesIO(); h.save(b, format="JPEG")
+        if k == 3:
+            assert b.getvalue() == _pillow(np.asarray(h)) and np.asarray(h)[5, 5, 0] == 9
+        else:
+            assert b.getvalue() == marker and np.array_equal(np.asarray(h), pristine)
+
+
+def test_device_frame_is_an_ordinary_array(hook):
+    handoff, _ = hook
+    fr, pristine, _ = _frame(handoff, seed=5)
+    assert isinstance(fr, np.ndarray) and fr.flags.writeable and fr.dtype == np.uint8
+    assert (fr.astype(np.float32).mean() - pristine.mean()) < 1e-3
+    import pickle
+    back = pickle.loads(pickle.dumps(fr))
+    assert type(back) is np.ndarray and np.array_equal(back, pristine)
+    fr[0, 0, 0] ^= 255                                   # caller-owned: writable, and then no longer "the frame"
+    assert handoff.precoded_jpeg(fr) is None

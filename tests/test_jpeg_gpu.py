@@ -146,3 +146,42 @@ def test_decoded_psnr_property_1080p(sage):
     mse = np.mean((dec - rgb.astype(np.float64)) ** 2)
     assert dec.shape == (1080, 1920, 3) and 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 25.0
     assert data == _pillow(rgb)
+
+
+def test_env_facade_handoff_serves_the_devices_bytes(sage, tmp_path):
+    """SimpleVLNEnv(jpeg_handoff=True): the caller's own Image.fromarray(rgb).save(..., 'JPEG')
+    (run_benchmark.py:1421, vlm_client_modular.py:445-455) returns the device's bytes — which equal
+    what Pillow makes of the same pixels — and a modified frame falls back to Pillow."""
+    from PIL import Image
+    from sage3d_official_b200 import handoff
+    from sage3d_official_b200.simple_env import SimpleVLNEnv
+    cloud, _ = sage.synthetic_room(0, 30_000)
+    try:
+        env = SimpleVLNEnv(str(tmp_path / "in_memory.npz"), resolution=(640, 480), gaussians=cloud, jpeg_handoff=True)
+        env.set_start_pose([1.5, 1.0, 0.85], [0.0, 0.0, 0.2, 0.98])
+        h0 = handoff.hook_stats()["hits"]
+        for step in range(3):
+            rgb = env.get_rgb()
+            assert isinstance(rgb, np.ndarray) and rgb.shape == (480, 640, 3) and rgb.flags.writeable
+            plain = np.array(rgb, copy=True).view(np.ndarray)
+            b = io.BytesIO(); Image.fromarray(rgb).convert("RGB").save(b, format="JPEG")
+            assert b.getvalue() == _pillow(plain), step
+            env.apply_cmd_for(0.0, 0.0, 0.4, 1.0)           # turn: a new frame next time
+        assert handoff.hook_stats()["hits"] == h0 + 3
+        rgb = env.get_rgb()
+        rgb[10:20, 10:20] = 0                               # caller draws on its array
+        b = io.BytesIO(); Image.fromarray(rgb).save(b, format="JPEG")
+        assert b.getvalue() == _pillow(np.asarray(rgb)) and handoff.hook_stats()["hits"] == h0 + 3
+        old = env.get_rgb()
+        env.apply_cmd_for(0.0, 0.0, 0.4, 1.0)
+        env.get_rgb()                                       # the pinned copy now holds another frame
+        b = io.BytesIO(); Image.fromarray(old).save(b, format="JPEG")
+        assert b.getvalue() == _pillow(np.asarray(old)) and handoff.hook_stats()["hits"] == h0 + 3
+        # depth and the frame itself are the same with and without the hand-off
+        env2 = SimpleVLNEnv(str(tmp_path / "in_memory.npz"), resolution=(640, 480), gaussians=cloud, jpeg_handoff=False)
+        env2.set_start_pose([1.5, 1.0, 0.85], [0.0, 0.0, 0.2, 0.98])
+        env.set_start_pose([1.5, 1.0, 0.85], [0.0, 0.0, 0.2, 0.98])
+        assert np.array_equal(env.get_rgb(), env2.get_rgb()) and np.array_equal(env.get_depth(), env2.get_depth())
+        assert type(env2.get_rgb()) is np.ndarray
+    finally:
+        handoff.uninstall_pillow_hook()

@@ -29,6 +29,11 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--capsule", action="store_true", help="also run the ellipsoid-vs-capsule test per step")
+    ap.add_argument("--vlm-client", action="store_true",
+                    help="also do, per step, the host work of the reference's RGB socket client "
+                         "(run_benchmark.py:1421 + vlm_client_modular.py:445-455): Image.fromarray(rgb), 8-frame "
+                         "history, convert('RGB') + JPEG + base64 of every history frame")
+    ap.add_argument("--jpeg-handoff", action="store_true", help="device-side JPEG + Pillow hook (handoff.py)")
     args = ap.parse_args()
     import sage3d_official_b200 as sage
     from sage3d_official_b200.simple_env import SimpleVLNEnv
@@ -40,7 +45,8 @@ def main():
     tmp = Path(tempfile.mkdtemp())
     map_path = write_semantic_map(layout, tmp / "map.json")
     env = SimpleVLNEnv(str(tmp / "scene_in_memory.npz"), resolution=(args.width, args.height),
-                       map_json_path=str(map_path), gaussians=cloud)
+                       map_json_path=str(map_path), gaussians=cloud, jpeg_handoff=args.jpeg_handoff)
+    history, t_client, payload = [], 0.0, 0
     env.set_log_function(lambda m: None)
     bodies = None
     if args.capsule:
@@ -73,6 +79,27 @@ def main():
             timed += 1
             for k_, v_ in env._scene.stage_times(0).items():
                 stage_acc[k_] += v_
+        if args.vlm_client:
+            import base64
+            import io
+            from PIL import Image
+            e0 = time.perf_counter()
+            history.append(Image.fromarray(rgb))
+            history = history[-8:]
+            seq = list(history)
+            while len(seq) < 8:
+                seq.insert(0, seq[0])
+            enc_imgs = []
+            for img in seq:
+                img = img.convert("RGB")
+                buf = io.BytesIO()
+                img.save(buf, format="JPEG")
+                enc_imgs.append(base64.b64encode(buf.getvalue()).decode())
+            data = json.dumps({"images": enc_imgs, "query": "go"}).encode("utf-8")
+            payload = len(data)
+            e1 = time.perf_counter()
+            t_client += e1 - e0
+            b = e1                 # the collide split below starts after the client work
         r = rng.uniform()
         if r < 0.6:
             cmd = (0.25, 0.0, 0.0, 1.0)
@@ -98,7 +125,10 @@ def main():
         "render_ms": 1000 * t_render / args.steps,
         "collide_ms": 1000 * t_collide / args.steps,
         "capsule_ms": 1000 * t_capsule / args.steps if bodies is not None else None,
-        "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule) / args.steps,
+        "vlm_client_ms": 1000 * t_client / args.steps if args.vlm_client else None,
+        "vlm_payload_bytes": payload if args.vlm_client else None,
+        "jpeg_handoff": bool(args.jpeg_handoff),
+        "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule - t_client) / args.steps,
         "render_ms_p50_p90_max": [float(np.percentile(frame_ms, 50)), float(np.percentile(frame_ms, 90)), float(np.max(frame_ms))],
         "instances_p50_p90_max": [int(np.percentile(inst, 50)), int(np.percentile(inst, 90)), int(np.max(inst))],
         "stage_ms_mean": {k_: v_ / max(timed, 1) for k_, v_ in stage_acc.items()},
