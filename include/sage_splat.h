@@ -220,6 +220,35 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
 int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host,
                           int64_t cap, int64_t* size_out);
 
+/* ---- map building and path planning ---------------------------------------
+ * The callers either side of the collide path work on the same occupancy grid
+ * (data_pipeline/trajectory_generation/vln_trajectory_generator.py).
+ * sage_grid_inflate: robot-radius inflation, `distance_transform_edt(raw == 0, sampling=scale)
+ *   <= radius` (collision_detector.py:119-127; vln_trajectory_generator.py:549-552).  Host in,
+ *   host out, u8 [H][W]; radius <= 0 copies (the reference inflates only for a positive radius).
+ * sage_grid_components: 4-connected components of the free cells — the partition
+ *   build_connectivity_map's union-find computes (vln_trajectory_generator.py:639-666).  labels
+ *   int32 [H][W]: smallest linear index y*W+x of the cell's component, -1 for obstacle cells. */
+int sage_grid_inflate(int device, const uint8_t* raw_host, int H, int W, double scale,
+                      double radius, uint8_t* out_host, sage_stream_t stream);
+int sage_grid_components(int device, const uint8_t* grid_host, int H, int W,
+                         int32_t* labels_host, sage_stream_t stream);
+/* Batched astar_pixel (vln_trajectory_generator.py:253-286): the PATH the reference returns
+ * (same neighbour order, tie-breaking and binary64 arithmetic), one search per GPU thread,
+ * `slots` searches side by side (each owns H*W*12 bytes of state + heap_capacity*16 bytes).
+ * max_path <= 0 picks 4(H+W); heap_capacity <= 0 picks 3HW+16.
+ * starts/goals int32 [Q][2] = (x, y).  path_len[q]: n >= 1 points written to
+ * path_xy[q][0..n) (int32 [Q][max_path][2], start -> goal); 0: no path (the reference returns
+ * None); -2: heap_capacity exceeded; -3: path longer than max_path (recreate with more room). */
+typedef struct sage_planner sage_planner;
+int sage_planner_create(sage_planner** out, int device, const uint8_t* grid_host, int H, int W,
+                        int slots, int max_path, int64_t heap_capacity);
+int sage_planner_destroy(sage_planner* p);
+int sage_planner_limits(sage_planner* p, int* max_path_out, int64_t* heap_capacity_out);
+int sage_plan_astar(sage_planner* p, const int32_t* starts_xy_host, const int32_t* goals_xy_host,
+                    int Q, int32_t* path_len_host, int32_t* path_xy_host,
+                    int64_t* expansions_host, sage_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

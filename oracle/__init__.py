@@ -174,3 +174,47 @@ def jpeg_encode(rgb, quality: int = 75, want_coefs: bool = False):
         raise RuntimeError(f"so_jpeg_encode failed rc={rc}")
     data = out[:n.value].tobytes()
     return (data, coefs) if want_coefs else data
+
+
+def grid_inflate(raw, scale: float, radius: float):
+    """Restatement of ``distance_transform_edt(raw == 0, sampling=scale) <= radius`` (plan_oracle.c)."""
+    raw = np.ascontiguousarray(raw, np.uint8)
+    H, W = raw.shape
+    out = np.zeros((H, W), np.uint8)
+    L = lib()
+    L.so_grid_inflate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    rc = L.so_grid_inflate(raw.ctypes.data, H, W, float(scale), float(radius), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"so_grid_inflate rc={rc}")
+    return out
+
+
+def grid_components(grid):
+    """4-connected components of the free cells: int32 labels (smallest linear index; -1 = obstacle)."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    H, W = grid.shape
+    lab = np.zeros((H, W), np.int32)
+    L = lib()
+    L.so_grid_components.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rc = L.so_grid_components(grid.ctypes.data, H, W, lab.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"so_grid_components rc={rc}")
+    return lab
+
+
+def astar(grid, start, goal, max_path: int = 0, want_expansions: bool = False):
+    """Restatement of ``astar_pixel(grid, start, goal)`` (vln_trajectory_generator.py:253-286):
+    list of (x, y) from start to goal, or None."""
+    grid = np.ascontiguousarray(grid, np.uint8)
+    H, W = grid.shape
+    mp = int(max_path) if max_path else H * W
+    path = np.zeros((mp, 2), np.int32)
+    nexp = C.c_int64(0)
+    L = lib()
+    L.so_astar.argtypes = [C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    n = L.so_astar(grid.ctypes.data, H, W, int(start[0]), int(start[1]), int(goal[0]), int(goal[1]),
+                   path.ctypes.data, mp, C.byref(nexp))
+    if n < 0:
+        raise RuntimeError(f"so_astar rc={n}")
+    res = None if n == 0 else [(int(x), int(y)) for x, y in path[:n]]
+    return (res, int(nexp.value)) if want_expansions else res

@@ -22,6 +22,8 @@ EXPORTS = [
     "sage_bodies_create", "sage_bodies_destroy", "sage_collide_capsule",
     "sage_jpeg_create", "sage_jpeg_destroy", "sage_jpeg_max_bytes", "sage_jpeg_encode", "sage_jpeg_encode_host",
     "sage_jpeg_debug", "sage_render_jpeg_async", "sage_render_jpeg_wait",
+    "sage_grid_inflate", "sage_grid_components", "sage_planner_create", "sage_planner_destroy",
+    "sage_planner_limits", "sage_plan_astar",
 ]
 
 
@@ -106,6 +108,12 @@ def lib():
     L.sage_jpeg_debug.argtypes = [vp, i32, vp, vp, vp]
     L.sage_render_jpeg_async.argtypes = [vp, C.POINTER(CCamera), vp, i32, vp, vp]
     L.sage_render_jpeg_wait.argtypes = [vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.sage_grid_inflate.argtypes = [i32, vp, i32, i32, dbl, dbl, vp, vp]
+    L.sage_grid_components.argtypes = [i32, vp, i32, i32, vp, vp]
+    L.sage_planner_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, i32, i32, i64]
+    L.sage_planner_destroy.argtypes = [vp]
+    L.sage_planner_limits.argtypes = [vp, C.POINTER(i32), C.POINTER(i64)]
+    L.sage_plan_astar.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name != "sage_last_error":

@@ -4,6 +4,7 @@
 // frames alternate contexts, so a caller that alternates two streams gets frame N+1's projection /
 // sorts running while frame N is still compositing — the issue-bound blend kernel and the
 // latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -23,6 +24,8 @@ struct FrameCtx {
     uint32_t* counters_host = nullptr;   // pinned copy of the counters
     cudaEvent_t done = nullptr;      // end of the last frame that used this context
     cudaStream_t stream = nullptr;   // internal stream of the asynchronous host path
+    cudaStream_t front = nullptr;    // highest-priority internal stream: every stage before the composite
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint8_t* out_rgb = nullptr;      // internal device frame (host paths)
     float* out_depth = nullptr;
     size_t out_px = 0;
@@ -92,6 +95,17 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
     memset(c.counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
     CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    {
+        // The stages before the composite are a chain of small latency-bound kernels; the composite
+        // is one long issue-bound kernel.  Run the chain on a highest-priority stream: its CTAs are
+        // then dispatched ahead of the queued composite CTAs of the previous frame (other context),
+        // so frame i+1's projection/sorts run INSIDE frame i's composite instead of behind it.
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&c.front, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+    }
     return alloc_instances(s, c, cap);
 }
 
@@ -105,6 +119,9 @@ static void free_ctx(FrameCtx& c)
     if (c.counters_host) cudaFreeHost(c.counters_host);
     if (c.done) cudaEventDestroy(c.done);
     if (c.stream) cudaStreamDestroy(c.stream);
+    if (c.front) cudaStreamDestroy(c.front);
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
     cudaFree(c.out_rgb); cudaFree(c.out_depth);
     c = FrameCtx{};
 }
@@ -221,19 +238,28 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     REQUIRE(tbits <= 24, "sage_render: too many tiles");
     const int tpasses = (tbits + 7) / 8;
     int launches = 0;
-    if (c.used) CK(cudaStreamWaitEvent(st, c.done, 0));     // previous frame on this context has drained
-    CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, st));
+    // fork: everything up to the tile ranges runs on the context's high-priority stream `fs`, ordered
+    // after the caller's stream so far; the composite joins back onto the caller's stream
+    static const bool fork_on = getenv("SAGE_NO_FORK") == nullptr;
+    cudaStream_t fs = fork_on ? c.front : st;
+    if (fork_on) {
+        CK(cudaEventRecord(c.ev_fork, st));
+        CK(cudaStreamWaitEvent(fs, c.ev_fork, 0));
+    }
+    if (c.used) CK(cudaStreamWaitEvent(fs, c.done, 0));     // previous frame on this context has drained
+    CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, fs));
     next_epoch(c);
     cudaEvent_t* ev = s->n_slots > 0
         ? &s->events[(size_t)(s->timed_frames % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     if (ev) s->timed_frames++;
     s->frame_index++;
-#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], st)); } while (0)
+#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], fs)); } while (0)
+#define JOIN() do { if (fork_on) { CK(cudaEventRecord(c.ev_join, fs)); CK(cudaStreamWaitEvent(st, c.ev_join, 0)); } } while (0)
     if (n_tiles > 0 && s->sc.n > 0) {
         int ob = 0;
-        if (front_half(s, c, cd, &launches, ev, st, &ob)) return 1;     // stages 0..2
+        if (front_half(s, c, cd, &launches, ev, fs, &ob)) return 1;     // stages 0..2
         const uint32_t* order = c.fr.dval[ob];
-        sage_launch_emit(cd, c.fr, order, s->sc.n, c.cap, tpasses, c.epoch + 3, st);
+        sage_launch_emit(cd, c.fr, order, s->sc.n, c.cap, tpasses, c.epoch + 3, fs);
         STAGE_MARK(4);
         SageSortPlan tp{};
         tp.keys[0] = c.fr.ikey[0]; tp.keys[1] = c.fr.ikey[1];
@@ -243,19 +269,25 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
         tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true; tp.items_per_thread = 16;   // measured: 16 beats 8 and 32
         tp.hist = c.fr.tile_hist; tp.total_out = nullptr;
         tp.lookback = c.fr.lookback; tp.tickets = c.fr.tickets + SAGE_TICKET_TILE; tp.epoch0 = c.epoch + 4;
-        const int ires = sage_radix_sort(tp, &launches, st);
+        const int ires = sage_radix_sort(tp, &launches, fs);
         REQUIRE(ires >= 0, "tile sort: unsupported key width");
-        sage_launch_ranges(c.fr, c.fr.ikey[ires], c.cap, n_tiles, st);
+        sage_launch_ranges(c.fr, c.fr.ikey[ires], c.cap, n_tiles, fs);
         STAGE_MARK(5);
+        JOIN();
         sage_launch_composite(cd, c.fr, c.fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
         launches += 3;
-        STAGE_MARK(6);
+        if (ev) CK(cudaEventRecord(ev[6], st));
     } else if (n_tiles > 0) {
-        for (int k = 0; k <= SAGE_N_STAGES; ++k) STAGE_MARK(k);
-        sage_launch_ranges(c.fr, c.fr.ikey[0], c.cap, n_tiles, st);        // D = 0: all ranges empty
+        for (int k = 0; k < SAGE_N_STAGES; ++k) STAGE_MARK(k);
+        sage_launch_ranges(c.fr, c.fr.ikey[0], c.cap, n_tiles, fs);        // D = 0: all ranges empty
+        JOIN();
         sage_launch_composite(cd, c.fr, c.fr.ival[0], n_peers, rgb_peers, depth_peers, st);
+        if (ev) CK(cudaEventRecord(ev[6], st));
         launches += 1;
+    } else {
+        JOIN();
     }
+#undef JOIN
 #undef STAGE_MARK
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c.counters_host, c.fr.counters, sizeof(uint32_t) * CNT_COUNT, cudaMemcpyDeviceToHost, st));

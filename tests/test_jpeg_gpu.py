@@ -185,3 +185,42 @@ def test_env_facade_handoff_serves_the_devices_bytes(sage, tmp_path):
         assert type(env2.get_rgb()) is np.ndarray
     finally:
         handoff.uninstall_pillow_hook()
+
+
+def test_isaac_shim_handoff_generate_images_save_line(sage, tmp_path):
+    """generate_images.py:426-432 verbatim against the stand-ins with the hand-off on: the .jpg on
+    disk is the device's stream and equals Pillow's encode of the same frame."""
+    from PIL import Image
+    from sage3d_official_b200 import handoff
+    from sage3d_official_b200.scene_io import save_ply
+    import sage3d_official_b200.isaac_shim as shim
+    cloud, _ = sage.synthetic_room(4, 20_000)
+    save_ply(tmp_path / "0009.ply", cloud)
+    (tmp_path / "0009.usda").write_text('#usda 1.0\ndef Xform "World" { def "gauss" ( prepend references = @./0009.usdz@</World/gauss> ) {} }\n')
+    try:
+        shim.install(jpeg_handoff=True)
+        from omni.isaac.core import World
+        from omni.isaac.core.utils.stage import open_stage
+        from omni.isaac.sensor import Camera
+        assert open_stage(usd_path=str(tmp_path / "0009.usda"))
+        world = World()
+        cam = Camera(prim_path="/World/NaVILACamera", frequency=30, resolution=(1024, 768))   # generate_images.py:43
+        cam.initialize()
+        h0 = handoff.hook_stats()["hits"]
+        for idx, (x, qz) in enumerate([(1.5, 0.1), (2.0, 0.5), (2.5, -0.3)]):
+            position = np.array([x, 1.0, 0.3], dtype=np.float32)
+            position[2] = 1.2
+            cam.set_world_pose(position=position, orientation=np.array([0.0, 0.0, qz, 0.9], dtype=np.float32))
+            for _ in range(3):
+                world.step(render=True)
+            img = cam.get_rgba()
+            img_array = img[:, :, :3].copy()
+            Image.fromarray(img_array).save(tmp_path / f"s_t_{idx:03d}.jpg")
+            got = (tmp_path / f"s_t_{idx:03d}.jpg").read_bytes()
+            assert got == _pillow(np.asarray(img_array)), idx
+        assert handoff.hook_stats()["hits"] == h0 + 3
+    finally:
+        shim.install(jpeg_handoff=False)
+        handoff.uninstall_pillow_hook()
+        import omni.usd
+        omni.usd.get_context().close_stage()

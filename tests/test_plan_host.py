@@ -1,0 +1,65 @@
+"""CPU: host-side logic of planner.py (the reference's build_2d_map / nearest-free-cell search)
+against goldens recorded from the unmodified reference, and the live reference where present."""
+import copy
+import glob
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLDEN = sorted(glob.glob(str(Path(__file__).parent / "golden" / "plan_*.npz")))
+REF = Path("/root/reference/Code/data_pipeline/trajectory_generation")
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[Path(p).stem for p in GOLDEN])
+def test_nearest_free_pixel_matches_reference_goldens(sage, path):
+    from sage3d_official_b200 import planner
+    z = np.load(path)
+    grid = z["grid"]
+    H, W = grid.shape
+    for k in range(len(z["nf_plain"])):
+        mask = [tuple(int(v) for v in yx) for yx in z["mask_yx"][z["mask_off"][k]:z["mask_off"][k + 1]]]
+        a = planner.get_nearest_free_pixel_on_side(mask, grid)
+        b = planner.get_nearest_free_pixel_on_side(mask, grid, towards_px=(W // 2, H // 2))
+        assert ((-1, -1) if a is None else tuple(int(v) for v in a)) == tuple(z["nf_plain"][k]), k
+        assert ((-1, -1) if b is None else tuple(int(v) for v in b)) == tuple(z["nf_side"][k]), k
+
+
+def test_build_2d_map_without_inflation_needs_no_gpu(sage):
+    from sage3d_official_b200 import planner
+    sem = [{"category_label": "Wall", "mask_coords_m": [["0.00", "0.00"], ["1.00", "2.00"], ["bad", "1.00"]]},
+           {"category_label": "chair", "mask_coords_m": [["0.50", "0.75"]]}]
+    grid, s, min_x, min_y = planner.build_2d_map(sem, 0.05, 0.0)
+    assert grid.shape == (21, 41) and grid.sum() == 2 and grid[0, 0] == 1 and grid[20, 40] == 1
+    assert sem[1]["mask_coords"] == [(10, 15)] and (s, min_x, min_y) == (0.05, 0.0, 0.0)
+    assert planner.build_2d_map([{"mask_coords_m": []}]) == (None, None, None, None)
+
+
+def test_planner_fails_loudly_without_gpu(sage):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from sage3d_official_b200 import planner
+    with pytest.raises(sage.SageError, match="no CPU fallback"):
+        planner.astar_pixel(np.zeros((4, 4), np.uint8), (0, 0), (3, 3))
+    with pytest.raises(sage.SageError, match="no CPU fallback"):
+        planner.inflate_grid(np.zeros((4, 4), np.uint8), 0.05, 0.2)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present")
+def test_build_2d_map_raw_matches_live_reference(sage):
+    import contextlib, io
+    sys.path.insert(0, str(REF))
+    sys.path.insert(0, str(Path(__file__).parent / "golden"))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import vln_trajectory_generator as ref
+        import make_plan_golden as mk
+    from sage3d_official_b200 import planner
+    sem = mk.sem_map(9, 3.0, 2.5, 5)
+    a, b = copy.deepcopy(sem), copy.deepcopy(sem)
+    with contextlib.redirect_stdout(io.StringIO()):
+        want = ref.build_2d_map(a, robot_radius_m=0.0)
+    got = planner.build_2d_map(b, robot_radius_m=0.0)
+    assert np.array_equal(got[0], want[0]) and got[1:] == want[1:]
+    assert [i["mask_coords"] for i in a] == [i["mask_coords"] for i in b]

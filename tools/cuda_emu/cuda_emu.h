@@ -151,6 +151,11 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicCAS(int* p, int cmp, int val)
+{
+    __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
 inline unsigned atomicMin(unsigned* p, unsigned v)
 {
     unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);

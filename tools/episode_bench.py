@@ -99,7 +99,6 @@ def main():
             payload = len(data)
             e1 = time.perf_counter()
             t_client += e1 - e0
-            b = e1                 # the collide split below starts after the client work
         r = rng.uniform()
         if r < 0.6:
             cmd = (0.25, 0.0, 0.0, 1.0)
@@ -115,7 +114,7 @@ def main():
             bodies.check(pos)
         d = time.perf_counter()
         moved += int(np.linalg.norm(env.get_agent_pos()[:2] - before[:2]) > 1e-6)
-        t_render += b - a; t_collide += c - b; t_capsule += d - c
+        t_render += b - a; t_collide += c - max(b, e1 if args.vlm_client else b); t_capsule += d - c
     total = time.perf_counter() - t0
     out = {
         "workload": f"{args.steps}-step episode, {args.width}x{args.height} RGB+depth, N={args.n}, grid collide march"

@@ -1,7 +1,13 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --no-header -rf --timeout 600 > gpurun_out/r01b_pytest.log 2>&1
-tail -40 gpurun_out/r01b_pytest.log
-timeout 600 python bench.py --steps 500 --warmup 50 > gpurun_out/r01b_bench.json 2> gpurun_out/r01b_bench.err; tail -3 gpurun_out/r01b_bench.err
-timeout 300 python tools/jpeg_prof.py > gpurun_out/r01b_jpeg_prof.log 2>&1; cat gpurun_out/r01b_jpeg_prof.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_jpeg --launch-skip 12 -c 6 -o gpurun_out/r01b_jpeg_full -f python tools/jpeg_prof.py > gpurun_out/r01b_ncu.log 2>&1; tail -3 gpurun_out/r01b_ncu.log
-head -c 6000 gpurun_out/r01b_bench.json
+python -m pytest tests -m gpu -q --no-header -rf --timeout 600 -x > gpurun_out/r01d_pytest.log 2>&1
+tail -5 gpurun_out/r01d_pytest.log
+SAGE_NO_FORK=1 timeout 600 python bench.py --steps 500 --warmup 50 --no-cpu-baseline > gpurun_out/r01d_bench_nofork.json 2> gpurun_out/r01d_bench_nofork.err; tail -2 gpurun_out/r01d_bench_nofork.err
+timeout 600 python bench.py --steps 500 --warmup 50 --no-cpu-baseline > gpurun_out/r01d_bench_fork.json 2> gpurun_out/r01d_bench_fork.err; tail -2 gpurun_out/r01d_bench_fork.err
+python - <<'PY'
+import json
+for n in ("nofork","fork"):
+    try:
+        j=json.load(open(f"gpurun_out/r01d_bench_{n}.json"))
+        print(n, "value", round(j["value"],1), "e2e", round(j["e2e"]["value"],1), "handoff", round(j["handoff_jpeg"]["value"],1), "enc_ms", round(j["handoff_jpeg"]["jpeg_encode_ms_device"],4), j["roofline"]["frame"]["stage_ms"])
+    except Exception as e: print(n, "ERR", e)
+PY
