@@ -236,7 +236,8 @@ int sage_grid_components(int device, const uint8_t* grid_host, int H, int W,
 /* Batched astar_pixel (vln_trajectory_generator.py:253-286): the PATH the reference returns
  * (same neighbour order, tie-breaking and binary64 arithmetic), one search per GPU thread,
  * `slots` searches side by side (each owns H*W*12 bytes of state + heap_capacity*16 bytes).
- * max_path <= 0 picks 4(H+W); heap_capacity <= 0 picks 3HW+16.
+ * max_path <= 0 picks 4(H+W); heap_capacity <= 0 picks HW/2+1024 (the open list of a grid search
+ * stays far below the cell count; -2 tells the caller to retry with more).
  * starts/goals int32 [Q][2] = (x, y).  path_len[q]: n >= 1 points written to
  * path_xy[q][0..n) (int32 [Q][max_path][2], start -> goal); 0: no path (the reference returns
  * None); -2: heap_capacity exceeded; -3: path longer than max_path (recreate with more room). */

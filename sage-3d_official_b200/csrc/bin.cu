@@ -22,16 +22,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
     return v;
 }
 
-// which 8x8 quadrants of tile (tx,ty) the inclusive pixel box [px0,px1]x[py0,py1] overlaps:
-// bit (qy*2 + qx), matching the warp -> quadrant map of the composite kernel
-__device__ __forceinline__ uint32_t quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
-{
-    const int bx = tx * SAGE_TILE, by = ty * SAGE_TILE;
-    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
-    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
-    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
-}
-
 __device__ __forceinline__ unsigned long long cs_load(const unsigned long long* p)
 {
     unsigned long long v;
@@ -43,10 +33,14 @@ __device__ __forceinline__ void cs_store(unsigned long long* p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Load-balanced expansion: a block takes 256 depth-sorted Gaussians, scans their tile counts and
-// lets its threads walk the concatenated instance list (binary search for the owner), so a splat
-// covering thousands of tiles costs the same per instance as one covering four, and consecutive
-// threads write consecutive instance slots (coalesced).
+// Load-balanced two-level expansion.  A block takes 256 depth-sorted Gaussians; its unit of work is
+// the ROW ITEM (Gaussian, tile row): one thread intersects the splat's {alpha >= 1/255} ellipse with
+// the two 8-row halves of that tile row (sage_band_row, binary64) and gets the exact tile range and
+// the column spans that later give every tile its 8x8-quadrant mask.  Items are processed 256 at a
+// time: scan their tile counts, then let the threads walk the concatenated instance list (binary
+// search for the owning item), so consecutive threads write consecutive instance slots (coalesced)
+// whatever the splat sizes.  The per-Gaussian totals equal k_project's counts (same function, same
+// inputs), which is what the chained scan across blocks is built on.
 template <int TBITS_LO, int NP>
 __global__ void __launch_bounds__(B_THREADS)
 k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ ikey,
@@ -55,12 +49,18 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
 {
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t nblk = (V + B_THREADS - 1) / B_THREADS;
-    __shared__ uint32_t s_off[B_THREADS + 1];
+    __shared__ SageBand s_band[B_THREADS];
+    __shared__ uint32_t s_roff[B_THREADS + 1];      // row items before Gaussian k of the block
     __shared__ uint32_t s_g[B_THREADS];
     __shared__ uint2 s_rc[B_THREADS];
-    __shared__ uint32_t wsum[B_THREADS / 32];
-    __shared__ uint32_t s_blk, s_base;
+    __shared__ uint32_t wsum[B_THREADS / 32], wsum2[B_THREADS / 32];
+    __shared__ uint32_t s_blk, s_base, s_total;
     __shared__ uint32_t s_hist[NP][256];
+    // one chunk of row items
+    __shared__ uint32_t s_ioff[B_THREADS + 1];      // instances before item j of the chunk
+    __shared__ uint32_t s_it_g[B_THREADS];          // Gaussian id << 4
+    __shared__ uint32_t s_it_pos[B_THREADS];        // ty << 16 | first tile column
+    __shared__ uint2 s_it_span[B_THREADS];          // column spans of the upper / lower half
     if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
     for (int i = threadIdx.x; i < NP * 256; i += B_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -68,25 +68,31 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
     if (b >= nblk) return;
     const uint32_t r = b * B_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t g = 0, c = 0;
+    uint32_t g = 0, c = 0, nrows = 0;
     uint2 rc = make_uint2(0, 0);
     if (r < V) {
         g = __ldg(&order[r]);
         c = __ldg(&fr.ntiles[g]);
         rc = __ldg(&fr.rect[g]);
+        if (sage_box_cullable(rc.x & 0xFFFF, rc.x >> 16, rc.y & 0xFFFF, rc.y >> 16)) {
+            const float4 r0 = __ldg(&fr.rec[3 * (size_t)g]);         // gx gy qa thr
+            const float4 r1 = __ldg(&fr.rec[3 * (size_t)g + 1]);     // qb qc o z
+            s_band[threadIdx.x] = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+        }
+        nrows = (rc.y >> 16) / SAGE_TILE - (rc.y & 0xFFFFu) / SAGE_TILE + 1;
     }
-    uint32_t incl = warp_incl_scan_u32(c);
-    if (lane == 31) wsum[w] = incl;
+    const uint32_t incl = warp_incl_scan_u32(c), incl2 = warp_incl_scan_u32(nrows);
+    if (lane == 31) { wsum[w] = incl; wsum2[w] = incl2; }
     s_g[threadIdx.x] = g;
     s_rc[threadIdx.x] = rc;
     __syncthreads();
-    uint32_t woff = 0;
+    uint32_t woff = 0, woff2 = 0;
 #pragma unroll
-    for (int k = 0; k < B_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0u;
-    s_off[threadIdx.x] = woff + incl - c;
-    if (threadIdx.x == B_THREADS - 1) s_off[B_THREADS] = woff + incl;
+    for (int k = 0; k < B_THREADS / 32; ++k) { woff += (k < w) ? wsum[k] : 0u; woff2 += (k < w) ? wsum2[k] : 0u; }
+    s_roff[threadIdx.x] = woff2 + incl2 - nrows;
+    if (threadIdx.x == B_THREADS - 1) { s_roff[B_THREADS] = woff2 + incl2; s_total = woff + incl; }
     __syncthreads();
-    const uint32_t total = s_off[B_THREADS];
+    const uint32_t total = s_total, n_items = s_roff[B_THREADS];
 
     // chained scan across blocks: chain[b] = epoch(30) | state(2) | value(32)
     if (threadIdx.x == 0) {
@@ -128,31 +134,60 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
         }
     }
     __syncthreads();
-    const uint32_t base = s_base;
     const int tiles_x = cam.tiles_x, row0 = cam.row0;
-    for (uint32_t k = threadIdx.x; k < total; k += B_THREADS) {
-        int lo = 0, hi = B_THREADS - 1;            // owner = last o with s_off[o] <= k
+    uint32_t run = s_base;                          // instance slot of the chunk's first instance
+    for (uint32_t it0 = 0; it0 < n_items; it0 += B_THREADS) {
+        const uint32_t item = it0 + threadIdx.x;
+        uint32_t cnt = 0;
+        if (item < n_items) {
+            int lo = 0, hi = B_THREADS - 1;         // owner = last o with s_roff[o] <= item
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int mid = (lo + hi + 1) >> 1;
-            if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
+            for (int it = 0; it < 8; ++it) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_roff[mid] <= item) lo = mid; else hi = mid - 1;
+            }
+            const uint2 bx = s_rc[lo];
+            const int px0 = bx.x & 0xFFFF, px1 = bx.x >> 16, py0 = bx.y & 0xFFFF, py1 = bx.y >> 16;
+            const int ty = py0 / SAGE_TILE + (int)(item - s_roff[lo]);
+            const SageRowItem ri = sage_band_row(s_band[lo], px0, px1, py0, py1, ty);
+            cnt = (uint32_t)max(ri.tx1 - ri.tx0 + 1, 0);
+            s_it_g[threadIdx.x] = s_g[lo] << 4;
+            s_it_pos[threadIdx.x] = ((uint32_t)ty << 16) | (uint32_t)max(ri.tx0, 0);
+            s_it_span[threadIdx.x] = make_uint2(ri.top, ri.bot);
         }
-        const uint2 bx = s_rc[lo];
-        const int px0 = bx.x & 0xFFFF, px1 = bx.x >> 16, py0 = bx.y & 0xFFFF, py1 = bx.y >> 16;
-        const int tx0 = px0 / SAGE_TILE, ty0 = py0 / SAGE_TILE;
-        const uint32_t bw = (uint32_t)(px1 / SAGE_TILE - tx0 + 1);
-        const uint32_t local = k - s_off[lo];
-        const int ty = ty0 + (int)(local / bw), tx = tx0 + (int)(local % bw);
-        const uint32_t tile = (uint32_t)((ty - row0) * tiles_x + tx);
-        const uint32_t slot = base + k;
-        if (slot < cap) {
-            ikey[slot] = tile;
-            ival[slot] = (s_g[lo] << 4) | quad_mask(px0, px1, py0, py1, tx, ty);
+        const uint32_t ci = warp_incl_scan_u32(cnt);
+        if (lane == 31) wsum[w] = ci;
+        __syncthreads();
+        uint32_t wo = 0;
 #pragma unroll
-            for (int p = 0; p < NP; ++p) atomicAdd(&s_hist[p][(tile >> (TBITS_LO * p)) & 255u], 1u);
+        for (int k = 0; k < B_THREADS / 32; ++k) wo += (k < w) ? wsum[k] : 0u;
+        s_ioff[threadIdx.x] = wo + ci - cnt;
+        if (threadIdx.x == B_THREADS - 1) s_ioff[B_THREADS] = wo + ci;
+        __syncthreads();
+        const uint32_t chunk_total = s_ioff[B_THREADS];
+        for (uint32_t k = threadIdx.x; k < chunk_total; k += B_THREADS) {
+            int lo = 0, hi = B_THREADS - 1;         // owning item = last j with s_ioff[j] <= k
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_ioff[mid] <= k) lo = mid; else hi = mid - 1;
+            }
+            const uint32_t pos = s_it_pos[lo];
+            const int ty = (int)(pos >> 16), tx = (int)(pos & 0xFFFFu) + (int)(k - s_ioff[lo]);
+            SageRowItem ri;
+            ri.top = s_it_span[lo].x; ri.bot = s_it_span[lo].y; ri.tx0 = 0; ri.tx1 = 0;
+            const uint32_t tile = (uint32_t)((ty - row0) * tiles_x + tx);
+            const uint32_t slot = run + k;
+            if (slot < cap) {
+                ikey[slot] = tile;
+                ival[slot] = s_it_g[lo] | sage_row_quad_mask(ri, tx);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) atomicAdd(&s_hist[p][(tile >> (TBITS_LO * p)) & 255u], 1u);   // (warp-aggregating these with match.any measured slower)
+            }
         }
+        run += chunk_total;
+        __syncthreads();                            // the chunk arrays are rewritten by the next round
     }
-    __syncthreads();
     for (int i = threadIdx.x; i < NP * 256; i += B_THREADS) {
         const uint32_t cc = (&s_hist[0][0])[i];
         if (cc) atomicAdd(&tile_hist[i], cc);

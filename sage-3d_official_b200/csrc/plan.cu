@@ -305,7 +305,7 @@ int sage_planner_create(sage_planner** out, int device, const uint8_t* grid_host
     p->device = device; p->H = H; p->W = W; p->slots = slots;
     const size_t n = (size_t)H * W;
     p->max_path = max_path > 0 ? max_path : 4 * (H + W);
-    p->heap_cap = heap_capacity > 0 ? heap_capacity : (long long)(3 * n + 16);
+    p->heap_cap = heap_capacity > 0 ? heap_capacity : (long long)(n / 2 + 1024);
     auto bail = [&](int rc) { sage_planner_destroy(p); return rc; };
 #define CKB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bail(sage_fail(#call, __FILE__, __LINE__, e__)); } while (0)
     CKB(dalloc(&p->grid, n));

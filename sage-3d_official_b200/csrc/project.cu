@@ -129,13 +129,13 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 // Conservative bounding rectangle of {alpha >= 1/255}: derived in binary64 from
                 // the *rounded* conic the blend kernel will use, with 0.2 % + 0.02 slack on the
                 // log2 threshold.  Not part of the spec: it only has to be conservative.
-                float l2 = __log2f(255.0f * o);
-                double t2 = (double)l2 * 1.002 + 0.02;
-                double A = -(double)qa, Bq = -0.5 * (double)qb, Cq = -(double)qc;
-                double det2 = A * Cq - Bq * Bq;
-                bool unbounded = !(det2 > 0.0) || !(A > 0.0) || !(Cq > 0.0);
-                double hx = unbounded ? 1e30 : sqrt(t2 * Cq / det2);
-                double hy = unbounded ? 1e30 : sqrt(t2 * A / det2);
+                const float l2 = __log2f(255.0f * o);
+                const double t2 = (double)l2 * 1.002 + 0.02;
+                const double A = -(double)qa, Bq = -0.5 * (double)qb, Cq = -(double)qc;
+                const double det2 = A * Cq - Bq * Bq;
+                const bool unbounded = !(det2 > 0.0) || !(A > 0.0) || !(Cq > 0.0);
+                const double hx = unbounded ? 1e30 : sqrt(t2 * Cq / det2);
+                const double hy = unbounded ? 1e30 : sqrt(t2 * A / det2);
                 double xlo = floor((double)gx - hx - 0.5), xhi = ceil((double)gx + hx - 0.5);
                 double ylo = floor((double)gy - hy - 0.5), yhi = ceil((double)gy + hy - 0.5);
                 const double Wm = (double)(cam.W - 1), Hm = (double)(cam.H - 1);
@@ -146,16 +146,28 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                     iy0 = max(iy0, cam.row0 * SAGE_TILE);
                     iy1 = min(iy1, min(cam.row1 * SAGE_TILE, cam.H) - 1);
                     if (iy0 <= iy1 && ix0 <= ix1) {
-                        const int tx0 = ix0 / SAGE_TILE, tx1 = ix1 / SAGE_TILE;
+                        // exact tile count: per tile row, the tiles whose pixel centres the ellipse reaches
+                        // (k_emit walks the same rows with the same function)
                         const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
-                        vis = true;
-                        key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                        count = (uint32_t)(tx1 - tx0 + 1) * (uint32_t)(ty1 - ty0 + 1);
-                        fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
-                        fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
-                        // inclusive pixel bounding box (u16 each)
-                        fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
-                                                (uint32_t)iy0 | ((uint32_t)iy1 << 16));
+                        uint32_t cnt = (uint32_t)(ix1 / SAGE_TILE - ix0 / SAGE_TILE + 1) * (uint32_t)(ty1 - ty0 + 1);
+                        if (sage_box_cullable(ix0, ix1, iy0, iy1)) {
+                            const SageBand band = sage_band_make(gx, gy, qa, qb, qc, o);
+                            cnt = 0;
+                            for (int tyy = ty0; tyy <= ty1; ++tyy) {
+                                const SageRowItem it = sage_band_row(band, ix0, ix1, iy0, iy1, tyy);
+                                cnt += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
+                            }
+                        }
+                        if (cnt > 0) {
+                            vis = true;
+                            key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
+                            count = cnt;
+                            fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
+                            fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
+                            // inclusive pixel bounding box (u16 each)
+                            fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
+                                                    (uint32_t)iy0 | ((uint32_t)iy1 << 16));
+                        }
                     }
                 }
             }

@@ -58,6 +58,130 @@ __device__ __forceinline__ float sage_exp2(float x)
 }
 __device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_LOG2E); }
 
+// ---- exact tile culling: the {alpha >= 1/255} ellipse against bands of pixel rows -------------
+// Binning is not part of the numerical spec: it only has to be conservative.
+// The support of a splat is the ellipse  A dx^2 + 2B dx dy + C dy^2 <= t2  around (gx, gy), in the
+// log2-scaled units of the conic the blend kernel uses (A = -qa, B = -qb/2, C = -qc).  k_project
+// counts, and k_emit enumerates, exactly the tiles whose rows contain a pixel centre inside it;
+// both call the functions below on the same binary32 inputs, so their counts agree by
+// construction.  Binary32 arithmetic (binary64 sqrt/div sequences cost more than the instances
+// they save) made conservative by slack: t2 = log2(255 o) * 1.003 + 0.02 (the bounding box uses
+// 1.002) and every span is widened by 0.1 % of the half extent + 0.01 px;
+// tools/cuda_emu/band_check.cpp brute-forces the guarantee on CPU.
+// sqrt to ~2 ulp (one MUFU + one multiply); the spans carry 0.1 % of slack.  Negative -> 0.
+__device__ __forceinline__ float sage_sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
+
+// true: the pixel box spans at least 2 x 2 tiles — only then can the ellipse test remove a tile
+__device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int iy1)
+{
+    return (ix0 / SAGE_TILE != ix1 / SAGE_TILE) && (iy0 / SAGE_TILE != iy1 / SAGE_TILE);
+}
+
+struct SageBand {
+    float gx, gy, A, B, C, t2, det2, invA;
+    float hx, hy;       // half extents of the ellipse
+    float dyr;          // dy of its right-most point (-dyr: left-most)
+    float slack;        // outward widening of every span, pixels
+    int unbounded;      // degenerate conic: treat as covering everything
+};
+
+__device__ __forceinline__ SageBand sage_band_make(float gx, float gy, float qa, float qb, float qc, float o)
+{
+    SageBand b;
+    const float l2 = __log2f(255.0f * o);
+    b.t2 = l2 * 1.003f + 0.02f;
+    b.gx = gx; b.gy = gy;
+    b.A = -qa; b.B = -0.5f * qb; b.C = -qc;
+    b.det2 = b.A * b.C - b.B * b.B;
+    b.unbounded = (!(b.det2 > 0.0f) || !(b.A > 0.0f) || !(b.C > 0.0f) || !(b.t2 > 0.0f)) ? 1 : 0;
+    b.hx = b.unbounded ? 1e30f : sqrtf(b.t2 * b.C / b.det2);
+    b.hy = b.unbounded ? 1e30f : sqrtf(b.t2 * b.A / b.det2);
+    b.dyr = b.unbounded ? 0.0f : -(b.B * b.hx) / b.C;
+    b.invA = b.unbounded ? 0.0f : 1.0f / b.A;
+    b.slack = b.unbounded ? 0.0f : 1e-3f * fmaxf(b.hx, b.hy) + 0.01f;
+    if (!(b.hx < 1e9f) || !(b.hy < 1e9f)) b.unbounded = 1;       // overflow / NaN: cover everything
+    return b;
+}
+
+// Inclusive pixel-column range [*xs, *xe] (clamped to [ix0, ix1]) that contains every pixel of rows
+// y0..y1 (inclusive, y0 <= y1) whose centre lies in the ellipse.  Returns false if there is none.
+__device__ __forceinline__ bool sage_band_span(const SageBand& b, int ix0, int ix1, int y0, int y1, int* xs, int* xe)
+{
+    if (b.unbounded) { *xs = ix0; *xe = ix1; return ix0 <= ix1; }
+    float d0 = ((float)y0 + 0.5f) - b.gy, d1 = ((float)y1 + 0.5f) - b.gy;       // dy of the first / last row centre
+    if (d0 > b.hy + b.slack || d1 < -(b.hy + b.slack)) return false;
+    d0 = fmaxf(d0, -b.hy); d1 = fminf(d1, b.hy);
+    // right edge u(dy) = (-B dy + sqrt(A t2 - det2 dy^2)) / A is concave with its maximum hx at dyr
+    float xr;
+    if (d0 <= b.dyr && b.dyr <= d1) xr = b.hx;
+    else {
+        const float dy = b.dyr < d0 ? d0 : d1;
+        xr = (-(b.B * dy) + sage_sqrt_fast(b.A * b.t2 - b.det2 * dy * dy)) * b.invA;
+    }
+    // left edge l(dy) = (-B dy - sqrt(...)) / A is convex with its minimum -hx at -dyr
+    float xl;
+    if (d0 <= -b.dyr && -b.dyr <= d1) xl = -b.hx;
+    else {
+        const float dy = -b.dyr < d0 ? d0 : d1;
+        xl = (-(b.B * dy) - sage_sqrt_fast(b.A * b.t2 - b.det2 * dy * dy)) * b.invA;
+    }
+    const float lo = floorf((b.gx + xl) - 0.5f - b.slack), hi = ceilf((b.gx + xr) - 0.5f + b.slack);
+    if (hi < (float)ix0 || lo > (float)ix1) return false;
+    *xs = (int)fmaxf(lo, (float)ix0);
+    *xe = (int)fminf(hi, (float)ix1);
+    return *xs <= *xe;
+}
+
+// One tile row ty of a splat with pixel box [ix0,ix1] x [iy0,iy1]: spans of its upper and lower
+// 8-row halves (packed x0 | x1 << 16; 0xFFFF0000-style empty = x0 > x1) and the inclusive tile range.
+struct SageRowItem {
+    uint32_t top, bot;      // pixel spans of rows [16ty, 16ty+7] and [16ty+8, 16ty+15]; SAGE_SPAN_EMPTY if none
+    int tx0, tx1;           // tiles [tx0, tx1]; tx0 > tx1: the row is empty
+};
+#define SAGE_SPAN_EMPTY 0x0000FFFFu     /* x0 = 0xFFFF > x1 = 0 */
+
+__device__ __forceinline__ SageRowItem sage_band_row(const SageBand& b, int ix0, int ix1, int iy0, int iy1, int ty)
+{
+    SageRowItem it;
+    it.top = it.bot = SAGE_SPAN_EMPTY;
+    if (!sage_box_cullable(ix0, ix1, iy0, iy1)) {
+        // one row or one column of tiles (most splats): no tile can be culled, quadrants from the box
+        // (the band is not even evaluated: callers may pass an unset one)
+        const uint32_t sp = (uint32_t)ix0 | ((uint32_t)ix1 << 16);
+        if (iy0 <= ty * SAGE_TILE + 7 && iy1 >= ty * SAGE_TILE) it.top = sp;
+        if (iy1 >= ty * SAGE_TILE + 8 && iy0 <= ty * SAGE_TILE + 15) it.bot = sp;
+        it.tx0 = ix0 / SAGE_TILE; it.tx1 = ix1 / SAGE_TILE;
+        return it;
+    }
+    int lo = 1 << 30, hi = -1;
+    int xs, xe;
+    const int ya = max(ty * SAGE_TILE, iy0), yb = min(ty * SAGE_TILE + 7, iy1);
+    if (ya <= yb && sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) {
+        it.top = (uint32_t)xs | ((uint32_t)xe << 16);
+        lo = min(lo, xs); hi = max(hi, xe);
+    }
+    const int yc = max(ty * SAGE_TILE + 8, iy0), yd = min(ty * SAGE_TILE + 15, iy1);
+    if (yc <= yd && sage_band_span(b, ix0, ix1, yc, yd, &xs, &xe)) {
+        it.bot = (uint32_t)xs | ((uint32_t)xe << 16);
+        lo = min(lo, xs); hi = max(hi, xe);
+    }
+    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
+    else { it.tx0 = lo / SAGE_TILE; it.tx1 = hi / SAGE_TILE; }
+    return it;
+}
+
+// 8x8-quadrant mask (bit qy*2+qx, the warp -> quadrant map of the composite kernel) of tile tx
+__device__ __forceinline__ uint32_t sage_row_quad_mask(const SageRowItem& it, int tx)
+{
+    const int bx = tx * SAGE_TILE;
+    const int t0 = (int)(it.top & 0xFFFFu), t1 = (int)(it.top >> 16);
+    const int b0 = (int)(it.bot & 0xFFFFu), b1 = (int)(it.bot >> 16);
+    uint32_t m = 0;
+    if (t0 <= t1) m |= ((t0 <= bx + 7 && t1 >= bx) ? 1u : 0u) | ((t0 <= bx + 15 && t1 >= bx + 8) ? 2u : 0u);
+    if (b0 <= b1) m |= ((b0 <= bx + 7 && b1 >= bx) ? 4u : 0u) | ((b0 <= bx + 15 && b1 >= bx + 8) ? 8u : 0u);
+    return m;
+}
+
 // ---- frame workspace ---------------------------------------------------------------------
 #define SAGE_RADIX_MAX_BINS 512
 #define SAGE_MAX_PASSES 4

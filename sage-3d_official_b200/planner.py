@@ -59,7 +59,7 @@ def connectivity_labels(grid, device: int = 0) -> np.ndarray:
 class GridPlanner:
     """Batched A* on one grid (handle of ``sage_planner``): ``slots`` searches run side by side."""
 
-    def __init__(self, grid, slots: int = 512, max_path: int = 0, heap_capacity: int = 0, device: int = 0):
+    def __init__(self, grid, slots: int = 4096, max_path: int = 0, heap_capacity: int = 0, device: int = 0):
         _lib.require_gpu()
         self.grid = _u8(grid)
         self.H, self.W = self.grid.shape
@@ -122,7 +122,7 @@ class GridPlanner:
                     redo.append(q)
             todo = np.asarray(redo, dtype=np.int64)
             if todo.size:
-                self._make(min(self.max_path * 4, self.H * self.W), min(self.heap_capacity * 3, 8 * self.H * self.W + 16))
+                self._make(min(self.max_path * 4, self.H * self.W), min(self.heap_capacity * 4, 8 * self.H * self.W + 16))
         if todo.size:
             raise SageError("A* search exceeded the planner's capacity even at the theoretical maximum")
         return (out, nexp_all) if want_expansions else out

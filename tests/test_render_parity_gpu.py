@@ -71,20 +71,22 @@ def test_projection_elementwise(sage, oracle):
     assert not np.any(vis & ~o_vis), "GPU kept a Gaussian the spec culls"
     for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b"):
         assert np.array_equal(rec[k][vis].view(np.uint32), o_rec[k][vis].view(np.uint32)), k
-    # Gaussians the GPU dropped beyond the spec's cull rules: their {alpha >= 1/255} ellipse
-    # (binary64, from the binary32 conic, no slack) must miss every pixel centre of the image.
+    # Gaussians the GPU dropped beyond the spec's cull rules (exact tile culling): their
+    # {alpha >= 1/255} ellipse (binary64, from the binary32 conic, no slack) must miss EVERY pixel
+    # centre of the image — checked by brute force over the ellipse's bounding rows/columns.
     extra = o_vis & ~vis
-    if extra.any():
-        r = o_rec[extra]
-        A, B, Cq = -r["qa"].astype(np.float64), -0.5 * r["qb"].astype(np.float64), -r["qc"].astype(np.float64)
+    for r in o_rec[extra]:
+        A, B, Cq = -float(r["qa"]), -0.5 * float(r["qb"]), -float(r["qc"])
+        t2 = np.log2(255.0 * float(r["opacity"]))
         det = A * Cq - B * B
-        t2 = np.log2(255.0 * r["opacity"].astype(np.float64))
-        ok = det > 0
-        hx = np.where(ok, np.sqrt(np.maximum(t2 * Cq / np.where(ok, det, 1.0), 0.0)), np.inf)
-        hy = np.where(ok, np.sqrt(np.maximum(t2 * A / np.where(ok, det, 1.0), 0.0)), np.inf)
-        gx, gy = r["gx"].astype(np.float64), r["gy"].astype(np.float64)
-        off = (gx + hx < 0.5) | (gx - hx > cam.width - 0.5) | (gy + hy < 0.5) | (gy - hy > cam.height - 0.5)
-        assert off.all()
+        assert det > 0 and A > 0 and Cq > 0, "a degenerate conic must never be culled by the tile test"
+        hx, hy = np.sqrt(t2 * Cq / det), np.sqrt(t2 * A / det)
+        gx, gy = float(r["gx"]), float(r["gy"])
+        xs = np.arange(max(int(np.floor(gx - hx - 1)), 0), min(int(np.ceil(gx + hx + 1)), cam.width - 1) + 1)
+        ys = np.arange(max(int(np.floor(gy - hy - 1)), 0), min(int(np.ceil(gy + hy + 1)), cam.height - 1) + 1)
+        if xs.size and ys.size:
+            DX, DY = np.meshgrid(xs + 0.5 - gx, ys + 0.5 - gy)
+            assert not np.any(A * DX * DX + 2 * B * DX * DY + Cq * DY * DY <= t2), "culled a splat that reaches a pixel centre"
 
 
 def test_empty_and_tiny_scenes(sage, oracle):

@@ -193,3 +193,5 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { mem
 
 #define SAGE_KLAUNCH(kernel, grid, block, stream, ...) \
     cuda_emu::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+inline float __log2f(float x) { return log2f(x); }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }

@@ -1,13 +1,9 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q --no-header -rf --timeout 600 -x > gpurun_out/r01d_pytest.log 2>&1
-tail -5 gpurun_out/r01d_pytest.log
-SAGE_NO_FORK=1 timeout 600 python bench.py --steps 500 --warmup 50 --no-cpu-baseline > gpurun_out/r01d_bench_nofork.json 2> gpurun_out/r01d_bench_nofork.err; tail -2 gpurun_out/r01d_bench_nofork.err
-timeout 600 python bench.py --steps 500 --warmup 50 --no-cpu-baseline > gpurun_out/r01d_bench_fork.json 2> gpurun_out/r01d_bench_fork.err; tail -2 gpurun_out/r01d_bench_fork.err
+python -m pytest tests/test_render_parity_gpu.py tests/test_multigpu.py tests/test_env_facade.py -m gpu -q --no-header -rf --timeout 900 > gpurun_out/r01g_pytest.log 2>&1
+tail -6 gpurun_out/r01g_pytest.log
+timeout 600 python bench.py --steps 500 --warmup 50 --no-cpu-baseline > gpurun_out/r01g_bench.json 2> gpurun_out/r01g_bench.err; tail -2 gpurun_out/r01g_bench.err
 python - <<'PY'
 import json
-for n in ("nofork","fork"):
-    try:
-        j=json.load(open(f"gpurun_out/r01d_bench_{n}.json"))
-        print(n, "value", round(j["value"],1), "e2e", round(j["e2e"]["value"],1), "handoff", round(j["handoff_jpeg"]["value"],1), "enc_ms", round(j["handoff_jpeg"]["jpeg_encode_ms_device"],4), j["roofline"]["frame"]["stage_ms"])
-    except Exception as e: print(n, "ERR", e)
+j=json.load(open("gpurun_out/r01g_bench.json"))
+print("value", round(j["value"],1), "e2e", round(j["e2e"]["value"],1), "V", j["config"]["mean_visible"], "D", j["config"]["mean_instances"]); print(j["roofline"]["frame"]["stage_ms_serial"])
 PY

@@ -19,8 +19,8 @@ sys.path.insert(0, str(ROOT))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--queries", type=int, default=4096)
-    ap.add_argument("--slots", type=int, default=1024)
+    ap.add_argument("--queries", type=int, default=16384)
+    ap.add_argument("--slots", type=int, default=8192)
     ap.add_argument("--scale", type=float, default=0.05)
     ap.add_argument("--cpu-queries", type=int, default=64)
     args = ap.parse_args()
