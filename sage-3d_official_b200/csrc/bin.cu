@@ -33,66 +33,91 @@ __device__ __forceinline__ void cs_store(unsigned long long* p, unsigned long lo
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Load-balanced two-level expansion.  A block takes 256 depth-sorted Gaussians; its unit of work is
-// the ROW ITEM (Gaussian, tile row): one thread intersects the splat's {alpha >= 1/255} ellipse with
-// the two 8-row halves of that tile row (sage_band_row, binary64) and gets the exact tile range and
-// the column spans that later give every tile its 8x8-quadrant mask.  Items are processed 256 at a
-// time: scan their tile counts, then let the threads walk the concatenated instance list (binary
-// search for the owning item), so consecutive threads write consecutive instance slots (coalesced)
-// whatever the splat sizes.  The per-Gaussian totals equal k_project's counts (same function, same
-// inputs), which is what the chained scan across blocks is built on.
+// which 8x8 quadrants of tile (tx,ty) the inclusive pixel box [px0,px1]x[py0,py1] overlaps:
+// bit (qy*2 + qx), matching the warp -> quadrant map of the composite kernel
+__device__ __forceinline__ uint32_t box_quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
+{
+    const int bx = tx * SAGE_TILE, by = ty * SAGE_TILE;
+    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
+    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
+    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
+}
+
+constexpr int ROW_POOL = 1536;      // tile-row entries of the block's cullable splats (typically ~300 used)
+#define ROWS_NONE 0xFFFFFFFFu
+
+// Load-balanced expansion with exact tile culling.  A block takes 256 depth-sorted Gaussians.  Setup
+// (thread per Gaussian): a splat whose pixel box spans >= 2 x 2 tiles intersects its
+// {alpha >= 1/255} ellipse with the two 8-row halves of every tile row (sage_band_row) and keeps the
+// column spans + running tile counts in a shared-memory pool; the others (one row or one column of
+// tiles: nothing to cull) keep their box.  The per-Gaussian totals are scanned (chained scan across
+// blocks, decoupled look-back), then the threads walk the concatenated instance list: binary search
+// for the owning Gaussian, a second short one for its tile row, so consecutive threads write
+// consecutive instance slots (coalesced) whatever the splat sizes.
 template <int TBITS_LO, int NP>
-__global__ void __launch_bounds__(B_THREADS)
+__global__ void __launch_bounds__(B_THREADS, 6)
 k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ ikey,
        uint32_t* __restrict__ ival, uint32_t cap, unsigned long long* __restrict__ chain,
        uint32_t* __restrict__ ticket, uint32_t epoch, uint32_t* __restrict__ tile_hist)
 {
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t nblk = (V + B_THREADS - 1) / B_THREADS;
-    __shared__ SageBand s_band[B_THREADS];
-    __shared__ uint32_t s_roff[B_THREADS + 1];      // row items before Gaussian k of the block
+    __shared__ uint32_t s_off[B_THREADS + 1];
     __shared__ uint32_t s_g[B_THREADS];
     __shared__ uint2 s_rc[B_THREADS];
-    __shared__ uint32_t wsum[B_THREADS / 32], wsum2[B_THREADS / 32];
-    __shared__ uint32_t s_blk, s_base, s_total;
+    __shared__ uint32_t s_rows[B_THREADS];          // first pool entry of the splat, or ROWS_NONE (box mode)
+    __shared__ uint2 s_pool_span[ROW_POOL];         // (upper, lower) column spans of one tile row
+    __shared__ uint16_t s_pool_cum[ROW_POOL];       // tiles of the splat up to and including this row
+    __shared__ uint32_t wsum[B_THREADS / 32];
+    __shared__ uint32_t s_blk, s_base, s_pool_used;
     __shared__ uint32_t s_hist[NP][256];
-    // one chunk of row items
-    __shared__ uint32_t s_ioff[B_THREADS + 1];      // instances before item j of the chunk
-    __shared__ uint32_t s_it_g[B_THREADS];          // Gaussian id << 4
-    __shared__ uint32_t s_it_pos[B_THREADS];        // ty << 16 | first tile column
-    __shared__ uint2 s_it_span[B_THREADS];          // column spans of the upper / lower half
-    if (threadIdx.x == 0) s_blk = atomicAdd(ticket, 1u);
+    if (threadIdx.x == 0) { s_blk = atomicAdd(ticket, 1u); s_pool_used = 0; }
     for (int i = threadIdx.x; i < NP * 256; i += B_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const uint32_t b = s_blk;
     if (b >= nblk) return;
     const uint32_t r = b * B_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t g = 0, c = 0, nrows = 0;
+    uint32_t g = 0, c = 0, rows_at = ROWS_NONE;
     uint2 rc = make_uint2(0, 0);
     if (r < V) {
         g = __ldg(&order[r]);
-        c = __ldg(&fr.ntiles[g]);
         rc = __ldg(&fr.rect[g]);
-        if (sage_box_cullable(rc.x & 0xFFFF, rc.x >> 16, rc.y & 0xFFFF, rc.y >> 16)) {
-            const float4 r0 = __ldg(&fr.rec[3 * (size_t)g]);         // gx gy qa thr
-            const float4 r1 = __ldg(&fr.rec[3 * (size_t)g + 1]);     // qb qc o z
-            s_band[threadIdx.x] = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+        const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
+        const int ty0 = py0 / SAGE_TILE, ty1 = py1 / SAGE_TILE;
+        c = (uint32_t)(px1 / SAGE_TILE - px0 / SAGE_TILE + 1) * (uint32_t)(ty1 - ty0 + 1);
+        if (sage_box_cullable(px0, px1, py0, py1)) {
+            const uint32_t nrows = (uint32_t)(ty1 - ty0 + 1);
+            const uint32_t at = atomicAdd(&s_pool_used, nrows);
+            if (at + nrows <= ROW_POOL) {            // (a full pool only costs the culling, never correctness)
+                const float4 r0 = __ldg(&fr.rec[3 * (size_t)g]);         // gx gy qa thr
+                const float4 r1 = __ldg(&fr.rec[3 * (size_t)g + 1]);     // qb qc o z
+                const SageBand band = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                uint32_t cum = 0;
+                for (uint32_t j = 0; j < nrows; ++j) {
+                    const SageRowItem it = sage_band_row(band, px0, px1, py0, py1, ty0 + (int)j);
+                    cum += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
+                    s_pool_span[at + j] = make_uint2(it.top, it.bot);
+                    s_pool_cum[at + j] = (uint16_t)cum;
+                }
+                c = cum;
+                rows_at = at;
+            }
         }
-        nrows = (rc.y >> 16) / SAGE_TILE - (rc.y & 0xFFFFu) / SAGE_TILE + 1;
     }
-    const uint32_t incl = warp_incl_scan_u32(c), incl2 = warp_incl_scan_u32(nrows);
-    if (lane == 31) { wsum[w] = incl; wsum2[w] = incl2; }
+    uint32_t incl = warp_incl_scan_u32(c);
+    if (lane == 31) wsum[w] = incl;
     s_g[threadIdx.x] = g;
     s_rc[threadIdx.x] = rc;
+    s_rows[threadIdx.x] = rows_at;
     __syncthreads();
-    uint32_t woff = 0, woff2 = 0;
+    uint32_t woff = 0;
 #pragma unroll
-    for (int k = 0; k < B_THREADS / 32; ++k) { woff += (k < w) ? wsum[k] : 0u; woff2 += (k < w) ? wsum2[k] : 0u; }
-    s_roff[threadIdx.x] = woff2 + incl2 - nrows;
-    if (threadIdx.x == B_THREADS - 1) { s_roff[B_THREADS] = woff2 + incl2; s_total = woff + incl; }
+    for (int k = 0; k < B_THREADS / 32; ++k) woff += (k < w) ? wsum[k] : 0u;
+    s_off[threadIdx.x] = woff + incl - c;
+    if (threadIdx.x == B_THREADS - 1) s_off[B_THREADS] = woff + incl;
     __syncthreads();
-    const uint32_t total = s_total, n_items = s_roff[B_THREADS];
+    const uint32_t total = s_off[B_THREADS];
 
     // chained scan across blocks: chain[b] = epoch(30) | state(2) | value(32)
     if (threadIdx.x == 0) {
@@ -134,60 +159,48 @@ k_emit(SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order, uint32_
         }
     }
     __syncthreads();
+    const uint32_t base = s_base;
     const int tiles_x = cam.tiles_x, row0 = cam.row0;
-    uint32_t run = s_base;                          // instance slot of the chunk's first instance
-    for (uint32_t it0 = 0; it0 < n_items; it0 += B_THREADS) {
-        const uint32_t item = it0 + threadIdx.x;
-        uint32_t cnt = 0;
-        if (item < n_items) {
-            int lo = 0, hi = B_THREADS - 1;         // owner = last o with s_roff[o] <= item
+    for (uint32_t k = threadIdx.x; k < total; k += B_THREADS) {
+        int lo = 0, hi = B_THREADS - 1;            // owner = last o with s_off[o] <= k
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_roff[mid] <= item) lo = mid; else hi = mid - 1;
-            }
-            const uint2 bx = s_rc[lo];
-            const int px0 = bx.x & 0xFFFF, px1 = bx.x >> 16, py0 = bx.y & 0xFFFF, py1 = bx.y >> 16;
-            const int ty = py0 / SAGE_TILE + (int)(item - s_roff[lo]);
-            const SageRowItem ri = sage_band_row(s_band[lo], px0, px1, py0, py1, ty);
-            cnt = (uint32_t)max(ri.tx1 - ri.tx0 + 1, 0);
-            s_it_g[threadIdx.x] = s_g[lo] << 4;
-            s_it_pos[threadIdx.x] = ((uint32_t)ty << 16) | (uint32_t)max(ri.tx0, 0);
-            s_it_span[threadIdx.x] = make_uint2(ri.top, ri.bot);
+        for (int it = 0; it < 8; ++it) {
+            int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= k) lo = mid; else hi = mid - 1;
         }
-        const uint32_t ci = warp_incl_scan_u32(cnt);
-        if (lane == 31) wsum[w] = ci;
-        __syncthreads();
-        uint32_t wo = 0;
-#pragma unroll
-        for (int k = 0; k < B_THREADS / 32; ++k) wo += (k < w) ? wsum[k] : 0u;
-        s_ioff[threadIdx.x] = wo + ci - cnt;
-        if (threadIdx.x == B_THREADS - 1) s_ioff[B_THREADS] = wo + ci;
-        __syncthreads();
-        const uint32_t chunk_total = s_ioff[B_THREADS];
-        for (uint32_t k = threadIdx.x; k < chunk_total; k += B_THREADS) {
-            int lo = 0, hi = B_THREADS - 1;         // owning item = last j with s_ioff[j] <= k
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (s_ioff[mid] <= k) lo = mid; else hi = mid - 1;
+        const uint2 bx = s_rc[lo];
+        const int px0 = bx.x & 0xFFFF, px1 = bx.x >> 16, py0 = bx.y & 0xFFFF, py1 = bx.y >> 16;
+        const int tx0 = px0 / SAGE_TILE, ty0 = py0 / SAGE_TILE;
+        const uint32_t local = k - s_off[lo];
+        const uint32_t at = s_rows[lo];
+        int tx, ty;
+        uint32_t mask;
+        if (at == ROWS_NONE) {                     // box mode
+            const uint32_t bw = (uint32_t)(px1 / SAGE_TILE - tx0 + 1);
+            ty = ty0 + (int)(local / bw); tx = tx0 + (int)(local % bw);
+            mask = box_quad_mask(px0, px1, py0, py1, tx, ty);
+        } else {                                   // row = first j with cum[j] > local
+            int a = 0, z = py1 / SAGE_TILE - ty0;
+            while (a < z) {
+                const int mid = (a + z) >> 1;
+                if ((uint32_t)s_pool_cum[at + mid] > local) z = mid; else a = mid + 1;
             }
-            const uint32_t pos = s_it_pos[lo];
-            const int ty = (int)(pos >> 16), tx = (int)(pos & 0xFFFFu) + (int)(k - s_ioff[lo]);
-            SageRowItem ri;
-            ri.top = s_it_span[lo].x; ri.bot = s_it_span[lo].y; ri.tx0 = 0; ri.tx1 = 0;
-            const uint32_t tile = (uint32_t)((ty - row0) * tiles_x + tx);
-            const uint32_t slot = run + k;
-            if (slot < cap) {
-                ikey[slot] = tile;
-                ival[slot] = s_it_g[lo] | sage_row_quad_mask(ri, tx);
-#pragma unroll
-                for (int p = 0; p < NP; ++p) atomicAdd(&s_hist[p][(tile >> (TBITS_LO * p)) & 255u], 1u);   // (warp-aggregating these with match.any measured slower)
-            }
+            const uint32_t before = a > 0 ? (uint32_t)s_pool_cum[at + a - 1] : 0u;
+            const uint2 sp = s_pool_span[at + a];
+            const SageRowItem ri = sage_row_from_spans(sp.x, sp.y);
+            ty = ty0 + a; tx = ri.tx0 + (int)(local - before);
+            mask = sage_row_quad_mask(ri, tx);
         }
-        run += chunk_total;
-        __syncthreads();                            // the chunk arrays are rewritten by the next round
+        const uint32_t tile = (uint32_t)((ty - row0) * tiles_x + tx);
+        const uint32_t slot = base + k;
+        if (slot < cap) {
+            ikey[slot] = tile;
+            ival[slot] = (s_g[lo] << 4) | mask;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) atomicAdd(&s_hist[p][(tile >> (TBITS_LO * p)) & 255u], 1u);
+        }
     }
+    __syncthreads();
     for (int i = threadIdx.x; i < NP * 256; i += B_THREADS) {
         const uint32_t cc = (&s_hist[0][0])[i];
         if (cc) atomicAdd(&tile_hist[i], cc);

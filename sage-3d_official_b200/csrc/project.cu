@@ -81,7 +81,7 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
-    uint32_t key = SAGE_KEY_CULLED, count = 0;
+    uint32_t key = SAGE_KEY_CULLED;
     if (i < sc.n) {
         const float4 g0 = __ldg(&sc.geo0[i]);
         const float mx = g0.x, my = g0.y, mz = g0.z, o = g0.w;
@@ -146,34 +146,19 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                     iy0 = max(iy0, cam.row0 * SAGE_TILE);
                     iy1 = min(iy1, min(cam.row1 * SAGE_TILE, cam.H) - 1);
                     if (iy0 <= iy1 && ix0 <= ix1) {
-                        // exact tile count: per tile row, the tiles whose pixel centres the ellipse reaches
-                        // (k_emit walks the same rows with the same function)
-                        const int ty0 = iy0 / SAGE_TILE, ty1 = iy1 / SAGE_TILE;
-                        uint32_t cnt = (uint32_t)(ix1 / SAGE_TILE - ix0 / SAGE_TILE + 1) * (uint32_t)(ty1 - ty0 + 1);
-                        if (sage_box_cullable(ix0, ix1, iy0, iy1)) {
-                            const SageBand band = sage_band_make(gx, gy, qa, qb, qc, o);
-                            cnt = 0;
-                            for (int tyy = ty0; tyy <= ty1; ++tyy) {
-                                const SageRowItem it = sage_band_row(band, ix0, ix1, iy0, iy1, tyy);
-                                cnt += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
-                            }
-                        }
-                        if (cnt > 0) {
-                            vis = true;
-                            key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                            count = cnt;
-                            fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
-                            fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
-                            // inclusive pixel bounding box (u16 each)
-                            fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
-                                                    (uint32_t)iy0 | ((uint32_t)iy1 << 16));
-                        }
+                        vis = true;
+                        key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
+                        fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
+                        fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
+                        // inclusive pixel bounding box (u16 each); the exact tile ranges are taken by
+                        // k_emit, which walks only the visible set
+                        fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
+                                                (uint32_t)iy0 | ((uint32_t)iy1 << 16));
                     }
                 }
             }
         }
         fr.dkey[0][i] = key;
-        fr.ntiles[i] = count;
     }
     // one atomic per warp for the visible counter
     const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -248,6 +233,7 @@ k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __rest
         acc[c] = fmaxf(a + 0.5f, 0.0f);
     }
     fr.rec[3 * (size_t)i + 2] = make_float4(acc[0], acc[1], acc[2], 0.0f);
+
 }
 
 void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)

@@ -170,6 +170,19 @@ __device__ __forceinline__ SageRowItem sage_band_row(const SageBand& b, int ix0,
     return it;
 }
 
+// rebuild a row item from its two stored spans
+__device__ __forceinline__ SageRowItem sage_row_from_spans(uint32_t top, uint32_t bot)
+{
+    SageRowItem it;
+    it.top = top; it.bot = bot;
+    int lo = 1 << 30, hi = -1;
+    if ((top & 0xFFFFu) <= (top >> 16)) { lo = min(lo, (int)(top & 0xFFFFu)); hi = max(hi, (int)(top >> 16)); }
+    if ((bot & 0xFFFFu) <= (bot >> 16)) { lo = min(lo, (int)(bot & 0xFFFFu)); hi = max(hi, (int)(bot >> 16)); }
+    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
+    else { it.tx0 = lo / SAGE_TILE; it.tx1 = hi / SAGE_TILE; }
+    return it;
+}
+
 // 8x8-quadrant mask (bit qy*2+qx, the warp -> quadrant map of the composite kernel) of tile tx
 __device__ __forceinline__ uint32_t sage_row_quad_mask(const SageRowItem& it, int tx)
 {
@@ -193,7 +206,7 @@ struct SageFrame {
     uint32_t* dkey[2];   // depth keys bits(z) - bits(near) (or CULLED), ping-pong
     uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
-    uint32_t* ntiles;    // tiles touched
+    uint32_t* ntiles;    // (unused: k_emit counts its own tiles)
     // per-instance (capacity cap)
     uint32_t* ikey[2];   // tile id, ping-pong
     uint32_t* ival[2];   // id << 4 | quadrant mask, ping-pong
