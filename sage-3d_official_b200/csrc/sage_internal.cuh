@@ -206,7 +206,6 @@ struct SageFrame {
     uint32_t* dkey[2];   // depth keys bits(z) - bits(near) (or CULLED), ping-pong
     uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
-    uint32_t* ntiles;    // (unused: k_emit counts its own tiles)
     // per-instance (capacity cap)
     uint32_t* ikey[2];   // tile id, ping-pong
     uint32_t* ival[2];   // id << 4 | quadrant mask, ping-pong

@@ -84,7 +84,6 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
         CK(dalloc(&c.fr.dval[k], n));
     }
     CK(dalloc(&c.fr.rect, n));
-    CK(dalloc(&c.fr.ntiles, n));
     CK(dalloc(&c.fr.chain, n / 256 + 2));
     CK(cudaMemset(c.fr.chain, 0, (n / 256 + 2) * sizeof(unsigned long long)));
     CK(dalloc(&c.fr.counters, (size_t)SAGE_ZERO_WORDS));
@@ -113,7 +112,7 @@ static void free_ctx(FrameCtx& c)
 {
     cudaFree(c.fr.rec);
     for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
-    cudaFree(c.fr.rect); cudaFree(c.fr.ntiles); cudaFree(c.fr.chain);
+    cudaFree(c.fr.rect); cudaFree(c.fr.chain);
     free_instances(c);
     cudaFree(c.fr.ranges); cudaFree(c.fr.tile_order); cudaFree(c.fr.counters);
     if (c.counters_host) cudaFreeHost(c.counters_host);
