@@ -1,0 +1,102 @@
+"""CPU: the SOURCE of two CUDA translation units (csrc/jpeg.cu, csrc/plan.cu) compiled with g++ under
+the development-only lock-step emulator (tools/cuda_emu/cuda_emu.h: CUDA threads -> OS threads,
+barriers, shuffles, ballots) and checked against the pinned oracle / Pillow / the reference goldens.
+
+This is NOT a product path and not a fallback — the emulated build is never part of libsage_splat.so
+and nothing in the package can reach it; it exists so that the no-GPU suite exercises the kernels'
+logic (bit positions, scans, heap order) and not only their host-side wrappers.  The real parity
+tests are the gpu-marked ones."""
+import ctypes as C
+import io
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+EMU = ROOT / "tools" / "cuda_emu"
+
+
+def _build(name, tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("emu") / f"lib{name}.so"
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-x", "c++", "-DSAGE_CUDA_EMU", "-shared", "-fPIC", "-pthread", "-w",
+                        "-o", str(out), str(EMU / f"{name}.cpp")], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("emulated build failed: " + r.stderr[-400:])
+    L = C.CDLL(str(out))
+    L.sage_last_error.restype = C.c_char_p
+    return L
+
+
+@pytest.fixture(scope="module")
+def jpeg_emu(tmp_path_factory):
+    L = _build("jpeg_emu", tmp_path_factory)
+    vp = C.c_void_p
+    L.sage_jpeg_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+    L.sage_jpeg_encode_host.argtypes = [vp, vp, C.c_int, vp, C.c_int64, vp, vp]
+    L.sage_jpeg_destroy.argtypes = [vp]
+    return L
+
+
+@pytest.fixture(scope="module")
+def plan_emu(tmp_path_factory):
+    L = _build("plan_emu", tmp_path_factory)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    L.sage_grid_inflate.argtypes = [i32, vp, i32, i32, dbl, dbl, vp, vp]
+    L.sage_grid_components.argtypes = [i32, vp, i32, i32, vp, vp]
+    L.sage_planner_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, i32, i32, i64]
+    L.sage_planner_destroy.argtypes = [vp]
+    L.sage_plan_astar.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp]
+    return L
+
+
+def test_jpeg_kernels_emulated_match_pillow_and_oracle(jpeg_emu, oracle):
+    from PIL import Image
+    rng = np.random.default_rng(7)
+    for (H, W), q in (((24, 40), 75), ((17, 33), 90)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        a = np.stack([127 + 120 * np.sin(xx / 7 + yy / 11), xx * 255 / (W - 1), yy * 255 / (H - 1)], -1).astype(np.uint8)
+        m = rng.uniform(size=(H, W)) < 0.2
+        a[m] = rng.integers(0, 256, (int(m.sum()), 3), dtype=np.uint8)
+        fr = np.ascontiguousarray(np.stack([a, a[::-1].copy()]))
+        h = C.c_void_p()
+        assert jpeg_emu.sage_jpeg_create(C.byref(h), 0, W, H, q, 2, W * H * 4 + 8192) == 0
+        cap = W * H * 4 + 8192
+        out = np.zeros((2, cap), np.uint8)
+        sizes = np.zeros(2, np.int64)
+        rc = jpeg_emu.sage_jpeg_encode_host(h, fr.ctypes.data, 2, out.ctypes.data, cap, sizes.ctypes.data, None)
+        jpeg_emu.sage_jpeg_destroy(h)
+        assert rc == 0, jpeg_emu.sage_last_error()
+        for f in range(2):
+            got = out[f, :sizes[f]].tobytes()
+            b = io.BytesIO()
+            Image.fromarray(fr[f]).save(b, format="JPEG", quality=q)
+            assert got == b.getvalue() == oracle.jpeg_encode(fr[f], q), (H, W, q, f)
+
+
+def test_plan_kernels_emulated_match_reference_goldens(plan_emu, oracle):
+    z = np.load(ROOT / "tests" / "golden" / "plan_rooms_a.npz")
+    raw, grid = np.ascontiguousarray(z["raw"]), np.ascontiguousarray(z["grid"])
+    H, W = grid.shape
+    out = np.zeros_like(raw)
+    assert plan_emu.sage_grid_inflate(0, raw.ctypes.data, H, W, float(z["scale"]), float(z["radius"]), out.ctypes.data, None) == 0
+    assert np.array_equal(out, grid)
+    lab = np.zeros((H, W), np.int32)
+    assert plan_emu.sage_grid_components(0, grid.ctypes.data, H, W, lab.ctypes.data, None) == 0
+    assert np.array_equal(lab, oracle.grid_components(grid))
+    starts, goals = np.ascontiguousarray(z["starts"]), np.ascontiguousarray(z["goals"])
+    Q = len(starts)
+    h = C.c_void_p()
+    assert plan_emu.sage_planner_create(C.byref(h), 0, grid.ctypes.data, H, W, 8, 0, 0) == 0
+    mp = 4 * (H + W)
+    plen = np.zeros(Q, np.int32)
+    pxy = np.zeros((Q, mp, 2), np.int32)
+    assert plan_emu.sage_plan_astar(h, starts.ctypes.data, goals.ctypes.data, Q, plen.ctypes.data, pxy.ctypes.data, None, None) == 0
+    plan_emu.sage_planner_destroy(h)
+    for k in range(Q):
+        want = z["path_xy"][z["path_off"][k]:z["path_off"][k + 1]]
+        assert plen[k] == z["path_len"][k] and np.array_equal(pxy[k, :plen[k]], want), k
