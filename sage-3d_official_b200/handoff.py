@@ -19,6 +19,9 @@ Pillow's default encoder).  This module lets the unmodified callers pick them up
   ``save(fp, format='JPEG')`` / ``save('x.jpg')`` with no encoder options writes the device's
   bytes.  Any mutation (Pillow mutators copy-on-write a read-only image; we detect the swap), any
   option (quality=, optimize=, ...), any other format or mode falls through to Pillow itself.
+  The image owns a private copy of the pixels and unpacks it into Pillow storage only when something
+  asks for pixels (``load()``): a frame that is only wrapped, kept in a history and saved as JPEG —
+  the VLM client's whole use of it — never pays Pillow's per-frame unpack either.
 
 The rule is airtight by construction: pre-encoded bytes are used only when the pixels being saved
 are provably the pixels that were encoded, and for those pixels the two encoders agree byte for
@@ -54,6 +57,13 @@ class DeviceFrame(np.ndarray):
         return np.asarray(self).__reduce__()
 
 
+def _same_bytes(a: np.ndarray, b: np.ndarray) -> bool:
+    """Exact equality of two same-shape uint8 arrays; 8 bytes per comparison when both are contiguous."""
+    if a.flags.c_contiguous and b.flags.c_contiguous and a.nbytes % 8 == 0:
+        return bool(np.array_equal(a.reshape(-1).view(np.uint64), b.reshape(-1).view(np.uint64)))
+    return bool(np.array_equal(a, b))
+
+
 def precoded_jpeg(arr) -> Optional[bytes]:
     """The device's JPEG of ``arr`` if ``arr`` is bit-identical to the encoded frame, else None."""
     meta = getattr(arr, "_sage", None)
@@ -63,7 +73,7 @@ def precoded_jpeg(arr) -> Optional[bytes]:
     try:
         if arr.dtype != np.uint8 or arr.shape != pristine.shape or not valid():
             return None
-        if not np.array_equal(np.asarray(arr), pristine):
+        if not _same_bytes(np.asarray(arr), pristine):
             return None
     except Exception:
         return None
@@ -77,19 +87,40 @@ def hook_stats() -> dict:
     return {"hits": _hook_state["hits"], "misses": _hook_state["misses"]}
 
 
+def _core(im):
+    """The image's core storage or None, without tripping Pillow >= 10's asserting ``im`` property
+    (older Pillow keeps it as a plain attribute)."""
+    d = im.__dict__
+    return d["_im"] if "_im" in d else d.get("im")
+
+
 def _precoded_class():
     if _hook_state["cls"] is not None:
         return _hook_state["cls"]
     from PIL import Image
 
     class PrecodedImage(Image.Image):
-        """A normal RGB image that can also hand out the JPEG its pixels already have."""
+        """An RGB image that can hand out the JPEG its pixels already have.  Pixel storage is
+        created lazily (``load()``, which every Pillow operation calls before touching ``im``): a
+        frame that is only ever saved as a default JPEG never pays Pillow's 6 MB unpack."""
         _sage_jpeg: Optional[bytes] = None
-        _sage_im = None
+        _sage_im = None          # the core image the bytes describe, once materialised
+        _sage_arr = None         # private copy of the pixels, until materialised
+
+        def load(self):
+            if self._sage_arr is not None and _core(self) is None:
+                core = _hook_state["orig"](self._sage_arr)
+                self.im = core.im
+                self._sage_im = self.im
+                self._sage_arr = None            # (readonly stays 1: Pillow's mutators copy on write)
+            return super().load()
 
         def _sage_valid(self) -> bool:
-            return (self._sage_jpeg is not None and bool(self.readonly) and self.im is self._sage_im
-                    and self.mode == "RGB" and not self.info)
+            if self._sage_jpeg is None or self.mode != "RGB" or self.info:
+                return False
+            if self._sage_arr is not None:                  # never materialised: nothing could have changed
+                return _core(self) is None
+            return bool(self.readonly) and _core(self) is self._sage_im
 
         def save(self, fp, format=None, **params):
             if not params and self._sage_valid():
@@ -112,8 +143,10 @@ def _precoded_class():
 
         def convert(self, mode=None, *args, **kwargs):
             # img.convert('RGB') on an RGB image is an identity copy (vlm_client_modular.py:448-451):
-            # share the read-only core image instead of copying 6 MB; Pillow's mutators copy on write
+            # share the (read-only) pixels instead of copying 6 MB; Pillow's mutators copy on write
             if mode in (None, "RGB") and not args and not kwargs and self._sage_valid():
+                if self._sage_arr is not None:
+                    return _lazy(self._sage_arr, self._sage_jpeg)
                 new = self._new(self.im)
                 return _promote(new, self._sage_jpeg)
             return super().convert(mode, *args, **kwargs)
@@ -126,7 +159,20 @@ def _promote(im, jpeg: bytes):
     im.__class__ = _precoded_class()
     im._sage_jpeg = jpeg
     im._sage_im = im.im
+    im._sage_arr = None
     im.readonly = 1
+    return im
+
+
+def _lazy(arr: np.ndarray, jpeg: bytes):
+    """A PrecodedImage over a PRIVATE pixel array (never written again); no Pillow storage yet."""
+    im = _precoded_class()()
+    im._size = (int(arr.shape[1]), int(arr.shape[0]))
+    im._mode = "RGB"
+    im.readonly = 1              # from birth: putpixel / paste / ImageDraw then _copy() before writing
+    im._sage_jpeg = jpeg
+    im._sage_arr = arr
+    im._sage_im = None
     return im
 
 
@@ -139,17 +185,17 @@ def install_pillow_hook() -> bool:
     except Exception:
         return False
     orig = Image.fromarray
+    _hook_state["orig"] = orig
     _precoded_class()
 
     def fromarray(obj, mode=None, *a, **kw):
-        im = orig(obj, mode, *a, **kw) if (mode is not None or a or kw) else orig(obj)
         if mode is None and not a and not kw:
             data = precoded_jpeg(obj)
-            if data is not None and im.mode == "RGB":
-                if im.readonly:            # shares memory with the caller's array: own the pixels
-                    im = im.copy()
-                return _promote(im, data)
-        return im
+            if data is not None and obj.ndim == 3 and obj.shape[2] == 3:
+                # own the pixels (the caller may write to its array later); ~0.3 ms per 1080p frame
+                return _lazy(np.array(obj, dtype=np.uint8, order="C", copy=True).view(np.ndarray), data)
+            return orig(obj)
+        return orig(obj, mode, *a, **kw)
 
     fromarray.__doc__ = orig.__doc__
     fromarray._sage_hook = True

@@ -116,3 +116,31 @@ def test_device_frame_is_an_ordinary_array(hook):
     assert type(back) is np.ndarray and np.array_equal(back, pristine)
     fr[0, 0, 0] ^= 255                                   # caller-owned: writable, and then no longer "the frame"
     assert handoff.precoded_jpeg(fr) is None
+
+
+def test_lazy_image_materialises_on_demand_and_stays_safe(hook):
+    handoff, _ = hook
+    fr, pristine, marker = _frame(handoff, seed=6)
+    im = Image.fromarray(fr)
+    fr[:] = 0                                            # the caller reuses its array: the image owns its pixels
+    assert handoff._core(im) is None                      # nothing unpacked yet
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == marker and handoff._core(im) is None
+    assert im.size == (64, 48) and im.mode == "RGB"
+    assert np.array_equal(np.asarray(im), pristine)      # materialised from the private copy
+    assert handoff._core(im) is not None
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == marker                        # still untouched
+    try:                                                 # direct pixel access is read-only
+        px = im.load()
+        px[0, 0] = (9, 9, 9)
+        wrote = True
+    except (ValueError, TypeError):
+        wrote = False
+    if wrote:
+        b = io.BytesIO(); im.save(b, format="JPEG")
+        assert b.getvalue() == _pillow(np.asarray(im))
+    thumb = Image.fromarray(handoff.DeviceFrame(pristine.copy(), marker, pristine, lambda: True))
+    thumb.thumbnail((16, 16))                            # in-place resize replaces the core image
+    b = io.BytesIO(); thumb.save(b, format="JPEG")
+    assert b.getvalue() != marker and thumb.size[0] <= 16
