@@ -137,6 +137,16 @@ class World:
         pass
 
 
+def _rgb_to_rgba(rgb: np.ndarray) -> np.ndarray:
+    """(H,W,3) -> (H,W,4) with alpha 255.  NumPy's 3-of-4-byte strided copy runs at ~0.5 GB/s;
+    OpenCV's is ~10x faster when it is installed (it is in the reference's environment)."""
+    try:
+        import cv2
+        return cv2.cvtColor(rgb, cv2.COLOR_RGB2RGBA)
+    except Exception:
+        return np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+
+
 class Camera:
     """``omni.isaac.sensor.Camera`` stand-in: pose in, frame out."""
 
@@ -208,7 +218,7 @@ class Camera:
         if f is None:
             return None
         rgb = f[0]
-        rgba = np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
+        rgba = _rgb_to_rgba(rgb)
         if getattr(self, "_jpeg", None) is not None:
             from ..handoff import DeviceFrame
             return DeviceFrame(rgba, self._jpeg, rgb, lambda: True)     # rgb is this frame's private copy
