@@ -98,8 +98,11 @@ int sage_render(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_
 int sage_render_host(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1_tiles,
                      uint8_t* rgb_host, float* depth_host, sage_stream_t stream);
 
-/* Pipelined host path: two frames can be in flight (slot 0 / 1, each with its own frame context and
- * internal stream).  sage_render_host_async returns at once; sage_host_wait(slot) blocks until that
+/* Number of frame contexts of a scene = frames that can be in flight at once (3). */
+int sage_pipeline_depth(void);
+
+/* Pipelined host path: sage_pipeline_depth() frames can be in flight (slot 0 .. depth-1, each with
+ * its own frame context and internal stream).  sage_render_host_async returns at once; sage_host_wait(slot) blocks until that
  * slot's RGB/depth have landed in the host buffers passed to it (keep them alive and distinct per
  * slot).  Submitting frame i+1 on the other slot before waiting for frame i overlaps frame i's
  * device->host copy and compositing with frame i+1's projection and sorts. */
@@ -212,7 +215,7 @@ int sage_jpeg_debug(sage_jpeg* j, int frame, int16_t* coef_host, uint32_t* mcu_b
  * slot's frame context (as sage_render_host_async), encode on the same stream, and move only
  * what the caller asks for across PCIe.  rgb_host / depth_host may be NULL (then the raw
  * frame / depth never leave the device).  The encoder must match the camera's resolution and
- * have max_batch >= 2 (slot = scratch slot).  sage_render_jpeg_wait blocks until slot's frame
+ * have max_batch > slot (slot = scratch slot).  sage_render_jpeg_wait blocks until slot's frame
  * is done, copies exactly the encoded bytes into jpeg_host (capacity cap) and returns their
  * count in *size_out. */
 int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,

@@ -85,6 +85,8 @@ class GaussianScene:
         check(_lib.lib().sage_scene_create(C.byref(self._h), self.device, n, deg, _ptr(xyz), _ptr(ls),
                                            _ptr(q), _ptr(op), _ptr(sh), int(max_instances)))
         self._pinned = {}
+        #: frames that can be in flight at once (slots of render_host_async / render_jpeg_async)
+        self.pipeline_depth = int(_lib.lib().sage_pipeline_depth())
 
     # -- lifetime --
     def close(self):
@@ -184,19 +186,20 @@ class GaussianScene:
     def render_batch_host(self, cams, want_depth: bool = True):
         """Render a sequence of camera poses (e.g. every sampled waypoint of a trajectory, as
         generate_images.py does one by one) keeping two frames in flight.  Yields
-        ``(index, rgb, depth)`` in order; the arrays are views of pinned buffers that are reused two
-        frames later — copy or encode them before advancing the generator twice."""
+        ``(index, rgb, depth)`` in order; the arrays are views of pinned buffers that are reused a few
+        frames later — copy or encode them before advancing the generator ``pipeline_depth`` times."""
         cams = list(cams)
         bufs = {}
+        d = self.pipeline_depth
         for i, cam in enumerate(cams):
-            slot = i % 2
-            if i >= 2:
+            slot = i % d
+            if i >= d:
                 self.host_wait(slot)
-                yield (i - 2,) + bufs[slot]
+                yield (i - d,) + bufs[slot]
             bufs[slot] = self.render_host_async(cam, slot, want_depth=want_depth)
-        for i in range(max(0, len(cams) - 2), len(cams)):
-            self.host_wait(i % 2)
-            yield (i,) + bufs[i % 2]
+        for i in range(max(0, len(cams) - d), len(cams)):
+            self.host_wait(i % d)
+            yield (i,) + bufs[i % d]
 
     def host_wait(self, slot: int):
         check(_lib.lib().sage_host_wait(self._h, int(slot)))
@@ -234,12 +237,18 @@ class GaussianScene:
         generate_images.py:408-456 does one waypoint at a time with 3 RTX frames, a 3 MB
         read-back and a host-side Pillow encode each).  Yields ``(index, jpeg_bytes)`` in order."""
         cams = list(cams)
+        d = min(self.pipeline_depth, encoder.max_batch)
         for i, cam in enumerate(cams):
-            if i >= 2:
-                yield i - 2, self.jpeg_wait(encoder, i % 2)
-            self.render_jpeg_async(cam, encoder, i % 2)
-        for i in range(max(0, len(cams) - 2), len(cams)):
-            yield i, self.jpeg_wait(encoder, i % 2)
+            if i >= d:
+                yield i - d, self.jpeg_wait(encoder, i % d)
+            self.render_jpeg_async(cam, encoder, i % d)
+        for i in range(max(0, len(cams) - d), len(cams)):
+            yield i, self.jpeg_wait(encoder, i % d)
+
+    def host_wait_all(self):
+        for k in range(self.pipeline_depth):
+            self.host_wait(k)
+
 
     def stats(self) -> dict:
         st = CFrameStats()
@@ -386,7 +395,7 @@ class JpegEncoder:
     reference makes on the host for every frame (generate_images.py:431-432,
     vlm_client_modular.py:351,402,453)."""
 
-    def __init__(self, width: int, height: int, quality: int = 75, max_batch: int = 2, device: int = 0,
+    def __init__(self, width: int, height: int, quality: int = 75, max_batch: int = 4, device: int = 0,
                  max_bytes_per_frame: int = 0):
         _lib.require_gpu()
         self.width, self.height, self.quality = int(width), int(height), int(quality)

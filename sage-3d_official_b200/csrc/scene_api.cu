@@ -1,6 +1,6 @@
 // C-ABI of libsage_splat.so, part 2: scene upload and rendering.
 //
-// A scene owns SAGE_N_CTX frame contexts (all per-frame device state, double-buffered).  Consecutive
+// A scene owns SAGE_N_CTX frame contexts (all per-frame device state, multi-buffered).  Consecutive
 // frames alternate contexts, so a caller that alternates two streams gets frame N+1's projection /
 // sorts running while frame N is still compositing — the issue-bound blend kernel and the
 // latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host.
@@ -11,7 +11,7 @@
 #include "api_common.cuh"
 
 #ifndef SAGE_N_CTX
-#define SAGE_N_CTX 2
+#define SAGE_N_CTX 3      // measured: 1975 / 2077 / 2050 frames/s with 2 / 3 / 4 contexts in flight
 #endif
 
 namespace {
@@ -437,14 +437,16 @@ int sage_render_host_async(sage_scene* s, const sage_camera* cam, int row0_tiles
                            uint8_t* rgb_host, float* depth_host, int slot)
 {
     REQUIRE(s != nullptr, "sage_render_host_async: NULL scene");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_host_async: slot must be 0 or 1");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_host_async: slot must be in [0, sage_pipeline_depth())");
     return render_to_host(s, slot, cam, row0_tiles, row1_tiles, rgb_host, depth_host, s->ctx[slot].stream);
 }
+
+int sage_pipeline_depth(void) { return SAGE_N_CTX; }
 
 int sage_host_wait(sage_scene* s, int slot)
 {
     REQUIRE(s != nullptr, "sage_host_wait: NULL scene");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_host_wait: slot must be 0 or 1");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_host_wait: slot must be in [0, sage_pipeline_depth())");
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->ctx[slot].stream));
     return 0;
@@ -454,11 +456,11 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
                            uint8_t* rgb_host, float* depth_host)
 {
     REQUIRE(s != nullptr && cam != nullptr && j != nullptr, "sage_render_jpeg_async: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_async: slot must be 0 or 1");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_async: slot must be in [0, sage_pipeline_depth())");
     REQUIRE(sage_jpeg_device(j) == s->device, "sage_render_jpeg_async: encoder lives on another device");
     REQUIRE(sage_jpeg_width(j) == cam->width && sage_jpeg_height(j) == cam->height,
             "sage_render_jpeg_async: encoder resolution differs from the camera's");
-    REQUIRE(sage_jpeg_max_batch(j) >= SAGE_N_CTX, "sage_render_jpeg_async: encoder needs max_batch >= 2");
+    REQUIRE(sage_jpeg_max_batch(j) > slot, "sage_render_jpeg_async: encoder needs max_batch > slot (one scratch slot per frame in flight)");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     cudaStream_t st = c.stream;
@@ -482,7 +484,7 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
 int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host, int64_t cap, int64_t* size_out)
 {
     REQUIRE(s != nullptr && j != nullptr && jpeg_host != nullptr && size_out != nullptr, "sage_render_jpeg_wait: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_wait: slot must be 0 or 1");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_wait: slot must be in [0, sage_pipeline_depth())");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     CK(cudaStreamSynchronize(c.stream));
