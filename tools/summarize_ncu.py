@@ -37,8 +37,9 @@ def main(rep, out):
                 f = float(v)
                 if n == "time_us" and U[i] == "ns":
                     f /= 1000.0
-                if n.endswith("_MB") and U[i].lower().startswith("byte"):
-                    f /= 1e6
+                if n.endswith("_MB"):
+                    u = U[i].lower()
+                    f *= {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(u, 1e-6)
                 vals.append(f"{f:.1f}" if f < 1e6 else f"{f:.3e}")
             except ValueError:
                 vals.append(v)
