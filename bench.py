@@ -285,9 +285,13 @@ def run_native(args):
     for i in range(64):
         scene.render(cams[(args.warmup + i) % len(cams)], rows=rows if world > 1 else None, out=(rgb[0], dep[0]))
     stage_serial = {k: 0.0 for k in scene.STAGES}
+    serial_frames = []
     for s_ in range(64):
+        tot = 0.0
         for k, v in scene.stage_times(s_).items():
             stage_serial[k] += v / 64
+            tot += v
+        serial_frames.append(tot)
     scene.set_stage_timing(0)
 
     # frame-averaged counters over a sample of the walk (V, D vary per pose)
@@ -435,7 +439,9 @@ def run_native(args):
                          "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg[dom],
                          "traffic_source": traffic_src,
                          "frame": {"algorithmic_bytes": B, "stage_ms": stage, "stage_ms_serial": stage_serial,
-                                   "serial_frame_ms": sum(stage_serial.values()), "frame_ms": frame_ms,
+                                   "serial_frame_ms": sum(stage_serial.values()),
+                                   "serial_frame_ms_p50_p99_max": [float(np.percentile(serial_frames, 50)), float(np.percentile(serial_frames, 99)), float(np.max(serial_frames))],
+                                   "frame_ms": frame_ms,
                                    "achieved_gbs": B / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0}},
         }
         if handoff is not None:

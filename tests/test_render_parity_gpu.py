@@ -269,3 +269,17 @@ def test_randomised_stress_parity(sage, oracle, seed):
     cam = sage.Camera.from_isaac_pose(pos, q, W, H, focal_mm=float(rng.uniform(3.0, 30.0)),
                                       near=float(rng.uniform(0.01, 0.5)), far=float(rng.uniform(3.0, 80.0)))
     _check_frame(sage, oracle, cloud, cam)
+
+
+def test_tall_splats_overflow_the_row_pool(sage, oracle):
+    """Camera 20 cm from a wall: nearly every visible splat spans a dozen or more tile rows, so a block
+    of 256 needs far more than k_emit's 1536-entry shared-memory row pool.  The splats past the pool
+    fall back to their bounding box (only the culling is lost) and the frame must stay bit-exact; the
+    pooled ones exercise the per-row binary search over many rows."""
+    cloud, _ = sage.synthetic_room(8, 3_000)
+    cam = sage.Camera.look_heading((0.2, 2.0, 1.2), np.radians(180.0), 960, 540)     # facing the x = 0 wall
+    st = _check_frame(sage, oracle, cloud, cam)
+    assert st["n_instances"] > 40 * st["n_visible"]          # really large footprints
+    # and a grazing view: long, thin, diagonal ellipses — where exact culling removes the most tiles
+    cam = sage.Camera.look_heading((0.25, 0.4, 1.2), np.radians(92.0), 960, 540)
+    _check_frame(sage, oracle, cloud, cam)
