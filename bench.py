@@ -13,7 +13,7 @@ native arm  (this repository's CUDA path)
              CUDA events between barriers, max over ranks.
   e2e        frames/s through the host-facing call (sage_render_host_async + sage_host_wait: host
              camera in, RGB+depth of EVERY frame copied device->pinned host inside the timed region,
-             two frames in flight).
+             sage_pipeline_depth() = 3 frames in flight).
   roofline   dominant kernel by device time (per-stage CUDA events recorded on the launch stream
              inside the timed region): algorithmic bytes per launch / its mean duration, against
              MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s).
@@ -227,7 +227,7 @@ def run_native(args):
         from sage3d_official_b200.multigpu import PeerFrames
         peers = PeerFrames(rgb, dep, rank, world)
 
-    # single GPU: consecutive frames alternate two streams (and the scene's two frame contexts), so
+    # single GPU: consecutive frames rotate over the scene's frame contexts, one stream each, so
     # frame i+1's projection/sorts overlap frame i's compositing
     streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)]
 

@@ -168,8 +168,8 @@ class GaussianScene:
         return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
 
     def render_host_async(self, cam: Camera, slot: int, rows=None, want_depth: bool = True):
-        """Submit a frame on pipeline slot 0/1; returns the slot's pinned host arrays (valid after
-        :meth:`host_wait`).  Alternate slots to keep two frames in flight."""
+        """Submit a frame on pipeline slot 0 .. pipeline_depth-1; returns the slot's pinned host arrays
+        (valid after :meth:`host_wait`).  Rotate the slots to keep pipeline_depth frames in flight."""
         torch = _torch()
         key = (cam.height, cam.width, "async", int(slot))
         if key not in self._pinned:
@@ -185,7 +185,7 @@ class GaussianScene:
 
     def render_batch_host(self, cams, want_depth: bool = True):
         """Render a sequence of camera poses (e.g. every sampled waypoint of a trajectory, as
-        generate_images.py does one by one) keeping two frames in flight.  Yields
+        generate_images.py does one by one) keeping pipeline_depth frames in flight.  Yields
         ``(index, rgb, depth)`` in order; the arrays are views of pinned buffers that are reused a few
         frames later — copy or encode them before advancing the generator ``pipeline_depth`` times."""
         cams = list(cams)
@@ -207,7 +207,7 @@ class GaussianScene:
     # -- frame hand-off: render -> JPEG on the device --
     def render_jpeg_async(self, cam: Camera, encoder: "JpegEncoder", slot: int, want_rgb: bool = False,
                           want_depth: bool = False):
-        """Submit render + JPEG encode on pipeline slot 0/1.  Only what is asked for crosses PCIe:
+        """Submit render + JPEG encode on a pipeline slot (< min(pipeline_depth, encoder.max_batch)).  Only what is asked for crosses PCIe:
         the encoded bytes (always, fetched by :meth:`jpeg_wait`), the raw RGB frame and/or depth
         (optional; returned as pinned host arrays valid after :meth:`jpeg_wait`)."""
         torch = _torch()
@@ -233,7 +233,7 @@ class GaussianScene:
         return buf.numpy()[:n.value].tobytes()
 
     def render_batch_jpeg(self, cams, encoder: "JpegEncoder"):
-        """Every pose of a trajectory -> JPEG bytes, two frames in flight (what
+        """Every pose of a trajectory -> JPEG bytes, several frames in flight (what
         generate_images.py:408-456 does one waypoint at a time with 3 RTX frames, a 3 MB
         read-back and a host-side Pillow encode each).  Yields ``(index, jpeg_bytes)`` in order."""
         cams = list(cams)

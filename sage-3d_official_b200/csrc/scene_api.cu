@@ -1,7 +1,7 @@
 // C-ABI of libsage_splat.so, part 2: scene upload and rendering.
 //
 // A scene owns SAGE_N_CTX frame contexts (all per-frame device state, multi-buffered).  Consecutive
-// frames alternate contexts, so a caller that alternates two streams gets frame N+1's projection /
+// frames rotate over the contexts, so a caller that rotates as many streams gets frame N+1's projection /
 // sorts running while frame N is still compositing — the issue-bound blend kernel and the
 // latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host.
 #include <cstdlib>
