@@ -73,8 +73,8 @@ __device__ __forceinline__ float2 sage_exp2_x2(float2 x)
     return r;
 }
 
-// 12 CTAs per SM (40 registers, no spills; 14+ would spill inside the blend loop): measured
-// 2075 -> 2157 frames/s over the uncapped 50-register build.
+// 12 CTAs per SM (40 registers, no spills): measured 2075 -> 2157 frames/s over the uncapped
+// 50-register build; 16 CTAs (32 registers, 40 B of spill in the blend loop) drops to 2015.
 __global__ void __launch_bounds__(C_THREADS, 12)
 k_composite(SageCamDev cam, const float4* __restrict__ rec, const uint32_t* __restrict__ vals,
             const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, PeerOut out)
