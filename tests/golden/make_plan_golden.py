@@ -30,11 +30,11 @@ def sem_map(seed, w_m, h_m, n_boxes, scale=0.05):
     occ[0, :] = occ[-1, :] = occ[:, 0] = occ[:, -1] = True
     for _ in range(3):                                   # partitions with a door
         if rng.uniform() < 0.5:
-            x = rng.integers(nx // 5, 4 * nx // 5); d = rng.integers(2, ny - 14)
-            occ[:, x] = True; occ[d:d + 12, x] = False
+            x = rng.integers(nx // 5, 4 * nx // 5); d = rng.integers(2, ny - 20)
+            occ[:, x] = True; occ[d:d + 18, x] = False
         else:
-            y = rng.integers(ny // 5, 4 * ny // 5); d = rng.integers(2, nx - 14)
-            occ[y, :] = True; occ[y, d:d + 12] = False
+            y = rng.integers(ny // 5, 4 * ny // 5); d = rng.integers(2, nx - 20)
+            occ[y, :] = True; occ[y, d:d + 18] = False
     insts = [{"category_label": "Wall", "item_id": "wall_0",
               "mask_coords_m": [[f"{y * scale:.2f}", f"{x * scale:.2f}"] for y, x in np.argwhere(occ)]}]
     for k in range(n_boxes):
@@ -102,7 +102,7 @@ def record(name, seed, w_m, h_m, n_boxes, radius, n_queries):
 
 
 if __name__ == "__main__":
-    record("rooms_a", 1, 4.0, 3.0, 6, 0.2, 24)      # ROBOT_RADIUS_M of the trajectory generator (:64)
-    record("rooms_b", 2, 6.0, 5.0, 10, 0.2, 24)
-    record("rooms_c", 3, 5.0, 4.0, 8, 0.08, 16)     # the env's detector radius (simple_env.py:136-140)
-    record("rooms_d", 4, 3.0, 3.0, 4, 0.25, 12)     # r/s = 5: the (5,0)/(3,4) tie radius
+    record("rooms_a", 1, 4.0, 3.0, 6, 0.2, 40)      # ROBOT_RADIUS_M of the trajectory generator (:64)
+    record("rooms_b", 2, 6.0, 5.0, 10, 0.2, 40)
+    record("rooms_c", 3, 5.0, 4.0, 8, 0.08, 32)     # the env's detector radius (simple_env.py:136-140)
+    record("rooms_d", 4, 3.0, 3.0, 4, 0.25, 24)     # r/s = 5: the (5,0)/(3,4) tie radius
