@@ -8,6 +8,7 @@ on that path — same names, arguments, return values and error behaviour —
     build_2d_map(sem_data, scale, robot_radius_m)      :487-559   (inflation on the GPU, K8)
     build_connectivity_map(grid_map, itemid2inst)      :639-689   (components on the GPU, K9)
     astar_pixel(grid, start, goal)                     :253-286   (K10)
+    generate_trajectory_points(path, scale, ...)       :703-741   (host arithmetic)
 
 and adds the batched form the GPU wants: :class:`GridPlanner` / :func:`astar_pixel_batch`.
 Paths are the reference's paths point for point (tests/test_plan_gpu.py, goldens recorded from the
@@ -26,6 +27,8 @@ from ._lib import SageError, check
 
 SCALE_M_PER_PX = 0.05      # vln_trajectory_generator.py:65
 ROBOT_RADIUS_M = 0.2       # vln_trajectory_generator.py:64
+FIXED_Z = 0.5              # vln_trajectory_generator.py:66
+SAMPLE_STEP = 1            # vln_trajectory_generator.py:67
 OBSTACLE_LABELS = ("unable area", "wall")
 
 
@@ -249,10 +252,45 @@ def build_connectivity_map(grid_map: np.ndarray, itemid2inst: Dict[str, Dict]) -
     return dict(groups)
 
 
+def generate_trajectory_points(path, scale: float, min_x: float, min_y: float, fixed_z: float = FIXED_Z,
+                               sample_step: int = SAMPLE_STEP) -> List[Dict]:
+    """Drop-in for vln_trajectory_generator.generate_trajectory_points (:703-741): path cells ->
+    way-points in the trajectory JSON format (cell centres in metres, heading towards the next
+    sampled point as a z-rotation quaternion [0, 0, sin(yaw/2), cos(yaw/2)]; the last point keeps
+    yaw 0).  Pure host arithmetic in binary64, same expressions as the reference."""
+    import math
+    world = [(min_x + (x + 0.5) * scale, min_y + (y + 0.5) * scale) for x, y in path][::sample_step]
+    points = []
+    for j, (wx, wy) in enumerate(world):
+        nx, ny = world[j + 1] if j < len(world) - 1 else world[j]
+        yaw = math.atan2(ny - wy, nx - wx)
+        points.append({
+            "point": str(j),
+            "position": [wx, wy, fixed_z],
+            "rotation": [0.0, 0.0, math.sin(yaw / 2.0), math.cos(yaw / 2.0)],
+            "action": [],
+            "camera_images": [],
+            "focal_length": 7.0,
+            "horizontal_aperture": 20.954999923706055,
+            "vertical_aperture": 20.954999923706055,
+            "focus_distance": 0.0,
+            "clipping_range": [1.0, 1000000.0],
+        })
+    return points
+
+
+def plan_trajectories(grid_map, starts, goals, scale: float, min_x: float, min_y: float) -> List[Optional[List[Dict]]]:
+    """Many start/goal cell pairs -> way-point lists (None where no path exists): one batched A*
+    launch, then the reference's path -> pose conversion."""
+    return [None if p is None else generate_trajectory_points(p, scale, min_x, min_y)
+            for p in astar_pixel_batch(grid_map, starts, goals)]
+
+
 def are_items_connected(item1: str, item2: str, connectivity_map) -> bool:
     return any(item1 in items and item2 in items for items in connectivity_map.values())
 
 
 __all__ = ["GridPlanner", "astar_pixel", "astar_pixel_batch", "build_2d_map", "build_connectivity_map",
+           "generate_trajectory_points", "plan_trajectories",
            "are_items_connected", "get_nearest_free_pixel_on_side", "boundary_pixels", "inflate_grid",
            "connectivity_labels"]

@@ -63,3 +63,30 @@ def test_build_2d_map_raw_matches_live_reference(sage):
     got = planner.build_2d_map(b, robot_radius_m=0.0)
     assert np.array_equal(got[0], want[0]) and got[1:] == want[1:]
     assert [i["mask_coords"] for i in a] == [i["mask_coords"] for i in b]
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree not present")
+def test_trajectory_points_match_live_reference(sage):
+    import contextlib, io
+    sys.path.insert(0, str(REF))
+    with contextlib.redirect_stdout(io.StringIO()):
+        import vln_trajectory_generator as ref
+    from sage3d_official_b200 import planner
+    z = np.load(GOLDEN[1])
+    k = int(np.argmax(z["path_len"]))
+    path = [tuple(int(v) for v in p) for p in z["path_xy"][z["path_off"][k]:z["path_off"][k + 1]]]
+    for step in (1, 3):
+        want = ref.generate_trajectory_points(path, float(z["scale"]), float(z["min_x"]), float(z["min_y"]), sample_step=step)
+        got = planner.generate_trajectory_points(path, float(z["scale"]), float(z["min_x"]), float(z["min_y"]), sample_step=step)
+        assert got == want                       # dicts of Python floats: exact equality
+    assert planner.generate_trajectory_points([(3, 4)], 0.05, 1.0, 2.0)[0]["rotation"] == [0.0, 0.0, 0.0, 1.0]
+
+
+def test_trajectory_points_known_answer(sage):
+    from sage3d_official_b200 import planner
+    pts = planner.generate_trajectory_points([(0, 0), (1, 0), (1, 1)], 0.05, -1.0, 2.0)
+    assert [p["point"] for p in pts] == ["0", "1", "2"]
+    assert pts[0]["position"] == [-1.0 + 0.5 * 0.05, 2.0 + 0.5 * 0.05, 0.5]
+    assert pts[0]["rotation"][2] == 0.0 and pts[0]["rotation"][3] == 1.0             # heading +x
+    assert abs(pts[1]["rotation"][2] - np.sin(np.pi / 4)) < 1e-15                     # heading +y
+    assert pts[2]["rotation"] == [0.0, 0.0, 0.0, 1.0] and pts[2]["focal_length"] == 7.0
