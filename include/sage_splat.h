@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SAGE_ABI_VERSION 1
+#define SAGE_ABI_VERSION 2
 #define SAGE_TILE 16
 
 typedef struct sage_scene sage_scene;   /* device-resident Gaussian scene + frame workspace */
@@ -51,7 +51,7 @@ typedef struct sage_camera {
 typedef struct sage_frame_stats {
     int64_t n_gaussians;      /* N */
     int64_t n_visible;        /* V: survivors of the cull */
-    int64_t n_instances;      /* D: (tile, Gaussian) pairs (clamped to the capacity) */
+    int64_t n_instances;      /* D: (8x8 bin, Gaussian) pairs (clamped to the capacity) */
     int64_t n_instances_wanted; /* D before clamping: what sage_scene_reserve needs after an overflow */
     int64_t instance_capacity;
     int64_t algorithmic_bytes;/* N*44 + V*12*(deg+1)^2 + V*32 + D*24 + D*32 + W*H*(3+4*depth) */
@@ -61,8 +61,8 @@ typedef struct sage_frame_stats {
 
 /* One row of sage_project's debug output (element-wise parity of the projection kernel). */
 typedef struct sage_splat_record {
-    float gx, gy, qa, qb, qc, opacity, z, r, g, b;
-    int32_t tile_x0, tile_y0, tile_x1, tile_y1; /* inclusive tile rectangle after clipping */
+    float gx, gy, qa, qb, qc, log2_opacity, z, r, g, b;
+    int32_t tile_x0, tile_y0, tile_x1, tile_y1; /* inclusive 16-px tile rectangle of the pixel box after clipping */
 } sage_splat_record;
 
 const char* sage_last_error(void);
@@ -122,10 +122,23 @@ int sage_render_peers(sage_scene* s, const sage_camera* cam, int row0_tiles, int
  * lo > hi disables it (default). */
 int sage_scene_set_depth_clip(sage_scene* s, float lo, float hi);
 
+/* Colour output format of every later render call on the scene: 0 (default) RGB u8 [H,W,3];
+ * 1 RGBA u8 [H,W,4] with alpha = 255 — the array Isaac's Camera.get_rgba() returns
+ * (simple_env.py:1380; generate_images.py:428), written as one 8-byte store per pixel pair, so the
+ * Isaac shim needs no host-side expansion.  rgb buffers passed to render calls must then hold
+ * 4 bytes per pixel. */
+int sage_scene_set_rgba(sage_scene* s, int on);
+
+/* Frames replay as one CUDA graph per frame context (default on; SAGE_NO_GRAPH=1 in the environment
+ * or on = 0 launches every kernel directly).  sage_scene_graph_stats reports how many frames went
+ * each way. */
+int sage_scene_set_graph(sage_scene* s, int on);
+int sage_scene_graph_stats(sage_scene* s, int64_t* graph_launches_out, int64_t* direct_frames_out);
+
 /* Synchronises with the last frame on the scene and returns its counters. */
 int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out);
 
-/* (tile, Gaussian) instances per tile row of the last frame (load-balancing the multi-GPU row split). */
+/* (bin, Gaussian) instances per 16-pixel tile row of the last frame (load-balancing the multi-GPU row split). */
 int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows);
 
 /* Per-stage device timing (bench/roofline): with n_slots > 0 every frame records CUDA events

@@ -38,7 +38,7 @@ class Camera(C.Structure):
 
 
 SPLAT_DTYPE = np.dtype([(k, np.float32) for k in
-                        ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b", "cov_a", "cov_c")])
+                        ("gx", "gy", "qa", "qb", "qc", "lo", "z", "r", "g", "b", "cov_a", "cov_c")])
 
 
 def lib():

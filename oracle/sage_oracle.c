@@ -40,8 +40,8 @@
 #endif
 
 #define SO_TILE 16
-#define SO_ALPHA_MIN 0.003921569f /* 1/255 rounded to binary32 */
-#define SO_ALPHA_MAX 0.99f
+#define SO_L255 (-7.99435344f)  /* log2(1/255) rounded to binary32: a splat is skipped where log2(alpha) < this */
+#define SO_L099 (-0.0144995697f) /* log2(0.99) rounded to binary32: alpha is capped at 0.99 in the exponent domain */
 #define SO_T_MIN 1e-4f
 #define SO_BLUR 0.3f
 #define SO_LOG2E 1.44269504f
@@ -59,7 +59,7 @@ typedef struct {
 typedef struct {
     float gx, gy;       /* mean in continuous pixel coordinates */
     float qa, qb, qc;   /* log2e-folded conic: power2 = qa dx^2 + qb dx dy + qc dy^2 */
-    float opacity;      /* sigmoid(raw) */
+    float lo;           /* log2(sigmoid(raw)) by so_log2 */
     float z;            /* planar view depth */
     float r, g, b;      /* SH colour, clamped >= 0 */
     float cov_a, cov_c; /* blurred 2-D covariance diagonal (oracle-side bounding only) */
@@ -88,6 +88,41 @@ float so_exp2(float x)
 }
 
 float so_exp(float x) { return so_exp2(x * SO_LOG2E); }
+
+/* The blend's exp2: same split, degree-3 polynomial (max rel. error 7.5e-5, far below
+ * the 1/255 colour quantum); callers guarantee x in [SO_L255, SO_L099], so no clamp. */
+float so_exp2_fast(float x)
+{
+    const float magic = 12582912.0f;
+    float t = x + magic;
+    float n = t - magic;
+    float f = x - n;
+    float p = 0x1.c3f760p-5f;
+    p = fmaf(p, f, 0x1.f0de1ap-3f);
+    p = fmaf(p, f, 0x1.62f31ap-1f);
+    p = fmaf(p, f, 0x1.fff692p-1f);
+    return so_u2f(so_f2u(p) + (so_f2u(t) << 23));
+}
+
+/* Deterministic binary32 log2 for x in (0, 1]: exponent/mantissa split,
+ * m in (sqrt(1/2), sqrt(2)], log(m) = 2 atanh((m-1)/(m+1)) as an odd series to s^9.
+ * x == 0 (a Gaussian dropped at load) returns -127: below every threshold. */
+float so_log2(float x)
+{
+    uint32_t u = so_f2u(x);
+    float e = (float)((int)((u >> 23) & 255u) - 127);
+    float m = so_u2f((u & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e = e + 1.0f; }
+    float s = (m - 1.0f) / (m + 1.0f);
+    float s2 = s * s;
+    float p = 0x1.c71c72p-4f;             /* 1/9 */
+    p = fmaf(p, s2, 0x1.24924ap-3f);      /* 1/7 */
+    p = fmaf(p, s2, 0x1.99999ap-3f);      /* 1/5 */
+    p = fmaf(p, s2, 0x1.555556p-2f);      /* 1/3 */
+    p = fmaf(p, s2, 1.0f);
+    float ln_m = (2.0f * s) * p;
+    return fmaf(ln_m, SO_LOG2E, e);
+}
 
 /* ------------------------------------------------------------------ per-Gaussian projection */
 
@@ -180,7 +215,8 @@ static int so_project_one(const so_camera* cam, int deg, const float* xyz, const
     if (!(tz > cam->near_z) || !(tz < cam->far_z)) return 0;
 
     float o = 1.0f / (1.0f + so_exp(-op_raw));
-    if (!(o >= SO_ALPHA_MIN)) return 0;
+    float lo = so_log2(o);
+    if (!(lo >= SO_L255)) return 0;       /* peak alpha below 1/255 */
 
     float S[6];
     so_cov3d(ls, q, S);
@@ -221,7 +257,7 @@ static int so_project_one(const so_camera* cam, int deg, const float* xyz, const
     out->qa = conic_a * (-0.5f * SO_LOG2E);
     out->qb = conic_b * (-SO_LOG2E);
     out->qc = conic_c * (-0.5f * SO_LOG2E);
-    out->opacity = o;
+    out->lo = lo;
     out->z = tz;
     out->cov_a = a;
     out->cov_c = c;
@@ -274,13 +310,11 @@ static inline int so_blend(const so_splat* s, float pxc, float pyc, float* T, fl
     float dy = pyc - s->gy;
     float bdy = s->qb * dy;
     float cdy = s->qc * dy;
-    float cdy2 = cdy * dy;
+    float cdy2 = fmaf(cdy, dy, s->lo);           /* opacity folded into the exponent */
     float w = fmaf(s->qa, dx, bdy);
-    float power2 = fmaf(dx, w, cdy2);
-    if (power2 > 0.0f) return 0;
-    float e = so_exp2(power2);
-    float alpha = fminf(SO_ALPHA_MAX, s->opacity * e);
-    if (alpha < SO_ALPHA_MIN) return 0;
+    float power2 = fmaf(dx, w, cdy2);            /* log2(alpha) before the cap */
+    if (!(power2 >= SO_L255)) return 0;          /* alpha < 1/255 */
+    float alpha = so_exp2_fast(fminf(power2, SO_L099));
     float Tn = *T * (1.0f - alpha);
     if (Tn < SO_T_MIN) return 1;
     float wgt = alpha * *T;
@@ -299,7 +333,7 @@ static inline void so_finish(float T, const float* C, float Dz, uint8_t* rgb, fl
         rgb[c] = (uint8_t)(v * 255.0f + 0.5f);
     }
     float cover = 1.0f - T;
-    if (depth) *depth = cover > 1e-6f ? Dz / cover : 0.0f;
+    if (depth) *depth = cover > 1e-6f ? Dz / cover : INFINITY;   /* nothing hit: Isaac's distance_to_image_plane is inf there */
     if (finalT) *finalT = T;
 }
 
@@ -358,7 +392,7 @@ int so_render(const so_camera* cam, int64_t n, int deg, const float* xyz, const 
            1 % + 1 px of slack swallows every binary32 rounding in the blend path. */
         for (int64_t r = 0; r < V; ++r) {
             const so_splat* s = &sp[order[r].idx];
-            double tau = 2.0 * log(255.0 * (double)s->opacity) * 1.01 + 0.01;
+            double tau = 2.0 * (((double)s->lo - (double)SO_L255) / 1.4426950408889634) * 1.01 + 0.01;
             if (tau < 0.01) tau = 0.01;
             double hx = sqrt(tau * (double)s->cov_a) + 1.0, hy = sqrt(tau * (double)s->cov_c) + 1.0;
             double x0 = floor(((double)s->gx - hx) / SO_TILE), x1 = floor(((double)s->gx + hx) / SO_TILE);
@@ -539,4 +573,4 @@ void so_collide_capsule(int64_t m, const float* mu, const float* log_scale, cons
     }
 }
 
-int so_abi_version(void) { return 1; }
+int so_abi_version(void) { return 2; }

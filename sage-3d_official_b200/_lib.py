@@ -14,6 +14,7 @@ LIB_PATH = _HERE / "libsage_splat.so"
 EXPORTS = [
     "sage_last_error", "sage_abi_version", "sage_device_count",
     "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy", "sage_scene_set_depth_clip",
+    "sage_scene_set_rgba", "sage_scene_set_graph", "sage_scene_graph_stats",
     "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_pipeline_depth", "sage_render_peers", "sage_frame_stats_get", "sage_project",
     "sage_frame_row_instances", "sage_set_stage_timing", "sage_stage_times_get",
     "sage_ipc_export", "sage_ipc_open", "sage_ipc_close",
@@ -44,7 +45,7 @@ class CFrameStats(C.Structure):
 
 
 class CSplatRecord(C.Structure):
-    _fields_ = [(k, C.c_float) for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b")] + \
+    _fields_ = [(k, C.c_float) for k in ("gx", "gy", "qa", "qb", "qc", "log2_opacity", "z", "r", "g", "b")] + \
                [(k, C.c_int32) for k in ("tile_x0", "tile_y0", "tile_x1", "tile_y1")]
 
 
@@ -78,6 +79,9 @@ def lib():
     L.sage_scene_reserve.argtypes = [vp, i64]
     L.sage_scene_destroy.argtypes = [vp]
     L.sage_scene_set_depth_clip.argtypes = [vp, C.c_float, C.c_float]
+    L.sage_scene_set_rgba.argtypes = [vp, i32]
+    L.sage_scene_set_graph.argtypes = [vp, i32]
+    L.sage_scene_graph_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.sage_render.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
     L.sage_render_host.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, vp]
     L.sage_render_host_async.argtypes = [vp, C.POINTER(CCamera), i32, i32, vp, vp, i32]

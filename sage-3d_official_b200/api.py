@@ -107,6 +107,26 @@ class GaussianScene:
     def reserve(self, max_instances: int):
         check(_lib.lib().sage_scene_reserve(self._h, int(max_instances)))
 
+    def set_rgba(self, on: bool = True):
+        """Colour output as RGBA u8 [H,W,4] (alpha 255) — what Isaac's ``Camera.get_rgba()`` returns —
+        instead of RGB u8 [H,W,3].  Applies to every later render call on the scene."""
+        check(_lib.lib().sage_scene_set_rgba(self._h, 1 if on else 0))
+        self._rgba = bool(on)
+        self._pinned = {}
+
+    def set_graph(self, on: bool = True):
+        """Replay frames as one CUDA graph per frame context (default) or launch every kernel directly."""
+        check(_lib.lib().sage_scene_set_graph(self._h, 1 if on else 0))
+
+    def graph_stats(self) -> dict:
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().sage_scene_graph_stats(self._h, C.byref(a), C.byref(b)))
+        return {"graph_launches": int(a.value), "direct_frames": int(b.value)}
+
+    @property
+    def channels(self) -> int:
+        return 4 if getattr(self, "_rgba", False) else 3
+
     # -- render --
     @staticmethod
     def _rows(cam: Camera, rows):
@@ -121,7 +141,7 @@ class GaussianScene:
         torch = _torch()
         dev = torch.device("cuda", self.device)
         if out is None:
-            rgb = torch.empty((cam.height, cam.width, 3), dtype=torch.uint8, device=dev)
+            rgb = torch.empty((cam.height, cam.width, self.channels), dtype=torch.uint8, device=dev)
             depth = torch.empty((cam.height, cam.width), dtype=torch.float32, device=dev) if want_depth else None
             if rows is not None:
                 rgb.zero_()
@@ -151,7 +171,7 @@ class GaussianScene:
         torch = _torch()
         key = (cam.height, cam.width)
         if key not in self._pinned:
-            self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+            self._pinned[key] = (torch.zeros((cam.height, cam.width, self.channels), dtype=torch.uint8).pin_memory(),
                                  torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
         rgb_t, dep_t = self._pinned[key]
         r0, r1 = self._rows(cam, rows)
@@ -173,7 +193,7 @@ class GaussianScene:
         torch = _torch()
         key = (cam.height, cam.width, "async", int(slot))
         if key not in self._pinned:
-            self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+            self._pinned[key] = (torch.zeros((cam.height, cam.width, self.channels), dtype=torch.uint8).pin_memory(),
                                  torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
         rgb_t, dep_t = self._pinned[key]
         r0, r1 = self._rows(cam, rows)
@@ -215,7 +235,7 @@ class GaussianScene:
         if want_rgb or want_depth:
             key = (cam.height, cam.width, "async", int(slot))
             if key not in self._pinned:
-                self._pinned[key] = (torch.zeros((cam.height, cam.width, 3), dtype=torch.uint8).pin_memory(),
+                self._pinned[key] = (torch.zeros((cam.height, cam.width, self.channels), dtype=torch.uint8).pin_memory(),
                                      torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
             rgb_t, dep_t = self._pinned[key]
         cc = _ccam(cam)
@@ -278,7 +298,7 @@ class GaussianScene:
         r0, r1 = self._rows(cam, rows)
         cc = _ccam(cam)
         check(_lib.lib().sage_project(self._h, C.byref(cc), r0, r1, C.cast(rec, C.c_void_p), _ptr(vis)))
-        dt = np.dtype([(k, np.float32) for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b")] +
+        dt = np.dtype([(k, np.float32) for k in ("gx", "gy", "qa", "qb", "qc", "log2_opacity", "z", "r", "g", "b")] +
                       [(k, np.int32) for k in ("tile_x0", "tile_y0", "tile_x1", "tile_y1")])
         arr = np.frombuffer(rec, dtype=dt, count=self.n).copy()
         return arr, vis[:self.n].astype(bool)

@@ -1,4 +1,6 @@
 // K0 precompute (scene upload), K1a project + cull (per frame), K1b SH colour (per frame).
+// The per-frame kernels read the camera from the frame context's device-resident parameter block
+// (SageFrameParams), so their launch parameters are frame-invariant and a frame replays as a graph.
 //
 // Stands in for the per-Gaussian work hidden inside Isaac's world.step(render=True)
 // (reference call sites simple_env.py:1369, generate_images.py:426).  The arithmetic follows
@@ -10,7 +12,9 @@
 // the SH coefficients repacked as 16-byte chunks, contiguous per Gaussian (a visible Gaussian's
 // 192 B are six whole 32-byte sectors, so a scattered visible set wastes no DRAM traffic).
 // Gaussians with a non-finite attribute or an SH coefficient >= 1e30 in magnitude are dropped at
-// load (spec rule): their opacity is stored as 0, which the per-frame cull rejects.
+// load (spec rule): their log2-opacity is stored as -127, which the per-frame cull rejects.
+// Opacity is kept as lo = log2(sigmoid(raw)) (deterministic sage_log2): the blend adds it to the
+// exponent instead of multiplying alpha by it.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __restrict__ log_scale,
@@ -36,7 +40,7 @@ k_precompute(SageSceneDev sc, const float* __restrict__ xyz, const float* __rest
                 quat[4 * i + 2] + quat[4 * i + 3] + opacity[i];
     ok = ok && (chk - chk == 0.0f);
     float o = ok ? 1.0f / (1.0f + sage_exp(-opacity[i])) : 0.0f;
-    sc.geo0[i] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], o);
+    sc.geo0[i] = make_float4(xyz[3 * i + 0], xyz[3 * i + 1], xyz[3 * i + 2], sage_log2(o));
 
     float sx = sage_exp(log_scale[3 * i + 0]);
     float sy = sage_exp(log_scale[3 * i + 1]);
@@ -68,7 +72,7 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
-    k_precompute<<<blocks, 256, 0, st>>>(sc, xyz, log_scale, quat, opacity, sh);
+    SAGE_KLAUNCH(k_precompute, blocks, 256, st, sc, xyz, log_scale, quat, opacity, sh);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -77,19 +81,20 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 // (bits(z) - bits(near), or CULLED) that the first radix pass compacts and sorts in one go.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
+k_project(SageSceneDev sc, SageFrame fr)
 {
+    const SageCamDev& cam = fr.fp->cam;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool vis = false;
     uint32_t key = SAGE_KEY_CULLED;
     if (i < sc.n) {
         const float4 g0 = __ldg(&sc.geo0[i]);
-        const float mx = g0.x, my = g0.y, mz = g0.z, o = g0.w;
+        const float mx = g0.x, my = g0.y, mz = g0.z, lo = g0.w;
         const float* R = cam.R;
         float tx = fmaf(R[2], mz, fmaf(R[1], my, fmaf(R[0], mx, cam.t[0])));
         float ty = fmaf(R[5], mz, fmaf(R[4], my, fmaf(R[3], mx, cam.t[1])));
         float tz = fmaf(R[8], mz, fmaf(R[7], my, fmaf(R[6], mx, cam.t[2])));
-        if (tz > cam.near_z && tz < cam.far_z && o >= SAGE_ALPHA_MIN) {
+        if (tz > cam.near_z && tz < cam.far_z && lo >= SAGE_L255) {
             const float4 g1 = __ldg(&sc.geo1[i]);
             const float2 g2 = __ldg(&sc.geo2[i]);
             const float S00 = g1.x, S01 = g1.y, S02 = g1.z, S11 = g1.w, S12 = g2.x, S22 = g2.y;
@@ -129,7 +134,7 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 // Conservative bounding rectangle of {alpha >= 1/255}: derived in binary64 from
                 // the *rounded* conic the blend kernel will use, with 0.2 % + 0.02 slack on the
                 // log2 threshold.  Not part of the spec: it only has to be conservative.
-                const float l2 = __log2f(255.0f * o);
+                const float l2 = lo - SAGE_L255;                 // log2(255 o)
                 const double t2 = (double)l2 * 1.002 + 0.02;
                 const double A = -(double)qa, Bq = -0.5 * (double)qb, Cq = -(double)qc;
                 const double det2 = A * Cq - Bq * Bq;
@@ -142,15 +147,15 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 if ((chk - chk == 0.0f) && xhi >= 0.0 && xlo <= Wm && yhi >= 0.0 && ylo <= Hm) {
                     int ix0 = (int)fmax(xlo, 0.0), ix1 = (int)fmin(xhi, Wm);
                     int iy0 = (int)fmax(ylo, 0.0), iy1 = (int)fmin(yhi, Hm);
-                    // clip to the tile rows this call renders (multi-GPU row sharding)
-                    iy0 = max(iy0, cam.row0 * SAGE_TILE);
-                    iy1 = min(iy1, min(cam.row1 * SAGE_TILE, cam.H) - 1);
+                    // clip to the rows this call renders (multi-GPU row sharding)
+                    iy0 = max(iy0, cam.bin_row0 * SAGE_BIN);
+                    iy1 = min(iy1, min(cam.bin_row1 * SAGE_BIN, cam.H) - 1);
                     if (iy0 <= iy1 && ix0 <= ix1) {
                         vis = true;
                         key = __float_as_uint(tz) - __float_as_uint(cam.near_z);
-                        fr.rec[3 * i + 0] = make_float4(gx, gy, qa, -l2 - 0.01f);
-                        fr.rec[3 * i + 1] = make_float4(qb, qc, o, tz);
-                        // inclusive pixel bounding box (u16 each); the exact tile ranges are taken by
+                        fr.rec[3 * i + 0] = make_float4(gx, gy, qa, lo);
+                        fr.rec[3 * i + 1] = make_float4(qb, qc, 0.0f, 0.0f);
+                        // inclusive pixel bounding box (u16 each); the exact bin ranges are taken by
                         // k_emit, which walks only the visible set
                         fr.rect[i] = make_uint2((uint32_t)ix0 | ((uint32_t)ix1 << 16),
                                                 (uint32_t)iy0 | ((uint32_t)iy1 << 16));
@@ -158,7 +163,7 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
                 }
             }
         }
-        fr.dkey[0][i] = key;
+        fr.dkey_src[i] = key;
     }
     // one atomic per warp for the visible counter
     const unsigned m = __ballot_sync(0xffffffffu, vis);
@@ -166,8 +171,12 @@ k_project(SageSceneDev sc, SageCamDev cam, SageFrame fr)
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1b: view-dependent SH colour for the V visible Gaussians (walks the depth-sorted id list).
-// Separate from K1a so that neither kernel carries the other's registers.
+// K1b: view-dependent SH colour of the visible Gaussians, in INDEX order (a thread per Gaussian
+// checks its depth key): independent of the depth sort, so it runs on the frame's side stream /
+// a parallel graph branch between the projection and the composite.  With a spatially ordered
+// scene (Morton order at ingest) the visible set is contiguous runs: the 192-byte SH gathers of a
+// warp land in neighbouring sectors.  Also writes the view depth z next to the colour (same fmaf
+// chain as K1a: the same bits).
 // ---------------------------------------------------------------------------------------------
 __device__ __constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f,
                                             0.31539156525252005f, -1.0925484305920792f,
@@ -179,15 +188,15 @@ __device__ __constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640
 
 template <int DEG>
 __global__ void __launch_bounds__(256, 4)
-k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __restrict__ order)
+k_sh_color(SageSceneDev sc, SageFrame fr)
 {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     constexpr int NF = 3 * NB;
     constexpr int NC = (NF + 3) / 4;
-    const uint32_t V = fr.counters[CNT_VISIBLE];
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= V) return;
-    const uint32_t i = __ldg(&order[r]);
+    const SageCamDev& cam = fr.fp->cam;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sc.n) return;
+    if (__ldg(&fr.dkey_src[i]) == SAGE_KEY_CULLED) return;
     const float4 g0 = __ldg(&sc.geo0[i]);
     float shv[NC * 4];
     const float4* sp = sc.shc + (size_t)i * NC;
@@ -232,26 +241,26 @@ k_sh_color(SageSceneDev sc, SageCamDev cam, SageFrame fr, const uint32_t* __rest
         for (int k = 1; k < NB; ++k) a = fmaf(basis[k], shv[3 * k + c], a);
         acc[c] = fmaxf(a + 0.5f, 0.0f);
     }
-    fr.rec[3 * (size_t)i + 2] = make_float4(acc[0], acc[1], acc[2], 0.0f);
-
+    const float* R = cam.R;
+    const float tz = fmaf(R[8], g0.z, fmaf(R[7], g0.y, fmaf(R[6], g0.x, cam.t[2])));
+    fr.rec[3 * (size_t)i + 2] = make_float4(acc[0], acc[1], acc[2], tz);
 }
 
-void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st)
+void sage_launch_project(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
-    k_project<<<blocks, 256, 0, st>>>(sc, cam, fr);
+    SAGE_KLAUNCH(k_project, blocks, 256, st, sc, fr);
 }
 
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
-                          const uint32_t* order, cudaStream_t st)
+void sage_launch_sh_color(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
     switch (sc.deg) {
-        case 0: k_sh_color<0><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        case 1: k_sh_color<1><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        case 2: k_sh_color<2><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
-        default: k_sh_color<3><<<blocks, 256, 0, st>>>(sc, cam, fr, order); break;
+        case 0: SAGE_KLAUNCH(k_sh_color<0>, blocks, 256, st, sc, fr); break;
+        case 1: SAGE_KLAUNCH(k_sh_color<1>, blocks, 256, st, sc, fr); break;
+        case 2: SAGE_KLAUNCH(k_sh_color<2>, blocks, 256, st, sc, fr); break;
+        default: SAGE_KLAUNCH(k_sh_color<3>, blocks, 256, st, sc, fr); break;
     }
 }

@@ -10,19 +10,22 @@
 #else
 #include <cuda_runtime.h>
 #define SAGE_KLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define SAGE_KLAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define SAGE_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
 #include <stdint.h>
 
 #include "../../include/sage_splat.h"
 
-#define SAGE_ALPHA_MIN 0.003921569f
-#define SAGE_ALPHA_MAX 0.99f
+#define SAGE_L255 (-7.99435344f)      /* log2(1/255): skip where log2(alpha) < this */
+#define SAGE_L099 (-0.0144995697f)    /* log2(0.99): alpha cap, applied to the exponent */
 #define SAGE_T_MIN 1e-4f
+#define SAGE_BIN 8                    /* internal binning granularity: 8 x 8 pixels, one warp per bin */
 #define SAGE_BLUR 0.3f
 #define SAGE_LOG2E 1.44269504f
 #define SAGE_KEY_CULLED 0xFFFFFFFFu
-// instance value = Gaussian id (28 bits) << 4 | 8x8-quadrant overlap mask of the tile (4 bits)
-#define SAGE_ID_MASK 0x0FFFFFFFu
+#define SAGE_ID_MASK 0x0FFFFFFFu      /* scene size limit (2^28 - 1 Gaussians) */
+#define SAGE_MAX_PEERS 8
 
 // device counters (uint32 each)
 enum { CNT_VISIBLE = 0, CNT_INSTANCES = 1, CNT_OVERFLOW = 2, CNT_WANTED = 3, CNT_COUNT = 8 };
@@ -35,9 +38,32 @@ struct SageCamDev {
     float limx, limy;
     float near_z, far_z;
     int W, H;
-    int tiles_x, tiles_y;  // full-frame tile grid
+    int tiles_x, tiles_y;  // full-frame grid of 16 x 16 tiles (the public sharding unit)
     int row0, row1;        // tile rows rendered by this call
     float depth_lo, depth_hi;  // output clamp of the depth map (lo > hi: off)
+    int bins_x;            // 8 x 8 bins per image row
+    int bin_row0, bin_row1;    // bin rows rendered by this call
+    int n_bins;            // bins_x * (bin_row1 - bin_row0)
+    int tile_passes;       // radix passes of the by-bin sort (8 bits each)
+};
+
+// destination frame buffers of one render call (several: peer GPUs, NVLink)
+struct SageOutDev {
+    uint8_t* rgb[SAGE_MAX_PEERS];
+    float* depth[SAGE_MAX_PEERS];
+    int n;
+    int wide;     // 8-byte stores allowed: W % 8 == 0 and every buffer 8-byte aligned
+    int rgba;     // 4 bytes per pixel (alpha = 255) instead of 3
+};
+
+// Everything that changes from frame to frame.  Lives in DEVICE memory (one block per frame
+// context, refreshed by a 400-byte host-to-device copy), so the kernels' launch parameters never
+// change and a whole frame replays as one CUDA graph.
+struct SageFrameParams {
+    SageCamDev cam;
+    SageOutDev out;
+    uint32_t epoch;       // look-back epochs epoch .. epoch+7 are fresh for this frame
+    uint32_t cap;         // instance capacity of the frame context
 };
 
 // ---- deterministic exp2 (mirrors the spec) --------------------------------
@@ -58,23 +84,40 @@ __device__ __forceinline__ float sage_exp2(float x)
 }
 __device__ __forceinline__ float sage_exp(float x) { return sage_exp2(x * SAGE_LOG2E); }
 
-// ---- exact tile culling: the {alpha >= 1/255} ellipse against bands of pixel rows -------------
+// deterministic log2 for x in (0, 1] (mirrors so_log2); 0 -> -127
+__device__ __forceinline__ float sage_log2(float x)
+{
+    const uint32_t u = __float_as_uint(x);
+    float e = (float)((int)((u >> 23) & 255u) - 127);
+    float m = __uint_as_float((u & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e = e + 1.0f; }
+    const float s = (m - 1.0f) / (m + 1.0f);
+    const float s2 = s * s;
+    float p = 0x1.c71c72p-4f;
+    p = fmaf(p, s2, 0x1.24924ap-3f);
+    p = fmaf(p, s2, 0x1.99999ap-3f);
+    p = fmaf(p, s2, 0x1.555556p-2f);
+    p = fmaf(p, s2, 1.0f);
+    const float ln_m = (2.0f * s) * p;
+    return fmaf(ln_m, SAGE_LOG2E, e);
+}
+
+// ---- exact bin culling: the {alpha >= 1/255} ellipse against bands of 8 pixel rows -------------
 // Binning is not part of the numerical spec: it only has to be conservative.
 // The support of a splat is the ellipse  A dx^2 + 2B dx dy + C dy^2 <= t2  around (gx, gy), in the
-// log2-scaled units of the conic the blend kernel uses (A = -qa, B = -qb/2, C = -qc).  k_project
-// counts, and k_emit enumerates, exactly the tiles whose rows contain a pixel centre inside it;
-// both call the functions below on the same binary32 inputs, so their counts agree by
-// construction.  Binary32 arithmetic (binary64 sqrt/div sequences cost more than the instances
-// they save) made conservative by slack: t2 = log2(255 o) * 1.003 + 0.02 (the bounding box uses
-// 1.002) and every span is widened by 0.1 % of the half extent + 0.01 px;
-// tools/cuda_emu/band_check.cpp brute-forces the guarantee on CPU.
+// log2-scaled units of the conic the blend kernel uses (A = -qa, B = -qb/2, C = -qc; t2 = lo - L255).
+// k_emit enumerates, per band of 8 pixel rows, exactly the 8 x 8 bins whose rows contain a pixel
+// centre inside it.  Binary32 arithmetic (binary64 sqrt/div sequences cost more than the instances
+// they save) made conservative by slack: t2 * 1.003 + 0.02 (the bounding box uses 1.002) and every
+// span is widened by 0.1 % of the half extent + 0.01 px; tools/cuda_emu/band_check.cpp brute-forces
+// the guarantee on CPU.
 // sqrt to ~2 ulp (one MUFU + one multiply); the spans carry 0.1 % of slack.  Negative -> 0.
 __device__ __forceinline__ float sage_sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
 
-// true: the pixel box spans at least 2 x 2 tiles — only then can the ellipse test remove a tile
+// true: the pixel box spans at least 2 x 2 bins — only then can the ellipse test remove a bin
 __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int iy1)
 {
-    return (ix0 / SAGE_TILE != ix1 / SAGE_TILE) && (iy0 / SAGE_TILE != iy1 / SAGE_TILE);
+    return (ix0 / SAGE_BIN != ix1 / SAGE_BIN) && (iy0 / SAGE_BIN != iy1 / SAGE_BIN);
 }
 
 struct SageBand {
@@ -85,10 +128,10 @@ struct SageBand {
     int unbounded;      // degenerate conic: treat as covering everything
 };
 
-__device__ __forceinline__ SageBand sage_band_make(float gx, float gy, float qa, float qb, float qc, float o)
+// l2 = log2(255 * opacity) = lo - SAGE_L255
+__device__ __forceinline__ SageBand sage_band_make(float gx, float gy, float qa, float qb, float qc, float l2)
 {
     SageBand b;
-    const float l2 = __log2f(255.0f * o);
     b.t2 = l2 * 1.003f + 0.02f;
     b.gx = gx; b.gy = gy;
     b.A = -qa; b.B = -0.5f * qb; b.C = -qc;
@@ -132,112 +175,69 @@ __device__ __forceinline__ bool sage_band_span(const SageBand& b, int ix0, int i
     return *xs <= *xe;
 }
 
-// One tile row ty of a splat with pixel box [ix0,ix1] x [iy0,iy1]: spans of its upper and lower
-// 8-row halves (packed x0 | x1 << 16; 0xFFFF0000-style empty = x0 > x1) and the inclusive tile range.
-struct SageRowItem {
-    uint32_t top, bot;      // pixel spans of rows [16ty, 16ty+7] and [16ty+8, 16ty+15]; SAGE_SPAN_EMPTY if none
-    int tx0, tx1;           // tiles [tx0, tx1]; tx0 > tx1: the row is empty
-};
-#define SAGE_SPAN_EMPTY 0x0000FFFFu     /* x0 = 0xFFFF > x1 = 0 */
-
-__device__ __forceinline__ SageRowItem sage_band_row(const SageBand& b, int ix0, int ix1, int iy0, int iy1, int ty)
+// Bins [*b0, *b1] (inclusive; *b0 > *b1: none) that band `by` (pixel rows 8by .. 8by+7) of a splat with
+// pixel box [ix0,ix1] x [iy0,iy1] touches.  `cull` false: the box decides (the band is not evaluated).
+__device__ __forceinline__ void sage_band_bins(const SageBand& b, bool cull, int ix0, int ix1, int iy0, int iy1,
+                                               int by, int* b0, int* b1)
 {
-    SageRowItem it;
-    it.top = it.bot = SAGE_SPAN_EMPTY;
-    if (!sage_box_cullable(ix0, ix1, iy0, iy1)) {
-        // one row or one column of tiles (most splats): no tile can be culled, quadrants from the box
-        // (the band is not even evaluated: callers may pass an unset one)
-        const uint32_t sp = (uint32_t)ix0 | ((uint32_t)ix1 << 16);
-        if (iy0 <= ty * SAGE_TILE + 7 && iy1 >= ty * SAGE_TILE) it.top = sp;
-        if (iy1 >= ty * SAGE_TILE + 8 && iy0 <= ty * SAGE_TILE + 15) it.bot = sp;
-        it.tx0 = ix0 / SAGE_TILE; it.tx1 = ix1 / SAGE_TILE;
-        return it;
-    }
-    int lo = 1 << 30, hi = -1;
-    int xs, xe;
-    const int ya = max(ty * SAGE_TILE, iy0), yb = min(ty * SAGE_TILE + 7, iy1);
-    if (ya <= yb && sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) {
-        it.top = (uint32_t)xs | ((uint32_t)xe << 16);
-        lo = min(lo, xs); hi = max(hi, xe);
-    }
-    const int yc = max(ty * SAGE_TILE + 8, iy0), yd = min(ty * SAGE_TILE + 15, iy1);
-    if (yc <= yd && sage_band_span(b, ix0, ix1, yc, yd, &xs, &xe)) {
-        it.bot = (uint32_t)xs | ((uint32_t)xe << 16);
-        lo = min(lo, xs); hi = max(hi, xe);
-    }
-    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
-    else { it.tx0 = lo / SAGE_TILE; it.tx1 = hi / SAGE_TILE; }
-    return it;
-}
-
-// rebuild a row item from its two stored spans
-__device__ __forceinline__ SageRowItem sage_row_from_spans(uint32_t top, uint32_t bot)
-{
-    SageRowItem it;
-    it.top = top; it.bot = bot;
-    int lo = 1 << 30, hi = -1;
-    if ((top & 0xFFFFu) <= (top >> 16)) { lo = min(lo, (int)(top & 0xFFFFu)); hi = max(hi, (int)(top >> 16)); }
-    if ((bot & 0xFFFFu) <= (bot >> 16)) { lo = min(lo, (int)(bot & 0xFFFFu)); hi = max(hi, (int)(bot >> 16)); }
-    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
-    else { it.tx0 = lo / SAGE_TILE; it.tx1 = hi / SAGE_TILE; }
-    return it;
-}
-
-// 8x8-quadrant mask (bit qy*2+qx, the warp -> quadrant map of the composite kernel) of tile tx
-__device__ __forceinline__ uint32_t sage_row_quad_mask(const SageRowItem& it, int tx)
-{
-    const int bx = tx * SAGE_TILE;
-    const int t0 = (int)(it.top & 0xFFFFu), t1 = (int)(it.top >> 16);
-    const int b0 = (int)(it.bot & 0xFFFFu), b1 = (int)(it.bot >> 16);
-    uint32_t m = 0;
-    if (t0 <= t1) m |= ((t0 <= bx + 7 && t1 >= bx) ? 1u : 0u) | ((t0 <= bx + 15 && t1 >= bx + 8) ? 2u : 0u);
-    if (b0 <= b1) m |= ((b0 <= bx + 7 && b1 >= bx) ? 4u : 0u) | ((b0 <= bx + 15 && b1 >= bx + 8) ? 8u : 0u);
-    return m;
+    const int ya = max(by * SAGE_BIN, iy0), yb = min(by * SAGE_BIN + SAGE_BIN - 1, iy1);
+    *b0 = 1; *b1 = 0;
+    if (ya > yb) return;
+    int xs = ix0, xe = ix1;
+    if (cull && !sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) return;
+    *b0 = xs / SAGE_BIN; *b1 = xe / SAGE_BIN;
 }
 
 // ---- frame workspace ---------------------------------------------------------------------
 #define SAGE_RADIX_MAX_BINS 512
 #define SAGE_MAX_PASSES 4
-enum { SAGE_TICKET_DEPTH = 0, SAGE_TICKET_EMIT = 4, SAGE_TICKET_TILE = 5, SAGE_TICKET_COUNT = 12 };
+#define SAGE_N_CLASSES 33          /* list-length classes of the bins: 0 = empty, k: 2^(k-1) <= n < 2^k */
+enum { SAGE_TICKET_DEPTH = 0, SAGE_TICKET_EMIT = 4, SAGE_TICKET_TILE = 5, SAGE_TICKET_COMPOSITE = 9,
+       SAGE_TICKET_ORDER = 10, SAGE_TICKET_COUNT = 12 };
 
 struct SageFrame {
+    const SageFrameParams* fp;   // device copy of the frame parameters (camera + output buffers)
     // per-Gaussian (capacity n)
-    float4* rec;         // 3 float4 per Gaussian (one 48-byte TMA block): gx gy qa thr | qb qc o z | r g b 0
-    uint32_t* dkey[2];   // depth keys bits(z) - bits(near) (or CULLED), ping-pong
+    float4* rec;         // 3 float4 per Gaussian (one 48-byte block): gx gy qa lo | qb qc - - | r g b z
+    uint32_t* dkey_src;  // depth keys bits(z) - bits(near) (or CULLED) in index order; never overwritten by the sort
+    uint32_t* dkey[2];   // sort ping-pong
     uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     // per-instance (capacity cap)
-    uint32_t* ikey[2];   // tile id, ping-pong
-    uint32_t* ival[2];   // id << 4 | quadrant mask, ping-pong
+    uint32_t* ikey[2];   // bin id, ping-pong
+    uint32_t* ival[2];   // Gaussian id, ping-pong
     // sort / scan state
     unsigned long long* lookback;  // [blocks][SAGE_RADIX_MAX_BINS] epoch|state|value words (never cleared)
     unsigned long long* chain;     // [n/256 + 1] chained-scan words of the emission kernel
-    // one block cleared per frame: counters | tickets | depth_hist | tile_hist
+    // one block cleared per frame: counters | tickets | depth_hist | tile_hist | class_count
     uint32_t* counters;     // CNT_COUNT
     uint32_t* tickets;      // SAGE_TICKET_COUNT
     uint32_t* depth_hist;   // [SAGE_MAX_PASSES][SAGE_RADIX_MAX_BINS]
     uint32_t* tile_hist;    // [SAGE_MAX_PASSES][256]
-    // per-tile
-    uint2* ranges;
-    uint32_t* tile_order;   // tiles by descending list length: CTA b of the composite takes tile_order[b]
+    uint32_t* class_count;  // [SAGE_N_CLASSES]
+    // per-bin (capacity max_bins)
+    uint2* ranges;          // [begin, end) of the bin's list in the sorted instances (cleared per frame)
+    uint32_t* class_seg;    // [SAGE_N_CLASSES][max_bins] bins of each length class, in arrival order
+    uint32_t* bin_order;    // bins by descending length class: the composite's work queue
+    int max_bins;
 };
-#define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS + SAGE_MAX_PASSES * 256)
+#define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS + SAGE_MAX_PASSES * 256 + SAGE_N_CLASSES + 3)
 
 struct SageSortPlan {
+    const uint32_t* keys_src;  // input keys of pass 0 (may alias keys[0])
     uint32_t* keys[2];
-    uint32_t* vals[2];
+    uint32_t* vals[2];         // pass 0 reads vals[0] unless vals_are_iota
     const uint32_t* n_first;   // element count of pass 0 (device)
     const uint32_t* n_rest;    // element count of the later passes (device)
-    int64_t capacity;
     int lo_bit, n_bits;
     int digit_bits, passes;    // from sage_sort_shape, or forced by the caller
-    int items_per_thread;      // 8, 16 or 32 (x 512 threads = items per block; fewer blocks = shorter look-back chains)
+    int items_per_thread;      // 8 or 16 (x 512 threads = items per block)
     bool vals_are_iota, compact_first, hist_ready;
     uint32_t* hist;            // [passes][1 << digit_bits], zeroed (or pre-accumulated if hist_ready)
-    uint32_t* total_out;       // optional: total of pass 0's histogram
     unsigned long long* lookback;
     uint32_t* tickets;         // [passes], zeroed
-    uint32_t epoch0;           // epochs epoch0 .. epoch0 + passes - 1 must be fresh
+    const SageFrameParams* fp; // epochs fp->epoch + epoch_off .. + passes - 1 must be fresh
+    uint32_t epoch_off;
 };
 
 // ---- kernel launchers (defined in the .cu files) -------------------------------------------
@@ -245,7 +245,7 @@ struct SageSceneDev {
     int64_t n;
     int deg;
     int n_chunks;       // float4 chunks of SH per Gaussian
-    float4* geo0;       // mu.xyz, sigmoid(opacity)
+    float4* geo0;       // mu.xyz, log2(sigmoid(opacity))
     float4* geo1;       // S00 S01 S02 S11
     float2* geo2;       // S12 S22
     float4* shc;        // [n][n_chunks]: SH coefficients, contiguous per Gaussian
@@ -253,22 +253,32 @@ struct SageSceneDev {
 
 void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const float* log_scale,
                             const float* quat, const float* opacity, const float* sh, cudaStream_t st);
-void sage_launch_project(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr, cudaStream_t st);
-void sage_launch_sh_color(const SageSceneDev& sc, const SageCamDev& cam, const SageFrame& fr,
-                          const uint32_t* order, cudaStream_t st);
+void sage_launch_project(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st);
+void sage_launch_sh_color(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st);
 
-// Stable LSD radix sort, one kernel per pass (decoupled look-back).  Returns the index (0/1) of the
-// buffer pair that holds the result, or -1 for an unsupported shape.
+// Stable LSD radix sort, one persistent kernel per pass (decoupled look-back).  Returns the index
+// (0/1) of the buffer pair that holds the result, or -1 for an unsupported shape.
 int sage_radix_sort(const SageSortPlan& plan, int* launches, cudaStream_t st);
 void sage_sort_shape(int n_bits, int* digit_bits, int* passes);
 size_t sage_sort_lookback_words(int64_t capacity);
 
-void sage_launch_emit(const SageCamDev& cam, const SageFrame& fr, const uint32_t* order, int64_t n,
-                      int64_t cap, int tile_passes, uint32_t epoch, cudaStream_t st);
-void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, int64_t cap, int n_tiles, cudaStream_t st);
-void sage_launch_composite(const SageCamDev& cam, const SageFrame& fr, const uint32_t* sorted_vals,
-                           int n_peers, uint8_t* const* rgb_peers, float* const* depth_peers,
-                           cudaStream_t st);
+void sage_launch_emit(const SageFrame& fr, const uint32_t* order, int tile_passes, cudaStream_t st);
+void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, cudaStream_t st);
+void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, cudaStream_t st);
+
+// One whole frame (every launch between the parameter upload and the counter read-back): the front
+// half on stream `fs`, the view-dependent colours on `ss`, the composite on the caller's stream
+// `cs` (forked from / joined to it with the four events).  Pure launch sequence: capturable into a
+// CUDA graph.  ev: optional per-stage timing events (SAGE_N_STAGES + 1) — then everything runs in
+// line on `cs`.  Returns the number of kernel launches, or -1 for an unsupported sort shape.
+struct SageFrameShape {
+    int depth_bits;      // significant bits of the depth keys
+    int tile_passes;     // 8-bit passes of the by-bin sort
+};
+int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFrameShape& shape,
+                       const uint32_t* n_dev, cudaStream_t cs, cudaStream_t fs, cudaStream_t ss,
+                       cudaEvent_t* fork_join, cudaEvent_t* ev, int n_bins);
+void sage_sort_configure(void);
 
 void sage_launch_collide_grid(const uint8_t* map, int H, int W, double min_x, double max_x,
                               double min_y, double max_y, double scale, const float* pos_f32,

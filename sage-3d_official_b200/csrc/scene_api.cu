@@ -3,7 +3,13 @@
 // A scene owns SAGE_N_CTX frame contexts (all per-frame device state, multi-buffered).  Consecutive
 // frames rotate over the contexts, so a caller that rotates as many streams gets frame N+1's projection /
 // sorts running while frame N is still compositing — the issue-bound blend kernel and the
-// latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host.
+// latency-bound sort kernels fill each other's gaps.  sage_render never synchronises the host
+// (beyond waiting for the frame that used the same context SAGE_N_CTX frames ago).
+//
+// Everything that varies per frame (camera, output buffers, look-back epoch) is written into the
+// context's pinned SageFrameParams block and reaches the kernels through a 400-byte host-to-device
+// copy; all grids are fixed.  The launch sequence of a frame (frame.cu) is therefore captured ONCE
+// per context into a CUDA graph and every later frame is a single cudaGraphLaunch.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -11,27 +17,51 @@
 #include "api_common.cuh"
 
 #ifndef SAGE_N_CTX
-#define SAGE_N_CTX 3      // measured: 1975 / 2077 / 2050 frames/s with 2 / 3 / 4 contexts in flight
+#define SAGE_N_CTX 3      // measured (round 1): 1975 / 2077 / 2050 frames/s with 2 / 3 / 4 contexts in flight
 #endif
 
 namespace {
 
+struct GraphKey {
+    int W = 0, H = 0, row0 = 0, row1 = 0, depth_bits = 0;
+    long generation = -1;
+    bool operator==(const GraphKey& o) const
+    {
+        return W == o.W && H == o.H && row0 == o.row0 && row1 == o.row1 && depth_bits == o.depth_bits &&
+               generation == o.generation;
+    }
+};
+
+struct GraphSlot {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+    int launches = 0;
+    long last_use = 0;
+};
+
+constexpr int N_GRAPH_SLOTS = 4;
+
 struct FrameCtx {
     SageFrame fr{};
     int64_t cap = 0;                 // instance capacity of this context
-    int max_tiles = 0;               // capacity of fr.ranges
     uint32_t epoch = 8;              // look-back epochs: 8 fresh values per frame
+    long generation = 0;             // bumped whenever a device buffer of the context is reallocated
+    SageFrameParams* fp_host = nullptr;  // pinned staging copy of the frame parameters
+    SageFrameParams* fp_dev = nullptr;
     uint32_t* counters_host = nullptr;   // pinned copy of the counters
     cudaEvent_t done = nullptr;      // end of the last frame that used this context
     cudaStream_t stream = nullptr;   // internal stream of the asynchronous host path
     cudaStream_t front = nullptr;    // highest-priority internal stream: every stage before the composite
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side = nullptr;     // highest-priority internal stream: the SH-colour branch
+    cudaStream_t low = nullptr;      // capture origin (stands in for the caller's stream)
+    cudaEvent_t fork_join[4] = {nullptr, nullptr, nullptr, nullptr};
+    GraphSlot graphs[N_GRAPH_SLOTS];
     uint8_t* out_rgb = nullptr;      // internal device frame (host paths)
     float* out_depth = nullptr;
     size_t out_px = 0;
     cudaStream_t last_stream = nullptr;
     int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
-    int last_row0 = 0, last_row1 = 0, last_tiles_x = 0;
+    int last_row0 = 0, last_row1 = 0, last_bins_x = 0;
     bool used = false;
 };
 
@@ -49,7 +79,18 @@ struct sage_scene {
     int n_slots = 0;
     long timed_frames = 0;
     float depth_lo = 1.0f, depth_hi = 0.0f;   // depth output clamp (off while lo > hi)
+    int rgba = 0;                    // colour output: 0 = RGB u8 x 3, 1 = RGBA u8 x 4 (alpha 255)
+    bool use_graph = true;
+    long graph_launches = 0, direct_frames = 0;
 };
+
+static void drop_graphs(FrameCtx& c)
+{
+    for (auto& g : c.graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g = GraphSlot{};
+    }
+}
 
 static void free_instances(FrameCtx& c)
 {
@@ -58,6 +99,7 @@ static void free_instances(FrameCtx& c)
         cudaFree(c.fr.ival[k]); c.fr.ival[k] = nullptr;
     }
     cudaFree(c.fr.lookback); c.fr.lookback = nullptr;
+    c.generation++;
 }
 
 static int alloc_instances(sage_scene* s, FrameCtx& c, int64_t cap)
@@ -79,6 +121,7 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
 {
     const size_t n = (size_t)s->sc.n;
     CK(dalloc(&c.fr.rec, 3 * n));
+    CK(dalloc(&c.fr.dkey_src, n));
     for (int k = 0; k < 2; ++k) {
         CK(dalloc(&c.fr.dkey[k], n));
         CK(dalloc(&c.fr.dval[k], n));
@@ -90,8 +133,13 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
     c.fr.tickets = c.fr.counters + CNT_COUNT;
     c.fr.depth_hist = c.fr.tickets + SAGE_TICKET_COUNT;
     c.fr.tile_hist = c.fr.depth_hist + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS;
+    c.fr.class_count = c.fr.tile_hist + SAGE_MAX_PASSES * 256;
     CK(cudaHostAlloc((void**)&c.counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
     memset(c.counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
+    CK(cudaHostAlloc((void**)&c.fp_host, sizeof(SageFrameParams), cudaHostAllocDefault));
+    memset(c.fp_host, 0, sizeof(SageFrameParams));
+    CK(dalloc(&c.fp_dev, 1));
+    c.fr.fp = c.fp_dev;
     CK(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     {
@@ -102,25 +150,30 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
         int lo = 0, hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CK(cudaStreamCreateWithPriority(&c.front, cudaStreamNonBlocking, hi));
-        CK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming));
+        CK(cudaStreamCreateWithPriority(&c.side, cudaStreamNonBlocking, hi));
+        CK(cudaStreamCreateWithPriority(&c.low, cudaStreamNonBlocking, lo));
+        for (auto& e : c.fork_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     return alloc_instances(s, c, cap);
 }
 
 static void free_ctx(FrameCtx& c)
 {
-    cudaFree(c.fr.rec);
+    drop_graphs(c);
+    cudaFree(c.fr.rec); cudaFree(c.fr.dkey_src);
     for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
     cudaFree(c.fr.rect); cudaFree(c.fr.chain);
     free_instances(c);
-    cudaFree(c.fr.ranges); cudaFree(c.fr.tile_order); cudaFree(c.fr.counters);
+    cudaFree(c.fr.ranges); cudaFree(c.fr.class_seg); cudaFree(c.fr.counters);
+    cudaFree(c.fp_dev);
+    if (c.fp_host) cudaFreeHost(c.fp_host);
     if (c.counters_host) cudaFreeHost(c.counters_host);
     if (c.done) cudaEventDestroy(c.done);
     if (c.stream) cudaStreamDestroy(c.stream);
     if (c.front) cudaStreamDestroy(c.front);
-    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
-    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    if (c.side) cudaStreamDestroy(c.side);
+    if (c.low) cudaStreamDestroy(c.low);
+    for (auto& e : c.fork_join) if (e) cudaEventDestroy(e);
     cudaFree(c.out_rgb); cudaFree(c.out_depth);
     c = FrameCtx{};
 }
@@ -131,6 +184,7 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     REQUIRE(cam->width > 0 && cam->height > 0 && cam->width <= 16384 && cam->height <= 16384, "camera: bad resolution");
     REQUIRE(cam->fx > 0.0f && cam->fy > 0.0f, "camera: focal length must be positive");
     REQUIRE(cam->near_z > 0.0f && cam->far_z > cam->near_z, "camera: need 0 < near < far");
+    memset(d, 0, sizeof *d);
     memcpy(d->R, cam->R, sizeof d->R);
     memcpy(d->t, cam->t, sizeof d->t);
     memcpy(d->campos, cam->campos, sizeof d->campos);
@@ -144,30 +198,42 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= d->tiles_y, "tile-row range out of bounds");
     d->row0 = row0; d->row1 = row1;
     d->depth_lo = 1.0f; d->depth_hi = 0.0f;
+    const int per = SAGE_TILE / SAGE_BIN;
+    const int bins_y = (cam->height + SAGE_BIN - 1) / SAGE_BIN;
+    d->bins_x = (cam->width + SAGE_BIN - 1) / SAGE_BIN;
+    d->bin_row0 = row0 * per;
+    d->bin_row1 = row1 * per < bins_y ? row1 * per : bins_y;
+    if (d->bin_row1 < d->bin_row0) d->bin_row1 = d->bin_row0;
+    d->n_bins = d->bins_x * (d->bin_row1 - d->bin_row0);
+    int tbits = 1;
+    while ((1 << tbits) < d->n_bins) ++tbits;
+    d->tile_passes = (tbits + 7) / 8;
+    REQUIRE(d->tile_passes <= 3, "sage_render: too many bins");
     return 0;
 }
 
-// resolution-dependent scratch (tile ranges) grows on first use
-static int ensure_tiles(FrameCtx& c, int n_tiles, cudaStream_t st)
+// resolution-dependent scratch (bin ranges, class segments) grows on first use
+static int ensure_bins(FrameCtx& c, int n_bins)
 {
-    if (n_tiles > c.max_tiles) {
-        CK(cudaStreamSynchronize(st));
-        cudaFree(c.fr.ranges); cudaFree(c.fr.tile_order);
-        c.fr.ranges = nullptr; c.fr.tile_order = nullptr; c.max_tiles = 0;
-        CK(dalloc(&c.fr.ranges, (size_t)n_tiles));
-        CK(dalloc(&c.fr.tile_order, (size_t)n_tiles));
-        c.max_tiles = n_tiles;
+    if (n_bins > c.fr.max_bins) {
+        if (c.used) CK(cudaEventSynchronize(c.done));
+        cudaFree(c.fr.ranges); cudaFree(c.fr.class_seg);
+        c.fr.ranges = nullptr; c.fr.class_seg = nullptr; c.fr.max_bins = 0;
+        CK(dalloc(&c.fr.ranges, (size_t)n_bins));
+        CK(dalloc(&c.fr.class_seg, (size_t)n_bins * SAGE_N_CLASSES));
+        c.fr.max_bins = n_bins;
+        c.generation++;
     }
     return 0;
 }
 
-static int ensure_out(FrameCtx& c, size_t px, cudaStream_t st)
+static int ensure_out(FrameCtx& c, size_t px)
 {
     if (px > c.out_px) {
-        CK(cudaStreamSynchronize(st));
+        if (c.used) CK(cudaEventSynchronize(c.done));
         cudaFree(c.out_rgb); cudaFree(c.out_depth);
         c.out_rgb = nullptr; c.out_depth = nullptr; c.out_px = 0;
-        CK(dalloc(&c.out_rgb, px * 3));
+        CK(dalloc(&c.out_rgb, px * 4));          // room for RGBA
         CK(dalloc(&c.out_depth, px));
         c.out_px = px;
     }
@@ -185,36 +251,43 @@ static int depth_key_bits(const SageCamDev& cd)
     return dbits;
 }
 
-// project -> depth sort (+compaction) -> SH colour; *order_buf = buffer index holding order[]
-static int front_half(sage_scene* s, FrameCtx& c, const SageCamDev& cd, int* launches, cudaEvent_t* ev,
-                      cudaStream_t st, int* order_buf)
-{
-    if (ev) CK(cudaEventRecord(ev[0], st));
-    sage_launch_project(s->sc, cd, c.fr, st);
-    if (ev) CK(cudaEventRecord(ev[1], st));
-    SageSortPlan dp{};
-    dp.keys[0] = c.fr.dkey[0]; dp.keys[1] = c.fr.dkey[1];
-    dp.vals[0] = c.fr.dval[0]; dp.vals[1] = c.fr.dval[1];
-    dp.n_first = s->n_dev; dp.n_rest = c.fr.counters + CNT_VISIBLE;
-    dp.capacity = s->sc.n; dp.lo_bit = 0; dp.n_bits = depth_key_bits(cd);
-    sage_sort_shape(dp.n_bits, &dp.digit_bits, &dp.passes);
-    dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false; dp.items_per_thread = 8;    // measured: 8 beats 16 here
-    dp.hist = c.fr.depth_hist; dp.total_out = nullptr;
-    dp.lookback = c.fr.lookback; dp.tickets = c.fr.tickets + SAGE_TICKET_DEPTH; dp.epoch0 = c.epoch;
-    const int res = sage_radix_sort(dp, launches, st);
-    REQUIRE(res >= 0, "depth sort: unsupported key width");
-    if (ev) CK(cudaEventRecord(ev[2], st));
-    sage_launch_sh_color(s->sc, cd, c.fr, c.fr.dval[res], st);
-    if (ev) CK(cudaEventRecord(ev[3], st));
-    *launches += 2;
-    *order_buf = res;
-    return 0;
-}
-
 static void next_epoch(FrameCtx& c)
 {
     c.epoch += 8;
     if (c.epoch > (1u << 30) - 16) c.epoch = 8;
+}
+
+// Build (capture + instantiate) the frame graph of context c for `key`; nullptr on any failure (the
+// caller then launches directly).
+static GraphSlot* get_graph(sage_scene* s, FrameCtx& c, const GraphKey& key, const SageFrameShape& shape, int n_bins)
+{
+    GraphSlot* victim = &c.graphs[0];
+    for (auto& g : c.graphs) {
+        if (g.exec && g.key == key) { g.last_use = s->frame_index; return &g; }
+        if (!g.exec) { victim = &g; break; }
+        if (g.last_use < victim->last_use) victim = &g;
+    }
+    if (victim->exec) { cudaGraphExecDestroy(victim->exec); *victim = GraphSlot{}; }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(c.low, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaMemcpyAsync(c.fp_dev, c.fp_host, sizeof(SageFrameParams), cudaMemcpyHostToDevice, c.low);
+    const int launches = sage_frame_enqueue(s->sc, c.fr, shape, s->n_dev, c.low, c.front, c.side, c.fork_join, nullptr, n_bins);
+    cudaMemcpyAsync(c.counters_host, c.fr.counters, sizeof(uint32_t) * CNT_COUNT, cudaMemcpyDeviceToHost, c.low);
+    const cudaError_t e_end = cudaStreamEndCapture(c.low, &graph);
+    if (e_end != cudaSuccess || graph == nullptr || launches < 0) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        return nullptr;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e_inst != cudaSuccess || exec == nullptr) { cudaGetLastError(); return nullptr; }
+    victim->key = key;
+    victim->exec = exec;
+    victim->launches = launches;
+    victim->last_use = s->frame_index;
+    return victim;
 }
 
 // One frame on context `ci` (or the next context in rotation when ci < 0), on stream `st`.
@@ -222,7 +295,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
                        uint8_t* const* rgb_peers, float* const* depth_peers, cudaStream_t st)
 {
     REQUIRE(s != nullptr, "sage_render: NULL scene");
-    REQUIRE(n_peers >= 1 && n_peers <= 8, "sage_render: n_peers must be 1..8");
+    REQUIRE(n_peers >= 1 && n_peers <= SAGE_MAX_PEERS, "sage_render: n_peers must be 1..8");
     for (int k = 0; k < n_peers; ++k) REQUIRE(rgb_peers[k] != nullptr, "sage_render: NULL rgb buffer");
     SageCamDev cd;
     if (make_cam(cam, row0, row1, &cd)) return 1;
@@ -230,73 +303,63 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     CK(cudaSetDevice(s->device));
     if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
     FrameCtx& c = s->ctx[ci];
-    const int n_tiles = (row1 - row0) * cd.tiles_x;
-    if (ensure_tiles(c, n_tiles, st)) return 1;
-    int tbits = 1;
-    while ((1 << tbits) < n_tiles) ++tbits;
-    REQUIRE(tbits <= 24, "sage_render: too many tiles");
-    const int tpasses = (tbits + 7) / 8;
-    int launches = 0;
-    // fork: everything up to the tile ranges runs on the context's high-priority stream `fs`, ordered
-    // after the caller's stream so far; the composite joins back onto the caller's stream
-    static const bool fork_on = getenv("SAGE_NO_FORK") == nullptr;
-    cudaStream_t fs = fork_on ? c.front : st;
-    if (fork_on) {
-        CK(cudaEventRecord(c.ev_fork, st));
-        CK(cudaStreamWaitEvent(fs, c.ev_fork, 0));
-    }
-    if (c.used) CK(cudaStreamWaitEvent(fs, c.done, 0));     // previous frame on this context has drained
-    CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, fs));
+    // the context's pinned parameter block and counters are reused: the frame that used them
+    // SAGE_N_CTX frames ago must have drained (normally long done; bounds the host's run-ahead)
+    if (c.used) CK(cudaEventSynchronize(c.done));
+    if (ensure_bins(c, cd.n_bins)) return 1;
     next_epoch(c);
+    SageFrameParams& P = *c.fp_host;
+    P.cam = cd;
+    P.epoch = c.epoch;
+    P.cap = (uint32_t)c.cap;
+    bool aligned = (cd.W % 8) == 0;
+    P.out.n = n_peers;
+    P.out.rgba = s->rgba;
+    for (int k = 0; k < SAGE_MAX_PEERS; ++k) {
+        P.out.rgb[k] = k < n_peers ? rgb_peers[k] : nullptr;
+        P.out.depth[k] = (k < n_peers && depth_peers) ? depth_peers[k] : nullptr;
+        if (k < n_peers && (((uintptr_t)P.out.rgb[k] & 7u) || ((uintptr_t)P.out.depth[k] & 7u))) aligned = false;
+    }
+    P.out.wide = aligned ? 1 : 0;
+    SageFrameShape shape;
+    shape.depth_bits = depth_key_bits(cd);
+    shape.tile_passes = cd.tile_passes;
+    {
+        int rb = 0, np = 0;
+        sage_sort_shape(shape.depth_bits, &rb, &np);
+        REQUIRE(np <= SAGE_MAX_PASSES && !(rb == 9 && np > 3), "depth sort: unsupported key width");
+    }
     cudaEvent_t* ev = s->n_slots > 0
         ? &s->events[(size_t)(s->timed_frames % s->n_slots) * (SAGE_N_STAGES + 1)] : nullptr;
     if (ev) s->timed_frames++;
     s->frame_index++;
-#define STAGE_MARK(k) do { if (ev) CK(cudaEventRecord(ev[k], fs)); } while (0)
-#define JOIN() do { if (fork_on) { CK(cudaEventRecord(c.ev_join, fs)); CK(cudaStreamWaitEvent(st, c.ev_join, 0)); } } while (0)
-    if (n_tiles > 0 && s->sc.n > 0) {
-        int ob = 0;
-        if (front_half(s, c, cd, &launches, ev, fs, &ob)) return 1;     // stages 0..2
-        const uint32_t* order = c.fr.dval[ob];
-        sage_launch_emit(cd, c.fr, order, s->sc.n, c.cap, tpasses, c.epoch + 3, fs);
-        STAGE_MARK(4);
-        SageSortPlan tp{};
-        tp.keys[0] = c.fr.ikey[0]; tp.keys[1] = c.fr.ikey[1];
-        tp.vals[0] = c.fr.ival[0]; tp.vals[1] = c.fr.ival[1];
-        tp.n_first = tp.n_rest = c.fr.counters + CNT_INSTANCES;
-        tp.capacity = c.cap; tp.lo_bit = 0; tp.n_bits = tbits; tp.digit_bits = 8; tp.passes = tpasses;
-        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true; tp.items_per_thread = 16;   // measured: 16 beats 8 and 32
-        tp.hist = c.fr.tile_hist; tp.total_out = nullptr;
-        tp.lookback = c.fr.lookback; tp.tickets = c.fr.tickets + SAGE_TICKET_TILE; tp.epoch0 = c.epoch + 4;
-        const int ires = sage_radix_sort(tp, &launches, fs);
-        REQUIRE(ires >= 0, "tile sort: unsupported key width");
-        sage_launch_ranges(c.fr, c.fr.ikey[ires], c.cap, n_tiles, fs);
-        STAGE_MARK(5);
-        JOIN();
-        sage_launch_composite(cd, c.fr, c.fr.ival[ires], n_peers, rgb_peers, depth_peers, st);
-        launches += 3;
-        if (ev) CK(cudaEventRecord(ev[6], st));
-    } else if (n_tiles > 0) {
-        for (int k = 0; k < SAGE_N_STAGES; ++k) STAGE_MARK(k);
-        sage_launch_ranges(c.fr, c.fr.ikey[0], c.cap, n_tiles, fs);        // D = 0: all ranges empty
-        JOIN();
-        sage_launch_composite(cd, c.fr, c.fr.ival[0], n_peers, rgb_peers, depth_peers, st);
-        if (ev) CK(cudaEventRecord(ev[6], st));
-        launches += 1;
-    } else {
-        JOIN();
+    int launches = -1;
+    if (!ev && s->use_graph) {
+        GraphKey key;
+        key.W = cd.W; key.H = cd.H; key.row0 = row0; key.row1 = row1; key.depth_bits = shape.depth_bits;
+        key.generation = c.generation;
+        GraphSlot* g = get_graph(s, c, key, shape, cd.n_bins);
+        if (g) {
+            CK(cudaGraphLaunch(g->exec, st));
+            launches = g->launches;
+            s->graph_launches++;
+        }
     }
-#undef JOIN
-#undef STAGE_MARK
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(c.counters_host, c.fr.counters, sizeof(uint32_t) * CNT_COUNT, cudaMemcpyDeviceToHost, st));
+    if (launches < 0) {                 // stage timing on, graphs off, or capture unavailable: direct launches
+        CK(cudaMemcpyAsync(c.fp_dev, c.fp_host, sizeof(SageFrameParams), cudaMemcpyHostToDevice, st));
+        launches = sage_frame_enqueue(s->sc, c.fr, shape, s->n_dev, st, c.front, c.side, c.fork_join, ev, cd.n_bins);
+        REQUIRE(launches >= 0, "sage_render: unsupported sort shape");
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c.counters_host, c.fr.counters, sizeof(uint32_t) * CNT_COUNT, cudaMemcpyDeviceToHost, st));
+        s->direct_frames++;
+    }
     CK(cudaEventRecord(c.done, st));
     c.used = true;
     c.last_stream = st;
     c.last_W = cd.W; c.last_H = cd.H;
     c.last_depth = (depth_peers && depth_peers[0]) ? 1 : 0;
     c.last_launches = launches;
-    c.last_row0 = row0; c.last_row1 = row1; c.last_tiles_x = cd.tiles_x;
+    c.last_row0 = row0; c.last_row1 = row1; c.last_bins_x = cd.bins_x;
     s->last_ctx = ci;
     return 0;
 }
@@ -314,10 +377,12 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sage_scene_create: sh_degree must be 0..3");
     REQUIRE(n == 0 || (xyz && log_scale && quat_wxyz && opacity_raw && sh), "sage_scene_create: NULL attribute pointer");
     CK(cudaSetDevice(device));
+    sage_sort_configure();
     sage_scene* s = new sage_scene();
     s->device = device;
     s->sc.n = n;
     s->sc.deg = sh_degree;
+    s->use_graph = getenv("SAGE_NO_GRAPH") == nullptr;
     const int nf = 3 * (sh_degree + 1) * (sh_degree + 1);
     s->sc.n_chunks = (nf + 3) / 4;
     auto bail = [&](int rc) { sage_scene_destroy(s); return rc; };
@@ -362,8 +427,10 @@ int sage_scene_reserve(sage_scene* s, int64_t max_instances)
     REQUIRE(max_instances > 0 && max_instances < (int64_t)0xFFFFFFFF, "sage_scene_reserve: bad capacity");
     CK(cudaSetDevice(s->device));
     CK(cudaDeviceSynchronize());
-    for (int k = 0; k < SAGE_N_CTX; ++k)
+    for (int k = 0; k < SAGE_N_CTX; ++k) {
+        drop_graphs(s->ctx[k]);
         if (alloc_instances(s, s->ctx[k], max_instances)) return 1;
+    }
     return 0;
 }
 
@@ -408,7 +475,7 @@ static int render_to_host(sage_scene* s, int ci, const sage_camera* cam, int row
     CK(cudaSetDevice(s->device));
     if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
     FrameCtx& c = s->ctx[ci];
-    if (ensure_out(c, (size_t)cam->width * (size_t)cam->height, st)) return 1;
+    if (ensure_out(c, (size_t)cam->width * (size_t)cam->height)) return 1;
     uint8_t* rgbs[1] = {c.out_rgb};
     float* deps[1] = {c.out_depth};
     if (render_impl(s, ci, cam, row0, row1, 1, rgbs, depth_host ? deps : nullptr, st)) return 1;
@@ -416,8 +483,9 @@ static int render_to_host(sage_scene* s, int ci, const sage_camera* cam, int row
     int y1 = row1 * SAGE_TILE;
     if (y1 > cam->height) y1 = cam->height;
     if (y1 > y0) {
+        const size_t bpp = s->rgba ? 4 : 3;
         const size_t off = (size_t)y0 * cam->width, cnt = (size_t)(y1 - y0) * cam->width;
-        CK(cudaMemcpyAsync(rgb_host + off * 3, c.out_rgb + off * 3, cnt * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rgb_host + off * bpp, c.out_rgb + off * bpp, cnt * bpp, cudaMemcpyDeviceToHost, st));
         if (depth_host)
             CK(cudaMemcpyAsync(depth_host + off, c.out_depth + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
@@ -461,11 +529,12 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
     REQUIRE(sage_jpeg_width(j) == cam->width && sage_jpeg_height(j) == cam->height,
             "sage_render_jpeg_async: encoder resolution differs from the camera's");
     REQUIRE(sage_jpeg_max_batch(j) > slot, "sage_render_jpeg_async: encoder needs max_batch > slot (one scratch slot per frame in flight)");
+    REQUIRE(!s->rgba, "sage_render_jpeg_async: the JPEG encoder reads RGB frames (turn the RGBA output off)");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     cudaStream_t st = c.stream;
     const size_t px = (size_t)cam->width * (size_t)cam->height;
-    if (ensure_out(c, px, st)) return 1;
+    if (ensure_out(c, px)) return 1;
     uint8_t* rgbs[1] = {c.out_rgb};
     float* deps[1] = {c.out_depth};
     const int rows = (cam->height + SAGE_TILE - 1) / SAGE_TILE;
@@ -505,6 +574,28 @@ int sage_scene_set_depth_clip(sage_scene* s, float lo, float hi)
     return 0;
 }
 
+int sage_scene_set_rgba(sage_scene* s, int on)
+{
+    REQUIRE(s != nullptr, "sage_scene_set_rgba: NULL scene");
+    s->rgba = on ? 1 : 0;
+    return 0;
+}
+
+int sage_scene_set_graph(sage_scene* s, int on)
+{
+    REQUIRE(s != nullptr, "sage_scene_set_graph: NULL scene");
+    s->use_graph = on != 0;
+    return 0;
+}
+
+int sage_scene_graph_stats(sage_scene* s, int64_t* graph_launches_out, int64_t* direct_frames_out)
+{
+    REQUIRE(s != nullptr, "sage_scene_graph_stats: NULL scene");
+    if (graph_launches_out) *graph_launches_out = s->graph_launches;
+    if (direct_frames_out) *direct_frames_out = s->direct_frames;
+    return 0;
+}
+
 int sage_frame_stats_get(sage_scene* s, sage_frame_stats* out)
 {
     REQUIRE(s != nullptr && out != nullptr, "sage_frame_stats_get: NULL argument");
@@ -537,15 +628,21 @@ int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows)
     CK(cudaEventSynchronize(c.done));
     const int rows = c.last_row1 - c.last_row0;
     REQUIRE(n_rows == rows, "sage_frame_row_instances: n_rows must equal the rows of the last frame");
-    std::vector<uint2> rg((size_t)rows * c.last_tiles_x);
+    const int per = SAGE_TILE / SAGE_BIN;
+    const int bins_y = (c.last_H + SAGE_BIN - 1) / SAGE_BIN;
+    int bin_rows = rows * per;
+    if (c.last_row0 * per + bin_rows > bins_y) bin_rows = bins_y - c.last_row0 * per;
+    if (bin_rows < 0) bin_rows = 0;
+    std::vector<uint2> rg((size_t)bin_rows * c.last_bins_x);
     if (!rg.empty()) CK(cudaMemcpy(rg.data(), c.fr.ranges, rg.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
-    for (int r = 0; r < rows; ++r) {
+    for (int r = 0; r < rows; ++r) rows_out_host[r] = 0;
+    for (int br = 0; br < bin_rows; ++br) {
         int64_t acc = 0;
-        for (int x = 0; x < c.last_tiles_x; ++x) {
-            const uint2 v = rg[(size_t)r * c.last_tiles_x + x];
+        for (int x = 0; x < c.last_bins_x; ++x) {
+            const uint2 v = rg[(size_t)br * c.last_bins_x + x];
             acc += (int64_t)v.y - (int64_t)v.x;
         }
-        rows_out_host[r] = acc;
+        rows_out_host[br / per] += acc;
     }
     return 0;
 }
@@ -586,34 +683,31 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
     CK(cudaSetDevice(s->device));
     CK(cudaDeviceSynchronize());
     FrameCtx& c = s->ctx[0];
+    c.fp_host->cam = cd;
+    CK(cudaMemcpy(c.fp_dev, c.fp_host, sizeof(SageFrameParams), cudaMemcpyHostToDevice));
     CK(cudaMemsetAsync(c.fr.counters, 0, sizeof(uint32_t) * SAGE_ZERO_WORDS, nullptr));
-    next_epoch(c);
-    int launches = 0, ob = 0;
-    if (front_half(s, c, cd, &launches, nullptr, nullptr, &ob)) return 1;
+    sage_launch_project(s->sc, c.fr, nullptr);
+    sage_launch_sh_color(s->sc, c.fr, nullptr);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     const size_t n = (size_t)s->sc.n;
-    uint32_t V = 0;
-    CK(cudaMemcpy(&V, c.fr.counters + CNT_VISIBLE, sizeof V, cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> vlist(V);
-    if (V) CK(cudaMemcpy(vlist.data(), c.fr.dval[ob], V * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    std::vector<uint8_t> visv(n, 0);
-    for (uint32_t g : vlist) visv[g] = 1;
+    std::vector<uint32_t> keys(n);
     std::vector<float4> rr(3 * n);
     std::vector<uint2> rc(n);
     if (n) {
+        CK(cudaMemcpy(keys.data(), c.fr.dkey_src, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(rr.data(), c.fr.rec, 3 * n * sizeof(float4), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(rc.data(), c.fr.rect, n * sizeof(uint2), cudaMemcpyDeviceToHost));
     }
     for (size_t i = 0; i < n; ++i) {
         sage_splat_record& o = records_host[i];
         memset(&o, 0, sizeof o);
-        visible_host[i] = visv[i];
+        visible_host[i] = keys[i] != SAGE_KEY_CULLED ? 1 : 0;
         if (!visible_host[i]) continue;
         const float4 r0 = rr[3 * i], r1 = rr[3 * i + 1], r2 = rr[3 * i + 2];
-        o.gx = r0.x; o.gy = r0.y; o.qa = r0.z;
-        o.qb = r1.x; o.qc = r1.y; o.opacity = r1.z; o.z = r1.w;
-        o.r = r2.x; o.g = r2.y; o.b = r2.z;
+        o.gx = r0.x; o.gy = r0.y; o.qa = r0.z; o.log2_opacity = r0.w;
+        o.qb = r1.x; o.qc = r1.y;
+        o.r = r2.x; o.g = r2.y; o.b = r2.z; o.z = r2.w;
         o.tile_x0 = (rc[i].x & 0xFFFF) / SAGE_TILE; o.tile_x1 = (rc[i].x >> 16) / SAGE_TILE;
         o.tile_y0 = (rc[i].y & 0xFFFF) / SAGE_TILE; o.tile_y1 = (rc[i].y >> 16) / SAGE_TILE;
     }

@@ -24,7 +24,7 @@ def test_header_symbols_all_exported(sage):
     for n in names:
         assert hasattr(L, n), f"{n} declared in sage_splat.h but not exported"
     assert sorted(_lib.EXPORTS) == names, "EXPORTS list out of sync with the header"
-    assert L.sage_abi_version() == 1
+    assert L.sage_abi_version() == 2
 
 
 def test_struct_layouts_match_header(sage):

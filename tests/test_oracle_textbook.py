@@ -2,8 +2,9 @@
 NumPy statement of the textbook 3DGS forward pass (Kerbl et al. 2023 equations).  Render parity is
 UNPINNED by the reference (no source / golden image), so this guards against common-mode formula
 errors in the spec itself.  Tolerances: colour 2e-3 (pre-quantisation), depth 2e-3 m, excluding
-pixels where a skip/stop decision is within 5e-5 (alpha) / 2e-4 (T), relative, of its threshold
-in the float64 evaluation."""
+pixels where a skip/stop decision is within 3e-4 (alpha; the blend's degree-3 exp2 is good to
+7.5e-5) / 1e-3 (T), relative, of its threshold in the float64 evaluation.  Pixels nothing covers
+carry depth +inf on both sides."""
 import numpy as np
 import pytest
 
@@ -73,10 +74,10 @@ def textbook_render(cam, cloud):
         dx, dy = px - g[0], py - g[1]
         power = -0.5 * (conic[0, 0] * dx * dx + conic[1, 1] * dy * dy) - conic[0, 1] * dx * dy
         a = np.minimum(0.99, o * np.exp(power))
-        fragile |= (~done) & (np.abs(a - 1 / 255) < 5e-5 * (1 / 255))
+        fragile |= (~done) & (np.abs(a - 1 / 255) < 3e-4 * (1 / 255))
         use = (~done) & (power <= 0) & (a >= 1 / 255)
         Tn = T * (1 - a)
-        fragile |= use & (np.abs(Tn - 1e-4) < 2e-4 * 1e-4)
+        fragile |= use & (np.abs(Tn - 1e-4) < 1e-3 * 1e-4)
         stop = use & (Tn < 1e-4)
         done |= stop
         use &= ~stop
@@ -85,7 +86,8 @@ def textbook_render(cam, cloud):
         D += wgt * z
         T = np.where(use, Tn, T)
     cover = 1 - T
-    depth = np.where(cover > 1e-6, D / np.maximum(cover, 1e-30), 0.0)
+    depth = np.where(cover > 1e-6, D / np.maximum(cover, 1e-30), np.inf)
+    fragile |= np.abs(cover - 1e-6) < 1e-7
     return C, depth, T, fragile
 
 
@@ -98,7 +100,9 @@ def test_oracle_follows_textbook_equations(sage, oracle, seed, deg):
     ok = ~fragile
     assert ok.mean() > 0.97
     assert np.max(np.abs(fT - T)[ok]) < 2e-3
-    assert np.max(np.abs(dep - depth)[ok]) < 2e-3
+    hit = ok & np.isfinite(depth)
+    assert np.array_equal(np.isfinite(dep)[ok], np.isfinite(depth)[ok])
+    assert np.max(np.abs(dep - depth)[hit]) < 2e-3
     ref8 = (np.clip(C, 0, 1) * 255.0 + 0.5).astype(np.uint8)
     assert np.max(np.abs(rgb.astype(int) - ref8.astype(int))[ok]) <= 1
     assert (T < 0.9).mean() > 0.3, "scene too empty to mean anything"
@@ -111,6 +115,22 @@ def test_oracle_binned_equals_brute(sage, oracle):
     a = oracle.render(oc, *cloud.as_tuple(), brute=False)
     b = oracle.render(oc, *cloud.as_tuple(), brute=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_blend_exp2_and_log2_accuracy(oracle):
+    """The two helper functions the exponent-domain blend adds to the spec."""
+    import ctypes as C
+    L = oracle.lib()
+    L.so_exp2_fast.restype = C.c_float; L.so_exp2_fast.argtypes = [C.c_float]
+    L.so_log2.restype = C.c_float; L.so_log2.argtypes = [C.c_float]
+    xs = np.linspace(-7.99435344, -0.0144995697, 4001).astype(np.float32)
+    got = np.array([L.so_exp2_fast(float(x)) for x in xs], np.float64)
+    assert np.max(np.abs(got / 2.0 ** xs.astype(np.float64) - 1)) < 8e-5
+    assert np.all(np.diff(got) >= 0), "alpha must not decrease with the exponent"
+    os_ = np.concatenate([np.random.default_rng(0).uniform(1 / 300, 1, 4000), [1.0, 0.5, 1 / 255]]).astype(np.float32)
+    lg = np.array([L.so_log2(float(o)) for o in os_], np.float64)
+    assert np.max(np.abs(lg - np.log2(os_.astype(np.float64)))) < 1e-6
+    assert L.so_log2(1.0) == 0.0 and L.so_log2(0.5) == -1.0 and L.so_log2(0.0) == -127.0
 
 
 def test_exp2_polynomial_accuracy(oracle):

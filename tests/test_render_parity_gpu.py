@@ -69,15 +69,16 @@ def test_projection_elementwise(sage, oracle):
     o_rec, o_vis = oracle.project(oracle_camera(oracle, cam), *cloud.as_tuple())
     o_vis = o_vis.astype(bool)
     assert not np.any(vis & ~o_vis), "GPU kept a Gaussian the spec culls"
-    for k in ("gx", "gy", "qa", "qb", "qc", "opacity", "z", "r", "g", "b"):
-        assert np.array_equal(rec[k][vis].view(np.uint32), o_rec[k][vis].view(np.uint32)), k
+    for k, ok_ in (("gx", "gx"), ("gy", "gy"), ("qa", "qa"), ("qb", "qb"), ("qc", "qc"), ("log2_opacity", "lo"),
+                   ("z", "z"), ("r", "r"), ("g", "g"), ("b", "b")):
+        assert np.array_equal(rec[k][vis].view(np.uint32), o_rec[ok_][vis].view(np.uint32)), k
     # Gaussians the GPU dropped beyond the spec's cull rules (exact tile culling): their
     # {alpha >= 1/255} ellipse (binary64, from the binary32 conic, no slack) must miss EVERY pixel
     # centre of the image — checked by brute force over the ellipse's bounding rows/columns.
     extra = o_vis & ~vis
     for r in o_rec[extra]:
         A, B, Cq = -float(r["qa"]), -0.5 * float(r["qb"]), -float(r["qc"])
-        t2 = np.log2(255.0 * float(r["opacity"]))
+        t2 = float(r["lo"]) + 7.99435344          # log2(255 o): the blend skips where the exponent < log2(1/255)
         det = A * Cq - B * B
         assert det > 0 and A > 0 and Cq > 0, "a degenerate conic must never be culled by the tile test"
         hx, hy = np.sqrt(t2 * Cq / det), np.sqrt(t2 * A / det)
@@ -90,12 +91,13 @@ def test_projection_elementwise(sage, oracle):
 
 
 def test_empty_and_tiny_scenes(sage, oracle):
+    import torch
     cam = sage.Camera.look_heading((1.0, 1.0, 1.2), 0.0, 64, 48)
     cloud, _ = sage.synthetic_room(1, 64)
     empty = cloud.subset(np.zeros(0, np.int64))
     scene = sage.GaussianScene(empty)
     rgb, dep = scene.render(cam)
-    assert int(rgb.max()) == 0 and float(dep.abs().max()) == 0.0
+    assert int(rgb.max()) == 0 and bool(torch.isinf(dep).all()) and float(dep.min()) > 0      # nothing hit: +inf
     _check_frame(sage, oracle, cloud, cam)
     one = cloud.subset(np.array([3]))
     _check_frame(sage, oracle, one, cam)
@@ -141,8 +143,8 @@ def test_instance_overflow_is_reported(sage):
     assert scene.stats()["overflow"] == 0
 
 
-def test_long_tile_lists_use_the_global_sort_path(sage, oracle):
-    # > 2048 instances in single tiles: the per-tile sort leaves shared memory and ping-pongs in L2
+def test_long_bin_lists(sage, oracle):
+    # thousands of instances in single 8 x 8 bins: many 32-entry batches through one warp's two stages
     rng = np.random.default_rng(11)
     n = 9000
     cloud, _ = sage.synthetic_room(6, n)
@@ -228,8 +230,9 @@ def test_size_independent_properties(sage):
     assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
     # depth lies inside the clipping range wherever something was hit; colours are saturating u8
     d = a[1]
-    assert float(d.min()) >= 0.0 and float(d.max()) < cam.far
-    assert float(d[d > 0].min()) > cam.near * 0.99
+    hit = torch.isfinite(d)
+    assert float(d.min()) > cam.near * 0.99 and float(d[hit].max()) < cam.far
+    assert bool((d[~hit] == float("inf")).all())          # pixels nothing covers: +inf, never 0 or NaN
 
 
 def test_host_path_grows_capacity_on_overflow(sage, oracle):
@@ -272,10 +275,10 @@ def test_randomised_stress_parity(sage, oracle, seed):
 
 
 def test_tall_splats_overflow_the_row_pool(sage, oracle):
-    """Camera 20 cm from a wall: nearly every visible splat spans a dozen or more tile rows, so a block
-    of 256 needs far more than k_emit's 1536-entry shared-memory row pool.  The splats past the pool
-    fall back to their bounding box (only the culling is lost) and the frame must stay bit-exact; the
-    pooled ones exercise the per-row binary search over many rows."""
+    """Camera 20 cm from a wall: nearly every visible splat spans dozens of 8-row bands, so a batch of
+    256 needs far more than k_emit's 2048-entry shared-memory band pool.  The splats past the pool
+    fall back to their bounding box (only the culling is lost) and the frame must stay bit-exact; all
+    of them take the block-wide expansion path for large footprints."""
     cloud, _ = sage.synthetic_room(8, 3_000)
     cam = sage.Camera.look_heading((0.2, 2.0, 1.2), np.radians(180.0), 960, 540)     # facing the x = 0 wall
     st = _check_frame(sage, oracle, cloud, cam)
@@ -283,3 +286,50 @@ def test_tall_splats_overflow_the_row_pool(sage, oracle):
     # and a grazing view: long, thin, diagonal ellipses — where exact culling removes the most tiles
     cam = sage.Camera.look_heading((0.25, 0.4, 1.2), np.radians(92.0), 960, 540)
     _check_frame(sage, oracle, cloud, cam)
+
+
+def test_uncovered_pixels_read_far_not_near(sage, oracle):
+    """A window onto nothing: pixels no splat covers carry depth +inf (Isaac's distance_to_image_plane
+    there), which the facade's clip(0.1, 6.5) turns into 6.5 m — the FARTHEST value, not the nearest."""
+    import torch
+    cloud, _ = sage.synthetic_room(0, 4_000)
+    keep = cloud.xyz[:, 1] < 2.0                       # drop half the room: the camera looks into the void
+    part = cloud.subset(np.nonzero(keep)[0])
+    cam = sage.Camera.look_heading((3.0, 1.0, 1.2), np.radians(90.0), 320, 240)
+    scene = sage.GaussianScene(part)
+    st = _check_frame(sage, oracle, part, cam, scene=scene)
+    rgb, dep = scene.render(cam)
+    assert bool(torch.isinf(dep).any()) and st["n_visible"] > 0
+    scene.set_depth_clip(0.1, 6.5)
+    _, clipped = scene.render(cam)
+    assert float(clipped[torch.isinf(dep)].min()) == 6.5 and float(clipped.min()) >= 0.1
+
+
+def test_rgba_output_and_graph_replay(sage, oracle):
+    """RGBA u8 x 4 output (what Camera.get_rgba() returns) equals RGB + alpha 255; frames replayed from
+    the captured CUDA graph equal directly launched ones bit for bit."""
+    import torch
+    cloud, layout = sage.synthetic_room(0, 20_000)
+    cams = [sage.Camera.look_heading(p, h, 640, 480) for p, h in sage.camera_path(layout, 5, seed=3)]
+    scene = sage.GaussianScene(cloud)
+    ref = [tuple(t.clone() for t in scene.render(c)) for c in cams]        # graph path (default)
+    gs = scene.graph_stats()
+    assert gs["graph_launches"] >= len(cams) - 0 or gs["direct_frames"] == 0, gs
+    scene.set_graph(False)
+    for c, (r0, d0) in zip(cams, ref):
+        r1, d1 = scene.render(c)
+        assert torch.equal(r0, r1) and torch.equal(d0, d1)
+    scene.set_graph(True)
+    scene.set_rgba(True)
+    for c, (r0, d0) in zip(cams, ref):
+        r4, d4 = scene.render(c)
+        assert r4.shape == (480, 640, 4)
+        assert torch.equal(r4[..., :3], r0) and bool((r4[..., 3] == 255).all()) and torch.equal(d4, d0)
+    # odd width: the byte-wise epilogue
+    cam = sage.Camera.look_heading((1.5, 1.0, 1.2), 0.4, 333, 211)
+    r4, _ = scene.render(cam)
+    scene.set_rgba(False)
+    r3, _ = scene.render(cam)
+    assert torch.equal(r4[..., :3], r3) and bool((r4[..., 3] == 255).all())
+    o_rgb, _, _ = oracle.render(oracle_camera(oracle, cam), *cloud.as_tuple())
+    assert np.array_equal(r3.cpu().numpy(), o_rgb)

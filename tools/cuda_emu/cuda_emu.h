@@ -26,7 +26,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static
 #define __constant__ static const
 #define __grid_constant__
@@ -35,12 +35,18 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct uint2 { unsigned x, y; };
+struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) uint4 { unsigned x, y, z, w; };
-struct float2 { float x, y; };
+struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+inline float2 make_float2(float a, float b) { return float2{a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+// packed binary32 pair operations: IEEE per lane, exactly as the hardware's *.f32x2 forms
+inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 
 namespace cuda_emu {
 struct Cta {
@@ -117,6 +123,28 @@ inline unsigned __ballot_sync(unsigned, int pred)
     cuda_emu::warp_sync();
     return m;
 }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline int __all_sync(unsigned m, int pred)
+{
+    const int tid = cuda_emu::lin_tid(), w0 = tid & ~31;
+    int live = cuda_emu::t_cta->nthreads - w0; if (live > 32) live = 32;
+    return __ballot_sync(m, pred) == (live == 32 ? 0xFFFFFFFFu : ((1u << live) - 1u));
+}
+inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+    const int tid = cuda_emu::lin_tid(), w0 = tid & ~31;
+    cuda_emu::t_cta->slots[tid] = v;
+    cuda_emu::warp_sync();
+    unsigned m = 0;
+    for (int l = 0; l < 32 && w0 + l < cuda_emu::t_cta->nthreads; ++l)
+        if ((unsigned)cuda_emu::t_cta->slots[w0 + l] == v) m |= 1u << l;
+    cuda_emu::warp_sync();
+    return m;
+}
+template <typename T>
+inline T __ldg(const T* p) { return *p; }
+inline void __trap() { fprintf(stderr, "cuda_emu: __trap()\n"); abort(); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
 template <typename T>
 inline T __shfl_sync(unsigned, T v, int src)
 {
@@ -174,6 +202,26 @@ typedef int cudaError_t;
 #define cudaSuccess 0
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaStreamCaptureModeRelaxed = 2 };
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; return 0; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (void*)1; return 0; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.0f; return 0; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (void*)1; return 0; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (void*)1; return 0; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) { *lo = 0; *hi = -1; return 0; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, int) { return 1; }       // no graphs: direct launches
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t*) { return 1; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return 1; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return 0; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return 0; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return 1; }
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 #define cudaHostAllocDefault 0
 inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
@@ -193,5 +241,8 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { mem
 
 #define SAGE_KLAUNCH(kernel, grid, block, stream, ...) \
     cuda_emu::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+#define SAGE_KLAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+    cuda_emu::launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+#define SAGE_DYN_SMEM(type, name) static type name[49152]      /* CTAs run one after another */
 inline float __log2f(float x) { return log2f(x); }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
