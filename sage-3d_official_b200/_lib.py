@@ -5,10 +5,13 @@ There is no CPU fallback: a missing library or a missing CUDA device raises, lou
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "libsage_splat.so"
+if os.environ.get("SAGE_SPLAT_LIB"):       # tuning experiments: another build of the same sources (tools/build_variant.sh)
+    LIB_PATH = Path(os.environ["SAGE_SPLAT_LIB"]).resolve()
 
 #: every symbol declared in include/sage_splat.h (tests check the .so exports all of them)
 EXPORTS = [

@@ -1,4 +1,5 @@
-// K2 (instance emission, fused with its offset scan), K4 (bin ranges) and the bins' work queue.
+// K2 (instance emission, fused with its offset scan) and the bins' work queue (the bin ranges, K4,
+// come out of the last pass of the by-bin sort: sort.cu).
 //
 // The image is binned at 8 x 8 pixels — the footprint one warp of the composite kernel blends (two
 // pixels per lane) — not at the 16 x 16 tiles of round 1: the splats of an interior scene are small
@@ -11,23 +12,21 @@
 // Instances are emitted in depth order (order[] from the depth sort), so the stable by-bin radix
 // sort that follows leaves every bin's list depth-sorted.  The exclusive scan of the per-Gaussian
 // bin counts is fused into the emission kernel as a chained scan (decoupled look-back over one
-// 64-bit word per batch of 256 Gaussians, read a warp wide), and the digit histograms the sort
-// needs are accumulated on the fly — the instance keys are written once and never re-read before
-// the sort passes.  All kernels here are persistent (fixed grids, ticket loops, element counts
-// read on the device), so their launch shapes are frame-invariant.
+// 64-bit word per batch of 256 Gaussians, read a warp wide).  All kernels here are persistent (fixed
+// grids, ticket loops, element counts read on the device), so their launch shapes are frame-invariant.
 #include "sage_internal.cuh"
 
 namespace {
 
 constexpr int B_THREADS = 256;
 #ifdef SAGE_CUDA_EMU
-constexpr int E_GRID = 2, R_GRID = 2, O_GRID = 2;
+constexpr int E_GRID = 2, O_GRID = 2;
 #else
 constexpr int E_GRID = 148 * 4;       // persistent emission blocks
-constexpr int R_GRID = 148 * 4, O_GRID = 148;
+constexpr int O_GRID = 148;
 #endif
 constexpr int ROW_POOL = 2048;        // band entries of a batch's cullable splats (typically ~600 used)
-constexpr uint32_t E_BIG = 48;        // a splat with more bins than this is expanded by the whole block
+constexpr int E_IPT = 8;              // consecutive instance slots one thread fills per round
 #define ROWS_NONE 0xFFFFFFFFu
 #define BAND_EMPTY 0x00000001u        /* b0 = 1 > b1 = 0 */
 
@@ -67,11 +66,12 @@ __device__ __forceinline__ void cs_store(unsigned long long* p, unsigned long lo
 
 // Emission with exact bin culling.  A batch is 256 depth-sorted Gaussians, one per thread.  Setup: a
 // splat whose pixel box spans >= 2 x 2 bins intersects its {alpha >= 1/255} ellipse with every band
-// of 8 pixel rows (sage_band_bins) and keeps the bin spans in a shared-memory pool; the others (one
-// row or one column of bins: nothing to cull) keep their box.  The per-Gaussian totals are scanned
-// (chained scan across batches), then every thread writes the instances of its own splat — a
-// handful on average, consecutive slots, neighbouring threads neighbouring runs — and the few
-// splats with large footprints are expanded by the whole block.
+// of 8 pixel rows (sage_band_bins) and keeps the bin spans + running counts in a shared-memory pool;
+// the others (one row or one column of bins: nothing to cull) keep their box.  The per-Gaussian totals
+// are scanned (chained scan across batches).  Expansion is load-balanced over the OUTPUT: a thread
+// takes E_IPT consecutive instance slots, finds the owner of the first one (binary search over the
+// offsets, then over the owner's bands) and walks on from there — bin, next band, next Gaussian — so
+// every thread writes one 32-byte run per array whatever the splat sizes.
 __global__ void __launch_bounds__(B_THREADS, 4)
 k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ ikey,
        uint32_t* __restrict__ ival)
@@ -79,35 +79,24 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
     const SageCamDev& cam = fr.fp->cam;
     const uint32_t epoch = fr.fp->epoch + 3u;
     const uint32_t cap = fr.fp->cap;
-    const int np = cam.tile_passes;
     const int bins_x = cam.bins_x, bin_row0 = cam.bin_row0;
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t nblk = (V + B_THREADS - 1) / B_THREADS;
     unsigned long long* chain = fr.chain;
     uint32_t* ticket = fr.tickets + SAGE_TICKET_EMIT;
-    __shared__ uint32_t s_off[B_THREADS];
+    __shared__ uint32_t s_off[B_THREADS + 1];       // exclusive instance offsets of the batch's splats; [256] = total
     __shared__ uint32_t s_g[B_THREADS];
     __shared__ uint2 s_rc[B_THREADS];
     __shared__ uint32_t s_rows[B_THREADS];          // first pool entry of the splat, or ROWS_NONE (box mode)
     __shared__ uint32_t s_pool[ROW_POOL];           // bin span of one band: b0 | b1 << 16 (BAND_EMPTY: none)
-    __shared__ uint32_t s_big[B_THREADS];
+    __shared__ uint32_t s_cum[ROW_POOL];            // instances of the splat in the bands before this one
     __shared__ uint32_t wsum[B_THREADS / 32];
-    __shared__ uint32_t s_blk, s_base, s_pool_used, s_nbig;
-    __shared__ uint32_t s_hist[SAGE_MAX_PASSES][256];
-    for (int i = threadIdx.x; i < SAGE_MAX_PASSES * 256; i += B_THREADS) (&s_hist[0][0])[i] = 0;
+    __shared__ uint32_t s_blk, s_base, s_pool_used;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-
-    auto put = [&](uint32_t slot, uint32_t bin, uint32_t g) {
-        if (slot < cap) {
-            ikey[slot] = bin;
-            ival[slot] = g;
-            for (int p = 0; p < np; ++p) atomicAdd(&s_hist[p][(bin >> (8 * p)) & 255u], 1u);
-        }
-    };
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) { s_blk = atomicAdd(ticket, 1u); s_pool_used = 0; s_nbig = 0; }
+        if (threadIdx.x == 0) { s_blk = atomicAdd(ticket, 1u); s_pool_used = 0; }
         __syncthreads();
         const uint32_t b = s_blk;
         if (b >= nblk) break;
@@ -131,6 +120,7 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
                     for (uint32_t j = 0; j < nrows; ++j) {
                         int b0, b1;
                         sage_band_bins(band, true, px0, px1, py0, py1, by0 + (int)j, &b0, &b1);
+                        s_cum[at + j] = cum;
                         if (b0 <= b1) { cum += (uint32_t)(b1 - b0 + 1); s_pool[at + j] = (uint32_t)b0 | ((uint32_t)b1 << 16); }
                         else s_pool[at + j] = BAND_EMPTY;
                     }
@@ -148,8 +138,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
         uint32_t woff = 0, total = 0;
 #pragma unroll
         for (int k = 0; k < B_THREADS / 32; ++k) { woff += (k < w) ? wsum[k] : 0u; total += wsum[k]; }
-        const uint32_t off = woff + incl - c;
-        s_off[threadIdx.x] = off;
+        s_off[threadIdx.x] = woff + incl - c;
+        if (threadIdx.x == 0) s_off[B_THREADS] = total;
 
         // chained scan across batches: chain[b] = epoch(30) | state(2) | value(32); warp 0 looks back
         // over 32 predecessors per round trip
@@ -195,62 +185,66 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
         __syncthreads();
         const uint32_t base = s_base;
 
-        // every thread writes the instances of its own splat; large footprints are queued
-        if (c > E_BIG) {
-            s_big[atomicAdd(&s_nbig, 1u)] = threadIdx.x;
-        } else if (c > 0) {
-            const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
-            const int by0 = py0 / SAGE_BIN, by1 = py1 / SAGE_BIN;
-            uint32_t slot = base + off;
-            for (int by = by0; by <= by1; ++by) {
-                int b0 = px0 / SAGE_BIN, b1 = px1 / SAGE_BIN;
-                if (rows_at != ROWS_NONE) {
-                    const uint32_t sp = s_pool[rows_at + (uint32_t)(by - by0)];
-                    b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
+        // load-balanced expansion: E_IPT consecutive instance slots per thread and round
+        for (uint32_t k0 = threadIdx.x * E_IPT; k0 < total; k0 += B_THREADS * E_IPT) {
+            const uint32_t kend = min(k0 + (uint32_t)E_IPT, total);
+            int own = 0;
+            {
+                int lo = 0, hi = B_THREADS - 1;            // owner = last o with s_off[o] <= k0 (its count is > 0)
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= k0) lo = mid; else hi = mid - 1;
                 }
-                const uint32_t rowbin = (uint32_t)((by - bin_row0) * bins_x);
-                for (int bx = b0; bx <= b1; ++bx) put(slot++, rowbin + (uint32_t)bx, g);
+                own = lo;
+            }
+            // state of the walk: owner's box / pool, band j of nb, bin bx of [b0, b1]
+            uint2 bx2 = s_rc[own];
+            uint32_t at = s_rows[own], gg = s_g[own];
+            int bx0 = (int)(bx2.x & 0xFFFF) / SAGE_BIN, bx1 = (int)(bx2.x >> 16) / SAGE_BIN;
+            int by0 = (int)(bx2.y & 0xFFFF) / SAGE_BIN, nb = (int)(bx2.y >> 16) / SAGE_BIN - by0 + 1;
+            const uint32_t local = k0 - s_off[own];
+            int j, b0, b1, bx;
+            if (at == ROWS_NONE) {
+                const uint32_t bw = (uint32_t)(bx1 - bx0 + 1);
+                j = (int)(local / bw);
+                b0 = bx0; b1 = bx1; bx = bx0 + (int)(local - (uint32_t)j * bw);
+            } else {
+                int lo = 0, hi = nb - 1;                   // band = last j with cum[j] <= local (it is not empty)
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_cum[at + mid] <= local) lo = mid; else hi = mid - 1;
+                }
+                j = lo;
+                const uint32_t sp = s_pool[at + j];
+                b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
+                bx = b0 + (int)(local - s_cum[at + j]);
+            }
+            for (uint32_t k = k0; k < kend; ++k) {
+                const uint32_t slot = base + k;
+                if (slot < cap) {
+                    ikey[slot] = (uint32_t)((by0 + j - bin_row0) * bins_x + bx);
+                    ival[slot] = gg;
+                }
+                if (k + 1 == kend) break;
+                if (++bx <= b1) continue;
+                for (;;) {                                 // next non-empty band, of the next splat if need be
+                    if (++j >= nb) {
+                        do { ++own; } while (s_off[own + 1] == s_off[own]);     // k + 1 < total: one exists
+                        bx2 = s_rc[own]; at = s_rows[own]; gg = s_g[own];
+                        bx0 = (int)(bx2.x & 0xFFFF) / SAGE_BIN; bx1 = (int)(bx2.x >> 16) / SAGE_BIN;
+                        by0 = (int)(bx2.y & 0xFFFF) / SAGE_BIN; nb = (int)(bx2.y >> 16) / SAGE_BIN - by0 + 1;
+                        j = 0;
+                    }
+                    if (at == ROWS_NONE) { b0 = bx0; b1 = bx1; }
+                    else {
+                        const uint32_t sp = s_pool[at + j];
+                        b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
+                    }
+                    if (b0 <= b1) { bx = b0; break; }
+                }
             }
         }
-        __syncthreads();
-        const uint32_t nbig = s_nbig;
-        for (uint32_t i = 0; i < nbig; ++i) {              // block-wide expansion of the large splats
-            const uint32_t t = s_big[i];
-            const uint2 bx2 = s_rc[t];
-            const uint32_t at = s_rows[t], gg = s_g[t];
-            const int px0 = bx2.x & 0xFFFF, px1 = bx2.x >> 16, py0 = bx2.y & 0xFFFF, py1 = bx2.y >> 16;
-            const int by0 = py0 / SAGE_BIN, by1 = py1 / SAGE_BIN;
-            uint32_t slot = base + s_off[t];
-            for (int by = by0; by <= by1; ++by) {
-                int b0 = px0 / SAGE_BIN, b1 = px1 / SAGE_BIN;
-                if (at != ROWS_NONE) {
-                    const uint32_t sp = s_pool[at + (uint32_t)(by - by0)];
-                    b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
-                }
-                if (b0 > b1) continue;
-                const uint32_t rowbin = (uint32_t)((by - bin_row0) * bins_x);
-                for (int bx = b0 + (int)threadIdx.x; bx <= b1; bx += B_THREADS) put(slot + (uint32_t)(bx - b0), rowbin + (uint32_t)bx, gg);
-                slot += (uint32_t)(b1 - b0 + 1);
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < np * 256; i += B_THREADS) {
-        const uint32_t cc = (&s_hist[0][0])[i];
-        if (cc) atomicAdd(&fr.tile_hist[i], cc);
-    }
-}
-
-// [begin, end) of every non-empty bin's list in the sorted instances (ranges is cleared per frame)
-__global__ void __launch_bounds__(B_THREADS)
-k_bin_ranges(SageFrame fr, const uint32_t* __restrict__ keys)
-{
-    const uint32_t D = fr.counters[CNT_INSTANCES];
-    uint2* ranges = fr.ranges;
-    for (uint32_t j = blockIdx.x * B_THREADS + threadIdx.x; j < D; j += gridDim.x * B_THREADS) {
-        const uint32_t k = __ldg(&keys[j]);
-        if (j == 0 || __ldg(&keys[j - 1]) != k) ranges[k].x = j;
-        if (j == D - 1 || __ldg(&keys[j + 1]) != k) ranges[k].y = j + 1;
     }
 }
 
@@ -267,8 +261,8 @@ k_bin_order(SageFrame fr)
     for (int t = blockIdx.x * B_THREADS + threadIdx.x; t < n_round; t += gridDim.x * B_THREADS) {
         uint32_t cls = 0xFFFFFFFFu;
         if (t < n_bins) {
-            const uint2 r = fr.ranges[t];
-            const uint32_t n = r.y - r.x;
+            const uint2 r = fr.ranges[t];                          // (~begin, end); (0, 0): empty
+            const uint32_t n = r.y ? r.y - ~r.x : 0u;
             cls = n ? (uint32_t)(32 - __clz((int)n)) : 0u;      // class 0: empty, k: 2^(k-1) <= n < 2^k
         }
         const unsigned peers = __match_any_sync(0xffffffffu, cls);
@@ -282,14 +276,12 @@ k_bin_order(SageFrame fr)
 
 }  // namespace
 
-void sage_launch_emit(const SageFrame& fr, const uint32_t* order, int tile_passes, cudaStream_t st)
+void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t st)
 {
-    (void)tile_passes;
     SAGE_KLAUNCH(k_emit, E_GRID, B_THREADS, st, fr, order, fr.ikey[0], fr.ival[0]);
 }
 
-void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, cudaStream_t st)
+void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st)
 {
-    SAGE_KLAUNCH(k_bin_ranges, R_GRID, B_THREADS, st, fr, sorted_keys);
     SAGE_KLAUNCH(k_bin_order, O_GRID, B_THREADS, st, fr);
 }

@@ -27,7 +27,10 @@ namespace {
 
 constexpr int C_WARPS = 4;
 constexpr int C_THREADS = C_WARPS * 32;
-constexpr int C_CTAS_PER_SM = 12;
+#ifndef SAGE_COMPOSITE_CTAS
+#define SAGE_COMPOSITE_CTAS 12
+#endif
+constexpr int C_CTAS_PER_SM = SAGE_COMPOSITE_CTAS;
 #ifdef SAGE_CUDA_EMU
 constexpr int C_GRID = 2;
 #else
@@ -106,7 +109,8 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             cls = 0; idx = t - n_nonempty;                       // the empty bins come last
         }
         const int bin = (int)fr.class_seg[(size_t)cls * fr.max_bins + idx];
-        const uint2 rg = fr.ranges[bin];
+        uint2 rg = fr.ranges[bin];                               // (~begin, end); (0, 0) = empty
+        rg.x = rg.y ? ~rg.x : 0u;
         const int bx = bin % bins_x, by = bin_row0 + bin / bins_x;
         const int px = bx * SAGE_BIN + (lane & 3) * 2;
         const int py = by * SAGE_BIN + (lane >> 2);
@@ -159,16 +163,20 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
                 al.x = v0 ? al.x : 0.0f;                  // alpha 0: T, C, Dz stay bit-identical
                 al.y = v1 ? al.y : 0.0f;
                 const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));                // 1 - alpha
-                const float2 Tn = __fmul2_rn(T, om);
-                // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended
-                const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                float2 Tn = __fmul2_rn(T, om);
                 float2 wgt = __fmul2_rn(al, T);
-                wgt.x = s0 ? 0.0f : wgt.x;
-                wgt.y = s1 ? 0.0f : wgt.y;
-                T.x = s0 ? T.x : Tn.x;
-                T.y = s1 ? T.y : Tn.y;
-                pxc.x = s0 ? NAN_X : pxc.x;
-                pxc.y = s1 ? NAN_X : pxc.y;
+                // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
+                // Once per pixel, against dozens of blended splats: a rarely taken branch, not selects.
+                if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
+                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                    wgt.x = s0 ? 0.0f : wgt.x;
+                    wgt.y = s1 ? 0.0f : wgt.y;
+                    Tn.x = s0 ? T.x : Tn.x;
+                    Tn.y = s1 ? T.y : Tn.y;
+                    pxc.x = s0 ? NAN_X : pxc.x;
+                    pxc.y = s1 ? NAN_X : pxc.y;
+                }
+                T = Tn;
                 const float4 c = s_rec[3 * j + 2];                                    // r g b z
                 Cr = __ffma2_rn(f2(c.x), wgt, Cr);
                 Cg = __ffma2_rn(f2(c.y), wgt, Cg);

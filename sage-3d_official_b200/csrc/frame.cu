@@ -3,8 +3,8 @@
 // the sequence is captured once per frame context into a CUDA graph and replayed.
 //
 //   caller stream cs ──fork──► front stream fs (highest priority):
-//        memset(counters, ranges) → K1a project ─┬─► depth sort (hist, offsets, 3 passes) → K2 emit
-//                                                 │        → by-bin sort (offsets, 2 passes) → K4 ranges, order ─┐
+//        memset(counters, ranges) → K1a project ─┬─► depth sort (3 passes x hist/scan/scatter) → K2 emit
+//                                                 │        → by-bin sort (2 passes; the last writes K4 ranges) → order ─┐
 //                                                 └─► side stream ss: K1b SH colour ────────────────────────────┤
 //   cs ◄──join── K5 composite ◄─────────────────────────────────────────────────────────────────────────────────┘
 //
@@ -54,15 +54,14 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         dp.n_first = n_dev; dp.n_rest = fr.counters + CNT_VISIBLE;
         dp.lo_bit = 0; dp.n_bits = shape.depth_bits;
         dp.passes = depth_passes_of(shape.depth_bits, &dp.digit_bits);
-        dp.vals_are_iota = true; dp.compact_first = true; dp.hist_ready = false; dp.items_per_thread = 8;
-        dp.hist = fr.depth_hist;
-        dp.lookback = fr.lookback; dp.tickets = fr.tickets + SAGE_TICKET_DEPTH; dp.fp = fr.fp; dp.epoch_off = 0;
+        dp.vals_are_iota = true; dp.compact_first = true; dp.items_per_thread = 8;
+        dp.H = fr.sort_h; dp.ld = fr.sort_ld; dp.totals = fr.sort_totals; dp.ranges = nullptr;
         const int res = sage_radix_sort(dp, &launches, fs);
         if (res < 0) return -1;
         MARK(2);
         if (serial) { sage_launch_sh_color(sc, fr, cs); launches += 1; }
         MARK(3);
-        sage_launch_emit(fr, fr.dval[res], shape.tile_passes, fs);
+        sage_launch_emit(fr, fr.dval[res], fs);
         launches += 1;
         MARK(4);
         SageSortPlan tp{};
@@ -71,13 +70,12 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         tp.vals[0] = fr.ival[0]; tp.vals[1] = fr.ival[1];
         tp.n_first = tp.n_rest = fr.counters + CNT_INSTANCES;
         tp.lo_bit = 0; tp.n_bits = 8 * shape.tile_passes; tp.digit_bits = 8; tp.passes = shape.tile_passes;
-        tp.vals_are_iota = false; tp.compact_first = false; tp.hist_ready = true; tp.items_per_thread = 16;
-        tp.hist = fr.tile_hist;
-        tp.lookback = fr.lookback; tp.tickets = fr.tickets + SAGE_TICKET_TILE; tp.fp = fr.fp; tp.epoch_off = 4;
+        tp.vals_are_iota = false; tp.compact_first = false; tp.items_per_thread = 16;
+        tp.H = fr.sort_h; tp.ld = fr.sort_ld; tp.totals = fr.sort_totals; tp.ranges = fr.ranges;
         const int ires = sage_radix_sort(tp, &launches, fs);
         if (ires < 0) return -1;
-        sage_launch_ranges(fr, fr.ikey[ires], fs);
-        launches += 2;
+        sage_launch_bin_order(fr, fs);
+        launches += 1;
         MARK(5);
         if (!serial) {
             cudaEventRecord(fork_join[3], fs);
@@ -90,8 +88,8 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
     } else {
         for (int k = 1; k <= 5; ++k) MARK(k);
         if (n_bins > 0) {
-            sage_launch_ranges(fr, fr.ikey[0], fs);      // D = 0: every bin is empty
-            launches += 2;
+            sage_launch_bin_order(fr, fs);               // D = 0: every bin is empty
+            launches += 1;
         }
         if (!serial) {
             cudaEventRecord(fork_join[3], fs);

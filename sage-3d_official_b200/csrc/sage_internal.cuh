@@ -192,8 +192,7 @@ __device__ __forceinline__ void sage_band_bins(const SageBand& b, bool cull, int
 #define SAGE_RADIX_MAX_BINS 512
 #define SAGE_MAX_PASSES 4
 #define SAGE_N_CLASSES 33          /* list-length classes of the bins: 0 = empty, k: 2^(k-1) <= n < 2^k */
-enum { SAGE_TICKET_DEPTH = 0, SAGE_TICKET_EMIT = 4, SAGE_TICKET_TILE = 5, SAGE_TICKET_COMPOSITE = 9,
-       SAGE_TICKET_ORDER = 10, SAGE_TICKET_COUNT = 12 };
+enum { SAGE_TICKET_EMIT = 0, SAGE_TICKET_COMPOSITE = 1, SAGE_TICKET_COUNT = 4 };
 
 struct SageFrame {
     const SageFrameParams* fp;   // device copy of the frame parameters (camera + output buffers)
@@ -207,21 +206,21 @@ struct SageFrame {
     uint32_t* ikey[2];   // bin id, ping-pong
     uint32_t* ival[2];   // Gaussian id, ping-pong
     // sort / scan state
-    unsigned long long* lookback;  // [blocks][SAGE_RADIX_MAX_BINS] epoch|state|value words (never cleared)
-    unsigned long long* chain;     // [n/256 + 1] chained-scan words of the emission kernel
-    // one block cleared per frame: counters | tickets | depth_hist | tile_hist | class_count
+    uint32_t* sort_h;       // [SAGE_RADIX_MAX_BINS][sort_ld] per-tile digit histograms / exclusive prefixes of a pass
+    uint32_t* sort_totals;  // [SAGE_RADIX_MAX_BINS] digit totals of a pass
+    int sort_ld;
+    unsigned long long* chain;     // [n/256 + 1] chained-scan words of the emission kernel (epoch-tagged: never cleared)
+    // one block cleared per frame: counters | tickets | class_count
     uint32_t* counters;     // CNT_COUNT
     uint32_t* tickets;      // SAGE_TICKET_COUNT
-    uint32_t* depth_hist;   // [SAGE_MAX_PASSES][SAGE_RADIX_MAX_BINS]
-    uint32_t* tile_hist;    // [SAGE_MAX_PASSES][256]
     uint32_t* class_count;  // [SAGE_N_CLASSES]
     // per-bin (capacity max_bins)
-    uint2* ranges;          // [begin, end) of the bin's list in the sorted instances (cleared per frame)
+    uint2* ranges;          // (~begin, end) of the bin's list in the sorted instances; (0, 0) = empty (cleared per frame)
     uint32_t* class_seg;    // [SAGE_N_CLASSES][max_bins] bins of each length class, in arrival order
     uint32_t* bin_order;    // bins by descending length class: the composite's work queue
     int max_bins;
 };
-#define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS + SAGE_MAX_PASSES * 256 + SAGE_N_CLASSES + 3)
+#define SAGE_ZERO_WORDS (CNT_COUNT + SAGE_TICKET_COUNT + SAGE_N_CLASSES + 3)
 
 struct SageSortPlan {
     const uint32_t* keys_src;  // input keys of pass 0 (may alias keys[0])
@@ -231,13 +230,12 @@ struct SageSortPlan {
     const uint32_t* n_rest;    // element count of the later passes (device)
     int lo_bit, n_bits;
     int digit_bits, passes;    // from sage_sort_shape, or forced by the caller
-    int items_per_thread;      // 8 or 16 (x 512 threads = items per block)
-    bool vals_are_iota, compact_first, hist_ready;
-    uint32_t* hist;            // [passes][1 << digit_bits], zeroed (or pre-accumulated if hist_ready)
-    unsigned long long* lookback;
-    uint32_t* tickets;         // [passes], zeroed
-    const SageFrameParams* fp; // epochs fp->epoch + epoch_off .. + passes - 1 must be fresh
-    uint32_t epoch_off;
+    int items_per_thread;      // 8 or 16 (x 512 threads = items per tile)
+    bool vals_are_iota, compact_first;
+    uint32_t* H;               // [1 << digit_bits][ld] scratch (SageFrame::sort_h)
+    int ld;
+    uint32_t* totals;          // [1 << digit_bits] scratch
+    uint2* ranges;             // optional: the last pass writes ranges[key] = (~begin, end) (cleared by the caller)
 };
 
 // ---- kernel launchers (defined in the .cu files) -------------------------------------------
@@ -256,14 +254,15 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 void sage_launch_project(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st);
 void sage_launch_sh_color(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st);
 
-// Stable LSD radix sort, one persistent kernel per pass (decoupled look-back).  Returns the index
-// (0/1) of the buffer pair that holds the result, or -1 for an unsupported shape.
+// Stable LSD radix sort, three kernels per pass (tile histograms, scan, rank + scatter).  Returns the
+// index (0/1) of the buffer pair that holds the result, or -1 for an unsupported shape.
 int sage_radix_sort(const SageSortPlan& plan, int* launches, cudaStream_t st);
 void sage_sort_shape(int n_bits, int* digit_bits, int* passes);
-size_t sage_sort_lookback_words(int64_t capacity);
+int sage_sort_matrix_ld(int64_t capacity);
+size_t sage_sort_matrix_words(int64_t capacity);
 
-void sage_launch_emit(const SageFrame& fr, const uint32_t* order, int tile_passes, cudaStream_t st);
-void sage_launch_ranges(const SageFrame& fr, const uint32_t* sorted_keys, cudaStream_t st);
+void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t st);
+void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st);
 void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, cudaStream_t st);
 
 // One whole frame (every launch between the parameter upload and the counter read-back): the front

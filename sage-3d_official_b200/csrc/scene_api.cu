@@ -98,7 +98,7 @@ static void free_instances(FrameCtx& c)
         cudaFree(c.fr.ikey[k]); c.fr.ikey[k] = nullptr;
         cudaFree(c.fr.ival[k]); c.fr.ival[k] = nullptr;
     }
-    cudaFree(c.fr.lookback); c.fr.lookback = nullptr;
+    cudaFree(c.fr.sort_h); c.fr.sort_h = nullptr;
     c.generation++;
 }
 
@@ -110,9 +110,8 @@ static int alloc_instances(sage_scene* s, FrameCtx& c, int64_t cap)
         CK(dalloc(&c.fr.ival[k], (size_t)cap));
     }
     const int64_t mx = cap > s->sc.n ? cap : s->sc.n;
-    const size_t words = sage_sort_lookback_words(mx);
-    CK(dalloc(&c.fr.lookback, words));
-    CK(cudaMemset(c.fr.lookback, 0, words * sizeof(unsigned long long)));   // epoch 0 = never published
+    CK(dalloc(&c.fr.sort_h, sage_sort_matrix_words(mx)));
+    c.fr.sort_ld = sage_sort_matrix_ld(mx);
     c.cap = cap;
     return 0;
 }
@@ -131,9 +130,8 @@ static int alloc_ctx(sage_scene* s, FrameCtx& c, int64_t cap)
     CK(cudaMemset(c.fr.chain, 0, (n / 256 + 2) * sizeof(unsigned long long)));
     CK(dalloc(&c.fr.counters, (size_t)SAGE_ZERO_WORDS));
     c.fr.tickets = c.fr.counters + CNT_COUNT;
-    c.fr.depth_hist = c.fr.tickets + SAGE_TICKET_COUNT;
-    c.fr.tile_hist = c.fr.depth_hist + SAGE_MAX_PASSES * SAGE_RADIX_MAX_BINS;
-    c.fr.class_count = c.fr.tile_hist + SAGE_MAX_PASSES * 256;
+    c.fr.class_count = c.fr.tickets + SAGE_TICKET_COUNT;
+    CK(dalloc(&c.fr.sort_totals, (size_t)SAGE_RADIX_MAX_BINS));
     CK(cudaHostAlloc((void**)&c.counters_host, sizeof(uint32_t) * CNT_COUNT, cudaHostAllocDefault));
     memset(c.counters_host, 0, sizeof(uint32_t) * CNT_COUNT);
     CK(cudaHostAlloc((void**)&c.fp_host, sizeof(SageFrameParams), cudaHostAllocDefault));
@@ -162,7 +160,7 @@ static void free_ctx(FrameCtx& c)
     drop_graphs(c);
     cudaFree(c.fr.rec); cudaFree(c.fr.dkey_src);
     for (int k = 0; k < 2; ++k) { cudaFree(c.fr.dkey[k]); cudaFree(c.fr.dval[k]); }
-    cudaFree(c.fr.rect); cudaFree(c.fr.chain);
+    cudaFree(c.fr.rect); cudaFree(c.fr.chain); cudaFree(c.fr.sort_totals);
     free_instances(c);
     cudaFree(c.fr.ranges); cudaFree(c.fr.class_seg); cudaFree(c.fr.counters);
     cudaFree(c.fp_dev);
@@ -639,8 +637,8 @@ int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows)
     for (int br = 0; br < bin_rows; ++br) {
         int64_t acc = 0;
         for (int x = 0; x < c.last_bins_x; ++x) {
-            const uint2 v = rg[(size_t)br * c.last_bins_x + x];
-            acc += (int64_t)v.y - (int64_t)v.x;
+            const uint2 v = rg[(size_t)br * c.last_bins_x + x];      // (~begin, end); (0, 0) = empty
+            if (v.y) acc += (int64_t)v.y - (int64_t)(~v.x);
         }
         rows_out_host[br / per] += acc;
     }

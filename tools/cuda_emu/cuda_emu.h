@@ -184,6 +184,12 @@ inline int atomicCAS(int* p, int cmp, int val)
     __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
     return cmp;
 }
+inline unsigned atomicMax(unsigned* p, unsigned v)
+{
+    unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
 inline unsigned atomicMin(unsigned* p, unsigned v)
 {
     unsigned o = __atomic_load_n(p, __ATOMIC_RELAXED);
