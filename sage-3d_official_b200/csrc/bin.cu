@@ -1,17 +1,16 @@
-// K2 (instance emission, fused with its offset scan) and the bins' work queue (the bin ranges, K4,
-// come out of the last pass of the by-bin sort: sort.cu).
+// K2 (instance emission, fused with its offset scan) and the tiles' work queue (the tile ranges, K4,
+// come out of the last pass of the by-tile sort: sort.cu).
 //
-// The image is binned at 8 x 8 pixels — the footprint one warp of the composite kernel blends (two
-// pixels per lane) — not at the 16 x 16 tiles of round 1: the splats of an interior scene are small
-// (a visible Gaussian passes the alpha test on ~40 pixels of a 16 x 16 tile it touches), so a
-// per-tile list was mostly filtered again per quadrant by ballots, and the four warps of a tile
-// waited for each other at a barrier per batch.  With one list per warp-sized bin every entry a
-// warp reads is its own, warps never synchronise with each other, and the work items are 4x
-// smaller (better tails, also at 640 x 480).  Price: ~17 % more instances through the by-bin sort.
+// Binning is by 16 x 16 tiles, each instance carrying the mask of the tile's four 8 x 8 quadrants
+// the splat really reaches (exact culling: its {alpha >= 1/255} ellipse against the two 8-row halves
+// of every tile row).  The composite blends a quadrant per warp and drops the instances whose mask
+// bit is clear while it gathers, so the lists stay tile-sized (D ~ 2.4 M at 1080p) while the blend
+// works at quadrant granularity.  (Binning at 8 x 8 directly was measured: 2.2x the instances —
+// 5.2 M — through emission and the by-bin sort for the same blend work.)
 //
-// Instances are emitted in depth order (order[] from the depth sort), so the stable by-bin radix
-// sort that follows leaves every bin's list depth-sorted.  The exclusive scan of the per-Gaussian
-// bin counts is fused into the emission kernel as a chained scan (decoupled look-back over one
+// Instances are emitted in depth order (order[] from the depth sort), so the stable by-tile radix
+// sort that follows leaves every tile's list depth-sorted.  The exclusive scan of the per-Gaussian
+// tile counts is fused into the emission kernel as a chained scan (decoupled look-back over one
 // 64-bit word per batch of 256 Gaussians, read a warp wide).  All kernels here are persistent (fixed
 // grids, ticket loops, element counts read on the device), so their launch shapes are frame-invariant.
 #include "sage_internal.cuh"
@@ -25,10 +24,9 @@ constexpr int E_GRID = 2, O_GRID = 2;
 constexpr int E_GRID = 148 * 4;       // persistent emission blocks
 constexpr int O_GRID = 148;
 #endif
-constexpr int ROW_POOL = 2048;        // band entries of a batch's cullable splats (typically ~600 used)
+constexpr int ROW_POOL = 1536;        // tile-row entries of a batch's cullable splats (typically ~300 used)
 constexpr int E_IPT = 8;              // consecutive instance slots one thread fills per round
 #define ROWS_NONE 0xFFFFFFFFu
-#define BAND_EMPTY 0x00000001u        /* b0 = 1 > b1 = 0 */
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
 {
@@ -64,14 +62,14 @@ __device__ __forceinline__ void cs_store(unsigned long long* p, unsigned long lo
 }
 #endif
 
-// Emission with exact bin culling.  A batch is 256 depth-sorted Gaussians, one per thread.  Setup: a
-// splat whose pixel box spans >= 2 x 2 bins intersects its {alpha >= 1/255} ellipse with every band
-// of 8 pixel rows (sage_band_bins) and keeps the bin spans + running counts in a shared-memory pool;
-// the others (one row or one column of bins: nothing to cull) keep their box.  The per-Gaussian totals
-// are scanned (chained scan across batches).  Expansion is load-balanced over the OUTPUT: a thread
-// takes E_IPT consecutive instance slots, finds the owner of the first one (binary search over the
-// offsets, then over the owner's bands) and walks on from there — bin, next band, next Gaussian — so
-// every thread writes one 32-byte run per array whatever the splat sizes.
+// Emission with exact tile culling.  A batch is 256 depth-sorted Gaussians, one per thread.  Setup: a
+// splat whose pixel box spans >= 2 x 2 tiles intersects its {alpha >= 1/255} ellipse with the two
+// 8-row halves of every tile row (sage_band_row) and keeps the column spans + running tile counts in
+// a shared-memory pool; the others (one row or one column of tiles: nothing to cull) keep their box.
+// The per-Gaussian totals are scanned (chained scan across batches).  Expansion is load-balanced over
+// the OUTPUT: a thread takes E_IPT consecutive instance slots, finds the owner of the first one
+// (binary search over the offsets, then over the owner's tile rows) and walks on from there — tile,
+// next row, next Gaussian — so every thread writes one 32-byte run per array whatever the splat sizes.
 __global__ void __launch_bounds__(B_THREADS, 4)
 k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ ikey,
        uint32_t* __restrict__ ival)
@@ -88,8 +86,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
     __shared__ uint32_t s_g[B_THREADS];
     __shared__ uint2 s_rc[B_THREADS];
     __shared__ uint32_t s_rows[B_THREADS];          // first pool entry of the splat, or ROWS_NONE (box mode)
-    __shared__ uint32_t s_pool[ROW_POOL];           // bin span of one band: b0 | b1 << 16 (BAND_EMPTY: none)
-    __shared__ uint32_t s_cum[ROW_POOL];            // instances of the splat in the bands before this one
+    __shared__ uint2 s_pool[ROW_POOL];              // (upper, lower) column spans of one tile row
+    __shared__ uint32_t s_cum[ROW_POOL];            // tiles of the splat in the rows before this one
     __shared__ uint32_t wsum[B_THREADS / 32];
     __shared__ uint32_t s_blk, s_base, s_pool_used;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -107,8 +105,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
             g = __ldg(&order[r]);
             rc = __ldg(&fr.rect[g]);
             const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
-            const int by0 = py0 / SAGE_BIN, by1 = py1 / SAGE_BIN;
-            const uint32_t nrows = (uint32_t)(by1 - by0 + 1);
+            const int ty0 = py0 / SAGE_BIN, ty1 = py1 / SAGE_BIN;
+            const uint32_t nrows = (uint32_t)(ty1 - ty0 + 1);
             c = (uint32_t)(px1 / SAGE_BIN - px0 / SAGE_BIN + 1) * nrows;
             if (sage_box_cullable(px0, px1, py0, py1)) {
                 const uint32_t at = atomicAdd(&s_pool_used, nrows);
@@ -118,11 +116,10 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
                     const SageBand band = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r0.w - SAGE_L255);
                     uint32_t cum = 0;
                     for (uint32_t j = 0; j < nrows; ++j) {
-                        int b0, b1;
-                        sage_band_bins(band, true, px0, px1, py0, py1, by0 + (int)j, &b0, &b1);
+                        const SageRowItem it = sage_band_row(band, px0, px1, py0, py1, ty0 + (int)j);
                         s_cum[at + j] = cum;
-                        if (b0 <= b1) { cum += (uint32_t)(b1 - b0 + 1); s_pool[at + j] = (uint32_t)b0 | ((uint32_t)b1 << 16); }
-                        else s_pool[at + j] = BAND_EMPTY;
+                        s_pool[at + j] = make_uint2(it.top, it.bot);
+                        cum += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
                     }
                     c = cum;
                     rows_at = at;
@@ -198,60 +195,67 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
                 }
                 own = lo;
             }
-            // state of the walk: owner's box / pool, band j of nb, bin bx of [b0, b1]
+            // state of the walk: the owner's box / pool rows, tile row j of nr, tile tx of [t0, t1]
             uint2 bx2 = s_rc[own];
             uint32_t at = s_rows[own], gg = s_g[own];
-            int bx0 = (int)(bx2.x & 0xFFFF) / SAGE_BIN, bx1 = (int)(bx2.x >> 16) / SAGE_BIN;
-            int by0 = (int)(bx2.y & 0xFFFF) / SAGE_BIN, nb = (int)(bx2.y >> 16) / SAGE_BIN - by0 + 1;
+            int px0 = (int)(bx2.x & 0xFFFF), px1 = (int)(bx2.x >> 16), py0 = (int)(bx2.y & 0xFFFF), py1 = (int)(bx2.y >> 16);
+            int ty0 = py0 / SAGE_BIN, nr = py1 / SAGE_BIN - ty0 + 1;
             const uint32_t local = k0 - s_off[own];
-            int j, b0, b1, bx;
+            int j, t0, t1, tx;
+            uint2 sp = make_uint2(0, 0);
             if (at == ROWS_NONE) {
-                const uint32_t bw = (uint32_t)(bx1 - bx0 + 1);
+                t0 = px0 / SAGE_BIN; t1 = px1 / SAGE_BIN;
+                const uint32_t bw = (uint32_t)(t1 - t0 + 1);
                 j = (int)(local / bw);
-                b0 = bx0; b1 = bx1; bx = bx0 + (int)(local - (uint32_t)j * bw);
+                tx = t0 + (int)(local - (uint32_t)j * bw);
             } else {
-                int lo = 0, hi = nb - 1;                   // band = last j with cum[j] <= local (it is not empty)
+                int lo = 0, hi = nr - 1;                   // row = last j with cum[j] <= local (it is not empty)
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
                     if (s_cum[at + mid] <= local) lo = mid; else hi = mid - 1;
                 }
                 j = lo;
-                const uint32_t sp = s_pool[at + j];
-                b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
-                bx = b0 + (int)(local - s_cum[at + j]);
+                sp = s_pool[at + j];
+                const SageRowItem ri = sage_row_from_spans(sp.x, sp.y);
+                t0 = ri.tx0; t1 = ri.tx1;
+                tx = t0 + (int)(local - s_cum[at + j]);
             }
             for (uint32_t k = k0; k < kend; ++k) {
                 const uint32_t slot = base + k;
                 if (slot < cap) {
-                    ikey[slot] = (uint32_t)((by0 + j - bin_row0) * bins_x + bx);
-                    ival[slot] = gg;
+                    const int ty = ty0 + j;
+                    const uint32_t mask = at == ROWS_NONE ? sage_box_quad_mask(px0, px1, py0, py1, tx, ty)
+                                                          : sage_row_quad_mask(sp.x, sp.y, tx);
+                    ikey[slot] = (uint32_t)((ty - bin_row0) * bins_x + tx);
+                    ival[slot] = (gg << 4) | mask;
                 }
                 if (k + 1 == kend) break;
-                if (++bx <= b1) continue;
-                for (;;) {                                 // next non-empty band, of the next splat if need be
-                    if (++j >= nb) {
+                if (++tx <= t1) continue;
+                for (;;) {                                 // next non-empty tile row, of the next splat if need be
+                    if (++j >= nr) {
                         do { ++own; } while (s_off[own + 1] == s_off[own]);     // k + 1 < total: one exists
                         bx2 = s_rc[own]; at = s_rows[own]; gg = s_g[own];
-                        bx0 = (int)(bx2.x & 0xFFFF) / SAGE_BIN; bx1 = (int)(bx2.x >> 16) / SAGE_BIN;
-                        by0 = (int)(bx2.y & 0xFFFF) / SAGE_BIN; nb = (int)(bx2.y >> 16) / SAGE_BIN - by0 + 1;
+                        px0 = (int)(bx2.x & 0xFFFF); px1 = (int)(bx2.x >> 16); py0 = (int)(bx2.y & 0xFFFF); py1 = (int)(bx2.y >> 16);
+                        ty0 = py0 / SAGE_BIN; nr = py1 / SAGE_BIN - ty0 + 1;
                         j = 0;
                     }
-                    if (at == ROWS_NONE) { b0 = bx0; b1 = bx1; }
+                    if (at == ROWS_NONE) { t0 = px0 / SAGE_BIN; t1 = px1 / SAGE_BIN; }
                     else {
-                        const uint32_t sp = s_pool[at + j];
-                        b0 = (int)(sp & 0xFFFFu); b1 = (int)(sp >> 16);
+                        sp = s_pool[at + j];
+                        const SageRowItem ri = sage_row_from_spans(sp.x, sp.y);
+                        t0 = ri.tx0; t1 = ri.tx1;
                     }
-                    if (b0 <= b1) { bx = b0; break; }
+                    if (t0 <= t1) { tx = t0; break; }
                 }
             }
         }
     }
 }
 
-// Heaviest bins first: a bin is blended by one warp however long its list is, so the longest lists
-// must start early or they become the tail of the composite kernel.  Bins are appended to one
-// segment per power-of-two length class (order inside a class is irrelevant to the result); the
-// composite's warps then draw tickets and walk the classes from the heaviest down.
+// Heaviest tiles first: a quadrant is blended by one warp however long the tile's list is, so the
+// longest lists must start early or they become the tail of the composite kernel.  Tiles are appended
+// to one segment per power-of-two length class (order inside a class is irrelevant to the result);
+// the composite's warps then draw tickets (four per tile) and walk the classes from the heaviest down.
 __global__ void __launch_bounds__(B_THREADS)
 k_bin_order(SageFrame fr)
 {

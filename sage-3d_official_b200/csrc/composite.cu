@@ -3,18 +3,22 @@
 // Replaces cam.get_rgba() (simple_env.py:1380; generate_images.py:428) and
 // frame['distance_to_image_plane'] (simple_env.py:1425-1432).
 //
-// One WARP = one 8 x 8 bin with its own depth-sorted list: lane -> row lane>>2, two horizontally
-// adjacent pixels (lane&3)*2, so the blend arithmetic runs on Blackwell's packed binary32 pipe
+// One WARP = one 8 x 8 quadrant of a 16 x 16 tile: lane -> row lane>>2, two horizontally adjacent
+// pixels (lane&3)*2, so the blend arithmetic runs on Blackwell's packed binary32 pipe
 // (FFMA2/FMUL2/FADD2: fma.rn.f32x2), which is IEEE per lane and therefore bit-identical to the
-// scalar statement in the oracle.  Warps are persistent: each draws bins from a ticket counter,
-// heaviest length class first (k_bin_order), and never synchronises with another warp.
+// scalar statement in the oracle.  Warps are persistent and independent: each draws (tile, quadrant)
+// work items from a ticket counter, heaviest length class first (k_bin_order), walks the tile's
+// depth-sorted list 32 instances at a time, keeps those whose quadrant bit is set (ballot + popc: the
+// survivors' records are gathered straight into consecutive slots of the stage) and never
+// synchronises with another warp.  (Round 1 blended a tile with a CTA of four warps that met at a
+// barrier per batch — 24 % of its stall samples — and filtered every entry with a ballot/ffs loop.)
 //
-// Splat records (one 48-byte block per Gaussian, L2-resident) are gathered 32 at a time into the
-// warp's private shared-memory stage with cp.async (LDGSTS, 16 bytes x 3 per lane), two stages: the
-// gather of batch b+1 is in flight while batch b is blended.  (Round 1 issued one 48-byte TMA bulk
-// copy per record: UBLKCP is a uniform-datapath instruction, so a warp issued its 32 copies one lane
-// at a time — ~8 % of the kernel's instructions.  A per-lane gather is what LDGSTS is for; the bulk
-// engine is kept for contiguous blocks.)  The entry loop is warp-uniform: no ballots, no masks.
+// Splat records (one 48-byte block per Gaussian, L2-resident) are gathered into the warp's private
+// shared-memory stage with cp.async (LDGSTS, 16 bytes x 3 per lane), two stages: the gather of chunk
+// c+1 is in flight while chunk c is blended.  (Round 1 issued one 48-byte TMA bulk copy per record:
+// UBLKCP is a uniform-datapath instruction, so a warp issued its 32 copies one lane at a time — ~8 %
+// of the kernel's instructions.  A per-lane gather is what LDGSTS is for.)  The entry loop is
+// warp-uniform: no ballots, no masks.
 //
 // The blend: log2(alpha) = qa dx^2 + qb dx dy + qc dy^2 + lo with the opacity
 // already in the exponent; skip below log2(1/255); cap at log2(0.99); alpha by the degree-3
@@ -83,7 +87,8 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* ticket = fr.tickets + SAGE_TICKET_COMPOSITE;
 
-    // work queue: bins by descending length class; lane l holds the running count of classes 32 .. 32-l
+    // work queue: tiles by descending length class, 4 work items (quadrants) each; lane l holds the
+    // running count of classes 32 .. 32-l
     const uint32_t cls_n = fr.class_count[32 - lane];           // lane 0 <-> class 32 ... lane 31 <-> class 1
     uint32_t cls_incl = cls_n;
 #pragma unroll
@@ -98,22 +103,26 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= (uint32_t)n_bins) break;
+        if (t >= 4u * (uint32_t)n_bins) break;
+        const uint32_t tt = t >> 2;                              // position of the tile in the queue
+        const int quad = (int)(t & 3u);                          // quadrant: bit qy*2 + qx of the instance masks
         uint32_t cls, idx;
-        if (t < n_nonempty) {
-            const unsigned m = __ballot_sync(0xffffffffu, cls_incl > t);
+        if (tt < n_nonempty) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls_incl > tt);
             const int L = __ffs(m) - 1;
             cls = (uint32_t)(32 - L);
-            idx = t - (__shfl_sync(0xffffffffu, cls_incl, L) - __shfl_sync(0xffffffffu, cls_n, L));
+            idx = tt - (__shfl_sync(0xffffffffu, cls_incl, L) - __shfl_sync(0xffffffffu, cls_n, L));
         } else {
-            cls = 0; idx = t - n_nonempty;                       // the empty bins come last
+            cls = 0; idx = tt - n_nonempty;                      // the empty tiles come last
         }
         const int bin = (int)fr.class_seg[(size_t)cls * fr.max_bins + idx];
         uint2 rg = fr.ranges[bin];                               // (~begin, end); (0, 0) = empty
         rg.x = rg.y ? ~rg.x : 0u;
         const int bx = bin % bins_x, by = bin_row0 + bin / bins_x;
-        const int px = bx * SAGE_BIN + (lane & 3) * 2;
-        const int py = by * SAGE_BIN + (lane >> 2);
+        const int qx0 = bx * SAGE_BIN + (quad & 1) * 8, qy0 = by * SAGE_BIN + (quad >> 1) * 8;
+        if (qx0 >= W || qy0 >= H) continue;                      // quadrant entirely outside the image
+        const int px = qx0 + (lane & 3) * 2;
+        const int py = qy0 + (lane >> 2);
         const bool in0 = px < W && py < H, in1 = (px + 1) < W && py < H;
         float2 pxc = make_float2(in0 ? (float)px + 0.5f : NAN_X, in1 ? (float)(px + 1) + 0.5f : NAN_X);
         const float pyc = (float)py + 0.5f;
@@ -122,25 +131,30 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 
         const uint32_t n = rg.y - rg.x;
         const uint32_t* lst = vals + rg.x;
-        uint32_t v_next = lane < n ? __ldg(&lst[lane]) : 0u;
-        if (n > 0) {
-            if (lane < n) {
-                const float4* src = rec + (size_t)v_next * 3;
-                float4* dst = &srec[w][0][lane * 3];
+        // chunk c = list entries [32c, 32c+32); its survivors (quadrant bit set) land in slots 0 .. cnt-1
+        auto gather = [&](uint32_t v, bool have, int stage) -> int {
+            const bool rel = have && ((v >> quad) & 1u);
+            const unsigned m = __ballot_sync(0xffffffffu, rel);
+            if (rel) {
+                const float4* src = rec + (size_t)(v >> 4) * 3;
+                float4* dst = &srec[w][stage][__popc(m & ((1u << lane) - 1u)) * 3];
                 cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
             }
-            cp_async_commit();
+            cp_async_commit();                             // (possibly empty: keeps the group count uniform)
+            return __popc(m);
+        };
+        int cnt = 0, cnt_next = 0;
+        uint32_t v_next = 0;
+        if (n > 0) {
+            const uint32_t v0 = lane < n ? __ldg(&lst[lane]) : 0u;
+            cnt_next = gather(v0, lane < n, 0);
             v_next = 32 + lane < n ? __ldg(&lst[32 + lane]) : 0u;
         }
         int st = 0;
         for (uint32_t base = 0; base < n; base += 32, st ^= 1) {
-            const int cnt = (int)min(32u, n - base);
-            if (base + 32 + lane < n) {                    // next batch: gather in flight while this one is blended
-                const float4* src = rec + (size_t)v_next * 3;
-                float4* dst = &srec[w][st ^ 1][lane * 3];
-                cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
-            }
-            cp_async_commit();                             // (possibly empty: keeps the group count uniform)
+            cnt = cnt_next;
+            // next chunk: gather in flight while this one is blended
+            cnt_next = gather(v_next, base + 32 + lane < n, st ^ 1);
             v_next = base + 64 + lane < n ? __ldg(&lst[base + 64 + lane]) : 0u;
             cp_async_wait<1>();
             __syncwarp();
@@ -191,7 +205,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 #undef SAGE_LIVE
 
         // epilogue: quantise and store to every destination frame.  Wide path (frame width a multiple
-        // of 8, 8-byte aligned buffers, bin inside the image): the 24 RGB bytes of a bin row (4 lanes x
+        // of 8, 8-byte aligned buffers, quadrant inside the image): the 24 RGB bytes of a bin row (4 lanes x
         // 2 px) leave as three 8-byte words assembled with shuffles, RGBA as one 8-byte word per lane,
         // depth as one float2 per lane.
         uint32_t q[6];
@@ -212,7 +226,6 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             d1 = fminf(fmaxf(d1, depth_lo), depth_hi);
         }
         const size_t p = (size_t)py * W + px;
-        const int qx0 = bx * SAGE_BIN, qy0 = by * SAGE_BIN;
         const int n_out = fp->out.n;
         const bool rgba = fp->out.rgba != 0;
         const bool wide = fp->out.wide && (qx0 + 8 <= W) && (qy0 + 8 <= H);

@@ -11,7 +11,18 @@
 // The front half is a chain of small latency-bound kernels; the composite is one long issue-bound
 // kernel.  On a high-priority stream the front half of frame i+1 is dispatched ahead of the queued
 // composite CTAs of frame i (another context), so consecutive frames overlap.
+#include <cstdlib>
+
 #include "api_common.cuh"
+
+// tuning knobs (experiments): items per thread of the two sorts' tiles (8 or 16)
+static int env_ipt(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const int k = atoi(v);
+    return (k == 8 || k == 16) ? k : dflt;
+}
 
 static int depth_passes_of(int depth_bits, int* digit_bits)
 {
@@ -54,7 +65,8 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         dp.n_first = n_dev; dp.n_rest = fr.counters + CNT_VISIBLE;
         dp.lo_bit = 0; dp.n_bits = shape.depth_bits;
         dp.passes = depth_passes_of(shape.depth_bits, &dp.digit_bits);
-        dp.vals_are_iota = true; dp.compact_first = true; dp.items_per_thread = 8;
+        static const int depth_ipt = env_ipt("SAGE_DEPTH_IPT", 8);
+        dp.vals_are_iota = true; dp.compact_first = true; dp.items_per_thread = depth_ipt;
         dp.H = fr.sort_h; dp.ld = fr.sort_ld; dp.totals = fr.sort_totals; dp.ranges = nullptr;
         const int res = sage_radix_sort(dp, &launches, fs);
         if (res < 0) return -1;
@@ -70,7 +82,8 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         tp.vals[0] = fr.ival[0]; tp.vals[1] = fr.ival[1];
         tp.n_first = tp.n_rest = fr.counters + CNT_INSTANCES;
         tp.lo_bit = 0; tp.n_bits = 8 * shape.tile_passes; tp.digit_bits = 8; tp.passes = shape.tile_passes;
-        tp.vals_are_iota = false; tp.compact_first = false; tp.items_per_thread = 16;
+        static const int tile_ipt = env_ipt("SAGE_TILE_IPT", 16);
+        tp.vals_are_iota = false; tp.compact_first = false; tp.items_per_thread = tile_ipt;
         tp.H = fr.sort_h; tp.ld = fr.sort_ld; tp.totals = fr.sort_totals; tp.ranges = fr.ranges;
         const int ires = sage_radix_sort(tp, &launches, fs);
         if (ires < 0) return -1;

@@ -20,10 +20,11 @@
 #define SAGE_L255 (-7.99435344f)      /* log2(1/255): skip where log2(alpha) < this */
 #define SAGE_L099 (-0.0144995697f)    /* log2(0.99): alpha cap, applied to the exponent */
 #define SAGE_T_MIN 1e-4f
-#define SAGE_BIN 8                    /* internal binning granularity: 8 x 8 pixels, one warp per bin */
+#define SAGE_BIN 16                   /* binning granularity: 16 x 16 pixel tiles; a warp blends one 8 x 8 quadrant */
 #define SAGE_BLUR 0.3f
 #define SAGE_LOG2E 1.44269504f
 #define SAGE_KEY_CULLED 0xFFFFFFFFu
+// instance value = Gaussian id (28 bits) << 4 | 8x8-quadrant overlap mask of the tile (4 bits)
 #define SAGE_ID_MASK 0x0FFFFFFFu      /* scene size limit (2^28 - 1 Gaussians) */
 #define SAGE_MAX_PEERS 8
 
@@ -106,15 +107,15 @@ __device__ __forceinline__ float sage_log2(float x)
 // Binning is not part of the numerical spec: it only has to be conservative.
 // The support of a splat is the ellipse  A dx^2 + 2B dx dy + C dy^2 <= t2  around (gx, gy), in the
 // log2-scaled units of the conic the blend kernel uses (A = -qa, B = -qb/2, C = -qc; t2 = lo - L255).
-// k_emit enumerates, per band of 8 pixel rows, exactly the 8 x 8 bins whose rows contain a pixel
-// centre inside it.  Binary32 arithmetic (binary64 sqrt/div sequences cost more than the instances
+// k_emit intersects it with the two 8-row halves of every tile row: a tile is emitted when one of
+// its halves contains a pixel centre of the ellipse, with the mask of the 8 x 8 quadrants that do.  Binary32 arithmetic (binary64 sqrt/div sequences cost more than the instances
 // they save) made conservative by slack: t2 * 1.003 + 0.02 (the bounding box uses 1.002) and every
 // span is widened by 0.1 % of the half extent + 0.01 px; tools/cuda_emu/band_check.cpp brute-forces
 // the guarantee on CPU.
 // sqrt to ~2 ulp (one MUFU + one multiply); the spans carry 0.1 % of slack.  Negative -> 0.
 __device__ __forceinline__ float sage_sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
 
-// true: the pixel box spans at least 2 x 2 bins — only then can the ellipse test remove a bin
+// true: the pixel box spans at least 2 x 2 tiles — only then can the ellipse test remove a tile
 __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int iy1)
 {
     return (ix0 / SAGE_BIN != ix1 / SAGE_BIN) && (iy0 / SAGE_BIN != iy1 / SAGE_BIN);
@@ -175,17 +176,68 @@ __device__ __forceinline__ bool sage_band_span(const SageBand& b, int ix0, int i
     return *xs <= *xe;
 }
 
-// Bins [*b0, *b1] (inclusive; *b0 > *b1: none) that band `by` (pixel rows 8by .. 8by+7) of a splat with
-// pixel box [ix0,ix1] x [iy0,iy1] touches.  `cull` false: the box decides (the band is not evaluated).
-__device__ __forceinline__ void sage_band_bins(const SageBand& b, bool cull, int ix0, int ix1, int iy0, int iy1,
-                                               int by, int* b0, int* b1)
+// One tile row ty of a splat with pixel box [ix0,ix1] x [iy0,iy1]: spans of its upper and lower
+// 8-row halves (packed x0 | x1 << 16; SAGE_SPAN_EMPTY = x0 > x1) and the inclusive tile range.
+struct SageRowItem {
+    uint32_t top, bot;      // pixel spans of rows [16ty, 16ty+7] and [16ty+8, 16ty+15]; SAGE_SPAN_EMPTY if none
+    int tx0, tx1;           // tiles [tx0, tx1]; tx0 > tx1: the row is empty
+};
+#define SAGE_SPAN_EMPTY 0x0000FFFFu     /* x0 = 0xFFFF > x1 = 0 */
+
+// (cullable splats only: the box spans >= 2 x 2 tiles)
+__device__ __forceinline__ SageRowItem sage_band_row(const SageBand& b, int ix0, int ix1, int iy0, int iy1, int ty)
 {
-    const int ya = max(by * SAGE_BIN, iy0), yb = min(by * SAGE_BIN + SAGE_BIN - 1, iy1);
-    *b0 = 1; *b1 = 0;
-    if (ya > yb) return;
-    int xs = ix0, xe = ix1;
-    if (cull && !sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) return;
-    *b0 = xs / SAGE_BIN; *b1 = xe / SAGE_BIN;
+    SageRowItem it;
+    it.top = it.bot = SAGE_SPAN_EMPTY;
+    int lo = 1 << 30, hi = -1;
+    int xs, xe;
+    const int ya = max(ty * SAGE_BIN, iy0), yb = min(ty * SAGE_BIN + 7, iy1);
+    if (ya <= yb && sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) {
+        it.top = (uint32_t)xs | ((uint32_t)xe << 16);
+        lo = min(lo, xs); hi = max(hi, xe);
+    }
+    const int yc = max(ty * SAGE_BIN + 8, iy0), yd = min(ty * SAGE_BIN + 15, iy1);
+    if (yc <= yd && sage_band_span(b, ix0, ix1, yc, yd, &xs, &xe)) {
+        it.bot = (uint32_t)xs | ((uint32_t)xe << 16);
+        lo = min(lo, xs); hi = max(hi, xe);
+    }
+    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
+    else { it.tx0 = lo / SAGE_BIN; it.tx1 = hi / SAGE_BIN; }
+    return it;
+}
+
+// rebuild a row item from its two stored spans
+__device__ __forceinline__ SageRowItem sage_row_from_spans(uint32_t top, uint32_t bot)
+{
+    SageRowItem it;
+    it.top = top; it.bot = bot;
+    int lo = 1 << 30, hi = -1;
+    if ((top & 0xFFFFu) <= (top >> 16)) { lo = min(lo, (int)(top & 0xFFFFu)); hi = max(hi, (int)(top >> 16)); }
+    if ((bot & 0xFFFFu) <= (bot >> 16)) { lo = min(lo, (int)(bot & 0xFFFFu)); hi = max(hi, (int)(bot >> 16)); }
+    if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
+    else { it.tx0 = lo / SAGE_BIN; it.tx1 = hi / SAGE_BIN; }
+    return it;
+}
+
+// 8x8-quadrant mask (bit qy*2+qx, the work-item -> quadrant map of the composite kernel) of tile tx
+__device__ __forceinline__ uint32_t sage_row_quad_mask(uint32_t top, uint32_t bot, int tx)
+{
+    const int bx = tx * SAGE_BIN;
+    const int t0 = (int)(top & 0xFFFFu), t1 = (int)(top >> 16);
+    const int b0 = (int)(bot & 0xFFFFu), b1 = (int)(bot >> 16);
+    uint32_t m = 0;
+    if (t0 <= t1) m |= ((t0 <= bx + 7 && t1 >= bx) ? 1u : 0u) | ((t0 <= bx + 15 && t1 >= bx + 8) ? 2u : 0u);
+    if (b0 <= b1) m |= ((b0 <= bx + 7 && b1 >= bx) ? 4u : 0u) | ((b0 <= bx + 15 && b1 >= bx + 8) ? 8u : 0u);
+    return m;
+}
+
+// the same from the inclusive pixel box of a splat that is not culled per row
+__device__ __forceinline__ uint32_t sage_box_quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
+{
+    const int bx = tx * SAGE_BIN, by = ty * SAGE_BIN;
+    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
+    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
+    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
 }
 
 // ---- frame workspace ---------------------------------------------------------------------
@@ -203,8 +255,8 @@ struct SageFrame {
     uint32_t* dval[2];   // Gaussian ids, ping-pong
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     // per-instance (capacity cap)
-    uint32_t* ikey[2];   // bin id, ping-pong
-    uint32_t* ival[2];   // Gaussian id, ping-pong
+    uint32_t* ikey[2];   // tile id, ping-pong
+    uint32_t* ival[2];   // Gaussian id << 4 | quadrant mask, ping-pong
     // sort / scan state
     uint32_t* sort_h;       // [SAGE_RADIX_MAX_BINS][sort_ld] per-tile digit histograms / exclusive prefixes of a pass
     uint32_t* sort_totals;  // [SAGE_RADIX_MAX_BINS] digit totals of a pass

@@ -20,8 +20,20 @@ reference (file:line)                   here
 
 Shipped-but-dead behaviour is kept dead on purpose: ``_check_collision`` is never
 called by the motion code, so ``_total_collision_count`` / ``_collision_detected`` only change when a
-caller invokes it explicitly.  Error convention: render returns ``None`` on failure, collide
-``False``; nothing raises out of the hot path.
+caller invokes it explicitly.
+
+Error convention.  Per call, as the reference: render returns ``None`` on a failed frame, collide
+``False``; a missing or invalid 2-D map means "no collisions" (collision_detector.py:200-202).
+But a broken ENGINE is never papered over: no CUDA device, a missing ``libsage_splat.so``, a scene
+path without a Gaussian payload or a failed upload raise from the constructor / ``load_scene`` /
+``update_map`` — the reference fails just as loudly when Isaac cannot start, and a benchmark that
+completes on black frames and walks through walls is worse than one that stops.
+
+Frames.  ``get_rgb`` / ``get_depth`` hand out views of pinned host buffers from a pool; a buffer goes
+back to the pool only when the caller (and every view, PIL image ... derived from it) has dropped
+it, so the arrays are as safe to keep as the reference's copies but cost no 14 MB memcpy per step.
+After every pose change the next frame is submitted at once (asynchronously), so it renders and
+crosses PCIe while the caller is busy with the VLM; ``get_rgb`` then only waits for it.
 
 Candidate positions are generated with the same NumPy expressions as the reference so their dtypes
 (float32 on the straight march, float64 on the exploration directions) and values are identical
@@ -29,9 +41,12 @@ under whichever NumPy runs; the batched kernel honours the per-dtype promotion r
 """
 from __future__ import annotations
 
+import atexit
+import json
 import math
 import os
 import time
+import weakref
 from pathlib import Path
 from typing import List, Optional, Tuple
 
@@ -46,8 +61,59 @@ def _debug_print(msg: str) -> None:
         print(msg)
 
 
+def _default_resolution(resolution):
+    """The reference's callers never pass a resolution (run_benchmark.py:641,2188 -> 640 x 480); a
+    launcher can ask for another default (BASELINE configs 2-5 run at 1920 x 1080) without touching
+    them: SAGE_RESOLUTION=1920x1080 applies when the constructor is given the reference default."""
+    env = os.environ.get("SAGE_RESOLUTION", "").lower().strip()
+    if env and tuple(resolution) == (640, 480):
+        w, h = env.split("x")
+        return (int(w), int(h))
+    return resolution
+
+
+class _FramePool:
+    """Pinned host frame buffers handed out as NumPy views and taken back when the last reference to
+    the view (or to anything derived from it) is gone."""
+
+    def __init__(self, make_pair, limit: int = 16):
+        self._make, self._limit = make_pair, limit
+        self._free, self._n = [], 0
+
+    def take(self):
+        """(pair, token) — token must be passed to lend(); None when the pool is exhausted."""
+        if self._free:
+            return self._free.pop()
+        if self._n >= self._limit:
+            return None
+        self._n += 1
+        return self._make()
+
+    def lend(self, pair, arrays):
+        """The arrays (views of the pair's buffers) go to the caller; the pair returns to the pool
+        when all of them have been garbage-collected."""
+        state = {"left": len(arrays)}
+
+        def back(_state=state, _pair=pair, _pool=weakref.ref(self)):
+            _state["left"] -= 1
+            pool = _pool()
+            if _state["left"] == 0 and pool is not None:
+                pool._free.append(_pair)
+
+        for a in arrays:
+            weakref.finalize(a, back)
+
+    def give_back(self, pair):
+        self._free.append(pair)
+
+
 class SimpleVLNEnv:
     """VLN environment with the reference's public surface, rendered and collided on the GPU."""
+
+    #: test hooks (never set by the product): callables replacing the GPU scene / detector so the
+    #: façade's host logic can be exercised without a device — tests back them with the oracle
+    _scene_factory = None
+    _detector_factory = None
 
     CAMERA_HEIGHT = 1.2            # simple_env.py:1204
     DEPTH_CLIP = (0.1, 6.5)        # simple_env.py:1578
@@ -61,7 +127,7 @@ class SimpleVLNEnv:
         self.scene_usd_path = str(Path(scene_usd_path).resolve())
         self.hz = hz
         self.agent_prim_path = agent_prim_path
-        self.resolution = resolution
+        self.resolution = _default_resolution(resolution)
         self.headless = headless
         self.is_stop_called = False
         self.consecutive_collisions = 0
@@ -91,9 +157,18 @@ class SimpleVLNEnv:
         self._encoder = None
         self.render_calls = 0          # engine frames actually rendered (1 per distinct pose)
         self.collide_launches = 0      # batched collide launches
+        #: wall-clock accounting of the hot path (seconds / counts); dumped as JSON to $SAGE_PERF_JSON
+        self.perf = {"render_s": 0.0, "render_wait_s": 0.0, "collide_s": 0.0, "get_rgb_calls": 0, "get_depth_calls": 0,
+                     "apply_cmd_calls": 0, "prefetch_hits": 0, "prefetch_misses": 0, "first_call_t": None, "last_call_t": None}
         self._pos = np.array([0.0, 0.0, self.AGENT_CENTRE_Z], dtype=np.float32)
         self._yaw = 0.0
+        self._pool = None
+        self._pending = None           # (key, slot, pair) of the frame submitted ahead of the caller
+        self._slot = 0
+        self._served = {"rgb": False, "depth": False}
         self._init_engine()
+        if os.environ.get("SAGE_PERF_JSON"):
+            atexit.register(self._dump_perf)
 
     # ---- logging / time (simple_env.py:96-123) -------------------------------------------------
     def _log(self, msg: str) -> None:
@@ -122,73 +197,92 @@ class SimpleVLNEnv:
 
     # ---- engine ---------------------------------------------------------------------------------
     def _init_engine(self) -> None:
+        """Upload the scene.  Raises when the engine cannot work (no device, no library, no payload)."""
         from .scene_io import load_cloud, resolve_stage_assets
-        from .api import GaussianScene, CollisionBodies
+        make_scene = type(self)._scene_factory
+        if make_scene is None:
+            from .api import GaussianScene
+            make_scene = GaussianScene
+        self._drop_pending()
         self._scene = None
         self._bodies = None
+        self._pool = None
+        self._frame_key = None
+        bodies_src = None
         if self._preloaded[0] is not None:
             self._model_to_world = None
-            self._scene = GaussianScene(self._preloaded[0], device=self._device)
-            self._scene.set_depth_clip(*self.DEPTH_CLIP)
-            if self._preloaded[1] is not None:
-                self._bodies = CollisionBodies(*self._preloaded[1], device=self._device)
-            return
-        gauss, coll, is_stage = resolve_stage_assets(self.scene_usd_path)
-        # a USDA stage carries rotateXYZ(-90,0,0) on the Gaussian prim (template.usda:120)
-        self._model_to_world = USD_GAUSS_MODEL_TO_WORLD if is_stage else None
-        if gauss is None:
-            self._log(f"[ENV_INIT] no Gaussian payload (.ply/.npz) found for {self.scene_usd_path}; frames will be black")
-            return
-        try:
-            self._scene = GaussianScene(load_cloud(gauss), device=self._device)
-            self._scene.set_depth_clip(*self.DEPTH_CLIP)      # clip(0.1, 6.5) applied in the kernel epilogue
-            self._log(f"[ENV_INIT] scene {gauss}: {self._scene.n} Gaussians resident on cuda:{self._device}")
+            cloud, bodies_src = self._preloaded
+        else:
+            gauss, coll, is_stage = resolve_stage_assets(self.scene_usd_path)
+            # a USDA stage carries rotateXYZ(-90,0,0) on the Gaussian prim (template.usda:120)
+            self._model_to_world = USD_GAUSS_MODEL_TO_WORLD if is_stage else None
+            if gauss is None:
+                raise FileNotFoundError(f"[ENV_INIT] no Gaussian payload (.ply/.npz) found for {self.scene_usd_path}")
+            cloud = load_cloud(gauss)
             if coll is not None:
                 z = np.load(coll)
-                self._bodies = CollisionBodies(z["mu"], z["log_scale"], z["quat"], device=self._device)
-        except Exception as e:
-            self._log(f"[ENV_INIT] failed to load scene: {e}")
-            self._scene = None
+                bodies_src = (z["mu"], z["log_scale"], z["quat"])
+        self._scene = make_scene(cloud, device=self._device)
+        self._scene.set_depth_clip(*self.DEPTH_CLIP)      # clip(0.1, 6.5) applied in the kernel epilogue
+        self._log(f"[ENV_INIT] scene {self.scene_usd_path}: {self._scene.n} Gaussians resident on cuda:{self._device}")
+        if bodies_src is not None and type(self)._scene_factory is None:
+            from .api import CollisionBodies
+            self._bodies = CollisionBodies(*bodies_src, device=self._device)
 
     def _init_collision_detector(self, map_json_path: str) -> None:
         self.collision_detector = None
         if map_json_path and os.path.exists(map_json_path):
-            try:
-                self.collision_detector = SemanticMap2DCollisionDetector(
-                    map_json_path, robot_radius_m=0.08, scale=0.05, device=self._device)
-                info = self.collision_detector.get_collision_info()
-                self._log(f"[COLLISION_2D] map {map_json_path}: {info['obstacle_pixels']}/{info['total_pixels']} obstacle cells")
-            except Exception as e:
-                self._log(f"[COLLISION_2D] cannot load 2D semantic map collision detector: {e}")
-                self.collision_detector = None
+            make = type(self)._detector_factory or SemanticMap2DCollisionDetector
+            # an unreadable map leaves the detector without a grid (every query False, as the reference);
+            # a broken device raises out of here
+            self.collision_detector = make(map_json_path, robot_radius_m=0.08, scale=0.05, device=self._device)
+            info = self.collision_detector.get_collision_info()
+            self._log(f"[COLLISION_2D] map {map_json_path}: {info['obstacle_pixels']}/{info['total_pixels']} obstacle cells")
         else:
             self._log(f"[COLLISION_2D] no usable 2D semantic map ({map_json_path})")
 
     def load_scene(self, new_scene_usd_path: str) -> bool:
-        try:
-            self.scene_usd_path = str(Path(new_scene_usd_path).resolve())
-            self._frame_key = None
-            self._init_engine()
-            return self._scene is not None
-        except Exception as e:
-            self._log(f"[SCENE_SWITCH] Scene switch failed: {e}")
+        """Switch scenes (run_benchmark.py:621).  A path without a payload keeps the current scene and
+        returns False (the reference's switch is a no-op that returns False, simple_env.py:1104-1108);
+        an engine failure raises."""
+        from .scene_io import resolve_stage_assets
+        path = str(Path(new_scene_usd_path).resolve())
+        if self._preloaded[0] is None and resolve_stage_assets(path)[0] is None:
+            self._log(f"[SCENE_SWITCH] no Gaussian payload for {path}; keeping {self.scene_usd_path}")
             return False
+        old = (self._scene, self._bodies)
+        self.scene_usd_path = path
+        self._init_engine()
+        for h in old:
+            if h is not None:
+                h.close()
+        return True
 
     def update_map(self, new_map_path: str) -> bool:
-        try:
-            self._map_json_path = new_map_path
-            self.semantic_map_path = new_map_path
-            self._init_collision_detector(new_map_path)
-            return True
-        except Exception as e:
-            self._log(f"[MAP_SWITCH] Map switch failed: {e}")
-            return False
+        self._map_json_path = new_map_path
+        self.semantic_map_path = new_map_path
+        self._init_collision_detector(new_map_path)
+        return True
 
     def close(self) -> None:
+        self._dump_perf()
+        self._drop_pending()
         for h in (self._scene, self._bodies):
             if h is not None:
                 h.close()
         self._scene = self._bodies = None
+
+    def _dump_perf(self) -> None:
+        path = os.environ.get("SAGE_PERF_JSON")
+        if not path:
+            return
+        try:
+            out = dict(self.perf, render_calls=self.render_calls, collide_launches=self.collide_launches,
+                       resolution=list(self.resolution))
+            with open(path, "w") as f:
+                json.dump(out, f)
+        except Exception:
+            pass
 
     # ---- pose (simple_env.py:1149-1353) ---------------------------------------------------------
     def set_start_pose(self, position: List[float], rotation_xyzw: List[float]) -> None:
@@ -206,6 +300,7 @@ class SimpleVLNEnv:
             self._yaw -= 2 * math.pi
         self._initial_yaw = self._yaw
         self._update_camera_position()
+        self._prefetch()
 
     def _update_camera_position(self) -> None:
         camera_pos = self._pos.copy()
@@ -247,15 +342,83 @@ class SimpleVLNEnv:
         return Camera.from_isaac_pose(self._cam_position, self._cam_orientation, W, H,
                                       model_to_world=self._model_to_world)
 
+    def _frame_pair(self):
+        """A pinned (rgb, depth) buffer pair for the current resolution from the pool."""
+        W, H = int(self.resolution[0]), int(self.resolution[1])
+        if self._pool is None or self._pool_shape != (H, W):
+            scene = self._scene
+            self._pool = _FramePool(lambda: scene.alloc_host_frame(H, W))
+            self._pool_shape = (H, W)
+        return self._pool.take()
+
+    def _drop_pending(self) -> None:
+        if self._pending is not None and self._scene is not None:
+            _, slot, pair = self._pending
+            try:
+                self._scene.host_wait(slot)
+            except Exception:
+                pass
+            if pair is not None and self._pool is not None:
+                self._pool.give_back(pair)
+        self._pending = None
+
+    def _pose_key(self):
+        return (self._cam_position.tobytes(), self._cam_orientation.tobytes(), tuple(self.resolution))
+
+    def _submit(self, key):
+        """Start rendering the frame of the current pose (asynchronous: returns at once)."""
+        pair = self._frame_pair()
+        slot = self._slot
+        self._slot = (self._slot + 1) % max(1, int(getattr(self._scene, "pipeline_depth", 1)))
+        self._scene.render_host_async(self._camera(), slot, want_depth=True, out=pair)
+        return (key, slot, pair)
+
+    def _prefetch(self) -> None:
+        """After a pose change: submit the next frame now, so it renders and crosses PCIe while the
+        caller is elsewhere (run_benchmark.py:1473-1640: measures, VLM query)."""
+        if self._scene is None or self._jpeg_handoff or not hasattr(self._scene, "render_host_async"):
+            return
+        try:
+            key = self._pose_key()
+            if self._frame_key == key or (self._pending is not None and self._pending[0] == key):
+                return
+            self._drop_pending()
+            self._pending = self._submit(key)
+        except Exception as e:
+            _debug_print(f"[WARN] frame prefetch failed: {e}")
+            self._pending = None
+
     def _render_current(self):
         self._update_camera_position()
-        key = (self._cam_position.tobytes(), self._cam_orientation.tobytes(), tuple(self.resolution))
+        key = self._pose_key()
         if self._frame_key != key:
-            # views of the engine's pinned buffers; every getter hands out its own copy
+            t0 = time.perf_counter()
             if self._jpeg_handoff:
                 self._frame, self._jpeg = self._render_with_jpeg(self._camera())
-            else:
+            elif not hasattr(self._scene, "render_host_async"):
                 self._frame = self._scene.render_host(self._camera(), want_depth=True)
+            else:
+                for attempt in range(2):
+                    if self._pending is not None and self._pending[0] == key:
+                        self.perf["prefetch_hits"] += 1
+                    else:
+                        self.perf["prefetch_misses"] += 1
+                        self._drop_pending()
+                        self._pending = self._submit(key)
+                    _, slot, pair = self._pending
+                    self._pending = None
+                    self._scene.host_wait(slot)
+                    st = self._scene.stats()
+                    if not st["overflow"]:
+                        break
+                    # the (bin, Gaussian) lists did not fit (camera inside geometry): grow and redo
+                    self._pool.give_back(pair)
+                    self._scene.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)
+                rgb, depth = pair[0].numpy(), pair[1].numpy()
+                self._pool.lend(pair, (rgb, depth))
+                self._frame = (rgb, depth)
+            self.perf["render_s"] += time.perf_counter() - t0
+            self._served = {"rgb": False, "depth": False}
             self._frame_key = key
             self.render_calls += 1
         return self._frame
@@ -273,13 +436,29 @@ class SimpleVLNEnv:
             self._scene.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)    # as render_host does
         return frame, jpeg
 
+    def _tick(self, name: str) -> None:
+        now = time.perf_counter()
+        self.perf[name] += 1
+        if self.perf["first_call_t"] is None:
+            self.perf["first_call_t"] = now
+        self.perf["last_call_t"] = now
+
+    def _hand_out(self, which: int, name: str):
+        """The frame's array: zero-copy the first time it is asked for, a private copy afterwards (a
+        caller may have drawn on the first one)."""
+        arr = self._frame[which]
+        if self._jpeg_handoff or self._served[name] or not hasattr(self._scene, "render_host_async"):
+            return np.array(arr, copy=True)
+        self._served[name] = True
+        return arr
+
     def get_rgb(self) -> Optional[np.ndarray]:
-        W, H = int(self.resolution[0]), int(self.resolution[1])
         if self._scene is None:
-            return np.zeros((H, W, 3), dtype=np.uint8)
+            return None
         try:
+            self._tick("get_rgb_calls")
             frame = self._render_current()
-            rgb = np.array(frame[0], dtype=np.uint8, copy=True)
+            rgb = self._hand_out(0, "rgb")
             if self._jpeg_handoff and self._jpeg is not None:
                 from .handoff import DeviceFrame
                 # frame[0] is the engine's pinned copy: pristine until the next render replaces it
@@ -290,11 +469,12 @@ class SimpleVLNEnv:
             return None
 
     def get_depth(self) -> Optional[np.ndarray]:
-        W, H = int(self.resolution[0]), int(self.resolution[1])
         if self._scene is None:
-            return np.full((H, W), 5.0, dtype=np.float32)
+            return None
         try:
-            return np.array(self._render_current()[1], dtype=np.float32, copy=True)   # already clipped on the device
+            self._tick("get_depth_calls")
+            self._render_current()
+            return self._hand_out(1, "depth")                 # already clipped to [0.1, 6.5] on the device
         except Exception as e:
             _debug_print(f"[WARN] get_depth failed: {e}")
             return None
@@ -371,6 +551,8 @@ class SimpleVLNEnv:
         return cands, moved
 
     def apply_cmd_for(self, vx: float, vy: float, yaw_rate: float, duration_s: float) -> None:
+        t_apply = time.perf_counter()
+        self._tick("apply_cmd_calls")
         cos_yaw, sin_yaw = math.cos(self._yaw), math.sin(self._yaw)
         world_vx = vx * cos_yaw - vy * sin_yaw
         world_vy = vx * sin_yaw + vy * cos_yaw
@@ -392,6 +574,8 @@ class SimpleVLNEnv:
         self._yaw += total_dyaw
         self._yaw = ((self._yaw + math.pi) % (2 * math.pi)) - math.pi
         self._update_camera_position()
+        self.perf["collide_s"] += time.perf_counter() - t_apply
+        self._prefetch()
 
     def _safe_gradual_movement(self, start_pos, target_pos, target_distance) -> float:
         current_pos = self._pos.copy()
