@@ -187,15 +187,24 @@ class GaussianScene:
                 self.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)
         return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
 
-    def render_host_async(self, cam: Camera, slot: int, rows=None, want_depth: bool = True):
-        """Submit a frame on pipeline slot 0 .. pipeline_depth-1; returns the slot's pinned host arrays
-        (valid after :meth:`host_wait`).  Rotate the slots to keep pipeline_depth frames in flight."""
+    def alloc_host_frame(self, height: int, width: int):
+        """A pinned host (rgb u8 [H,W,C], depth f32 [H,W]) tensor pair for :meth:`render_host_async`'s ``out``."""
         torch = _torch()
-        key = (cam.height, cam.width, "async", int(slot))
-        if key not in self._pinned:
-            self._pinned[key] = (torch.zeros((cam.height, cam.width, self.channels), dtype=torch.uint8).pin_memory(),
-                                 torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
-        rgb_t, dep_t = self._pinned[key]
+        return (torch.zeros((height, width, self.channels), dtype=torch.uint8).pin_memory(),
+                torch.zeros((height, width), dtype=torch.float32).pin_memory())
+
+    def render_host_async(self, cam: Camera, slot: int, rows=None, want_depth: bool = True, out=None):
+        """Submit a frame on pipeline slot 0 .. pipeline_depth-1; returns the slot's pinned host arrays
+        (valid after :meth:`host_wait`).  Rotate the slots to keep pipeline_depth frames in flight.
+        ``out``: a caller-owned pinned tensor pair (see :meth:`alloc_host_frame`) to land the frame in."""
+        torch = _torch()
+        if out is not None:
+            rgb_t, dep_t = out
+        else:
+            key = (cam.height, cam.width, "async", int(slot))
+            if key not in self._pinned:
+                self._pinned[key] = self.alloc_host_frame(cam.height, cam.width)
+            rgb_t, dep_t = self._pinned[key]
         r0, r1 = self._rows(cam, rows)
         cc = _ccam(cam)
         with torch.cuda.device(self.device):

@@ -12,7 +12,9 @@ Same constructor, attributes and methods, same answers bit for bit:
   whole 1 cm / 5 mm march (simple_env.py:2116-2234, <= 60 samples) in one launch.
 
 Error convention of the reference is kept: a missing/invalid map leaves ``obstacle_map = None``
-and every query answers ``False`` (:200-202); nothing raises out of a query (:235-237).
+and every query answers ``False`` (:200-202); nothing raises out of a query (:235-237).  A grid that
+cannot be uploaded (no CUDA device, library missing) raises from the constructor: the engine has no
+CPU fallback and must not pretend the way is clear.
 """
 from __future__ import annotations
 
@@ -94,10 +96,13 @@ class SemanticMap2DCollisionDetector:
                 return
             self.map_height, self.map_width = grid.shape
             self.obstacle_map = grid
-            self._upload()
-        except Exception as e:  # same blanket policy as the reference (:89-92)
+        except Exception as e:  # same blanket policy as the reference (:89-92): a bad MAP means no collisions
             _say(f"[COLLISION_2D] Error: Failed to load map data: {e}")
             self.obstacle_map = None
+            return
+        # a bad DEVICE is not a bad map: no CUDA / no library raises out of the constructor instead of
+        # silently answering "no collision" for the rest of the run
+        self._upload()
 
     def _upload(self) -> None:
         from .api import ObstacleGrid

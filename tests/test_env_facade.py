@@ -61,19 +61,27 @@ def _same_numpy_major(z):
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: Path(p).stem)
-def test_motion_logic_matches_reference_cpu(sage, oracle, path, tmp_path):
+def test_motion_logic_matches_reference_cpu(sage, oracle, path, tmp_path, monkeypatch):
     from sage3d_official_b200.simple_env import SimpleVLNEnv
     z = np.load(path)
     if not _same_numpy_major(z):
         pytest.skip("golden recorded under a different NumPy major (dtype propagation differs)")
-    env = SimpleVLNEnv(str(tmp_path / "missing_scene.usda"), resolution=(64, 48))   # no payload: no GPU needed
+    from oracle_backend import OracleScene
+    cloud, _ = sage.synthetic_room(0, 300)
+    monkeypatch.setattr(SimpleVLNEnv, "_scene_factory", OracleScene)      # no GPU here: frames by the oracle
+    env = SimpleVLNEnv(str(tmp_path / "in_memory.npz"), resolution=(64, 48), gaussians=cloud)
     det = OracleDetector(oracle, str(z["map_json"]), np2=int(np.__version__.split(".")[0]) >= 2)
     env.collision_detector = det
     _replay(env, z)
     # batching: at most 2 dtype groups x 2 phases per command instead of <= 60 sequential lookups
     assert det.calls <= 4 * len(z["cmds"])
-    assert env.get_rgb().shape == (48, 64, 3) and env.get_depth().shape == (48, 64)
+    rgb, dep = env.get_rgb(), env.get_depth()
+    assert rgb.shape == (48, 64, 3) and dep.shape == (48, 64) and float(dep.min()) >= 0.1 and float(dep.max()) <= 6.5
+    assert env.perf["prefetch_hits"] >= 1          # the frame was submitted right after the last pose change
     assert env.get_collision_count() == 0          # _check_collision is dead code in the reference too
+    # a scene path without a Gaussian payload is an error, not a black frame
+    with pytest.raises(FileNotFoundError):
+        SimpleVLNEnv(str(tmp_path / "missing_scene.usda"), resolution=(64, 48))
 
 
 @pytest.mark.gpu

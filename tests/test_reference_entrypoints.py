@@ -35,7 +35,14 @@ def test_dropin_modules_expose_the_members_run_benchmark_uses():
     for m in ("check_collision_3d", "check_path_collision_3d", "check_collision_at_position", "get_collision_info",
               "forward_position_mapping", "_world_to_pixel", "_pixel_to_world"):
         assert callable(getattr(SemanticMap2DCollisionDetector, m)), m
-    env = SimpleVLNEnv(str(ROOT / "no_such_scene.usda"), resolution=(32, 24))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle_backend import OracleScene
+    import sage3d_official_b200 as sage
+    SimpleVLNEnv._scene_factory = OracleScene                 # CPU: frames by the oracle (test double)
+    try:
+        env = SimpleVLNEnv(str(ROOT / "in_memory.npz"), resolution=(32, 24), gaussians=sage.synthetic_room(0, 50)[0])
+    finally:
+        SimpleVLNEnv._scene_factory = None
     for a in ("is_stop_called", "_current_time", "_episode_start_time", "_collision_detected",
               "consecutive_collisions", "_total_collision_count", "semantic_map_path"):
         assert hasattr(env, a), a
