@@ -21,12 +21,16 @@ constexpr int B_THREADS = 256;
 #ifdef SAGE_CUDA_EMU
 constexpr int E_GRID = 2, O_GRID = 2;
 #else
-constexpr int E_GRID = 148 * 4;       // persistent emission blocks
+#ifndef SAGE_EMIT_CTAS
+#define SAGE_EMIT_CTAS 4
+#endif
+constexpr int E_GRID = 148 * SAGE_EMIT_CTAS;       // persistent emission blocks
 constexpr int O_GRID = 148;
 #endif
 constexpr int ROW_POOL = 1536;        // tile-row entries of a batch's cullable splats (typically ~300 used)
-constexpr int E_IPT = 8;              // consecutive instance slots one thread fills per round
+constexpr int ITEM_POOL = 1024;       // (splat, tile row) work items of a batch (typically ~450)
 #define ROWS_NONE 0xFFFFFFFFu
+#define ITEM_NONE 0xFFFFFFFFu
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v)
 {
@@ -62,14 +66,15 @@ __device__ __forceinline__ void cs_store(unsigned long long* p, unsigned long lo
 }
 #endif
 
-// Emission with exact tile culling.  A batch is 256 depth-sorted Gaussians, one per thread.  Setup: a
-// splat whose pixel box spans >= 2 x 2 tiles intersects its {alpha >= 1/255} ellipse with the two
-// 8-row halves of every tile row (sage_band_row) and keeps the column spans + running tile counts in
-// a shared-memory pool; the others (one row or one column of tiles: nothing to cull) keep their box.
-// The per-Gaussian totals are scanned (chained scan across batches).  Expansion is load-balanced over
-// the OUTPUT: a thread takes E_IPT consecutive instance slots, finds the owner of the first one
-// (binary search over the offsets, then over the owner's tile rows) and walks on from there — tile,
-// next row, next Gaussian — so every thread writes one 32-byte run per array whatever the splat sizes.
+// Emission with exact tile culling.  A batch is 256 depth-sorted Gaussians.  Every phase runs on a
+// DENSE set of work items, so the lanes of a warp stay busy whatever the mix of splat sizes:
+//   A1  thread / splat      box, tile rows; splats whose box spans >= 2 x 2 tiles are queued as "cullable"
+//   A2  thread / cullable   the {alpha >= 1/255} ellipse against the two 8-row halves of each of its tile
+//                           rows (sage_band_row): column spans + running tile counts into a row pool
+//   B   block scan of the per-splat tile counts, chained scan across batches (decoupled look-back,
+//       read a warp wide) -> first instance slot of every splat
+//   C   thread / (splat, tile row) item: writes the row's tiles — tile id, Gaussian id << 4 | mask of
+//       the 8 x 8 quadrants the splat reaches — to consecutive slots
 __global__ void __launch_bounds__(B_THREADS, 4)
 k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ ikey,
        uint32_t* __restrict__ ival)
@@ -82,62 +87,88 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
     const uint32_t nblk = (V + B_THREADS - 1) / B_THREADS;
     unsigned long long* chain = fr.chain;
     uint32_t* ticket = fr.tickets + SAGE_TICKET_EMIT;
-    __shared__ uint32_t s_off[B_THREADS + 1];       // exclusive instance offsets of the batch's splats; [256] = total
+    __shared__ uint32_t s_off[B_THREADS];           // exclusive instance offsets of the batch's splats
+    __shared__ uint32_t s_cnt[B_THREADS];           // tiles of the splat
     __shared__ uint32_t s_g[B_THREADS];
     __shared__ uint2 s_rc[B_THREADS];
     __shared__ uint32_t s_rows[B_THREADS];          // first pool entry of the splat, or ROWS_NONE (box mode)
+    __shared__ uint32_t s_cull[B_THREADS];          // queue of cullable splats (thread ids)
     __shared__ uint2 s_pool[ROW_POOL];              // (upper, lower) column spans of one tile row
     __shared__ uint32_t s_cum[ROW_POOL];            // tiles of the splat in the rows before this one
+    __shared__ uint32_t s_item[ITEM_POOL];          // (splat thread id) | (row j) << 8
     __shared__ uint32_t wsum[B_THREADS / 32];
-    __shared__ uint32_t s_blk, s_base, s_pool_used;
+    __shared__ uint32_t s_blk, s_base, s_pool_used, s_ncull, s_nitem;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+    auto put = [&](uint32_t slot, uint32_t tile, uint32_t v) {
+        if (slot < cap) { ikey[slot] = tile; ival[slot] = v; }
+    };
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) { s_blk = atomicAdd(ticket, 1u); s_pool_used = 0; }
+        if (threadIdx.x == 0) { s_blk = atomicAdd(ticket, 1u); s_pool_used = 0; s_ncull = 0; s_nitem = 0; }
         __syncthreads();
         const uint32_t b = s_blk;
         if (b >= nblk) break;
+        // ---- A1: one splat per thread ----
         const uint32_t r = b * B_THREADS + threadIdx.x;
-        uint32_t g = 0, c = 0, rows_at = ROWS_NONE;
+        uint32_t g = 0, c = 0, nrows = 0;
         uint2 rc = make_uint2(0, 0);
+        bool overflow_rows = false;                  // its rows do not fit the item pool: expanded by its own thread
         if (r < V) {
             g = __ldg(&order[r]);
             rc = __ldg(&fr.rect[g]);
             const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
-            const int ty0 = py0 / SAGE_BIN, ty1 = py1 / SAGE_BIN;
-            const uint32_t nrows = (uint32_t)(ty1 - ty0 + 1);
+            nrows = (uint32_t)(py1 / SAGE_BIN - py0 / SAGE_BIN + 1);
             c = (uint32_t)(px1 / SAGE_BIN - px0 / SAGE_BIN + 1) * nrows;
-            if (sage_box_cullable(px0, px1, py0, py1)) {
-                const uint32_t at = atomicAdd(&s_pool_used, nrows);
-                if (at + nrows <= ROW_POOL) {            // (a full pool only costs the culling, never correctness)
-                    const float4 r0 = __ldg(&fr.rec[3 * (size_t)g]);         // gx gy qa lo
-                    const float4 r1 = __ldg(&fr.rec[3 * (size_t)g + 1]);     // qb qc
-                    const SageBand band = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r0.w - SAGE_L255);
-                    uint32_t cum = 0;
-                    for (uint32_t j = 0; j < nrows; ++j) {
-                        const SageRowItem it = sage_band_row(band, px0, px1, py0, py1, ty0 + (int)j);
-                        s_cum[at + j] = cum;
-                        s_pool[at + j] = make_uint2(it.top, it.bot);
-                        cum += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
-                    }
-                    c = cum;
-                    rows_at = at;
-                }
+            if (sage_box_cullable(px0, px1, py0, py1)) s_cull[atomicAdd(&s_ncull, 1u)] = threadIdx.x;
+            const uint32_t it0 = atomicAdd(&s_nitem, nrows);
+            if (it0 + nrows <= ITEM_POOL) {
+                for (uint32_t j = 0; j < nrows; ++j) s_item[it0 + j] = threadIdx.x | (j << 8);
+            } else {
+                overflow_rows = true;
+                for (uint32_t k = it0; k < ITEM_POOL; ++k) s_item[k] = ITEM_NONE;    // the tail it could not use
             }
         }
-        uint32_t incl = warp_incl_scan_u32(c);
-        if (lane == 31) wsum[w] = incl;
         s_g[threadIdx.x] = g;
         s_rc[threadIdx.x] = rc;
-        s_rows[threadIdx.x] = rows_at;
+        s_rows[threadIdx.x] = ROWS_NONE;
+        s_cnt[threadIdx.x] = c;
+        __syncthreads();
+        // ---- A2: one cullable splat per thread (dense) ----
+        for (uint32_t k = threadIdx.x; k < s_ncull; k += B_THREADS) {
+            const uint32_t t = s_cull[k];
+            const uint2 q = s_rc[t];
+            const int px0 = q.x & 0xFFFF, px1 = q.x >> 16, py0 = q.y & 0xFFFF, py1 = q.y >> 16;
+            const int ty0 = py0 / SAGE_BIN;
+            const uint32_t nr = (uint32_t)(py1 / SAGE_BIN - ty0 + 1);
+            const uint32_t at = atomicAdd(&s_pool_used, nr);
+            if (at + nr > ROW_POOL) continue;            // (a full pool only costs the culling, never correctness)
+            const uint32_t gg = s_g[t];
+            const float4 r0 = __ldg(&fr.rec[3 * (size_t)gg]);         // gx gy qa lo
+            const float4 r1 = __ldg(&fr.rec[3 * (size_t)gg + 1]);     // qb qc
+            const SageBand band = sage_band_make(r0.x, r0.y, r0.z, r1.x, r1.y, r0.w - SAGE_L255);
+            uint32_t cum = 0;
+            for (uint32_t j = 0; j < nr; ++j) {
+                const SageRowItem it = sage_band_row(band, px0, px1, py0, py1, ty0 + (int)j);
+                s_cum[at + j] = cum;
+                s_pool[at + j] = make_uint2(it.top, it.bot);
+                cum += (uint32_t)max(it.tx1 - it.tx0 + 1, 0);
+            }
+            s_cnt[t] = cum;
+            s_rows[t] = at;
+        }
+        __syncthreads();
+        // ---- B: offsets ----
+        c = s_cnt[threadIdx.x];
+        const uint32_t incl = warp_incl_scan_u32(c);
+        if (lane == 31) wsum[w] = incl;
         __syncthreads();
         uint32_t woff = 0, total = 0;
 #pragma unroll
         for (int k = 0; k < B_THREADS / 32; ++k) { woff += (k < w) ? wsum[k] : 0u; total += wsum[k]; }
-        s_off[threadIdx.x] = woff + incl - c;
-        if (threadIdx.x == 0) s_off[B_THREADS] = total;
-
+        const uint32_t my_off = woff + incl - c;
+        s_off[threadIdx.x] = my_off;
         // chained scan across batches: chain[b] = epoch(30) | state(2) | value(32); warp 0 looks back
         // over 32 predecessors per round trip
         if (w == 0) {
@@ -181,74 +212,32 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
         }
         __syncthreads();
         const uint32_t base = s_base;
-
-        // load-balanced expansion: E_IPT consecutive instance slots per thread and round
-        for (uint32_t k0 = threadIdx.x * E_IPT; k0 < total; k0 += B_THREADS * E_IPT) {
-            const uint32_t kend = min(k0 + (uint32_t)E_IPT, total);
-            int own = 0;
-            {
-                int lo = 0, hi = B_THREADS - 1;            // owner = last o with s_off[o] <= k0 (its count is > 0)
-#pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_off[mid] <= k0) lo = mid; else hi = mid - 1;
-                }
-                own = lo;
-            }
-            // state of the walk: the owner's box / pool rows, tile row j of nr, tile tx of [t0, t1]
-            uint2 bx2 = s_rc[own];
-            uint32_t at = s_rows[own], gg = s_g[own];
-            int px0 = (int)(bx2.x & 0xFFFF), px1 = (int)(bx2.x >> 16), py0 = (int)(bx2.y & 0xFFFF), py1 = (int)(bx2.y >> 16);
-            int ty0 = py0 / SAGE_BIN, nr = py1 / SAGE_BIN - ty0 + 1;
-            const uint32_t local = k0 - s_off[own];
-            int j, t0, t1, tx;
-            uint2 sp = make_uint2(0, 0);
+        // ---- C: one (splat, tile row) item per thread (dense) ----
+        auto emit_row = [&](uint32_t t, uint32_t j) {
+            const uint2 q = s_rc[t];
+            const int px0 = q.x & 0xFFFF, px1 = q.x >> 16, py0 = q.y & 0xFFFF, py1 = q.y >> 16;
+            const int ty = py0 / SAGE_BIN + (int)j;
+            const uint32_t at = s_rows[t], gv = s_g[t] << 4;
+            const uint32_t rowtile = (uint32_t)((ty - bin_row0) * bins_x);
             if (at == ROWS_NONE) {
-                t0 = px0 / SAGE_BIN; t1 = px1 / SAGE_BIN;
-                const uint32_t bw = (uint32_t)(t1 - t0 + 1);
-                j = (int)(local / bw);
-                tx = t0 + (int)(local - (uint32_t)j * bw);
+                const int t0 = px0 / SAGE_BIN, t1 = px1 / SAGE_BIN;
+                uint32_t slot = base + s_off[t] + j * (uint32_t)(t1 - t0 + 1);
+                for (int tx = t0; tx <= t1; ++tx) put(slot++, rowtile + (uint32_t)tx, gv | sage_box_quad_mask(px0, px1, py0, py1, tx, ty));
             } else {
-                int lo = 0, hi = nr - 1;                   // row = last j with cum[j] <= local (it is not empty)
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_cum[at + mid] <= local) lo = mid; else hi = mid - 1;
-                }
-                j = lo;
-                sp = s_pool[at + j];
+                const uint2 sp = s_pool[at + j];
                 const SageRowItem ri = sage_row_from_spans(sp.x, sp.y);
-                t0 = ri.tx0; t1 = ri.tx1;
-                tx = t0 + (int)(local - s_cum[at + j]);
+                uint32_t slot = base + s_off[t] + s_cum[at + j];
+                for (int tx = ri.tx0; tx <= ri.tx1; ++tx) put(slot++, rowtile + (uint32_t)tx, gv | sage_row_quad_mask(sp.x, sp.y, tx));
             }
-            for (uint32_t k = k0; k < kend; ++k) {
-                const uint32_t slot = base + k;
-                if (slot < cap) {
-                    const int ty = ty0 + j;
-                    const uint32_t mask = at == ROWS_NONE ? sage_box_quad_mask(px0, px1, py0, py1, tx, ty)
-                                                          : sage_row_quad_mask(sp.x, sp.y, tx);
-                    ikey[slot] = (uint32_t)((ty - bin_row0) * bins_x + tx);
-                    ival[slot] = (gg << 4) | mask;
-                }
-                if (k + 1 == kend) break;
-                if (++tx <= t1) continue;
-                for (;;) {                                 // next non-empty tile row, of the next splat if need be
-                    if (++j >= nr) {
-                        do { ++own; } while (s_off[own + 1] == s_off[own]);     // k + 1 < total: one exists
-                        bx2 = s_rc[own]; at = s_rows[own]; gg = s_g[own];
-                        px0 = (int)(bx2.x & 0xFFFF); px1 = (int)(bx2.x >> 16); py0 = (int)(bx2.y & 0xFFFF); py1 = (int)(bx2.y >> 16);
-                        ty0 = py0 / SAGE_BIN; nr = py1 / SAGE_BIN - ty0 + 1;
-                        j = 0;
-                    }
-                    if (at == ROWS_NONE) { t0 = px0 / SAGE_BIN; t1 = px1 / SAGE_BIN; }
-                    else {
-                        sp = s_pool[at + j];
-                        const SageRowItem ri = sage_row_from_spans(sp.x, sp.y);
-                        t0 = ri.tx0; t1 = ri.tx1;
-                    }
-                    if (t0 <= t1) { tx = t0; break; }
-                }
-            }
+        };
+        const uint32_t n_items = min(s_nitem, (uint32_t)ITEM_POOL);
+        for (uint32_t k = threadIdx.x; k < s_nitem; k += B_THREADS) {
+            if (k >= n_items) break;
+            const uint32_t it = s_item[k];
+            if (it != ITEM_NONE) emit_row(it & 0xFFu, it >> 8);
         }
+        if (overflow_rows)                                   // (splats taller than the item pool has room for)
+            for (uint32_t j = 0; j < nrows; ++j) emit_row(threadIdx.x, j);
     }
 }
 
@@ -288,4 +277,12 @@ void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t s
 void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st)
 {
     SAGE_KLAUNCH(k_bin_order, O_GRID, B_THREADS, st, fr);
+}
+
+void sage_bin_configure(void)
+{
+#ifndef SAGE_CUDA_EMU
+    sage_prefer_smem(k_emit);
+    sage_prefer_smem(k_bin_order);
+#endif
 }

@@ -6,8 +6,9 @@
 // One WARP = one 8 x 8 quadrant of a 16 x 16 tile: lane -> row lane>>2, two horizontally adjacent
 // pixels (lane&3)*2, so the blend arithmetic runs on Blackwell's packed binary32 pipe
 // (FFMA2/FMUL2/FADD2: fma.rn.f32x2), which is IEEE per lane and therefore bit-identical to the
-// scalar statement in the oracle.  Warps are persistent and independent: each draws (tile, quadrant)
-// work items from a ticket counter, heaviest length class first (k_bin_order), walks the tile's
+// scalar statement in the oracle.  Warps are independent: CTA b holds the four quadrants of the b-th
+// heaviest tile (k_bin_order's length classes; CTAs are dispatched in index order, so the longest
+// lists start first), each warp walks the tile's
 // depth-sorted list 32 instances at a time, keeps those whose quadrant bit is set (ballot + popc: the
 // survivors' records are gathered straight into consecutive slots of the stage) and never
 // synchronises with another warp.  (Round 1 blended a tile with a CTA of four warps that met at a
@@ -32,14 +33,9 @@ namespace {
 constexpr int C_WARPS = 4;
 constexpr int C_THREADS = C_WARPS * 32;
 #ifndef SAGE_COMPOSITE_CTAS
-#define SAGE_COMPOSITE_CTAS 12
+#define SAGE_COMPOSITE_CTAS 10
 #endif
 constexpr int C_CTAS_PER_SM = SAGE_COMPOSITE_CTAS;
-#ifdef SAGE_CUDA_EMU
-constexpr int C_GRID = 2;
-#else
-constexpr int C_GRID = 148 * C_CTAS_PER_SM;
-#endif
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
@@ -85,7 +81,6 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
     const float depth_lo = fp->cam.depth_lo, depth_hi = fp->cam.depth_hi;
     const float4* __restrict__ rec = fr.rec;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t* ticket = fr.tickets + SAGE_TICKET_COMPOSITE;
 
     // work queue: tiles by descending length class, 4 work items (quadrants) each; lane l holds the
     // running count of classes 32 .. 32-l
@@ -99,13 +94,10 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
     const uint32_t n_nonempty = __shfl_sync(0xffffffffu, cls_incl, 31);
     const float NAN_X = __uint_as_float(0x7fc00000u);
 
-    for (;;) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= 4u * (uint32_t)n_bins) break;
-        const uint32_t tt = t >> 2;                              // position of the tile in the queue
-        const int quad = (int)(t & 3u);                          // quadrant: bit qy*2 + qx of the instance masks
+    // Not persistent on purpose: as CTAs retire, the SM's registers and shared memory go to the
+    // (higher-priority) front-half kernels of the next frame instead of staying pinned to this kernel.
+    for (uint32_t tt = blockIdx.x; tt < (uint32_t)n_bins; tt += gridDim.x) {     // (one trip: the grid is n_bins)
+        const int quad = w;                                      // quadrant: bit qy*2 + qx of the instance masks
         uint32_t cls, idx;
         if (tt < n_nonempty) {
             const unsigned m = __ballot_sync(0xffffffffu, cls_incl > tt);
@@ -282,7 +274,15 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 
 }  // namespace
 
-void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, cudaStream_t st)
+void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st)
 {
-    SAGE_KLAUNCH(k_composite, C_GRID, C_THREADS, st, fr, sorted_vals);
+    if (n_bins <= 0) return;
+    SAGE_KLAUNCH(k_composite, n_bins, C_THREADS, st, fr, sorted_vals);
+}
+
+void sage_composite_configure(void)
+{
+#ifndef SAGE_CUDA_EMU
+    sage_prefer_smem(k_composite);
+#endif
 }

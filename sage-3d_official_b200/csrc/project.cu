@@ -264,3 +264,12 @@ void sage_launch_sh_color(const SageSceneDev& sc, const SageFrame& fr, cudaStrea
         default: SAGE_KLAUNCH(k_sh_color<3>, blocks, 256, st, sc, fr); break;
     }
 }
+
+void sage_project_configure(void)
+{
+#ifndef SAGE_CUDA_EMU
+    sage_prefer_smem(k_project);
+    sage_prefer_smem(k_sh_color<0>); sage_prefer_smem(k_sh_color<1>);
+    sage_prefer_smem(k_sh_color<2>); sage_prefer_smem(k_sh_color<3>);
+#endif
+}

@@ -14,6 +14,7 @@
 #define SAGE_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/sage_splat.h"
 
@@ -315,7 +316,7 @@ size_t sage_sort_matrix_words(int64_t capacity);
 
 void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t st);
 void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st);
-void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, cudaStream_t st);
+void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st);
 
 // One whole frame (every launch between the parameter upload and the counter read-back): the front
 // half on stream `fs`, the view-dependent colours on `ss`, the composite on the caller's stream
@@ -330,6 +331,21 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
                        const uint32_t* n_dev, cudaStream_t cs, cudaStream_t fs, cudaStream_t ss,
                        cudaEvent_t* fork_join, cudaEvent_t* ev, int n_bins);
 void sage_sort_configure(void);
+void sage_bin_configure(void);
+void sage_composite_configure(void);
+void sage_project_configure(void);
+
+#ifndef SAGE_CUDA_EMU
+// Every kernel of a frame asks for the SAME shared-memory carve-out (the maximum): an SM whose
+// carve-out never changes can hold CTAs of different kernels — the composite of frame i and the
+// sorts of frame i+1 — at once, instead of draining between two configurations.
+template <typename K>
+inline void sage_prefer_smem(K kernel)
+{
+    static const bool off = getenv("SAGE_NO_CARVEOUT") != nullptr;
+    if (!off) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+#endif
 
 void sage_launch_collide_grid(const uint8_t* map, int H, int W, double min_x, double max_x,
                               double min_y, double max_y, double scale, const float* pos_f32,

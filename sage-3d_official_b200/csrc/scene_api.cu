@@ -376,6 +376,9 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     REQUIRE(n == 0 || (xyz && log_scale && quat_wxyz && opacity_raw && sh), "sage_scene_create: NULL attribute pointer");
     CK(cudaSetDevice(device));
     sage_sort_configure();
+    sage_bin_configure();
+    sage_composite_configure();
+    sage_project_configure();
     sage_scene* s = new sage_scene();
     s->device = device;
     s->sc.n = n;

@@ -28,8 +28,32 @@ constexpr int S_WARPS = S_THREADS / 32;
 #ifdef SAGE_CUDA_EMU
 constexpr int S_GRID = 2;
 #else
-constexpr int S_GRID = 148 * 2;                    // persistent: two blocks per SM, grid-stride over the tiles
+#ifndef SAGE_SORT_CTAS
+#define SAGE_SORT_CTAS 2
 #endif
+constexpr int S_GRID = 148 * SAGE_SORT_CTAS;       // persistent: blocks per SM, grid-stride over the tiles
+#endif
+
+// lanes of the warp holding the same digit (invalid lanes: d = 0xFFFFFFFF).  The hardware MATCH
+// instruction is one issue slot but has a long latency; the ballot form (one vote per digit bit) is
+// ~3 RB simple instructions with none.  SAGE_SORT_MATCH=1 builds the MATCH form for comparison.
+template <int RB>
+__device__ __forceinline__ unsigned digit_peers(uint32_t d)
+{
+#if defined(SAGE_SORT_MATCH)
+    return __match_any_sync(0xffffffffu, d);
+#else
+    unsigned m = __ballot_sync(0xffffffffu, d == 0xFFFFFFFFu);     // the invalid lanes
+    m = (d == 0xFFFFFFFFu) ? m : ~m;
+#pragma unroll
+    for (int b = 0; b < RB; ++b) {
+        const unsigned bit = (d >> b) & 1u;
+        const unsigned v = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? v : ~v;
+    }
+    return m;
+#endif
+}
 
 // ---- per-tile digit histograms --------------------------------------------------------------
 template <int RB, bool COMPACT, int S_IPT>
@@ -157,7 +181,7 @@ k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
             const uint32_t idx = wbase + i * 32 + lane;
             const bool valid = idx < n && (!COMPACT || key[i] != SAGE_KEY_CULLED);
             const uint32_t d = valid ? ((key[i] >> shift) & (RADIX - 1)) : 0xFFFFFFFFu;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const unsigned peers = digit_peers<RB>(d);
             const int leader = __ffs(peers) - 1;
             uint32_t prev = 0;
             if (valid && lane == leader) {
@@ -273,6 +297,12 @@ void sort_cfg()
     cudaFuncSetAttribute(k_sort_scatter<RB, true, S_IPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     cudaFuncSetAttribute(k_sort_scatter<RB, false, S_IPT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     cudaFuncSetAttribute(k_sort_scatter<RB, false, S_IPT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+    sage_prefer_smem(k_sort_scatter<RB, true, S_IPT, false>);
+    sage_prefer_smem(k_sort_scatter<RB, false, S_IPT, false>);
+    sage_prefer_smem(k_sort_scatter<RB, false, S_IPT, true>);
+    sage_prefer_smem(k_sort_hist<RB, true, S_IPT>);
+    sage_prefer_smem(k_sort_hist<RB, false, S_IPT>);
+    sage_prefer_smem(k_sort_scan<S_IPT>);
 #endif
 }
 
