@@ -33,7 +33,7 @@ namespace {
 constexpr int C_WARPS = 4;
 constexpr int C_THREADS = C_WARPS * 32;
 #ifndef SAGE_COMPOSITE_CTAS
-#define SAGE_COMPOSITE_CTAS 10
+#define SAGE_COMPOSITE_CTAS 8
 #endif
 constexpr int C_CTAS_PER_SM = SAGE_COMPOSITE_CTAS;
 

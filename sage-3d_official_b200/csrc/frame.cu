@@ -82,7 +82,7 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         tp.vals[0] = fr.ival[0]; tp.vals[1] = fr.ival[1];
         tp.n_first = tp.n_rest = fr.counters + CNT_INSTANCES;
         tp.lo_bit = 0; tp.n_bits = 8 * shape.tile_passes; tp.digit_bits = 8; tp.passes = shape.tile_passes;
-        static const int tile_ipt = env_ipt("SAGE_TILE_IPT", 16);
+        static const int tile_ipt = env_ipt("SAGE_TILE_IPT", 8);
         tp.vals_are_iota = false; tp.compact_first = false; tp.items_per_thread = tile_ipt;
         tp.H = fr.sort_h; tp.ld = fr.sort_ld; tp.totals = fr.sort_totals; tp.ranges = fr.ranges;
         const int ires = sage_radix_sort(tp, &launches, fs);

@@ -336,14 +336,14 @@ void sage_composite_configure(void);
 void sage_project_configure(void);
 
 #ifndef SAGE_CUDA_EMU
-// Every kernel of a frame asks for the SAME shared-memory carve-out (the maximum): an SM whose
-// carve-out never changes can hold CTAs of different kernels — the composite of frame i and the
-// sorts of frame i+1 — at once, instead of draining between two configurations.
+// Experiment knob (off by default): ask for the maximum shared-memory carve-out on every kernel of a
+// frame so an SM never changes configuration between them.  Measured (profiles/r02_variants.md):
+// it costs k_sh_color its L1 (0.043 -> 0.069 ms) and the frame 5 %; left in for SAGE_CARVEOUT=1.
 template <typename K>
 inline void sage_prefer_smem(K kernel)
 {
-    static const bool off = getenv("SAGE_NO_CARVEOUT") != nullptr;
-    if (!off) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    static const bool on = getenv("SAGE_CARVEOUT") != nullptr;
+    if (on) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 #endif
 

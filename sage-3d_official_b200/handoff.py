@@ -17,15 +17,18 @@ Pillow's default encoder).  This module lets the unmodified callers pick them up
   given IS, bit for bit, the frame the device encoded (checked with a full compare against the
   engine's pinned copy, ~0.3 ms), the returned image is a :class:`PrecodedImage` whose
   ``save(fp, format='JPEG')`` / ``save('x.jpg')`` with no encoder options writes the device's
-  bytes.  Any mutation (Pillow mutators copy-on-write a read-only image; we detect the swap), any
-  option (quality=, optimize=, ...), any other format or mode falls through to Pillow itself.
-  The image owns a private copy of the pixels and unpacks it into Pillow storage only when something
-  asks for pixels (``load()``): a frame that is only wrapped, kept in a history and saved as JPEG —
-  the VLM client's whole use of it — never pays Pillow's per-frame unpack either.
+  bytes.  Any option (quality=, optimize=, ...), any other format or mode falls through to Pillow.
+  The image owns a private copy of the pixels and has NO Pillow pixel storage until something asks
+  for pixels: a frame that is only wrapped, kept in a history and saved as JPEG — the VLM client's
+  whole use of it — never pays Pillow's per-frame unpack.
 
-The rule is airtight by construction: pre-encoded bytes are used only when the pixels being saved
-are provably the pixels that were encoded, and for those pixels the two encoders agree byte for
-byte (tests/test_jpeg_gpu.py).  The hook is opt-in: the launchers install it
+The rule holds by construction: the precoded bytes exist only while the image is "virtual".  Every
+Pillow path to the pixels goes through ``im``; the first access materialises ordinary, writable
+storage from the private copy and drops the bytes for good — including the in-place mutators that
+ignore ``readonly`` (``frombytes``, ``putdata``).  From then on the object is an ordinary image:
+writable through ``load()[x, y] = v``, equal to ``Image.fromarray(rgb)``, picklable (it reduces to a
+plain ``Image``).  For the untouched pixels the two encoders agree byte for byte
+(tests/test_jpeg_gpu.py).  The hook is opt-in: the launchers install it
 (tools/launch_sage_bench.py, isaac_shim.install(jpeg_handoff=True)) or ``SAGE_JPEG_HANDOFF=1``.
 """
 from __future__ import annotations
@@ -80,7 +83,7 @@ def precoded_jpeg(arr) -> Optional[bytes]:
     return jpeg
 
 
-_hook_state = {"installed": False, "orig": None, "cls": None, "hits": 0, "misses": 0}
+_hook_state = {"installed": False, "orig": None, "hits": 0, "misses": 0}
 
 
 def hook_stats() -> dict:
@@ -88,39 +91,84 @@ def hook_stats() -> dict:
 
 
 def _core(im):
-    """The image's core storage or None, without tripping Pillow >= 10's asserting ``im`` property
-    (older Pillow keeps it as a plain attribute)."""
-    d = im.__dict__
-    return d["_im"] if "_im" in d else d.get("im")
+    """The image's pixel storage or None, without materialising a virtual PrecodedImage."""
+    return im.__dict__.get("_im")
 
 
-def _precoded_class():
-    if _hook_state["cls"] is not None:
-        return _hook_state["cls"]
+def _plain_fromarray(arr):
+    """Pillow's own ``Image.fromarray`` (the un-hooked one)."""
+    if _hook_state["orig"] is not None:
+        return _hook_state["orig"](arr)
     from PIL import Image
+    return Image.fromarray(arr)
 
-    class PrecodedImage(Image.Image):
-        """An RGB image that can hand out the JPEG its pixels already have.  Pixel storage is
-        created lazily (``load()``, which every Pillow operation calls before touching ``im``): a
-        frame that is only ever saved as a default JPEG never pays Pillow's 6 MB unpack."""
+
+def _rebuild_plain(mode, size, data):
+    from PIL import Image
+    return Image.frombytes(mode, size, data)
+
+
+try:
+    from PIL import Image as _PILImage
+except Exception:                                   # Pillow is optional: without it there is no hook
+    _PILImage = None
+
+
+if _PILImage is not None:
+
+    class PrecodedImage(_PILImage.Image):
+        """An RGB image that can hand out the JPEG its pixels already have.
+
+        The invariant is structural: the precoded bytes are valid ONLY while the image has never
+        been given Pillow pixel storage.  The pixels live in a private NumPy copy; the moment anything
+        reaches for ``im`` — ``load()``, ``frombytes()``, ``putdata()``, ``tobytes()``, a filter, a
+        comparison — the storage is materialised from that copy and the JPEG is dropped for good, so no
+        in-place mutator (not even the ones that ignore ``readonly``) can leave stale bytes behind.
+        After that the object behaves exactly like the image ``Image.fromarray`` would have returned
+        (writable, comparable, picklable)."""
+
         _sage_jpeg: Optional[bytes] = None
-        _sage_im = None          # the core image the bytes describe, once materialised
-        _sage_arr = None         # private copy of the pixels, until materialised
+        _sage_arr = None         # private copy of the pixels while the image is still "virtual"
+
+        # ``im`` is what every Pillow code path touches before reading or writing pixels (a plain
+        # attribute up to Pillow 9, a property asserting on None from 10 on): materialise on demand.
+        @property
+        def im(self):
+            core = self.__dict__.get("_im")
+            if core is None and self._sage_arr is not None:
+                arr, self._sage_arr, self._sage_jpeg = self._sage_arr, None, None
+                core = _plain_fromarray(arr).im
+                self.__dict__["_im"] = core
+                self.readonly = 0
+            if core is None:
+                raise ValueError("image has no pixel storage")
+            return core
+
+        @im.setter
+        def im(self, core):
+            self._sage_arr, self._sage_jpeg = None, None
+            self.__dict__["_im"] = core
+
+        # Pillow >= 10 keeps the storage in ``_im`` and reads it directly in a few places
+        @property
+        def _im(self):
+            if self.__dict__.get("_im") is None and self._sage_arr is not None:
+                return self.im
+            return self.__dict__.get("_im")
+
+        @_im.setter
+        def _im(self, core):
+            if core is not None:
+                self._sage_arr, self._sage_jpeg = None, None
+            self.__dict__["_im"] = core
 
         def load(self):
-            if self._sage_arr is not None and _core(self) is None:
-                core = _hook_state["orig"](self._sage_arr)
-                self.im = core.im
-                self._sage_im = self.im
-                self._sage_arr = None            # (readonly stays 1: Pillow's mutators copy on write)
+            self.im                                  # materialise (drops the precoded state)
             return super().load()
 
         def _sage_valid(self) -> bool:
-            if self._sage_jpeg is None or self.mode != "RGB" or self.info:
-                return False
-            if self._sage_arr is not None:                  # never materialised: nothing could have changed
-                return _core(self) is None
-            return bool(self.readonly) and _core(self) is self._sage_im
+            return (self._sage_jpeg is not None and self._sage_arr is not None and self.__dict__.get("_im") is None
+                    and self.mode == "RGB" and not self.info)
 
         def save(self, fp, format=None, **params):
             if not params and self._sage_valid():
@@ -143,36 +191,39 @@ def _precoded_class():
 
         def convert(self, mode=None, *args, **kwargs):
             # img.convert('RGB') on an RGB image is an identity copy (vlm_client_modular.py:448-451):
-            # share the (read-only) pixels instead of copying 6 MB; Pillow's mutators copy on write
+            # share the private (never written) pixel array instead of copying 6 MB
             if mode in (None, "RGB") and not args and not kwargs and self._sage_valid():
-                if self._sage_arr is not None:
-                    return _lazy(self._sage_arr, self._sage_jpeg)
-                new = self._new(self.im)
-                return _promote(new, self._sage_jpeg)
+                return _lazy(self._sage_arr, self._sage_jpeg)
             return super().convert(mode, *args, **kwargs)
 
-    _hook_state["cls"] = PrecodedImage
-    return PrecodedImage
+        def copy(self):
+            if self._sage_valid():
+                return _lazy(self._sage_arr, self._sage_jpeg)
+            return super().copy()
 
+        def __eq__(self, other):
+            if not isinstance(other, _PILImage.Image):
+                return NotImplemented
+            return (self.mode == other.mode and self.size == other.size and self.info == other.info
+                    and self.getpalette() == other.getpalette() and self.tobytes() == other.tobytes())
 
-def _promote(im, jpeg: bytes):
-    im.__class__ = _precoded_class()
-    im._sage_jpeg = jpeg
-    im._sage_im = im.im
-    im._sage_arr = None
-    im.readonly = 1
-    return im
+        __hash__ = None
+
+        def __reduce__(self):                        # pickling / multiprocessing: a plain Image of the same pixels
+            return (_rebuild_plain, (self.mode, self.size, self.tobytes()))
+
+else:
+    PrecodedImage = None
 
 
 def _lazy(arr: np.ndarray, jpeg: bytes):
     """A PrecodedImage over a PRIVATE pixel array (never written again); no Pillow storage yet."""
-    im = _precoded_class()()
+    im = PrecodedImage()
     im._size = (int(arr.shape[1]), int(arr.shape[0]))
     im._mode = "RGB"
-    im.readonly = 1              # from birth: putpixel / paste / ImageDraw then _copy() before writing
+    im.readonly = 0
     im._sage_jpeg = jpeg
     im._sage_arr = arr
-    im._sage_im = None
     return im
 
 
@@ -186,7 +237,6 @@ def install_pillow_hook() -> bool:
         return False
     orig = Image.fromarray
     _hook_state["orig"] = orig
-    _precoded_class()
 
     def fromarray(obj, mode=None, *a, **kw):
         if mode is None and not a and not kw:

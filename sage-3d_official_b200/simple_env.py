@@ -163,6 +163,7 @@ class SimpleVLNEnv:
         self._pos = np.array([0.0, 0.0, self.AGENT_CENTRE_Z], dtype=np.float32)
         self._yaw = 0.0
         self._pool = None
+        self._scratch = None
         self._pending = None           # (key, slot, pair) of the frame submitted ahead of the caller
         self._slot = 0
         self._served = {"rgb": False, "depth": False}
@@ -207,6 +208,7 @@ class SimpleVLNEnv:
         self._scene = None
         self._bodies = None
         self._pool = None
+        self._scratch = None
         self._frame_key = None
         bodies_src = None
         if self._preloaded[0] is not None:
@@ -349,7 +351,15 @@ class SimpleVLNEnv:
             scene = self._scene
             self._pool = _FramePool(lambda: scene.alloc_host_frame(H, W))
             self._pool_shape = (H, W)
-        return self._pool.take()
+            self._scratch = None
+        pair = self._pool.take()
+        if pair is None:
+            # the caller keeps every frame it was given (run_benchmark.py:1422 appends them all to a
+            # list): stop lending pinned buffers, land frames in one scratch pair and hand out copies
+            if self._scratch is None:
+                self._scratch = self._scene.alloc_host_frame(H, W)
+            return self._scratch
+        return pair
 
     def _drop_pending(self) -> None:
         if self._pending is not None and self._scene is not None:
@@ -358,7 +368,7 @@ class SimpleVLNEnv:
                 self._scene.host_wait(slot)
             except Exception:
                 pass
-            if pair is not None and self._pool is not None:
+            if pair is not None and self._pool is not None and pair is not self._scratch:
                 self._pool.give_back(pair)
         self._pending = None
 
@@ -411,11 +421,15 @@ class SimpleVLNEnv:
                     st = self._scene.stats()
                     if not st["overflow"]:
                         break
-                    # the (bin, Gaussian) lists did not fit (camera inside geometry): grow and redo
-                    self._pool.give_back(pair)
+                    # the (tile, Gaussian) lists did not fit (camera inside geometry): grow and redo
+                    if pair is not self._scratch:
+                        self._pool.give_back(pair)
                     self._scene.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)
-                rgb, depth = pair[0].numpy(), pair[1].numpy()
-                self._pool.lend(pair, (rgb, depth))
+                if pair is self._scratch:
+                    rgb, depth = pair[0].numpy().copy(), pair[1].numpy().copy()
+                else:
+                    rgb, depth = pair[0].numpy(), pair[1].numpy()
+                    self._pool.lend(pair, (rgb, depth))
                 self._frame = (rgb, depth)
             self.perf["render_s"] += time.perf_counter() - t0
             self._served = {"rgb": False, "depth": False}

@@ -35,12 +35,12 @@ def test_untouched_frame_uses_precoded_bytes(hook):
     handoff, h0 = hook
     fr, pristine, marker = _frame(handoff)
     im = Image.fromarray(fr)
-    assert np.array_equal(np.asarray(im), pristine)        # a real image, pixels intact
     b = io.BytesIO(); im.save(b, format="JPEG")
     assert b.getvalue() == marker
     b = io.BytesIO(); im.convert("RGB").save(b, format="jpeg")        # vlm_client_modular.py:448-453
     assert b.getvalue() == marker
     assert handoff.hook_stats()["hits"] == h0["hits"] + 2
+    assert np.array_equal(np.asarray(im), pristine)        # a real image, pixels intact
 
 
 def test_path_save_by_extension(hook, tmp_path):
@@ -103,7 +103,8 @@ def test_history_of_converted_images_shares_pixels(hook):
         if k == 3:
             assert b.getvalue() == _pillow(np.asarray(h)) and np.asarray(h)[5, 5, 0] == 9
         else:
-            assert b.getvalue() == marker and np.array_equal(np.asarray(h), pristine)
+            assert b.getvalue() == marker
+            assert np.array_equal(np.asarray(h), pristine)
 
 
 def test_device_frame_is_an_ordinary_array(hook):
@@ -129,18 +130,58 @@ def test_lazy_image_materialises_on_demand_and_stays_safe(hook):
     assert im.size == (64, 48) and im.mode == "RGB"
     assert np.array_equal(np.asarray(im), pristine)      # materialised from the private copy
     assert handoff._core(im) is not None
+    # once real pixel storage exists the precoded bytes are gone for good: Pillow encodes (for the real
+    # device JPEG that is the same byte stream — tests/test_jpeg_gpu.py — here the marker is a fake)
     b = io.BytesIO(); im.save(b, format="JPEG")
-    assert b.getvalue() == marker                        # still untouched
-    try:                                                 # direct pixel access is read-only
-        px = im.load()
-        px[0, 0] = (9, 9, 9)
-        wrote = True
-    except (ValueError, TypeError):
-        wrote = False
-    if wrote:
-        b = io.BytesIO(); im.save(b, format="JPEG")
-        assert b.getvalue() == _pillow(np.asarray(im))
+    assert b.getvalue() == _pillow(pristine)
     thumb = Image.fromarray(handoff.DeviceFrame(pristine.copy(), marker, pristine, lambda: True))
     thumb.thumbnail((16, 16))                            # in-place resize replaces the core image
     b = io.BytesIO(); thumb.save(b, format="JPEG")
     assert b.getvalue() != marker and thumb.size[0] <= 16
+
+
+def test_inplace_mutators_and_stock_image_behaviour(hook):
+    """the in-place mutators that ignore `readonly`, pixel access, pickling and equality
+    all behave as on the image stock `Image.fromarray` returns — and never leave stale JPEG bytes."""
+    import pickle
+    handoff, _ = hook
+    fr, pristine, marker = _frame(handoff, seed=7)
+    other = np.random.default_rng(99).integers(0, 256, pristine.shape, dtype=np.uint8)
+    # frombytes() on a never-loaded image: works, and the new pixels are what gets saved
+    im = Image.fromarray(fr)
+    im.frombytes(other.tobytes())
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == _pillow(other)
+    # load() then frombytes(): same
+    im = Image.fromarray(fr)
+    im.load()
+    im.frombytes(other.tobytes())
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == _pillow(other)
+    # putdata()
+    im = Image.fromarray(fr)
+    im.putdata([tuple(int(v) for v in px) for px in other.reshape(-1, 3)])
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == _pillow(other)
+    # pixel access is writable, as on a stock fromarray image
+    im = Image.fromarray(fr)
+    px = im.load()
+    px[2, 3] = (9, 8, 7)
+    want = pristine.copy(); want[3, 2] = (9, 8, 7)
+    assert np.array_equal(np.asarray(im), want)
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == _pillow(want)
+    # equality with the stock image, both ways round
+    im = Image.fromarray(fr)
+    stock = handoff._plain_fromarray(pristine)
+    assert im == stock and stock == im and not (im != stock)
+    # pickling (multiprocessing hand-off): degrades to a plain Image with the same pixels
+    im = Image.fromarray(fr)
+    back = pickle.loads(pickle.dumps(im))
+    assert type(back) is Image.Image and np.array_equal(np.asarray(back), pristine)
+    b = io.BytesIO(); im.save(b, format="JPEG")          # pickling read the pixels: Pillow encodes from now on
+    assert b.getvalue() == _pillow(pristine)
+    # copy() of an untouched image keeps the precoded bytes; of a touched one it does not
+    im = Image.fromarray(fr)
+    b = io.BytesIO(); im.copy().save(b, format="JPEG")
+    assert b.getvalue() == marker

@@ -21,12 +21,13 @@ def _have_reference():
 @pytest.mark.skipif(not _have_reference(), reason="reference run_benchmark.py not present")
 def test_unmodified_run_benchmark_steps_through_the_dropin(oracle):
     import run_benchmark_episode as H
-    out = H.run(steps=3, width=64, height=48, n=3000, timeout=600,
+    # 20 steps: more frames than the facade's pinned-frame pool lends out (run_benchmark.py:1422 keeps them all)
+    out = H.run(steps=20, width=64, height=48, n=3000, timeout=600,
                 launcher=[sys.executable, str(ROOT / "tests" / "launch_with_oracle.py")])
     assert out["returncode"] == 0, out.get("stderr_tail")
-    assert out["steps"] == 3 and out["vlm_requests"] == 3, out
-    assert out["vlm_bad_images"] == 0 and out["vlm_images"] >= 3          # real JPEGs of the frames reached the server
-    assert out["engine_frames"] >= 3 and out["resolution"] == [64, 48]    # SAGE_RESOLUTION reached the unmodified ctor call
+    assert out["steps"] == 20 and out["vlm_requests"] == 20, out
+    assert out["vlm_bad_images"] == 0 and out["vlm_images"] >= 20         # real JPEGs of the frames reached the server
+    assert out["engine_frames"] >= 20 and out["resolution"] == [64, 48]   # a frame per step; SAGE_RESOLUTION reached the ctor
     assert out["collide_launches"] >= 1 and out["measurements_keys"]
 
 
