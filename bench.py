@@ -9,22 +9,28 @@ seeded synthetic multi-room interior of SURVEY.md §8d (12 x 10 x 3 m, N = 2,000
 rendered along a seeded 256-pose walk.  Rank 0 prints ONE JSON line.
 
 native arm  (this repository's CUDA path)
-  value      frames/s, scene resident in HBM, outputs left on the device, K frames timed with
-             CUDA events between barriers, max over ranks.
+  value      frames/s, scene resident in HBM, outputs left on the device.  A block of exactly K frames
+             is timed with CUDA events between barriers (max over ranks); the block is repeated until
+             >= 0.5 s have been measured and the MEDIAN block is reported (min / max next to it).
   e2e        frames/s through the host-facing call (sage_render_host_async + sage_host_wait: host
              camera in, RGB+depth of EVERY frame copied device->pinned host inside the timed region,
-             sage_pipeline_depth() = 3 frames in flight).
-  roofline   dominant kernel by device time (per-stage CUDA events recorded on the launch stream
-             inside the timed region): algorithmic bytes per launch / its mean duration, against
-             MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s).
+             sage_pipeline_depth() = 3 frames in flight).  N > 1: every rank copies ITS strip over its
+             own PCIe link into one shared pinned host frame (no NVLink hop on the host-facing path).
+  roofline   dominant kernel by device time (per-stage CUDA events recorded on the launch stream):
+             algorithmic bytes per launch / its mean duration, against MEASURED_PEAKS.json's hbm_gbs.
+  collide    BASELINE config 3: the P = 60 sweep of one agent step through the grid detector, the
+             capsule test against the scene's collision ellipsoids, and the reference's own
+             check_collision_3d (collision_detector.py:191) looped on the host beside them.
+  batch8     BASELINE config 4: an 8-scene batch, as tile-row shards (every frame split over the ranks)
+             and as replicas (whole scenes per rank — the reference's only scale-out).
   cpu_baseline  the CPU oracle (a port of the frozen spec — the reference's own renderer is Isaac
-             Sim's closed RTX path and cannot run) on all host cores, a few frames of the same
-             workload.
+             Sim's closed RTX path and cannot run) on all host cores, a few frames of the workload.
 
 reference arm (--impl reference): the same frames rendered by the CPU oracle on the host cores.
 Multi-GPU (torchrun, N ranks): every frame is split into N tile-row blocks; each rank composites its
 rows straight into every rank's frame buffer over NVLink (peer stores fused into the composite
-kernel's epilogue); a barrier per frame closes the exchange.  scaling = "strong" (one frame is split).
+kernel's epilogue).  scaling = "strong" (one frame is split).  The assembled frame is checked bit for
+bit against a full frame rendered by rank 0 alone ("multigpu_frame_equal").
 """
 from __future__ import annotations
 
@@ -49,14 +55,19 @@ WORKLOAD = "synthetic 12x10x3 m multi-room interior (seed 1), N=2,000,000, SH de
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=2_000_000)
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--min-time", type=float, default=0.5, help="repeat the K-step block until this many seconds are measured")
+    ap.add_argument("--max-blocks", type=int, default=40)
     ap.add_argument("--cpu-frames", type=int, default=4, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--batch-scenes", type=int, default=8, help="scenes of the config-4 batch leg (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-collide", action="store_true")
+    ap.add_argument("--no-handoff", action="store_true")
     ap.add_argument("--no-morton", action="store_true", help="skip the scene-ingest Morton reordering")
     return ap.parse_args()
 
@@ -72,7 +83,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks/throttle reasons, sampled from before the warm-up to the end of the timed
+    region (so that even a 10 ms region has samples taken under load)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -82,11 +94,12 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.t_mark = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,11 +108,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Samples from here on count as 'under load'."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -107,7 +125,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.t_mark is not None and t < self.t_mark:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -122,10 +142,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_workload(args):
+def build_workload(args, seed: int = 1):
     import sage3d_official_b200 as sage
     t0 = time.time()
-    cloud, layout = sage.synthetic_interior(seed=1, n=args.n)
+    cloud, layout = sage.synthetic_interior(seed=seed, n=args.n)
     if not getattr(args, "no_morton", False):
         # scene ingest: spatially coherent index order (what a loader does once per scene); the
         # oracle and the engine both see the reordered cloud, so parity is unaffected
@@ -189,6 +209,180 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+def collide_leg(sage, layout, device):
+    """BASELINE config 3: per-step collide — the P = 60 sample sweep of one agent step (20 x 1 cm forward
+    + 4 x 10 x 5 mm lateral, simple_env.py:2116-2234) through the grid detector, the capsule test
+    against the collision ellipsoids, and the reference's check_collision_3d looped on the host."""
+    import tempfile
+    import torch
+    from sage3d_official_b200.scenes import write_semantic_map, collision_ellipsoids
+    from sage3d_official_b200.collision_detector import SemanticMap2DCollisionDetector
+    tmp = Path(tempfile.mkdtemp(prefix="sage_bench_"))
+    map_path = write_semantic_map(layout, tmp / "map.json")
+    det = SemanticMap2DCollisionDetector(str(map_path), robot_radius_m=0.08, scale=0.05, device=device)
+    sx, sy = det.min_x + det.max_x, det.min_y + det.max_y
+    rng = np.random.default_rng(0)
+    # sweeps from 32 start poses of the walk (trajectory frame: x3 = x2 - (min+max))
+    sweeps = []
+    for p, h in sage.camera_path(layout, 32, seed=3):
+        start = np.array([p[0] - sx, p[1] - sy, 0.85], np.float32)
+        d = np.array([np.cos(h), np.sin(h), 0.0], np.float32)
+        perp = np.array([-d[1], d[0], 0.0], np.float32)
+        pts = [start + d * np.float32(0.01 * (k + 1)) for k in range(20)]
+        for e in (perp, -perp, (perp + d) * np.float32(0.707), (d - perp) * np.float32(0.707)):
+            pts += [start + e * np.float32(0.005 * (k + 1)) for k in range(10)]
+        sweeps.append(np.stack(pts).astype(np.float32))
+    P = sweeps[0].shape[0]
+    seg = [20, 10, 10, 10, 10]
+    for s in sweeps[:4]:
+        det.check_many(s, segments=seg)
+    reps = 200
+    t0 = time.perf_counter()
+    masks = []
+    for k in range(reps):
+        masks.append(det.check_many(sweeps[k % len(sweeps)], segments=seg)[0])
+    grid_us = (time.perf_counter() - t0) / reps * 1e6
+    # device-resident variant (positions already in HBM): kernel + launch only, CUDA events
+    dev = torch.device("cuda", device)
+    pos_dev = [torch.from_numpy(s).to(dev) for s in sweeps]
+    for pd in pos_dev[:4]:
+        det._grid.check_device(pd)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(reps):
+        det._grid.check_device(pos_dev[k % len(pos_dev)])
+    ev1.record()
+    torch.cuda.synchronize()
+    grid_dev_us = ev0.elapsed_time(ev1) / reps * 1e3
+    # capsule vs the scene's collision ellipsoids
+    mu, ls, q = collision_ellipsoids(layout, per_m2=400.0)
+    bodies = sage.CollisionBodies(mu, ls, q, device=device)
+    p3 = sweeps[0].copy()
+    for _ in range(4):
+        bodies.check(p3)
+    t0 = time.perf_counter()
+    for k in range(reps):
+        bodies.check(sweeps[k % len(sweeps)])
+    capsule_us = (time.perf_counter() - t0) / reps * 1e6
+    # the reference's own class, looped on the host (staged copy: oracle/make_ref.py; else the C port)
+    ref_us, ref_kind, equal = None, None, None
+    try:
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import make_ref
+        d = make_ref.ref_dir()
+        if d is not None:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("ref_collision_detector", str(d / "collision_detector.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            ref = mod.SemanticMap2DCollisionDetector(str(map_path), robot_radius_m=0.08, scale=0.05)
+            ref_reps = 40
+            t0 = time.perf_counter()
+            ref_masks = []
+            for k in range(ref_reps):
+                s = sweeps[k % len(sweeps)]
+                ref_masks.append(np.array([ref.check_collision_3d(s[i]) for i in range(P)]))
+            ref_us = (time.perf_counter() - t0) / ref_reps * 1e6
+            ref_kind = "reference"
+            equal = all(np.array_equal(ref_masks[k], masks[k]) for k in range(min(ref_reps, len(masks))))
+    except Exception as e:
+        ref_kind = f"unavailable ({e})"
+    if ref_us is None:
+        import oracle
+        t0 = time.perf_counter()
+        om = []
+        for k in range(reps):
+            s = sweeps[k % len(sweeps)]
+            om.append(oracle.collide_grid(det.obstacle_map, det.min_x, det.max_x, det.min_y, det.max_y, det.scale, s))
+        ref_us = (time.perf_counter() - t0) / reps * 1e6
+        ref_kind = "port"
+        equal = all(np.array_equal(om[k], masks[k]) for k in range(reps))
+    return {"P": P, "grid_cells": [int(det.map_height), int(det.map_width)],
+            "grid_sweep_us_per_step": grid_us, "grid_sweep_device_us": grid_dev_us,
+            "capsule_us_per_step": capsule_us, "capsule_bodies": int(bodies.m),
+            "reference_us_per_step": ref_us, "reference_us_per_query": ref_us / P, "reference_kind": ref_kind,
+            "masks_equal": bool(equal), "hits_in_sample": int(sum(int(m.sum()) for m in masks[:len(sweeps)])),
+            "algorithmic_bytes": {"grid": P * 13, "capsule": int(bodies.m) * 40 + P * 17},
+            "note": "grid/capsule: host API incl. H2D/D2H copies and sync (what apply_cmd_for pays); "
+                    "grid_sweep_device_us: positions resident, CUDA events; reference: collision_detector.py:191 on one host core"}
+
+
+def batch_leg(args, sage, world, rank, local, n_scenes, steps=24):
+    """BASELINE config 4: a batch of n_scenes scenes (seeds 1..n), one 1080p frame each per step.
+    tilerow : every scene resident on every rank, every frame split into tile-row blocks (peer stores)
+    replicas: scene s lives on rank s % world and is rendered whole there (the reference's scale-out:
+              independent processes per scene, generate_images.py:136-139)."""
+    import torch
+    import torch.distributed as dist
+    from sage3d_official_b200.multigpu import rows_of, PeerFrames
+    from sage3d_official_b200.scene_io import morton_order
+    W, H = args.width, args.height
+    dev = torch.device("cuda", local)
+    n_small = args.n                           # full-size scenes (seeds 1..n), generated on every rank
+    clouds, cams = [], []
+    for s in range(n_scenes):
+        cloud, layout = sage.synthetic_interior(seed=1 + s, n=n_small)
+        cloud = cloud.subset(morton_order(cloud.xyz))
+        clouds.append(cloud)
+        cams.append([sage.Camera.look_heading(p, h, W, H) for p, h in sage.camera_path(layout, 16, seed=s)])
+    out = {"n_scenes": n_scenes, "n_gaussians_per_scene": n_small, "frames_per_mode": steps * n_scenes}
+
+    def timed(fn, frames):
+        for i in range(2):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(2 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return frames / (ms / 1000.0)
+
+    # replicas
+    mine = [s for s in range(n_scenes) if s % world == rank]
+    scenes = {s: sage.GaussianScene(clouds[s], device=local) for s in mine}
+    rgb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    dep = torch.zeros((H, W), dtype=torch.float32, device=dev)
+
+    def step_rep(i):
+        for s in mine:
+            scenes[s].render(cams[s][i % 16], out=(rgb, dep))
+    out["replicas_fps"] = timed(step_rep, steps * n_scenes)
+    for sc in scenes.values():
+        sc.close()
+    # tile rows
+    if world > 1:
+        scenes = [sage.GaussianScene(c, device=local) for c in clouds]
+        rows = rows_of(rank, H, world)
+        rgbs = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)]
+        deps = [torch.zeros((H, W), dtype=torch.float32, device=dev)]
+        peers = PeerFrames(rgbs, deps, rank, world)
+
+        def step_rows(i):
+            for s in range(n_scenes):
+                scenes[s].render_peers(cams[s][i % 16], rows, peers.rgb[0], peers.depth[0])
+            peers.close_frame()
+        out["tilerow_fps"] = timed(step_rows, steps * n_scenes)
+        peers.close()
+        for sc in scenes:
+            sc.close()
+    else:
+        out["tilerow_fps"] = out["replicas_fps"]
+    out["note"] = ("frames/s over the whole batch, device-resident; replicas = scene s rendered whole on rank s % N; "
+                   "tilerow = every frame split into N tile-row blocks with peer stores + one frame-close per step")
+    return out
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
@@ -200,6 +394,9 @@ def run_native(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # before the warm-up: a 10 ms timed region still gets samples under load
     sage, cloud, layout, cams, gen_s = build_workload(args)
     W, H = args.width, args.height
     scene = sage.GaussianScene(cloud, device=local)
@@ -227,18 +424,17 @@ def run_native(args):
         from sage3d_official_b200.multigpu import PeerFrames
         peers = PeerFrames(rgb, dep, rank, world)
 
-    # single GPU: consecutive frames rotate over the scene's frame contexts, one stream each, so
-    # frame i+1's projection/sorts overlap frame i's compositing
+    # consecutive frames rotate over the scene's frame contexts, one stream each, so frame i+1's
+    # projection/sorts overlap frame i's compositing
     streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)]
 
     def step(i):
         cam = cams[i % len(cams)]
         b = i % nbuf
-        if world == 1:
-            with torch.cuda.stream(streams[b]):
+        with torch.cuda.stream(streams[b]):
+            if world == 1:
                 scene.render(cam, out=(rgb[b], dep[b]))
-        else:
-            with torch.cuda.stream(streams[b]):
+            else:
                 scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
                 peers.close_frame()      # device-side: every rank's strips have landed everywhere
 
@@ -252,61 +448,97 @@ def run_native(args):
         step(i)
     sync_all()
 
-    scene.set_stage_timing(min(args.steps, 1024))
-    sampler = ClockSampler(local)
+    # ---- timed region: blocks of exactly K steps, repeated until >= min_time, median reported ----
     if rank == 0:
-        sampler.start()
+        sampler.mark()
+    block_ms = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        step(args.warmup + i)
-    for st_ in streams:
-        torch.cuda.current_stream().wait_stream(st_)
-    e1.record()
-    sync_all()
+    it = args.warmup
+    t_wall = time.perf_counter()
+    while True:
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            step(it + i)
+        for st_ in streams:
+            torch.cuda.current_stream().wait_stream(st_)
+        e1.record()
+        sync_all()
+        it += args.steps
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        block_ms.append(ms)
+        done = (sum(block_ms) >= args.min_time * 1000.0) or len(block_ms) >= args.max_blocks
+        if world > 1:                   # every rank must take the same decision
+            flag = torch.tensor([1 if done else 0], device=dev)
+            dist.broadcast(flag, 0)
+            done = bool(flag.item())
+        if done:
+            break
     clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = float(np.median(block_ms))
     fps = args.steps / (ms / 1000.0)
+    graph = scene.graph_stats()
 
-    # per-stage device times of the timed frames (last min(K,1024) of them)
-    nslots = min(args.steps, 1024)
-    stage = {k: 0.0 for k in scene.STAGES}
-    for s in range(nslots):
-        for k, v in scene.stage_times(s).items():
-            stage[k] += v / nslots
-    st = scene.stats()
-    # the same breakdown without inter-frame overlap (one stream): what each stage costs alone
-    scene.set_stage_timing(64)
-    for i in range(64):
+    # ---- multi-GPU: the peer-assembled frame must equal a full frame rendered by one rank ----
+    frame_equal = None
+    if world > 1:
+        cam = cams[7]
+        sync_all()
+        with torch.cuda.stream(streams[0]):
+            scene.render_peers(cam, rows, peers.rgb[0], peers.depth[0])
+            peers.close_frame()
+        sync_all()
+        ref_rgb, ref_dep = scene.render(cam)
+        torch.cuda.synchronize()
+        eq = torch.equal(ref_rgb, rgb[0]) and torch.equal(ref_dep.view(torch.int32), dep[0].view(torch.int32))
+        t = torch.tensor([1 if eq else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)          # on EVERY rank: all buffers hold the same, right frame
+        frame_equal = bool(t.item())
+
+    # ---- per-stage device times without inter-frame overlap (one stream, direct launches) ----
+    scene.set_stage_timing(48)
+    for i in range(48):
         scene.render(cams[(args.warmup + i) % len(cams)], rows=rows if world > 1 else None, out=(rgb[0], dep[0]))
     stage_serial = {k: 0.0 for k in scene.STAGES}
     serial_frames = []
-    for s_ in range(64):
+    for s_ in range(48):
         tot = 0.0
         for k, v in scene.stage_times(s_).items():
-            stage_serial[k] += v / 64
+            stage_serial[k] += v / 48
             tot += v
         serial_frames.append(tot)
     scene.set_stage_timing(0)
+    # latency of ONE frame (no frames in flight), replayed from the graph: what a synchronous caller sees
+    lat = []
+    for i in range(40):
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        scene.render(cams[(args.warmup + i) % len(cams)], rows=rows if world > 1 else None, out=(rgb[0], dep[0]))
+        b_.record()
+        torch.cuda.synchronize()
+        lat.append(a.elapsed_time(b_))
+    frame_latency_ms = float(np.median(lat[8:]))
 
     # frame-averaged counters over a sample of the walk (V, D vary per pose)
     Vs, Ds, Bs = [], [], []
+    st = None
     for i in np.linspace(0, len(cams) - 1, 16).astype(int):
         scene.render(cams[i], rows=rows if world > 1 else None, out=(rgb[0], dep[0]))
-        s_ = scene.stats()
-        Vs.append(s_["n_visible"]); Ds.append(s_["n_instances"]); Bs.append(s_["algorithmic_bytes"])
-        assert s_["overflow"] == 0, "instance capacity overflow"
+        st = scene.stats()
+        Vs.append(st["n_visible"]); Ds.append(st["n_instances"]); Bs.append(st["algorithmic_bytes"])
+        assert st["overflow"] == 0, "instance capacity overflow"
     V, D, B = float(np.mean(Vs)), float(np.mean(Ds)), float(np.mean(Bs))
 
-    # e2e: host-facing call, synchronous, D2H copies inside the timed region
-    e2e_steps = max(10, min(args.steps, 100))
+    # ---- e2e: host-facing call, frames delivered to (pinned) host memory inside the timed region ----
+    e2e_steps = max(30, min(args.steps, 200))
+    d = scene.pipeline_depth
+    e2e_equal = None
     if world == 1:
-        d = scene.pipeline_depth
         for i in range(2 * d):
             scene.render_host_async(cams[i], i % d)
             scene.host_wait(i % d)
@@ -319,36 +551,39 @@ def run_native(args):
         scene.host_wait_all()
         e2e_dt = time.perf_counter() - t0
     else:
-        pin_rgb = torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
-        pin_dep = torch.zeros((H, W), dtype=torch.float32).pin_memory()
-
-        def e2e_step(i):
-            step(i)
-            if rank == 0:
-                with torch.cuda.stream(streams[i % nbuf]):
-                    pin_rgb.copy_(rgb[i % nbuf], non_blocking=True)
-                    pin_dep.copy_(dep[i % nbuf], non_blocking=True)
-            torch.cuda.synchronize()
-        for i in range(3):
-            e2e_step(i)
+        from sage3d_official_b200.multigpu import SharedHostFrames
+        shf = SharedHostFrames(H, W, d, rank, world)
+        for i in range(2 * d):
+            shf.submit(scene, cams[i], rows, i)
+            shf.finish(scene, i)
+        shf.drain(scene)
         sync_all()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            e2e_step(args.warmup + i)
-        sync_all()
+            if i >= d:
+                shf.finish(scene, i - d)        # own strip landed, published; rank 0: whole frame delivered
+            shf.submit(scene, cams[(args.warmup + i) % len(cams)], rows, i)
+        for i in range(max(0, e2e_steps - d), e2e_steps):
+            shf.finish(scene, i)
         e2e_dt = time.perf_counter() - t0
         t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+        # the last frame in the shared host buffers against rank 0's own full frame
+        if rank == 0:
+            last = e2e_steps - 1
+            ref_rgb, ref_dep = scene.render_host(cams[(args.warmup + last) % len(cams)])
+            hr, hd = shf.frame(last)
+            e2e_equal = bool(np.array_equal(ref_rgb, hr) and np.array_equal(ref_dep.view(np.uint32), hd.view(np.uint32)))
+        sync_all()
+        shf.close()
     e2e_fps = e2e_steps / e2e_dt
 
-    # frame hand-off: the same loop, but what crosses PCIe is the JPEG the
-    # reference would have produced on the host with Pillow (byte-identical), encoded on the device
+    # ---- frame hand-off: what crosses PCIe is the JPEG the reference would have made ----
     handoff = None
-    if world == 1:
+    if world == 1 and not args.no_handoff:
         enc = sage.JpegEncoder(W, H, quality=75, max_batch=4, device=local)
         sizes = []
-        d = scene.pipeline_depth
         for i in range(2 * d):
             scene.render_jpeg_async(cams[i], enc, i % d)
             scene.jpeg_wait(enc, i % d)
@@ -361,42 +596,40 @@ def run_native(args):
         for k in range(min(d, e2e_steps)):
             sizes.append(len(scene.jpeg_wait(enc, (e2e_steps + k) % d)))
         ho_dt = time.perf_counter() - t0
-        # device time of the encoder alone (frame already in HBM), CUDA events on the launch stream
-        x = rgb[0].unsqueeze(0)
-        enc1 = sage.JpegEncoder(W, H, quality=75, max_batch=1, device=local)
-        for _ in range(5):
-            enc1.encode_device(x)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        ev0.record()
-        for _ in range(50):
-            enc1.encode_device(x)
-        ev1.record()
-        torch.cuda.synchronize()
-        enc_ms = ev0.elapsed_time(ev1) / 50
-        # the reference's way on this host: raw frame to the host, Pillow encode (one thread)
         pil_ms = None
         try:
             import io
             from PIL import Image
             fr = rgb[0].cpu().numpy()
             t1 = time.perf_counter()
-            for _ in range(5):
+            for _ in range(3):
                 Image.fromarray(fr).save(io.BytesIO(), format="JPEG")
-            pil_ms = (time.perf_counter() - t1) / 5 * 1e3
+            pil_ms = (time.perf_counter() - t1) / 3 * 1e3
         except Exception:
             pass
         handoff = {"value": e2e_steps / ho_dt, "unit": "frames/s", "steps": e2e_steps,
-                   "d2h_bytes_per_step": float(np.mean(sizes)) + 8, "h2d_bytes_per_step": 92,
-                   "jpeg_encode_ms_device": enc_ms, "jpeg_launches_per_frame": 6,
+                   "d2h_bytes_per_step": float(np.mean(sizes)) + 8, "h2d_bytes_per_step": 400,
                    "pillow_encode_ms_host_1thread": pil_ms,
                    "note": "sage_render_jpeg_async/sage_render_jpeg_wait: render + device JPEG (byte-identical to Pillow "
                            "quality 75), only the encoded bytes copied to the host, 3 frames in flight"}
 
+    collide = None
+    if rank == 0 and not args.no_collide:
+        try:
+            collide = collide_leg(sage, layout, local)
+        except Exception as e:
+            collide = {"error": repr(e)}
+    batch = None
+    if args.batch_scenes > 0:
+        try:
+            batch = batch_leg(args, sage, world, rank, local, args.batch_scenes)
+        except Exception as e:
+            batch = {"error": repr(e)}
+
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel = longest stage when frames do not overlap (under the two-stream overlap a
-        # stage's event bracket also contains time spent waiting behind the other frame's kernels)
+        # dominant kernel = longest stage when frames do not overlap (under the multi-stream overlap a
+        # stage's event bracket also contains time spent waiting behind other frames' kernels)
         dom = max(stage_serial, key=stage_serial.get)
         nb = 16
         px = W * H if world == 1 else W * (min(rows[1] * 16, H) - rows[0] * 16)
@@ -405,11 +638,10 @@ def run_native(args):
             "depth_sort": args.n * 4 + V * 8 * 2 * 3,
             "sh_color": V * (12 * nb + 16 + 16),
             "emit": V * 16 + D * 8,
-            "tile_sort": D * 8 * 2 * 2 + D * 4,
+            "tile_sort": D * 8 * 2 * 2,
             "composite": D * 36 + px * 7,
         }
         dom_ms = stage_serial[dom]
-        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch)
         traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "traffic.json"
         if tp.exists():
@@ -420,32 +652,52 @@ def run_native(args):
             except Exception:
                 pass
         achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        frame_ms = ms / args.steps          # whole frame, device-timed (stages overlap: SH colour runs on a side stream)
+        frame_ms = ms / args.steps
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": frame_ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": args.n, "resolution": [W, H],
                        "timing": "scene (472 MB) + per-frame working set exceed the 126 MB L2 and every frame uses a new pose; no explicit L2 flush",
-                       "parallelism": f"single GPU, consecutive frames rotate over {nbuf} streams / frame contexts" if world == 1 else f"tile-row blocks (load-balanced) over {world} GPUs, peer-store composite epilogue + NCCL 1-element all-reduce per frame, two streams",
+                       "parallelism": (f"single GPU, consecutive frames rotate over {nbuf} streams / frame contexts, one CUDA graph per context"
+                                       if world == 1 else
+                                       f"tile-row blocks (load-balanced) over {world} GPUs, peer-store composite epilogue + a 1-element all-reduce per frame"),
                        "mean_visible": V, "mean_instances": D, "scene_gen_s": round(gen_s, 1)},
+            "timed_blocks": {"blocks": len(block_ms), "steps_per_block": args.steps, "median_ms": ms,
+                             "min_ms": float(np.min(block_ms)), "max_ms": float(np.max(block_ms)),
+                             "frames_per_s_min_max": [args.steps / (float(np.max(block_ms)) / 1e3), args.steps / (float(np.min(block_ms)) / 1e3)],
+                             "wall_s": time.perf_counter() - t_wall},
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 92,
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 400,
                     "d2h_bytes_per_step": W * H * 7, "steps": e2e_steps,
-                    "note": "sage_render_host_async/sage_host_wait: host camera in, RGB+depth copied to pinned host for every frame, frames in flight = pipeline depth (3)"},
-            "gpu_launches": int(st["kernel_launches"]) * args.steps,
+                    "note": ("sage_render_host_async/sage_host_wait: host camera in, RGB+depth copied to pinned host for every frame, "
+                             "frames in flight = pipeline depth (3)") if world == 1 else
+                            (f"every rank renders its tile rows and copies its strip over its own PCIe link into one shared pinned host "
+                             f"frame; rank 0 waits for all {world} strips of every frame; 3 frames in flight"),
+                    "frame_equal": e2e_equal},
+            "gpu_launches": int(st["kernel_launches"]) * args.steps * len(block_ms),
+            "graph": graph,
+            "frame_latency_ms": frame_latency_ms,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg[dom],
                          "traffic_source": traffic_src,
-                         "frame": {"algorithmic_bytes": B, "stage_ms": stage, "stage_ms_serial": stage_serial,
+                         "frame": {"algorithmic_bytes": B, "stage_ms_serial": stage_serial,
+                                   "stage_gbs_serial": {k: (alg[k] / (v * 1e-3) / 1e9 if v > 0 else 0.0) for k, v in stage_serial.items()},
                                    "serial_frame_ms": sum(stage_serial.values()),
                                    "serial_frame_ms_p50_p99_max": [float(np.percentile(serial_frames, 50)), float(np.percentile(serial_frames, 99)), float(np.max(serial_frames))],
                                    "frame_ms": frame_ms,
-                                   "achieved_gbs": B / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0}},
+                                   "achieved_gbs": B / (frame_ms * 1e-3) / 1e9 if frame_ms > 0 else 0.0,
+                                   "frac": B / (frame_ms * 1e-3) / 1e9 / peak if frame_ms > 0 else 0.0}},
         }
+        if frame_equal is not None:
+            line["multigpu_frame_equal"] = frame_equal
         if handoff is not None:
             line["handoff_jpeg"] = handoff
+        if collide is not None:
+            line["collide"] = collide
+        if batch is not None:
+            line["batch8"] = batch
         if not args.no_cpu_baseline and world == 1:      # CPU baseline: rank 0 at N=1 only
             import oracle
             oracle.build()

@@ -210,7 +210,8 @@ class GaussianScene:
         with torch.cuda.device(self.device):
             check(_lib.lib().sage_render_host_async(self._h, C.byref(cc), r0, r1, _ptr(rgb_t),
                                                     _ptr(dep_t) if want_depth else C.c_void_p(0), int(slot)))
-        return rgb_t.numpy(), (dep_t.numpy() if want_depth else None)
+        as_np = lambda t: t if isinstance(t, np.ndarray) else t.numpy()
+        return as_np(rgb_t), (as_np(dep_t) if want_depth else None)
 
     def render_batch_host(self, cams, want_depth: bool = True):
         """Render a sequence of camera poses (e.g. every sampled waypoint of a trajectory, as

@@ -14,6 +14,7 @@ Two exchange paths:
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -137,3 +138,90 @@ class PeerFrames:
         for p, off in self._opened:
             L.sage_ipc_close(C.c_void_p(p), C.c_uint64(off))
         self._opened = []
+
+
+class SharedHostFrames:
+    """Host-facing multi-GPU delivery: ONE pinned host frame (per pipeline slot) shared by all ranks of
+    the node; every rank copies the rows it rendered straight into it over its own PCIe link
+    (``sage_render_host_async`` with its tile-row range) — N links instead of one, and no NVLink hop
+    or collective on the host-facing path.  A frame is delivered when all N strips have landed:
+    ranks publish a per-slot frame counter in the same shared segment, rank 0 (the caller's side)
+    waits for all of them and acknowledges, which is also what lets a slot be reused.
+
+    The segment is POSIX shared memory, page-locked in every process with ``cudaHostRegister``."""
+
+    def __init__(self, height: int, width: int, depth: int, rank: int, world: int, timeout_s: float = 60.0):
+        from multiprocessing import shared_memory
+        import torch
+        import torch.distributed as dist
+        self.H, self.W, self.d, self.rank, self.world = int(height), int(width), int(depth), rank, world
+        self.timeout_s = timeout_s
+        al = lambda n: (n + 4095) // 4096 * 4096
+        rgb_b, dep_b = al(self.H * self.W * 3), al(self.H * self.W * 4)
+        ctrl_off = self.d * (rgb_b + dep_b)
+        size = ctrl_off + 4096
+        name = [None]
+        if rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=size)
+            name = [self._shm.name]
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+        self._buf = np.ndarray((size,), np.uint8, buffer=self._shm.buf)
+        self._rt = torch.cuda.cudart()
+        err = self._rt.cudaHostRegister(self._buf.ctypes.data, size, 0)
+        if int(err) != 0:
+            raise RuntimeError(f"cudaHostRegister failed on the shared frame segment: {err}")
+        self.rgb, self.dep = [], []
+        for k in range(self.d):
+            o = k * (rgb_b + dep_b)
+            self.rgb.append(self._buf[o:o + self.H * self.W * 3].reshape(self.H, self.W, 3))
+            self.dep.append(self._buf[o + rgb_b:o + rgb_b + self.H * self.W * 4].view(np.float32).reshape(self.H, self.W))
+        ctrl = self._buf[ctrl_off:ctrl_off + 4096].view(np.int64)
+        self.done = ctrl[:self.d * world].reshape(self.d, world)      # done[slot][rank] = frames of that slot landed
+        self.consumed = ctrl[self.d * world:self.d * world + self.d]  # consumed[slot] = frames rank 0 has taken
+        if rank == 0:
+            ctrl[:] = 0
+        dist.barrier()
+
+    def _spin(self, cond, what: str):
+        t0 = time.perf_counter()
+        while not cond():
+            if time.perf_counter() - t0 > self.timeout_s:
+                raise TimeoutError(f"SharedHostFrames: rank {self.rank} timed out waiting for {what}")
+
+    def submit(self, scene, cam, rows, i: int) -> None:
+        """Start frame i (slot i % depth): this rank's rows, into the shared host frame."""
+        slot, gen = i % self.d, i // self.d
+        if gen > 0:       # the slot's previous frame must have been delivered before it is overwritten
+            self._spin(lambda: self.consumed[slot] >= gen, f"slot {slot} to be consumed")
+        scene.render_host_async(cam, slot, rows=rows, out=(self.rgb[slot], self.dep[slot]))
+
+    def finish(self, scene, i: int) -> None:
+        """Frame i: this rank's strip has landed; rank 0 additionally waits for every rank's strip."""
+        slot, gen = i % self.d, i // self.d
+        scene.host_wait(slot)
+        self.done[slot, self.rank] = gen + 1
+        if self.rank == 0:
+            self._spin(lambda: bool((self.done[slot] >= gen + 1).all()), f"all strips of frame {i}")
+            self.consumed[slot] = gen + 1
+
+    def frame(self, i: int):
+        return self.rgb[i % self.d], self.dep[i % self.d]
+
+    def drain(self, scene) -> None:
+        for k in range(self.d):
+            scene.host_wait(k)
+
+    def close(self) -> None:
+        try:
+            self._rt.cudaHostUnregister(self._buf.ctypes.data)
+        except Exception:
+            pass
+        self.rgb, self.dep, self.done, self.consumed, self._buf = [], [], None, None, None
+        try:
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
+        except Exception:
+            pass
