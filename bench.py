@@ -563,15 +563,15 @@ def run_native(args):
             if i >= d:
                 shf.finish(scene, i - d)        # own strip landed, published; rank 0: whole frame delivered
             shf.submit(scene, cams[(args.warmup + i) % len(cams)], rows, i)
+        last = e2e_steps - 1
         for i in range(max(0, e2e_steps - d), e2e_steps):
-            shf.finish(scene, i)
+            shf.finish(scene, i, release=(i != last))      # the last frame stays in its slot for the check below
         e2e_dt = time.perf_counter() - t0
         t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
         # the last frame in the shared host buffers against rank 0's own full frame
         if rank == 0:
-            last = e2e_steps - 1
             ref_rgb, ref_dep = scene.render_host(cams[(args.warmup + last) % len(cams)])
             hr, hd = shf.frame(last)
             e2e_equal = bool(np.array_equal(ref_rgb, hr) and np.array_equal(ref_dep.view(np.uint32), hd.view(np.uint32)))

@@ -150,9 +150,9 @@ class SharedHostFrames:
 
     The segment is POSIX shared memory, page-locked in every process with ``cudaHostRegister``."""
 
-    def __init__(self, height: int, width: int, depth: int, rank: int, world: int, timeout_s: float = 60.0):
+    def __init__(self, height: int, width: int, depth: int, rank: int, world: int, timeout_s: float = 60.0,
+                 pin: bool = True):
         from multiprocessing import shared_memory
-        import torch
         import torch.distributed as dist
         self.H, self.W, self.d, self.rank, self.world = int(height), int(width), int(depth), rank, world
         self.timeout_s = timeout_s
@@ -168,10 +168,13 @@ class SharedHostFrames:
         if rank != 0:
             self._shm = shared_memory.SharedMemory(name=name[0])
         self._buf = np.ndarray((size,), np.uint8, buffer=self._shm.buf)
-        self._rt = torch.cuda.cudart()
-        err = self._rt.cudaHostRegister(self._buf.ctypes.data, size, 0)
-        if int(err) != 0:
-            raise RuntimeError(f"cudaHostRegister failed on the shared frame segment: {err}")
+        self._rt = None
+        if pin:                     # (pin=False: the CPU protocol test, no device in the process)
+            import torch
+            self._rt = torch.cuda.cudart()
+            err = self._rt.cudaHostRegister(self._buf.ctypes.data, size, 0)
+            if int(err) != 0:
+                raise RuntimeError(f"cudaHostRegister failed on the shared frame segment: {err}")
         self.rgb, self.dep = [], []
         for k in range(self.d):
             o = k * (rgb_b + dep_b)
@@ -197,14 +200,22 @@ class SharedHostFrames:
             self._spin(lambda: self.consumed[slot] >= gen, f"slot {slot} to be consumed")
         scene.render_host_async(cam, slot, rows=rows, out=(self.rgb[slot], self.dep[slot]))
 
-    def finish(self, scene, i: int) -> None:
-        """Frame i: this rank's strip has landed; rank 0 additionally waits for every rank's strip."""
+    def finish(self, scene, i: int, release: bool = True) -> None:
+        """Frame i: this rank's strip has landed; rank 0 additionally waits for every rank's strip — the
+        frame is then complete in :meth:`frame`.  ``release=False`` keeps the slot (rank 0 reads the frame
+        first and calls :meth:`release` itself)."""
         slot, gen = i % self.d, i // self.d
         scene.host_wait(slot)
         self.done[slot, self.rank] = gen + 1
         if self.rank == 0:
             self._spin(lambda: bool((self.done[slot] >= gen + 1).all()), f"all strips of frame {i}")
-            self.consumed[slot] = gen + 1
+            if release:
+                self.release(i)
+
+    def release(self, i: int) -> None:
+        """Rank 0: frame i has been taken; its slot may be overwritten."""
+        if self.rank == 0:
+            self.consumed[i % self.d] = i // self.d + 1
 
     def frame(self, i: int):
         return self.rgb[i % self.d], self.dep[i % self.d]
@@ -215,7 +226,8 @@ class SharedHostFrames:
 
     def close(self) -> None:
         try:
-            self._rt.cudaHostUnregister(self._buf.ctypes.data)
+            if self._rt is not None:
+                self._rt.cudaHostUnregister(self._buf.ctypes.data)
         except Exception:
             pass
         self.rgb, self.dep, self.done, self.consumed, self._buf = [], [], None, None, None

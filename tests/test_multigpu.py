@@ -1,5 +1,7 @@
-"""Multi-process paths: tile-row partition + strip gather on CPU (gloo, world_size 2), and the
-peer-store composite epilogue between two processes sharing the one GPU of the test box."""
+"""Multi-process paths: tile-row partition + strip gather and the shared-host-frame delivery protocol
+on CPU (gloo, world_size 2); the peer-store composite epilogue between two processes sharing the one
+GPU of the test box; and, where the box has two GPUs, the real thing: NCCL, one GPU per rank, the
+peer-assembled frame and the shared host frame against a frame rendered by one rank alone."""
 import os
 import socket
 import sys
@@ -131,3 +133,122 @@ def test_row_instances_sum_to_frame_total():
     scene.render(cam, rows=(10, 20))
     part = scene.row_instances(10)
     assert part.sum() == scene.stats()["n_instances"]
+
+
+class _FakeScene:
+    """Stands in for GaussianScene in the CPU protocol test: 'renders' its tile rows of a known frame."""
+
+    def __init__(self, h, w):
+        self.full = _fake_frame(h, w)
+
+    def render_host_async(self, cam, slot, rows=None, want_depth=True, out=None):
+        a, b = rows[0] * 16, min(rows[1] * 16, self.full.shape[0])
+        out[0][a:b] = (self.full[a:b].astype(np.int64) + cam) % 256          # cam = frame number here
+        out[1][a:b] = self.full[a:b, :, 0].astype(np.float32) + cam
+
+    def host_wait(self, slot):
+        pass
+
+
+def _shared_host_worker(rank, world, port, h, w, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from sage3d_official_b200.multigpu import SharedHostFrames, rows_of
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    scene, rows, d, n = _FakeScene(h, w), rows_of(rank, h, world), 3, 11
+    shf = SharedHostFrames(h, w, d, rank, world, timeout_s=60.0, pin=False)
+    ok = True
+    for i in range(n):                       # d frames in flight, as bench.py drives it
+        if i >= d:
+            shf.finish(scene, i - d, release=False)
+            if rank == 0:                    # delivered: the WHOLE frame i-d is in the shared buffer right now
+                r, dd = shf.frame(i - d)
+                ok &= bool(np.array_equal(r, (scene.full.astype(np.int64) + (i - d)) % 256))
+                ok &= bool(np.array_equal(dd, scene.full[:, :, 0].astype(np.float32) + (i - d)))
+            shf.release(i - d)
+        shf.submit(scene, i, rows, i)
+    for i in range(n - d, n):
+        shf.finish(scene, i)
+    dist.barrier()
+    shf.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_shared_host_frames_protocol_gloo_world2():
+    """Every rank lands its strip in one shared host frame; rank 0 sees a frame only when all strips are in,
+    and no rank overwrites a slot before rank 0 has taken the frame it held."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shared_host_worker, args=(r, 2, port, 100, 64, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
+
+
+def _two_gpu_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch
+    import torch.distributed as dist
+    import sage3d_official_b200 as sage
+    from sage3d_official_b200.multigpu import PeerFrames, SharedHostFrames, rows_of
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cloud, layout = sage.synthetic_room(0, 30_000)
+    cams = [sage.Camera.look_heading(p, h, 640, 480) for p, h in sage.camera_path(layout, 5, seed=2)]
+    scene = sage.GaussianScene(cloud, device=rank)
+    dev = torch.device("cuda", rank)
+    rgb = [torch.zeros((480, 640, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+    dep = [torch.zeros((480, 640), dtype=torch.float32, device=dev) for _ in range(2)]
+    peers = PeerFrames(rgb, dep, rank, world)
+    rows = rows_of(rank, 480, world)
+    ok = True
+    for i, cam in enumerate(cams):
+        b = i % 2
+        scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
+        peers.close_frame()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ref_rgb, ref_dep = scene.render(cam)
+        torch.cuda.synchronize()
+        ok &= bool(torch.equal(rgb[b], ref_rgb)) and bool(torch.equal(dep[b].view(torch.int32), ref_dep.view(torch.int32)))
+        dist.barrier()
+    peers.close()
+    shf = SharedHostFrames(480, 640, 3, rank, world)
+    for i, cam in enumerate(cams):
+        shf.submit(scene, cam, rows, i)
+        shf.finish(scene, i, release=False)
+        if rank == 0:
+            r, d_ = shf.frame(i)
+            ref_rgb, ref_dep = scene.render_host(cam)
+            ok &= bool(np.array_equal(r, ref_rgb)) and bool(np.array_equal(d_.view(np.uint32), ref_dep.view(np.uint32)))
+        shf.release(i)
+    dist.barrier()
+    shf.close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpus_peer_frame_and_shared_host_frame_equal_single_gpu_frame():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
