@@ -222,8 +222,8 @@ class SimpleVLNEnv:
                 raise FileNotFoundError(f"[ENV_INIT] no Gaussian payload (.ply/.npz) found for {self.scene_usd_path}")
             cloud = load_cloud(gauss)
             if coll is not None:
-                z = np.load(coll)
-                bodies_src = (z["mu"], z["log_scale"], z["quat"])
+                from .scene_io import load_collision_bodies
+                bodies_src = load_collision_bodies(coll)
         self._scene = make_scene(cloud, device=self._device)
         self._scene.set_depth_clip(*self.DEPTH_CLIP)      # clip(0.1, 6.5) applied in the kernel epilogue
         self._log(f"[ENV_INIT] scene {self.scene_usd_path}: {self._scene.n} Gaussians resident on cuda:{self._device}")
