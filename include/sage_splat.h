@@ -233,8 +233,46 @@ int sage_jpeg_debug(sage_jpeg* j, int frame, int16_t* coef_host, uint32_t* mcu_b
  * count in *size_out. */
 int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
                            uint8_t* rgb_host, float* depth_host);
+/* The same with a second, private host copy of the frame, always packed RGB u8 [H,W,3] whatever the
+ * scene's output mode: with sage_scene_set_rgba the caller gets the RGBA array Camera.get_rgba()
+ * returns (generate_images.py:428) in rgb_host AND the exact pixels the JPEG was made from in
+ * rgb_twin_host — what the hand-off compares a caller's array against before it lets
+ * Image.fromarray(img[:, :, :3].copy()).save(...) (generate_images.py:431-432) reuse the device's bytes. */
+int sage_render_jpeg_async2(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
+                            uint8_t* rgb_host, float* depth_host, uint8_t* rgb_twin_host);
 int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host,
                           int64_t cap, int64_t* size_out);
+
+/* ---- frame hand-off: depth PNG on the GPU -----------------------------------
+ * The RGB-D clients of the benchmark quantise and encode the depth map on the host for every query:
+ *   depth_array_encoded = (np.clip(depth_image, 0.0, 6.5) * 10000.0).astype(np.uint16)
+ *   cv2.imencode('.png', depth_array_encoded)                  (vlm_client_modular.py:354-364)
+ * sage_depth_png_* do both on the device: the uint16 pixels are bit-identical to that NumPy sequence
+ * (binary32 clip, binary32 multiply, truncation), the file is a valid 16-bit greyscale PNG of them
+ * (Sub filter, one fixed-Huffman deflate block with in-group run-length matches, 32 KB IDAT chunks) —
+ * NOT the bytes OpenCV's zlib build would produce (see csrc/png.cu); any reader decodes the same image.
+ * twin (optional): the uint16 pixels themselves [H][W] — what a hand-off hook compares a caller's array
+ * against before it substitutes the device's file. */
+typedef struct sage_png sage_png;
+int sage_png_create(sage_png** out, int device, int width, int height, int max_batch);
+int sage_png_destroy(sage_png* p);
+int sage_png_max_bytes(sage_png* p, int64_t* out);
+/* depth_dev f32 [H][W] -> out_dev (capacity out_cap bytes), *size_dev = bytes written, -(bytes needed)
+ * if out_cap is too small, -1 on internal overflow.  Asynchronous; device pointers. */
+int sage_depth_png_encode(sage_png* p, const float* depth_dev, float lo, float hi, float scale,
+                          uint8_t* out_dev, int64_t out_cap, int64_t* size_dev, uint16_t* twin_dev,
+                          sage_stream_t stream);
+/* Same, file bytes (and the optional uint16 twin) delivered to HOST memory; synchronises `stream`. */
+int sage_depth_png_encode_host(sage_png* p, const float* depth_dev, float lo, float hi, float scale,
+                               uint8_t* out_host, int64_t out_cap, int64_t* size_host,
+                               uint16_t* twin_host, sage_stream_t stream);
+/* Fused with the frame: encode the depth map of the frame last submitted on pipeline slot `slot`
+ * (sage_render_host_async / sage_render_jpeg_async with a depth buffer) on that slot's stream;
+ * sage_frame_depth_png_wait blocks until it is done and copies the file into png_host. */
+int sage_frame_depth_png_async(sage_scene* s, sage_png* p, int slot, float lo, float hi, float scale,
+                               uint16_t* twin_host);
+int sage_frame_depth_png_wait(sage_scene* s, sage_png* p, int slot, uint8_t* png_host, int64_t cap,
+                              int64_t* size_out);
 
 /* ---- map building and path planning ---------------------------------------
  * The callers either side of the collide path work on the same occupancy grid

@@ -218,3 +218,71 @@ def astar(grid, start, goal, max_path: int = 0, want_expansions: bool = False):
         raise RuntimeError(f"so_astar rc={n}")
     res = None if n == 0 else [(int(x), int(y)) for x, y in path[:n]]
     return (res, int(nexp.value)) if want_expansions else res
+
+
+# ---- depth PNG (csrc/png.cu) --------------------------------------------------------------------
+def depth_quantise(depth, lo=0.0, hi=6.5, scale=10000.0):
+    """The reference's own sequence (vlm_client_modular.py:354-355): binary32 clip, binary32 multiply,
+    truncation to uint16."""
+    d = np.asarray(depth, np.float32)
+    return (np.clip(d, np.float32(lo), np.float32(hi)) * np.float32(scale)).astype(np.uint16)
+
+
+def depth_png_encode(depth, lo=0.0, hi=6.5, scale=10000.0):
+    """NumPy restatement of the device's depth PNG stream, byte for byte (csrc/png.cu): Sub filter
+    (bpp 2), one fixed-Huffman deflate block, tokens per group of 32 filtered bytes (a run of >= 4 equal
+    bytes inside a group = literal + (length, distance 1)), zlib wrapper, 32 KB IDAT chunks.
+    The format itself is pinned by zlib/Pillow decoding it (tests/test_png_oracle.py)."""
+    import struct
+    import zlib
+    q = depth_quantise(depth, lo, hi, scale)
+    H, W = q.shape
+    raw = np.empty((H, 2 * W), np.uint8)
+    raw[:, 0::2] = (q >> 8).astype(np.uint8)
+    raw[:, 1::2] = (q & 0xFF).astype(np.uint8)
+    sub = raw.copy()
+    sub[:, 2:] = raw[:, 2:] - raw[:, :-2]
+    L = 1 + 2 * W
+    F = np.empty((H, L), np.uint8)
+    F[:, 0] = 1
+    F[:, 1:] = sub
+    G = (L + 31) // 32
+    P = np.zeros((H, G * 32), np.int32)
+    P[:, :L] = F
+    have = np.zeros((H, G * 32), bool)
+    have[:, :L] = True
+    P, have = P.reshape(H, G, 32), have.reshape(H, G, 32)
+    eq = np.zeros_like(have)
+    eq[:, :, 1:] = (P[:, :, 1:] == P[:, :, :-1]) & have[:, :, 1:]
+    lane = np.arange(32)
+    start = np.maximum.accumulate(np.where(~eq, lane, 0), axis=2)
+    nxt = np.where(~eq, lane, 32)                              # a lane that starts a run (or is past the data)
+    end = np.full_like(start, 32)
+    end[:, :, :-1] = np.minimum.accumulate(nxt[:, :, ::-1], axis=2)[:, :, ::-1][:, :, 1:]
+    rl, k = end - start, lane - start
+    lit = have & ((k == 0) | (rl < 4))
+    mat = have & ~lit & (k == 1)
+    rev = lambda v, n: sum(((v >> j) & 1) << (n - 1 - j) for j in range(n))
+    code = np.zeros(P.shape, np.int64)
+    nb = np.zeros(P.shape, np.int64)
+    small = lit & (P < 144)
+    big = lit & (P >= 144)
+    code[small], nb[small] = rev(0x30 + P[small], 8), 8
+    code[big], nb[big] = rev(0x190 + (P[big] - 144), 9), 9
+    ln = rl - 1
+    a, b, c = mat & (ln <= 10), mat & (ln > 10) & (ln <= 18), mat & (ln > 18)
+    code[a], nb[a] = rev(ln[a] - 2, 7), 12
+    code[b], nb[b] = rev(9 + ((ln[b] - 11) >> 1), 7) | (((ln[b] - 11) & 1) << 7), 13
+    code[c], nb[c] = rev(13 + ((ln[c] - 19) >> 2), 7) | (((ln[c] - 19) & 3) << 7), 14
+    tok = nb.ravel() > 0
+    cv, nv = code.ravel()[tok], nb.ravel()[tok]
+    bits = ((cv[:, None] >> np.arange(14)[None, :]) & 1).astype(np.uint8)
+    valid = np.arange(14)[None, :] < nv[:, None]
+    stream = np.concatenate([np.array([1, 1, 0], np.uint8), bits[valid], np.zeros(7, np.uint8)])
+    deflate = np.packbits(stream, bitorder="little").tobytes()
+    z = b"\x78\x01" + deflate + struct.pack(">I", zlib.adler32(F.tobytes()))
+    chunk = lambda t, d: struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    out = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 16, 0, 0, 0, 0))
+    for o in range(0, len(z), 32768):
+        out += chunk(b"IDAT", z[o:o + 32768])
+    return out + chunk(b"IEND", b"")

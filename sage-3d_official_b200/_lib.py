@@ -25,7 +25,9 @@ EXPORTS = [
     "sage_collide_grid_dev",
     "sage_bodies_create", "sage_bodies_destroy", "sage_collide_capsule",
     "sage_jpeg_create", "sage_jpeg_destroy", "sage_jpeg_max_bytes", "sage_jpeg_encode", "sage_jpeg_encode_host",
-    "sage_jpeg_debug", "sage_render_jpeg_async", "sage_render_jpeg_wait",
+    "sage_png_create", "sage_png_destroy", "sage_png_max_bytes", "sage_depth_png_encode", "sage_depth_png_encode_host",
+    "sage_frame_depth_png_async", "sage_frame_depth_png_wait",
+    "sage_jpeg_debug", "sage_render_jpeg_async", "sage_render_jpeg_async2", "sage_render_jpeg_wait",
     "sage_grid_inflate", "sage_grid_components", "sage_planner_create", "sage_planner_destroy",
     "sage_planner_limits", "sage_plan_astar",
 ]
@@ -114,7 +116,16 @@ def lib():
     L.sage_jpeg_encode_host.argtypes = [vp, vp, i32, vp, i64, vp, vp]
     L.sage_jpeg_debug.argtypes = [vp, i32, vp, vp, vp]
     L.sage_render_jpeg_async.argtypes = [vp, C.POINTER(CCamera), vp, i32, vp, vp]
+    L.sage_render_jpeg_async2.argtypes = [vp, C.POINTER(CCamera), vp, i32, vp, vp, vp]
     L.sage_render_jpeg_wait.argtypes = [vp, vp, i32, vp, i64, C.POINTER(i64)]
+    f32 = C.c_float
+    L.sage_png_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    L.sage_png_destroy.argtypes = [vp]
+    L.sage_png_max_bytes.argtypes = [vp, C.POINTER(i64)]
+    L.sage_depth_png_encode.argtypes = [vp, vp, f32, f32, f32, vp, i64, vp, vp, vp]
+    L.sage_depth_png_encode_host.argtypes = [vp, vp, f32, f32, f32, vp, i64, C.POINTER(i64), vp, vp]
+    L.sage_frame_depth_png_async.argtypes = [vp, vp, i32, f32, f32, f32, vp]
+    L.sage_frame_depth_png_wait.argtypes = [vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.sage_grid_inflate.argtypes = [i32, vp, i32, i32, dbl, dbl, vp, vp]
     L.sage_grid_components.argtypes = [i32, vp, i32, i32, vp, vp]
     L.sage_planner_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, i32, i32, i64]

@@ -236,30 +236,51 @@ class GaussianScene:
 
     # -- frame hand-off: render -> JPEG on the device --
     def render_jpeg_async(self, cam: Camera, encoder: "JpegEncoder", slot: int, want_rgb: bool = False,
-                          want_depth: bool = False):
+                          want_depth: bool = False, out=None, twin=None):
         """Submit render + JPEG encode on a pipeline slot (< min(pipeline_depth, encoder.max_batch)).  Only what is asked for crosses PCIe:
-        the encoded bytes (always, fetched by :meth:`jpeg_wait`), the raw RGB frame and/or depth
-        (optional; returned as pinned host arrays valid after :meth:`jpeg_wait`)."""
+        the encoded bytes (always, fetched by :meth:`jpeg_wait`), the raw frame (RGB, or RGBA after
+        :meth:`set_rgba`) and/or depth (optional; returned as pinned host arrays valid after :meth:`jpeg_wait`).
+        ``out``: a caller-owned pinned (rgb, depth) tensor pair (see :meth:`alloc_host_frame`) instead of the
+        slot's own; ``twin``: a pinned u8 [H,W,3] tensor that receives the frame once more, always as packed
+        RGB — the exact pixels the JPEG was made from (the hand-off's reference copy)."""
         torch = _torch()
         rgb_t = dep_t = None
-        if want_rgb or want_depth:
+        if out is not None:
+            rgb_t, dep_t = out
+        elif want_rgb or want_depth:
             key = (cam.height, cam.width, "async", int(slot))
             if key not in self._pinned:
-                self._pinned[key] = (torch.zeros((cam.height, cam.width, self.channels), dtype=torch.uint8).pin_memory(),
-                                     torch.zeros((cam.height, cam.width), dtype=torch.float32).pin_memory())
+                self._pinned[key] = self.alloc_host_frame(cam.height, cam.width)
             rgb_t, dep_t = self._pinned[key]
         cc = _ccam(cam)
         with torch.cuda.device(self.device):
-            check(_lib.lib().sage_render_jpeg_async(self._h, C.byref(cc), encoder._h, int(slot),
-                                                    _ptr(rgb_t) if want_rgb else C.c_void_p(0),
-                                                    _ptr(dep_t) if want_depth else C.c_void_p(0)))
-        return (rgb_t.numpy() if want_rgb else None), (dep_t.numpy() if want_depth else None)
+            check(_lib.lib().sage_render_jpeg_async2(self._h, C.byref(cc), encoder._h, int(slot),
+                                                     _ptr(rgb_t) if want_rgb else C.c_void_p(0),
+                                                     _ptr(dep_t) if want_depth else C.c_void_p(0),
+                                                     _ptr(twin) if twin is not None else C.c_void_p(0)))
+        as_np = lambda t: t if isinstance(t, np.ndarray) else t.numpy()
+        return (as_np(rgb_t) if want_rgb else None), (as_np(dep_t) if want_depth else None)
 
     def jpeg_wait(self, encoder: "JpegEncoder", slot: int) -> bytes:
         """Block until slot's frame is rendered and encoded; returns the JPEG file bytes."""
         buf = encoder._host_buf(slot)
         n = C.c_int64(0)
         check(_lib.lib().sage_render_jpeg_wait(self._h, encoder._h, int(slot), _ptr(buf), int(buf.numel()), C.byref(n)))
+        return buf.numpy()[:n.value].tobytes()
+
+    # -- frame hand-off: depth -> uint16 PNG on the device (SURVEY §8f N4) --
+    def depth_png_async(self, encoder: "DepthPngEncoder", slot: int, lo: float = 0.0, hi: float = 6.5,
+                        scale: float = 10000.0, twin=None):
+        """Encode the depth map of the frame last submitted on ``slot`` (with depth) as the 16-bit PNG of
+        ``(clip(depth, lo, hi) * scale).astype(uint16)`` (vlm_client_modular.py:354-364) on the slot's stream.
+        ``twin``: optional pinned uint16 [H,W] tensor receiving the quantised pixels themselves."""
+        check(_lib.lib().sage_frame_depth_png_async(self._h, encoder._h, int(slot), float(lo), float(hi), float(scale),
+                                                    _ptr(twin) if twin is not None else C.c_void_p(0)))
+
+    def depth_png_wait(self, encoder: "DepthPngEncoder", slot: int) -> bytes:
+        buf = encoder._host_buf(slot)
+        n = C.c_int64(0)
+        check(_lib.lib().sage_frame_depth_png_wait(self._h, encoder._h, int(slot), _ptr(buf), int(buf.numel()), C.byref(n)))
         return buf.numpy()[:n.value].tobytes()
 
     def render_batch_jpeg(self, cams, encoder: "JpegEncoder"):
@@ -503,6 +524,55 @@ class JpegEncoder:
         return coef, off, int(tot[0])
 
 
+class DepthPngEncoder:
+    """Depth map -> 16-bit greyscale PNG on the GPU (handle of ``sage_png``): the pixels are bit-identical to
+    the reference client's ``(np.clip(depth, 0.0, 6.5) * 10000.0).astype(np.uint16)``
+    (vlm_client_modular.py:354-355); the file is this encoder's own valid PNG of them, not OpenCV's bytes
+    (csrc/png.cu explains why)."""
+
+    def __init__(self, width: int, height: int, max_batch: int = 4, device: int = 0):
+        _lib.require_gpu()
+        self.width, self.height, self.max_batch, self.device = int(width), int(height), int(max_batch), int(device)
+        self._h = C.c_void_p()
+        check(_lib.lib().sage_png_create(C.byref(self._h), self.device, self.width, self.height, self.max_batch))
+        mb = C.c_int64(0)
+        check(_lib.lib().sage_png_max_bytes(self._h, C.byref(mb)))
+        self.max_bytes = int(mb.value)
+        self._bufs = {}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            _lib.lib().sage_png_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _host_buf(self, slot):
+        torch = _torch()
+        if slot not in self._bufs:
+            self._bufs[slot] = torch.zeros(self.max_bytes, dtype=torch.uint8).pin_memory()
+        return self._bufs[slot]
+
+    def encode(self, depth, lo: float = 0.0, hi: float = 6.5, scale: float = 10000.0, want_pixels: bool = False, stream=None):
+        """depth: CUDA float32 tensor [H,W] -> PNG file ``bytes`` (and the uint16 pixels if asked)."""
+        torch = _torch()
+        if tuple(depth.shape) != (self.height, self.width) or depth.dtype != torch.float32 or not depth.is_cuda:
+            raise ValueError(f"expected a CUDA float32 tensor [{self.height},{self.width}]")
+        depth = depth.contiguous()
+        out = self._host_buf("encode")
+        n = C.c_int64(0)
+        twin = np.zeros((self.height, self.width), np.uint16) if want_pixels else None
+        with torch.cuda.device(self.device):
+            check(_lib.lib().sage_depth_png_encode_host(self._h, _ptr(depth), float(lo), float(hi), float(scale), _ptr(out),
+                                                        self.max_bytes, C.byref(n), _ptr(twin), _stream_ptr(stream)))
+        data = out.numpy()[:n.value].tobytes()
+        return (data, twin) if want_pixels else data
+
+
 # ---- functional surface (north_star) ---------------------------------------------------------
 
 _scene_cache: dict = {}
@@ -539,4 +609,4 @@ def collide(agent_pose, collision, **kw):
     raise TypeError("collision must be an ObstacleGrid or CollisionBodies")
 
 
-__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "JpegEncoder", "render", "collide", "SageError", "Camera"]
+__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "JpegEncoder", "DepthPngEncoder", "render", "collide", "SageError", "Camera"]

@@ -83,6 +83,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
     const uint32_t epoch = fr.fp->epoch + 3u;
     const uint32_t cap = fr.fp->cap;
     const int bins_x = cam.bins_x, bin_row0 = cam.bin_row0;
+    SAGE_DEP_LAUNCH_TOP();
+    sage_dep_wait();
     const uint32_t V = fr.counters[CNT_VISIBLE];
     const uint32_t nblk = (V + B_THREADS - 1) / B_THREADS;
     unsigned long long* chain = fr.chain;
@@ -239,6 +241,7 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
         if (overflow_rows)                                   // (splats taller than the item pool has room for)
             for (uint32_t j = 0; j < nrows; ++j) emit_row(threadIdx.x, j);
     }
+    SAGE_DEP_LAUNCH_END();
 }
 
 // Heaviest tiles first: a quadrant is blended by one warp however long the tile's list is, so the
@@ -251,6 +254,8 @@ k_bin_order(SageFrame fr)
     const int n_bins = fr.fp->cam.n_bins;
     const int lane = threadIdx.x & 31;
     const int n_round = (n_bins + 31) & ~31;
+    SAGE_DEP_LAUNCH_TOP();
+    sage_dep_wait();
     for (int t = blockIdx.x * B_THREADS + threadIdx.x; t < n_round; t += gridDim.x * B_THREADS) {
         uint32_t cls = 0xFFFFFFFFu;
         if (t < n_bins) {
@@ -271,12 +276,12 @@ k_bin_order(SageFrame fr)
 
 void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t st)
 {
-    SAGE_KLAUNCH(k_emit, E_GRID, B_THREADS, st, fr, order, fr.ikey[0], fr.ival[0]);
+    SAGE_KLAUNCH_PDL(k_emit, E_GRID, B_THREADS, 0, st, fr, order, fr.ikey[0], fr.ival[0]);
 }
 
 void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st)
 {
-    SAGE_KLAUNCH(k_bin_order, O_GRID, B_THREADS, st, fr);
+    SAGE_KLAUNCH_PDL(k_bin_order, O_GRID, B_THREADS, 0, st, fr);
 }
 
 void sage_bin_configure(void)

@@ -232,7 +232,7 @@ struct __align__(16) J1Warp {
 };
 
 __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __restrict__ jd,
-                                                            const uint8_t* __restrict__ rgb_all,
+                                                            const uint8_t* __restrict__ rgb_all, int bpp,
                                                             int16_t* __restrict__ coef_all,
                                                             uint16_t* __restrict__ acbits_all,
                                                             int16_t* __restrict__ dcs_all)
@@ -253,13 +253,22 @@ __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __res
     const int mx = m % jd->mcux, my = m / jd->mcux;
     const int px0 = mx * 16, py0 = my * 16;
     J1Warp& s = s_warp[wid];
-    const uint8_t* src = rgb_all + (size_t)f * (size_t)W * (size_t)H * 3;
+    const uint8_t* src = rgb_all + (size_t)f * (size_t)W * (size_t)H * (size_t)bpp;      // bpp: 3 = RGB, 4 = RGBA (alpha ignored)
 
     // (1) stage the 16x16 pixels; rows/columns past the image replicate the last one
     //     (jcsample.c expand_right_edge, jcprepct.c expand_bottom_edge)
     const bool inside = (px0 + 16 <= W) && (py0 + 16 <= H);
     const bool aligned = (((size_t)W * 3) & 3) == 0 && (((uintptr_t)src) & 3) == 0;
-    if (inside && aligned) {
+    if (bpp == 4) {
+        // RGBA frames (the composite's get_rgba() output mode): one 32-bit load per pixel, alpha dropped
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int p = lane + 32 * i;             // pixel: row = p / 16, col = p % 16
+            const int sy = min(py0 + (p >> 4), H - 1), sx = min(px0 + (p & 15), W - 1);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + ((size_t)sy * W + sx) * 4);
+            s.rgb[p * 3] = (uint8_t)v; s.rgb[p * 3 + 1] = (uint8_t)(v >> 8); s.rgb[p * 3 + 2] = (uint8_t)(v >> 16);
+        }
+    } else if (inside && aligned) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(s.rgb);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -729,14 +738,18 @@ struct sage_jpeg {
     uint8_t* out_dev = nullptr;
     long long* sizes_dev = nullptr;
     long long* sizes_pinned = nullptr;
+    uint8_t* out_pinned = nullptr;      // [max_batch][max_bytes] host staging of the fused render -> JPEG path
+    long long* guess = nullptr;         // [max_batch] bytes copied speculatively with the frame (last size + slack)
 };
 
 // Enqueue the encode of `batch` frames on `st` (no synchronisation).  The encoder's scratch is an
 // array of max_batch frame slots; this call uses slots [slot0, slot0 + batch), so encodes running
 // concurrently on different streams must use disjoint slot ranges.
-int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int batch, int slot0, uint8_t* out_dev, int64_t out_stride,
+int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int bpp, int batch, int slot0, uint8_t* out_dev, int64_t out_stride,
                       long long* sizes_dev, cudaStream_t st)
 {
+    REQUIRE(bpp == 3 || bpp == 4, "sage_jpeg_encode: frames are RGB (3 bytes per pixel) or RGBA (4)");
+    REQUIRE(bpp == 3 || (((uintptr_t)rgb_dev) & 3) == 0, "sage_jpeg_encode: RGBA frames must be 4-byte aligned");
     REQUIRE(j != nullptr && rgb_dev != nullptr && out_dev != nullptr && sizes_dev != nullptr, "sage_jpeg_encode: NULL argument");
     REQUIRE(batch >= 1 && slot0 >= 0 && slot0 + batch <= j->max_batch, "sage_jpeg_encode: batch exceeds max_batch");
     REQUIRE(out_stride >= j->host.header_len + 2, "sage_jpeg_encode: out_stride too small");
@@ -750,7 +763,7 @@ int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int batch, int slot0
     uint32_t* ffcnt = j->ffcnt + z * h.n_chunks;
     JpegFrameInfo* info = j->info + z;
     CK(cudaMemsetAsync(raw, 0, (size_t)batch * h.raw_words * 4, st));
-    SAGE_KLAUNCH(k_jpeg_dct, dim3((h.nmcu + J1_WARPS - 1) / J1_WARPS, batch), J1_WARPS * 32, st, j->dev, rgb_dev, coef, acbits, dcs);
+    SAGE_KLAUNCH(k_jpeg_dct, dim3((h.nmcu + J1_WARPS - 1) / J1_WARPS, batch), J1_WARPS * 32, st, j->dev, rgb_dev, bpp, coef, acbits, dcs);
     SAGE_KLAUNCH(k_jpeg_scan, batch, 1024, st, j->dev, dcs, acbits, bitoff, raw, info);
     SAGE_KLAUNCH(k_jpeg_huff, dim3((h.nmcu + J3_WARPS - 1) / J3_WARPS, batch), J3_WARPS * 32, st, j->dev, coef, bitoff, info, raw);
     SAGE_KLAUNCH(k_jpeg_ffcount, dim3(h.n_chunks, batch), 256, st, j->dev, info, raw, ffcnt);
@@ -765,6 +778,8 @@ uint8_t* sage_jpeg_stage_out(sage_jpeg* j) { return j->out_dev; }
 long long* sage_jpeg_stage_sizes_dev(sage_jpeg* j) { return j->sizes_dev; }
 long long* sage_jpeg_stage_sizes_host(sage_jpeg* j) { return j->sizes_pinned; }
 int64_t sage_jpeg_stage_stride(const sage_jpeg* j) { return j->max_bytes; }
+uint8_t* sage_jpeg_stage_out_host(sage_jpeg* j) { return j->out_pinned; }
+long long* sage_jpeg_stage_guess(sage_jpeg* j) { return j->guess; }
 int sage_jpeg_width(const sage_jpeg* j) { return j->W; }
 int sage_jpeg_height(const sage_jpeg* j) { return j->H; }
 int sage_jpeg_device(const sage_jpeg* j) { return j->device; }
@@ -780,6 +795,8 @@ int sage_jpeg_destroy(sage_jpeg* j)
     cudaFree(j->dev); cudaFree(j->coef); cudaFree(j->acbits); cudaFree(j->dcs); cudaFree(j->mcu_bitoff); cudaFree(j->raw);
     cudaFree(j->ffcnt); cudaFree(j->info); cudaFree(j->out_dev); cudaFree(j->sizes_dev);
     if (j->sizes_pinned) cudaFreeHost(j->sizes_pinned);
+    if (j->out_pinned) cudaFreeHost(j->out_pinned);
+    free(j->guess);
     cudaGetLastError();
     delete j;
     return 0;
@@ -875,6 +892,10 @@ int sage_jpeg_create(sage_jpeg** out, int device, int width, int height, int qua
     CKB(dalloc(&j->out_dev, B * (size_t)mb));
     CKB(dalloc(&j->sizes_dev, B));
     CKB(cudaHostAlloc((void**)&j->sizes_pinned, sizeof(long long) * B, cudaHostAllocDefault));
+    CKB(cudaHostAlloc((void**)&j->out_pinned, B * (size_t)mb, cudaHostAllocDefault));
+    j->guess = (long long*)calloc(B, sizeof(long long));
+    if (!j->guess) { sage_jpeg_destroy(j); return 1; }
+    for (size_t k = 0; k < B; ++k) j->guess[k] = mb < (1 << 18) ? mb : (1 << 18);
 #undef CKB
     *out = j;
     return 0;
@@ -893,7 +914,7 @@ int sage_jpeg_encode(sage_jpeg* j, const uint8_t* rgb_dev, int batch, uint8_t* o
     REQUIRE(j != nullptr, "sage_jpeg_encode: NULL encoder");
     CK(cudaSetDevice(j->device));
     static_assert(sizeof(long long) == sizeof(int64_t), "int64");
-    return sage_jpeg_enqueue(j, rgb_dev, batch, 0, out_dev, out_stride, reinterpret_cast<long long*>(sizes_dev), (cudaStream_t)stream);
+    return sage_jpeg_enqueue(j, rgb_dev, 3, batch, 0, out_dev, out_stride, reinterpret_cast<long long*>(sizes_dev), (cudaStream_t)stream);
 }
 
 int sage_jpeg_encode_host(sage_jpeg* j, const uint8_t* rgb_dev, int batch, uint8_t* out_host, int64_t out_stride,
@@ -902,7 +923,7 @@ int sage_jpeg_encode_host(sage_jpeg* j, const uint8_t* rgb_dev, int batch, uint8
     REQUIRE(j != nullptr && out_host != nullptr && sizes_host != nullptr, "sage_jpeg_encode_host: NULL argument");
     CK(cudaSetDevice(j->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (sage_jpeg_enqueue(j, rgb_dev, batch, 0, j->out_dev, j->max_bytes, j->sizes_dev, st)) return 1;
+    if (sage_jpeg_enqueue(j, rgb_dev, 3, batch, 0, j->out_dev, j->max_bytes, j->sizes_dev, st)) return 1;
     CK(cudaMemcpyAsync(j->sizes_pinned, j->sizes_dev, sizeof(long long) * batch, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int rc = 0;

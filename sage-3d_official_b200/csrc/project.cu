@@ -85,6 +85,7 @@ k_project(SageSceneDev sc, SageFrame fr)
 {
     const SageCamDev& cam = fr.fp->cam;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    SAGE_DEP_LAUNCH_TOP();
     bool vis = false;
     uint32_t key = SAGE_KEY_CULLED;
     if (i < sc.n) {
@@ -168,6 +169,7 @@ k_project(SageSceneDev sc, SageFrame fr)
     // one atomic per warp for the visible counter
     const unsigned m = __ballot_sync(0xffffffffu, vis);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], (uint32_t)__popc(m));
+    SAGE_DEP_LAUNCH_END();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,6 +13,52 @@
 #define SAGE_KLAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define SAGE_DYN_SMEM(type, name) extern __shared__ type name[]
 #endif
+#include <stdlib.h>
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// The front half of a frame is a chain of ~18 small kernels on one stream; the gap between two of them
+// (completion -> launch -> first CTA) is a few microseconds each.  A kernel launched with
+// SAGE_KLAUNCH_PDL may start while its predecessor in the stream drains: it runs its prologue, then
+// sage_dep_wait() (griddepcontrol.wait) blocks until the predecessor grid has completed and its
+// writes are visible.  sage_dep_launch() (griddepcontrol.launch_dependents) is the predecessor's
+// "my dependents may be scheduled now".  Both are no-ops in a kernel launched without the attribute.
+// SAGE_NO_PDL=1 turns the attribute off (A/B).
+#ifdef SAGE_CUDA_EMU
+#define SAGE_KLAUNCH_PDL(kernel, grid, block, smem, stream, ...) SAGE_KLAUNCH(kernel, grid, block, stream, __VA_ARGS__)
+inline void sage_dep_wait() {}
+inline void sage_dep_launch() {}
+#else
+inline bool sage_pdl_enabled()
+{
+    static const bool on = getenv("SAGE_NO_PDL") == nullptr;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void sage_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sage_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#define SAGE_KLAUNCH_PDL(kernel, grid, block, smem, stream, ...) sage_launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+__device__ __forceinline__ void sage_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sage_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+// where a kernel says "dependents may be scheduled": at its end (default: the dependent's launch overlaps
+// only this kernel's drain, and no waiting CTA holds registers / shared memory the composite of the frame in
+// flight on another stream could use) or at its top (-DSAGE_PDL_EARLY: experiment)
+#ifdef SAGE_PDL_EARLY
+#define SAGE_DEP_LAUNCH_TOP() sage_dep_launch()
+#define SAGE_DEP_LAUNCH_END() do { } while (0)
+#else
+#define SAGE_DEP_LAUNCH_TOP() do { } while (0)
+#define SAGE_DEP_LAUNCH_END() sage_dep_launch()
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -362,13 +408,29 @@ int sage_capsule_max_poses(void);
 
 // ---- JPEG encoder internals shared with scene_api.cu (jpeg.cu) -------------------------------
 struct sage_jpeg;
-int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int batch, int slot0, uint8_t* out_dev, int64_t out_stride,
+int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int bpp, int batch, int slot0, uint8_t* out_dev, int64_t out_stride,
                       long long* sizes_dev, cudaStream_t st);
 uint8_t* sage_jpeg_stage_out(sage_jpeg* j);
 long long* sage_jpeg_stage_sizes_dev(sage_jpeg* j);
 long long* sage_jpeg_stage_sizes_host(sage_jpeg* j);
 int64_t sage_jpeg_stage_stride(const sage_jpeg* j);
+uint8_t* sage_jpeg_stage_out_host(sage_jpeg* j);
+long long* sage_jpeg_stage_guess(sage_jpeg* j);
 int sage_jpeg_width(const sage_jpeg* j);
 int sage_jpeg_height(const sage_jpeg* j);
 int sage_jpeg_device(const sage_jpeg* j);
 int sage_jpeg_max_batch(const sage_jpeg* j);
+
+// ---- depth PNG encoder internals shared with scene_api.cu (png.cu) ----------------------------
+struct sage_png;
+int sage_png_enqueue(sage_png* p, const float* depth_dev, float lo, float hi, float scale, int slot, uint8_t* out_dev,
+                     int64_t out_cap, long long* size_dev, uint16_t* twin_dev, cudaStream_t st);
+uint8_t* sage_png_stage_out(sage_png* p);
+uint8_t* sage_png_stage_out_host(sage_png* p);
+long long* sage_png_stage_sizes_dev(sage_png* p);
+long long* sage_png_stage_sizes_host(sage_png* p);
+int64_t sage_png_stage_stride(const sage_png* p);
+int sage_png_width(const sage_png* p);
+int sage_png_height(const sage_png* p);
+int sage_png_device(const sage_png* p);
+int sage_png_max_batch(const sage_png* p);

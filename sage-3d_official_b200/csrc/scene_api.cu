@@ -58,6 +58,10 @@ struct FrameCtx {
     GraphSlot graphs[N_GRAPH_SLOTS];
     uint8_t* out_rgb = nullptr;      // internal device frame (host paths)
     float* out_depth = nullptr;
+    uint8_t* out_pack = nullptr;     // packed RGB copy of an RGBA frame (hand-off twin), allocated on first use
+    uint16_t* out_u16 = nullptr;     // quantised depth (hand-off twin of the PNG), allocated on first use
+    int frame_w = 0, frame_h = 0;    // resolution of the frame last rendered into out_rgb / out_depth
+    bool frame_has_depth = false;
     size_t out_px = 0;
     cudaStream_t last_stream = nullptr;
     int last_W = 0, last_H = 0, last_depth = 0, last_launches = 0;
@@ -172,7 +176,7 @@ static void free_ctx(FrameCtx& c)
     if (c.side) cudaStreamDestroy(c.side);
     if (c.low) cudaStreamDestroy(c.low);
     for (auto& e : c.fork_join) if (e) cudaEventDestroy(e);
-    cudaFree(c.out_rgb); cudaFree(c.out_depth);
+    cudaFree(c.out_rgb); cudaFree(c.out_depth); cudaFree(c.out_pack); cudaFree(c.out_u16);
     c = FrameCtx{};
 }
 
@@ -229,8 +233,8 @@ static int ensure_out(FrameCtx& c, size_t px)
 {
     if (px > c.out_px) {
         if (c.used) CK(cudaEventSynchronize(c.done));
-        cudaFree(c.out_rgb); cudaFree(c.out_depth);
-        c.out_rgb = nullptr; c.out_depth = nullptr; c.out_px = 0;
+        cudaFree(c.out_rgb); cudaFree(c.out_depth); cudaFree(c.out_pack); cudaFree(c.out_u16);
+        c.out_rgb = nullptr; c.out_depth = nullptr; c.out_pack = nullptr; c.out_u16 = nullptr; c.out_px = 0;
         CK(dalloc(&c.out_rgb, px * 4));          // room for RGBA
         CK(dalloc(&c.out_depth, px));
         c.out_px = px;
@@ -480,6 +484,7 @@ static int render_to_host(sage_scene* s, int ci, const sage_camera* cam, int row
     uint8_t* rgbs[1] = {c.out_rgb};
     float* deps[1] = {c.out_depth};
     if (render_impl(s, ci, cam, row0, row1, 1, rgbs, depth_host ? deps : nullptr, st)) return 1;
+    c.frame_w = cam->width; c.frame_h = cam->height; c.frame_has_depth = depth_host != nullptr;
     const int y0 = row0 * SAGE_TILE;
     int y1 = row1 * SAGE_TILE;
     if (y1 > cam->height) y1 = cam->height;
@@ -521,8 +526,26 @@ int sage_host_wait(sage_scene* s, int slot)
     return 0;
 }
 
+// RGBA u8x4 -> packed RGB u8x3, four pixels (16 bytes in, 12 bytes out) per thread
+static __global__ void __launch_bounds__(256) k_pack_rgb(const uint4* __restrict__ rgba, uint32_t* __restrict__ rgb, size_t n_quads)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = rgba[i];
+        const uint32_t a = v.x & 0xFFFFFFu, b = v.y & 0xFFFFFFu, c = v.z & 0xFFFFFFu, d = v.w & 0xFFFFFFu;
+        rgb[3 * i + 0] = a | (b << 24);
+        rgb[3 * i + 1] = (b >> 8) | (c << 16);
+        rgb[3 * i + 2] = (c >> 16) | (d << 8);
+    }
+}
+
 int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
                            uint8_t* rgb_host, float* depth_host)
+{
+    return sage_render_jpeg_async2(s, cam, j, slot, rgb_host, depth_host, nullptr);
+}
+
+int sage_render_jpeg_async2(sage_scene* s, const sage_camera* cam, sage_jpeg* j, int slot,
+                            uint8_t* rgb_host, float* depth_host, uint8_t* rgb_twin_host)
 {
     REQUIRE(s != nullptr && cam != nullptr && j != nullptr, "sage_render_jpeg_async: NULL argument");
     REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_async: slot must be in [0, sage_pipeline_depth())");
@@ -530,7 +553,6 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
     REQUIRE(sage_jpeg_width(j) == cam->width && sage_jpeg_height(j) == cam->height,
             "sage_render_jpeg_async: encoder resolution differs from the camera's");
     REQUIRE(sage_jpeg_max_batch(j) > slot, "sage_render_jpeg_async: encoder needs max_batch > slot (one scratch slot per frame in flight)");
-    REQUIRE(!s->rgba, "sage_render_jpeg_async: the JPEG encoder reads RGB frames (turn the RGBA output off)");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     cudaStream_t st = c.stream;
@@ -540,13 +562,34 @@ int sage_render_jpeg_async(sage_scene* s, const sage_camera* cam, sage_jpeg* j, 
     float* deps[1] = {c.out_depth};
     const int rows = (cam->height + SAGE_TILE - 1) / SAGE_TILE;
     if (render_impl(s, slot, cam, 0, rows, 1, rgbs, depth_host ? deps : nullptr, st)) return 1;
+    c.frame_w = cam->width; c.frame_h = cam->height; c.frame_has_depth = depth_host != nullptr;
     const int64_t stride = sage_jpeg_stage_stride(j);
-    if (sage_jpeg_enqueue(j, c.out_rgb, 1, slot, sage_jpeg_stage_out(j) + (size_t)slot * stride, stride,
+    if (sage_jpeg_enqueue(j, c.out_rgb, s->rgba ? 4 : 3, 1, slot, sage_jpeg_stage_out(j) + (size_t)slot * stride, stride,
                           sage_jpeg_stage_sizes_dev(j) + slot, st)) return 1;
     CK(cudaMemcpyAsync(sage_jpeg_stage_sizes_host(j) + slot, sage_jpeg_stage_sizes_dev(j) + slot, sizeof(long long),
                        cudaMemcpyDeviceToHost, st));
-    if (rgb_host) CK(cudaMemcpyAsync(rgb_host, c.out_rgb, px * 3, cudaMemcpyDeviceToHost, st));
+    // the stream's size is unknown until the encode has run: copy last frame's size + slack along with the
+    // frame, so the wait normally finds the whole file already on the host (no second round trip)
+    {
+        long long g = sage_jpeg_stage_guess(j)[slot];
+        if (g > stride) g = stride;
+        CK(cudaMemcpyAsync(sage_jpeg_stage_out_host(j) + (size_t)slot * stride, sage_jpeg_stage_out(j) + (size_t)slot * stride,
+                           (size_t)g, cudaMemcpyDeviceToHost, st));
+    }
+    if (rgb_host) CK(cudaMemcpyAsync(rgb_host, c.out_rgb, px * (s->rgba ? 4 : 3), cudaMemcpyDeviceToHost, st));
     if (depth_host) CK(cudaMemcpyAsync(depth_host, c.out_depth, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rgb_twin_host) {                              // the frame once more, always as packed RGB
+        const uint8_t* src = c.out_rgb;
+        if (s->rgba) {
+            REQUIRE(px % 4 == 0, "sage_render_jpeg_async2: the packed twin of an RGBA frame needs width * height % 4 == 0");
+            if (!c.out_pack) CK(dalloc(&c.out_pack, c.out_px * 3));
+            const size_t quads = px / 4;
+            SAGE_KLAUNCH(k_pack_rgb, 148 * 4, 256, st, reinterpret_cast<const uint4*>(c.out_rgb),
+                         reinterpret_cast<uint32_t*>(c.out_pack), quads);
+            src = c.out_pack;
+        }
+        CK(cudaMemcpyAsync(rgb_twin_host, src, px * 3, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaEventRecord(c.done, st));
     return 0;
 }
@@ -562,7 +605,56 @@ int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_h
     *size_out = sz;
     REQUIRE(sz > 0, "sage_render_jpeg_wait: the encoded frame exceeds the encoder's max_bytes_per_frame");
     REQUIRE(sz <= cap, "sage_render_jpeg_wait: jpeg_host is too small (*size_out holds the size needed)");
-    CK(cudaMemcpyAsync(jpeg_host, sage_jpeg_stage_out(j) + (size_t)slot * sage_jpeg_stage_stride(j), (size_t)sz,
+    const int64_t stride = sage_jpeg_stage_stride(j);
+    long long& guess = sage_jpeg_stage_guess(j)[slot];
+    const long long have = guess < stride ? guess : stride;
+    uint8_t* stage = sage_jpeg_stage_out_host(j) + (size_t)slot * stride;
+    if (sz > have) {                                  // (a frame much larger than the previous one)
+        CK(cudaMemcpyAsync(stage + have, sage_jpeg_stage_out(j) + (size_t)slot * stride + have, (size_t)(sz - have),
+                           cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+    }
+    memcpy(jpeg_host, stage, (size_t)sz);
+    guess = sz + sz / 4 + 4096;
+    return 0;
+}
+
+int sage_frame_depth_png_async(sage_scene* s, sage_png* p, int slot, float lo, float hi, float scale, uint16_t* twin_host)
+{
+    REQUIRE(s != nullptr && p != nullptr, "sage_frame_depth_png_async: NULL argument");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_frame_depth_png_async: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(sage_png_device(p) == s->device, "sage_frame_depth_png_async: encoder lives on another device");
+    REQUIRE(sage_png_max_batch(p) > slot, "sage_frame_depth_png_async: encoder needs max_batch > slot (one scratch slot per frame in flight)");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[slot];
+    REQUIRE(c.frame_has_depth && c.out_depth != nullptr, "sage_frame_depth_png_async: the slot's last frame was rendered without depth");
+    REQUIRE(sage_png_width(p) == c.frame_w && sage_png_height(p) == c.frame_h,
+            "sage_frame_depth_png_async: encoder resolution differs from the slot's frame");
+    cudaStream_t st = c.stream;
+    const size_t px = (size_t)c.frame_w * (size_t)c.frame_h;
+    if (twin_host && !c.out_u16) CK(dalloc(&c.out_u16, c.out_px));
+    const int64_t stride = sage_png_stage_stride(p);
+    if (sage_png_enqueue(p, c.out_depth, lo, hi, scale, slot, sage_png_stage_out(p) + (size_t)slot * stride, stride,
+                         sage_png_stage_sizes_dev(p) + slot, twin_host ? c.out_u16 : nullptr, st)) return 1;
+    CK(cudaMemcpyAsync(sage_png_stage_sizes_host(p) + slot, sage_png_stage_sizes_dev(p) + slot, sizeof(long long),
+                       cudaMemcpyDeviceToHost, st));
+    if (twin_host) CK(cudaMemcpyAsync(twin_host, c.out_u16, px * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c.done, st));
+    return 0;
+}
+
+int sage_frame_depth_png_wait(sage_scene* s, sage_png* p, int slot, uint8_t* png_host, int64_t cap, int64_t* size_out)
+{
+    REQUIRE(s != nullptr && p != nullptr && png_host != nullptr && size_out != nullptr, "sage_frame_depth_png_wait: NULL argument");
+    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_frame_depth_png_wait: slot must be in [0, sage_pipeline_depth())");
+    CK(cudaSetDevice(s->device));
+    FrameCtx& c = s->ctx[slot];
+    CK(cudaStreamSynchronize(c.stream));
+    const long long sz = sage_png_stage_sizes_host(p)[slot];
+    *size_out = sz;
+    REQUIRE(sz > 0, "sage_frame_depth_png_wait: the encoder's stream buffer overflowed");
+    REQUIRE(sz <= cap, "sage_frame_depth_png_wait: png_host is too small (*size_out holds the size needed)");
+    CK(cudaMemcpyAsync(png_host, sage_png_stage_out(p) + (size_t)slot * sage_png_stage_stride(p), (size_t)sz,
                        cudaMemcpyDeviceToHost, c.stream));
     CK(cudaStreamSynchronize(c.stream));
     return 0;

@@ -64,6 +64,8 @@ k_sort_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_pt
     constexpr int RADIX = 1 << RB;
     constexpr int S_TILE = S_THREADS * S_IPT;
     __shared__ uint32_t h[RADIX];
+    SAGE_DEP_LAUNCH_TOP();
+    sage_dep_wait();
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
@@ -82,6 +84,7 @@ k_sort_hist(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ n_pt
         for (int i = threadIdx.x; i < RADIX; i += S_THREADS) H[(size_t)i * ld + b] = h[i];
         __syncthreads();
     }
+    SAGE_DEP_LAUNCH_END();
 }
 
 // ---- a warp per digit: exclusive scan over the tiles, digit totals ---------------------------
@@ -91,6 +94,8 @@ k_sort_scan(const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ H, int ld
             uint32_t* __restrict__ totals)
 {
     constexpr int S_TILE = S_THREADS * S_IPT;
+    SAGE_DEP_LAUNCH_TOP();
+    sage_dep_wait();
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
     const int lane = threadIdx.x & 31;
@@ -111,6 +116,7 @@ k_sort_scan(const uint32_t* __restrict__ n_ptr, uint32_t* __restrict__ H, int ld
         run += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (lane == 0) totals[d] = run;
+    SAGE_DEP_LAUNCH_END();
 }
 
 // ---- rank + scatter -------------------------------------------------------------------------
@@ -129,6 +135,8 @@ k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     constexpr int RADIX = 1 << RB;
     constexpr int S_TILE = S_THREADS * S_IPT;
     static_assert(RADIX <= S_THREADS, "one digit per thread");
+    SAGE_DEP_LAUNCH_TOP();
+    sage_dep_wait();
     const uint32_t n = *n_ptr;
     const uint32_t nb = (n + S_TILE - 1) / S_TILE;
     // dynamic shared memory: warp-private digit counters, then the staging area of the scatter
@@ -249,6 +257,7 @@ k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
             }
         }
     }
+    SAGE_DEP_LAUNCH_END();
 }
 
 template <int RB, int S_IPT>
@@ -272,18 +281,18 @@ void sort_impl(const SageSortPlan& pl, cudaStream_t st)
         const uint32_t* kin = p == 0 ? pl.keys_src : pl.keys[cur];
         const int shift = pl.lo_bit + RB * p;
         const int iota = (pl.vals_are_iota && p == 0) ? 1 : 0;
-        if (p == 0) SAGE_KLAUNCH(k_hist_first, S_GRID, S_THREADS, st, kin, n_dev, shift, pl.H, ld);
-        else SAGE_KLAUNCH(k_hist_rest, S_GRID, S_THREADS, st, kin, n_dev, shift, pl.H, ld);
-        SAGE_KLAUNCH(k_scan, (RADIX + 7) / 8, 256, st, n_dev, pl.H, ld, RADIX, pl.totals);
+        if (p == 0) SAGE_KLAUNCH_PDL(k_hist_first, S_GRID, S_THREADS, 0, st, kin, n_dev, shift, pl.H, ld);
+        else SAGE_KLAUNCH_PDL(k_hist_rest, S_GRID, S_THREADS, 0, st, kin, n_dev, shift, pl.H, ld);
+        SAGE_KLAUNCH_PDL(k_scan, (RADIX + 7) / 8, 256, 0, st, n_dev, pl.H, ld, RADIX, pl.totals);
         const bool last = pl.ranges != nullptr && p == NP - 1;
         if (last && !(COMPACT && p == 0))
-            SAGE_KLAUNCH_SMEM(k_last, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
+            SAGE_KLAUNCH_PDL(k_last, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
                               shift, pl.H, ld, pl.totals, iota, pl.ranges);
         else if (p == 0)
-            SAGE_KLAUNCH_SMEM(k_first, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
+            SAGE_KLAUNCH_PDL(k_first, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
                               shift, pl.H, ld, pl.totals, iota, (uint2*)nullptr);
         else
-            SAGE_KLAUNCH_SMEM(k_rest, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
+            SAGE_KLAUNCH_PDL(k_rest, S_GRID, S_THREADS, SMEM, st, kin, pl.vals[cur], pl.keys[cur ^ 1], pl.vals[cur ^ 1], n_dev,
                               shift, pl.H, ld, pl.totals, iota, (uint2*)nullptr);
         cur ^= 1;
     }

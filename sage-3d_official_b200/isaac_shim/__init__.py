@@ -25,6 +25,8 @@ import types
 import numpy as np
 
 from ..camera import Camera as _RasterCamera, FOCAL_LENGTH_MM, USD_GAUSS_MODEL_TO_WORLD
+from ..framepool import FramePool
+from ..handoff import PrivateTwin
 
 _state = {"stage": None, "jpeg_handoff": False}
 
@@ -66,6 +68,8 @@ class Stage:
             raise FileNotFoundError(f"no Gaussian payload (.ply/.npz) found for {usd_path}")
         self.model_to_world = USD_GAUSS_MODEL_TO_WORLD if is_stage else None
         self.scene = GaussianScene(load_cloud(gauss), device=device)
+        self.scene.set_rgba(True)                  # Camera.get_rgba() frames come out of the composite as RGBA
+        self._pool = self._pool_shape = self._scratch = None
         self.prims = {"/World": _Prim("/World")}
 
     def GetPrimAtPath(self, path):
@@ -137,16 +141,6 @@ class World:
         pass
 
 
-def _rgb_to_rgba(rgb: np.ndarray) -> np.ndarray:
-    """(H,W,3) -> (H,W,4) with alpha 255.  NumPy's 3-of-4-byte strided copy runs at ~0.5 GB/s;
-    OpenCV's is ~10x faster when it is installed (it is in the reference's environment)."""
-    try:
-        import cv2
-        return cv2.cvtColor(rgb, cv2.COLOR_RGB2RGBA)
-    except Exception:
-        return np.concatenate([rgb, np.full(rgb.shape[:2] + (1,), 255, np.uint8)], axis=2)
-
-
 class Camera:
     """``omni.isaac.sensor.Camera`` stand-in: pose in, frame out."""
 
@@ -160,6 +154,7 @@ class Camera:
         self._depth_enabled = False
         self._frame_key = None
         self._frame = None
+        self._served = False
         st = _state["stage"]
         if st is not None:
             st.prims[str(prim_path)] = _Prim(str(prim_path), self)
@@ -185,50 +180,98 @@ class Camera:
     def set_clipping_range(self, near, far):
         self.clipping_range = (float(near), float(far))
 
+    def _buffers(self, st):
+        """A pinned (rgba, depth, twin) buffer triple for this resolution: lent to the caller zero-copy and
+        taken back when the caller's arrays are garbage-collected; a scratch triple (and copies) when the
+        caller keeps every frame."""
+        W, H = self.resolution
+        pool = getattr(st, "_pool", None)
+        if pool is None or st._pool_shape != (H, W):
+            import torch
+            scene = st.scene
+
+            def make():
+                rgba, depth = scene.alloc_host_frame(H, W)
+                return rgba, depth, torch.zeros((H, W, 3), dtype=torch.uint8).pin_memory()
+
+            pool = st._pool = FramePool(make)
+            st._pool_shape, st._scratch = (H, W), None
+        triple = pool.take()
+        if triple is None:
+            if st._scratch is None:
+                st._scratch = pool._make()
+            return st._scratch, False
+        return triple, True
+
     def _render(self):
         st = _state["stage"]
         if st is None or st.scene is None:
             return None
-        key = (self._position.tobytes(), self._orientation.tobytes(), self.resolution, self.focal_length)
+        key = (self._position.tobytes(), self._orientation.tobytes(), self.resolution, self.focal_length,
+               self._depth_enabled)
         if key != self._frame_key:
             cam = _RasterCamera.from_isaac_pose(self._position, self._orientation, self.resolution[0],
                                                 self.resolution[1], model_to_world=st.model_to_world,
                                                 focal_mm=self.focal_length, near=self.clipping_range[0],
                                                 far=self.clipping_range[1])
-            self._jpeg = None
-            if _state["jpeg_handoff"]:
-                # frame hand-off: the JPEG generate_images.py:431-432 is about to make, made on the device
-                from ..api import JpegEncoder
-                enc = getattr(st, "_encoder", None)
-                if enc is None or (enc.width, enc.height) != self.resolution:
-                    enc = st._encoder = JpegEncoder(self.resolution[0], self.resolution[1], max_batch=2)
-                rgb, depth = st.scene.render_jpeg_async(cam, enc, 0, want_rgb=True, want_depth=True)
-                self._jpeg = st.scene.jpeg_wait(enc, 0)
-                if st.scene.stats()["overflow"]:
-                    self._jpeg = None
-                    rgb, depth = st.scene.render_host(cam, want_depth=True)
+            scene = st.scene
+            (rgba_t, dep_t, twin_t), lent = self._buffers(st)
+            handoff = _state["jpeg_handoff"] and (self.resolution[0] * self.resolution[1]) % 4 == 0
+            jpeg = None
+            for _ in range(2):
+                if handoff:
+                    # frame hand-off: the JPEG generate_images.py:431-432 is about to make, made on the device
+                    from ..api import JpegEncoder
+                    enc = getattr(st, "_encoder", None)
+                    if enc is None or (enc.width, enc.height) != self.resolution:
+                        enc = st._encoder = JpegEncoder(self.resolution[0], self.resolution[1], max_batch=2)
+                    scene.render_jpeg_async(cam, enc, 0, want_rgb=True, want_depth=self._depth_enabled,
+                                            out=(rgba_t, dep_t), twin=twin_t)
+                    jpeg = scene.jpeg_wait(enc, 0)
+                else:
+                    scene.render_host_async(cam, 0, want_depth=self._depth_enabled, out=(rgba_t, dep_t))
+                    scene.host_wait(0)
+                stats = scene.stats()
+                if not stats["overflow"]:
+                    break
+                # the (tile, Gaussian) lists did not fit (camera inside geometry): grow and redo
+                scene.reserve(int(stats["n_instances_wanted"] * 1.25) + 1024)
+            rgba, depth, twin = rgba_t.numpy(), (dep_t.numpy() if self._depth_enabled else None), None
+            if jpeg is not None:
+                twin = twin_t.numpy()
+            if not lent:
+                rgba, depth, twin = rgba.copy(), (None if depth is None else depth.copy()), (None if twin is None else twin.copy())
             else:
-                rgb, depth = st.scene.render_host(cam, want_depth=True)
-            self._frame = (rgb.copy(), depth.copy())
+                st._pool.lend((rgba_t, dep_t, twin_t), tuple(a for a in (rgba, depth, twin) if a is not None))
+            if twin is not None:
+                twin = twin.view(PrivateTwin)
+            self._frame = (rgba, depth, twin, jpeg)
             self._frame_key = key
+            self._served = False
         return self._frame
 
     def get_rgba(self):
+        """RGBA u8 [H,W,4] straight from the composite's epilogue (alpha 255): no host-side expansion."""
+        if self._served:
+            self._frame_key = None            # the caller may have drawn on the array it was given: render afresh
         f = self._render()
         if f is None:
             return None
-        rgb = f[0]
-        rgba = _rgb_to_rgba(rgb)
-        if getattr(self, "_jpeg", None) is not None:
-            from ..handoff import DeviceFrame
-            return DeviceFrame(rgba, self._jpeg, rgb, lambda: True)     # rgb is this frame's private copy
-        return rgba
+        self._served = True
+        rgba, _, twin, jpeg = f
+        from ..handoff import DeviceFrame
+        return DeviceFrame(rgba, jpeg, twin, lambda: True, rgba_root=True)
 
     def get_current_frame(self):
+        if not self._depth_enabled:
+            self._depth_enabled = True        # Isaac delivers the annotators that were added; here depth is one flag away
+        if self._served:
+            self._frame_key = None
         f = self._render()
         out = {"rendering_time": 0.0, "rendering_frame": 0}
         if f is not None:
-            out["rgba"] = np.concatenate([f[0], np.full(f[0].shape[:2] + (1,), 255, np.uint8)], axis=2)
+            self._served = True
+            out["rgba"] = f[0]
             out["distance_to_image_plane"] = f[1]
         return out
 

@@ -296,6 +296,19 @@ def write_semantic_map(layout, path, step: float = 0.05):
     return path
 
 
+def to_trajectory_frame(xyz: np.ndarray, map_bounds) -> np.ndarray:
+    """Points of a layout given in 2-D-semantic-map coordinates, moved into the frame the agent and
+    the USD stage live in.  The reference's 3-D trajectories are its 2-D ones mirrored about the map
+    centre and negated (trajectory_2d_to_3d.py:33-63; undone by collision_detector.py:146-189), a pure
+    translation: x3 = x2 - (min_x + max_x), y3 = y2 - (min_y + max_y).  ``map_bounds`` =
+    (min_x, max_x, min_y, max_y) of the obstacle grid built from the same map."""
+    min_x, max_x, min_y, max_y = map_bounds
+    out = np.array(xyz, dtype=np.float32, copy=True)
+    out[:, 0] -= np.float32(min_x + max_x)
+    out[:, 1] -= np.float32(min_y + max_y)
+    return out
+
+
 def collision_ellipsoids(layout, seed: int = 0, per_m2: float = 40.0):
     """Collision bodies as ellipsoids covering walls and furniture: (mu[M,3], log_scale[M,3], quat[M,4])."""
     rng = np.random.default_rng(seed + 77)

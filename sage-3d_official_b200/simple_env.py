@@ -72,39 +72,7 @@ def _default_resolution(resolution):
     return resolution
 
 
-class _FramePool:
-    """Pinned host frame buffers handed out as NumPy views and taken back when the last reference to
-    the view (or to anything derived from it) is gone."""
-
-    def __init__(self, make_pair, limit: int = 16):
-        self._make, self._limit = make_pair, limit
-        self._free, self._n = [], 0
-
-    def take(self):
-        """(pair, token) — token must be passed to lend(); None when the pool is exhausted."""
-        if self._free:
-            return self._free.pop()
-        if self._n >= self._limit:
-            return None
-        self._n += 1
-        return self._make()
-
-    def lend(self, pair, arrays):
-        """The arrays (views of the pair's buffers) go to the caller; the pair returns to the pool
-        when all of them have been garbage-collected."""
-        state = {"left": len(arrays)}
-
-        def back(_state=state, _pair=pair, _pool=weakref.ref(self)):
-            _state["left"] -= 1
-            pool = _pool()
-            if _state["left"] == 0 and pool is not None:
-                pool._free.append(_pair)
-
-        for a in arrays:
-            weakref.finalize(a, back)
-
-    def give_back(self, pair):
-        self._free.append(pair)
+from .framepool import FramePool as _FramePool  # noqa: E402
 
 
 class SimpleVLNEnv:
@@ -149,12 +117,14 @@ class SimpleVLNEnv:
         self._frame = None
         # frame hand-off (handoff.py): also encode every frame to JPEG on the device so an unmodified
         # caller's Image.fromarray(rgb).save(..., 'JPEG') costs a memcpy instead of a 13 ms encode
-        from .handoff import handoff_requested, install_pillow_hook
+        from .handoff import handoff_requested, install_cv2_hook, install_pillow_hook
         self._jpeg_handoff = handoff_requested() if jpeg_handoff is None else bool(jpeg_handoff)
         if self._jpeg_handoff:
             install_pillow_hook()
+            install_cv2_hook()
         self._jpeg = None
         self._encoder = None
+        self._png, self._png_frame, self._png_encoder, self._png_twin = (None, None), None, None, None
         self.render_calls = 0          # engine frames actually rendered (1 per distinct pose)
         self.collide_launches = 0      # batched collide launches
         #: wall-clock accounting of the hot path (seconds / counts); dumped as JSON to $SAGE_PERF_JSON
@@ -450,6 +420,27 @@ class SimpleVLNEnv:
             self._scene.reserve(int(st["n_instances_wanted"] * 1.25) + 1024)    # as render_host does
         return frame, jpeg
 
+    def _depth_png(self, frame):
+        """Hand-off of the depth map (vlm_client_modular.py:354-364): the 16-bit PNG of
+        ``(clip(depth, 0, 6.5) * 10000).astype(uint16)`` made on the device from the frame still resident in
+        the slot, fetched with its uint16 pixels (the hook's reference copy).  Cached per frame."""
+        if self._png_frame is frame:
+            return self._png
+        self._png, self._png_frame = (None, None), frame
+        try:
+            from .api import DepthPngEncoder
+            import torch
+            H, W = frame[1].shape
+            if self._png_encoder is None or (self._png_encoder.width, self._png_encoder.height) != (W, H):
+                self._png_encoder = DepthPngEncoder(W, H, max_batch=2, device=self._device)
+                self._png_twin = torch.zeros((H, W), dtype=torch.uint16).pin_memory()
+            self._scene.depth_png_async(self._png_encoder, 0, 0.0, 6.5, 10000.0, twin=self._png_twin)
+            data = self._scene.depth_png_wait(self._png_encoder, 0)
+            self._png = (data, self._png_twin.numpy().copy())
+        except Exception as e:
+            _debug_print(f"[WARN] depth PNG hand-off failed: {e}")
+        return self._png
+
     def _tick(self, name: str) -> None:
         now = time.perf_counter()
         self.perf[name] += 1
@@ -487,8 +478,14 @@ class SimpleVLNEnv:
             return None
         try:
             self._tick("get_depth_calls")
-            self._render_current()
-            return self._hand_out(1, "depth")                 # already clipped to [0.1, 6.5] on the device
+            frame = self._render_current()
+            depth = self._hand_out(1, "depth")                # already clipped to [0.1, 6.5] on the device
+            if self._jpeg_handoff:
+                png, pixels = self._depth_png(frame)
+                if png is not None:
+                    from .handoff import DeviceDepth
+                    return DeviceDepth(depth, png, pixels, lambda f=frame: self._frame is f)
+            return depth
         except Exception as e:
             _debug_print(f"[WARN] get_depth failed: {e}")
             return None
@@ -528,21 +525,31 @@ class SimpleVLNEnv:
         return bool(self._bodies.check(np.asarray(pos, np.float32)[None, :3], radius=self.AGENT_RADIUS,
                                        z0=z0, z1=z0 + self.AGENT_HEIGHT)[0][0])
 
-    def _safe_mask(self, candidates: List[np.ndarray]) -> np.ndarray:
-        """safe[k] for every candidate, one launch per dtype group (float32 / float64)."""
-        n = len(candidates)
+    def _safe_mask(self, marches: List[np.ndarray]) -> np.ndarray:
+        """safe[k] for every candidate of the given marches ([K,3] arrays), one launch per dtype group
+        (float32 / float64: the reference's positions drift between the two, and the grid rule differs)."""
+        n = sum(len(m) for m in marches)
         safe = np.ones(n, dtype=bool)
         det = self.collision_detector
         if det is None or n == 0:
             return safe
         try:
-            groups = {}
-            for k, c in enumerate(candidates):
-                groups.setdefault(np.asarray(c).dtype == np.float32, []).append(k)
-            for is32, idx in groups.items():
-                arr = np.stack([np.asarray(candidates[k]) for k in idx])
-                arr = arr.astype(np.float32) if is32 else arr.astype(np.float64)
-                safe[idx] = ~det.check_many(arr)
+            if len(marches) == 1 or all(m.dtype == marches[0].dtype for m in marches):
+                arr = marches[0] if len(marches) == 1 else np.concatenate(marches)
+                safe[:] = ~det.check_many(arr if arr.dtype == np.float32 else arr.astype(np.float64))
+                self.collide_launches += 1
+                return safe
+            bounds = np.cumsum([0] + [len(m) for m in marches])
+            for is32 in (True, False):
+                sel = [k for k, m in enumerate(marches) if (m.dtype == np.float32) == is32]
+                if not sel:
+                    continue
+                arr = np.concatenate([marches[k] for k in sel])
+                res = ~det.check_many(arr if is32 else arr.astype(np.float64))
+                o = 0
+                for k in sel:
+                    safe[bounds[k]:bounds[k + 1]] = res[o:o + len(marches[k])]
+                    o += len(marches[k])
                 self.collide_launches += 1
         except Exception:
             safe[:] = False
@@ -550,19 +557,26 @@ class SimpleVLNEnv:
 
     @staticmethod
     def _march(start_pos: np.ndarray, direction: np.ndarray, max_distance: float, step_size: float):
-        """Candidate positions and cumulative step lengths of a march (same arithmetic as
-        _try_direct_movement / _try_short_movement)."""
+        """Candidate positions [K,3] and cumulative step lengths of a march: the arithmetic of
+        _try_direct_movement / _try_short_movement (``next = current + direction * step`` sample after
+        sample, simple_env.py:2150-2234) as one sequential accumulate in the dtypes NumPy gives those
+        expressions, so every sample has the reference's bits."""
         total_moved = 0.0
-        current_pos = start_pos.copy()
-        cands, moved = [], []
+        steps, moved = [], []
         while total_moved < max_distance:
             step_distance = min(step_size, max_distance - total_moved)
-            next_pos = current_pos + direction * step_distance
-            cands.append(next_pos)
-            current_pos = next_pos
+            steps.append(step_distance)
             total_moved += step_distance
             moved.append(total_moved)
-        return cands, moved
+        if not steps:
+            return np.zeros((0, 3), np.result_type(start_pos.dtype, direction.dtype)), moved
+        # direction * python_float keeps direction's dtype (the scalar is rounded to it first)
+        delta = direction[None, :] * np.asarray(steps, dtype=direction.dtype)[:, None]
+        out_dt = np.result_type(start_pos.dtype, direction.dtype)
+        seq = np.empty((len(steps) + 1, 3), out_dt)
+        seq[0] = start_pos
+        seq[1:] = delta
+        return np.add.accumulate(seq, axis=0)[1:], moved
 
     def apply_cmd_for(self, vx: float, vy: float, yaw_rate: float, duration_s: float) -> None:
         t_apply = time.perf_counter()
@@ -602,7 +616,7 @@ class SimpleVLNEnv:
 
         # --- direct march: <= 20 samples, one launch ---
         cands, _ = self._march(current_pos, unit_direction, max_distance, 0.01)
-        safe = self._safe_mask(cands)
+        safe = self._safe_mask([cands])
         n_ok = int(np.argmin(safe)) if not safe.all() else len(cands)
         reached = cands[n_ok - 1] if n_ok > 0 else current_pos
         if n_ok > 0:
@@ -622,8 +636,7 @@ class SimpleVLNEnv:
             dn = np.linalg.norm(d[:2])
             if dn > 0.001:
                 marches.append(self._march(current_pos, d / dn, 0.05, 0.005))
-        flat = [c for cands_d, _ in marches for c in cands_d]
-        safe = self._safe_mask(flat)
+        safe = self._safe_mask([cands_d for cands_d, _ in marches])
         best_movement, best_pos, k0 = 0.0, current_pos.copy(), 0
         for cands_d, moved_d in marches:
             s = safe[k0:k0 + len(cands_d)]

@@ -185,3 +185,77 @@ def test_inplace_mutators_and_stock_image_behaviour(hook):
     im = Image.fromarray(fr)
     b = io.BytesIO(); im.copy().save(b, format="JPEG")
     assert b.getvalue() == marker
+
+
+def test_rgba_root_frame_fast_rgb_copy_and_private_twin(hook):
+    """Camera.get_rgba() frames: frame[:, :, :3].copy() (generate_images.py:431) takes the packed-conversion
+    path, is an ordinary writable array with the same bytes NumPy's strided copy gives, and the hook uses the
+    engine's private twin as the image's pixels (no copy) only while the caller's pixels equal it."""
+    handoff, h0 = hook
+    rng = np.random.default_rng(7)
+    pristine = rng.integers(0, 256, (48, 64, 3), dtype=np.uint8)
+    twin = pristine.copy().view(handoff.PrivateTwin)
+    marker = b"\xff\xd8SAGE-RGBA\xff\xd9"
+    rgba = np.concatenate([pristine, np.full((48, 64, 1), 255, np.uint8)], 2)
+    fr = handoff.DeviceFrame(rgba, marker, twin, lambda: True, rgba_root=True)
+    rgb = fr[:, :, :3].copy()
+    assert rgb.shape == (48, 64, 3) and rgb.flags.c_contiguous and rgb.flags.writeable
+    assert np.array_equal(np.asarray(rgb), pristine)
+    im = Image.fromarray(rgb)
+    b = io.BytesIO(); im.save(b, format="JPEG")
+    assert b.getvalue() == marker and handoff.hook_stats()["hits"] == h0["hits"] + 1
+    assert im._sage_arr is twin                                    # zero-copy: the twin is the pixel store
+    rgb[0, 0, 0] ^= 1                                              # the caller's array is its own: the image is unaffected
+    assert np.array_equal(np.asarray(im), pristine)
+    # other slices / orders / a caller that drew on the RGBA frame first: plain NumPy semantics, Pillow encodes
+    assert np.array_equal(np.asarray(fr[:, :, 1:4].copy()), rgba[:, :, 1:4])
+    assert np.array_equal(np.asarray(fr[::2, :, :3].copy()), rgba[::2, :, :3])
+    assert fr[:, :, :3].copy(order="F").flags.f_contiguous
+    fr[5, 5, 0] ^= 0x40
+    drawn = fr[:, :, :3].copy()
+    assert np.array_equal(np.asarray(drawn), np.asarray(fr)[:, :, :3])
+    b = io.BytesIO(); Image.fromarray(drawn).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(np.asarray(drawn)) and b.getvalue() != marker
+    # an RGBA frame without a JPEG (hand-off off) still gets the fast copy, and plain Pillow
+    plain = handoff.DeviceFrame(np.concatenate([pristine, np.full((48, 64, 1), 255, np.uint8)], 2), None, None, lambda: True, rgba_root=True)
+    c = plain[:, :, :3].copy()
+    assert np.array_equal(np.asarray(c), pristine)
+    b = io.BytesIO(); Image.fromarray(c).save(b, format="JPEG")
+    assert b.getvalue() == _pillow(pristine)
+
+
+def test_cv2_hook_returns_device_png_only_for_identical_uint16_pixels(sage):
+    """vlm_client_modular.py:354-364 verbatim on a DeviceDepth: the metadata survives np.clip / * / astype, and
+    cv2.imencode('.png', ...) hands back the precoded file only while the pixels equal the encoded image."""
+    cv2 = pytest.importorskip("cv2")
+    from sage3d_official_b200 import handoff
+    rng = np.random.default_rng(3)
+    depth = np.clip(rng.uniform(0, 9, size=(48, 64)).astype(np.float32), 0.1, 6.5)
+    pixels = (np.clip(depth, 0.0, 6.5) * 10000.0).astype(np.uint16)
+    marker = b"\x89PNG-SAGE-PRECODED"
+    live = [True]
+    handoff.install_cv2_hook()
+    try:
+        h0 = handoff.cv2_hook_stats()["hits"]
+        depth_image = handoff.DeviceDepth(depth.copy(), marker, pixels, lambda: live[0])
+        depth_array_clamped = np.clip(depth_image, 0.0, 6.5)
+        depth_array_encoded = (depth_array_clamped * 10000.0).astype(np.uint16)
+        ok, buf = cv2.imencode('.png', depth_array_encoded)
+        assert ok and buf.tobytes() == marker and handoff.cv2_hook_stats()["hits"] == h0 + 1
+        # a different scale, a touched pixel, an encoder option, a stale frame, another format: OpenCV encodes
+        for arr, params in (((depth_array_clamped * 1000.0).astype(np.uint16), None),
+                            (depth_array_encoded + np.uint16(1), None),
+                            (depth_array_encoded, [cv2.IMWRITE_PNG_COMPRESSION, 9])):
+            ok, buf = cv2.imencode('.png', arr) if params is None else cv2.imencode('.png', arr, params)
+            assert ok and buf.tobytes() != marker
+            assert np.array_equal(cv2.imdecode(buf, cv2.IMREAD_UNCHANGED), np.asarray(arr))
+        live[0] = False
+        ok, buf = cv2.imencode('.png', depth_array_encoded)
+        assert buf.tobytes() != marker
+        live[0] = True
+        ok, buf = cv2.imencode('.jpg', np.zeros((8, 8, 3), np.uint8))
+        assert ok and buf.tobytes()[:2] == b"\xff\xd8"
+        assert handoff.cv2_hook_stats()["hits"] == h0 + 1
+    finally:
+        handoff.uninstall_cv2_hook()
+    assert not getattr(cv2.imencode, "_sage_hook", False)

@@ -43,6 +43,17 @@ def jpeg_emu(tmp_path_factory):
 
 
 @pytest.fixture(scope="module")
+def png_emu(tmp_path_factory):
+    L = _build("png_emu", tmp_path_factory)
+    vp, f32 = C.c_void_p, C.c_float
+    L.sage_png_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.sage_png_max_bytes.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.sage_depth_png_encode_host.argtypes = [vp, vp, f32, f32, f32, vp, C.c_int64, C.POINTER(C.c_int64), vp, vp]
+    L.sage_png_destroy.argtypes = [vp]
+    return L
+
+
+@pytest.fixture(scope="module")
 def plan_emu(tmp_path_factory):
     L = _build("plan_emu", tmp_path_factory)
     vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -76,6 +87,42 @@ def test_jpeg_kernels_emulated_match_pillow_and_oracle(jpeg_emu, oracle):
             b = io.BytesIO()
             Image.fromarray(fr[f]).save(b, format="JPEG", quality=q)
             assert got == b.getvalue() == oracle.jpeg_encode(fr[f], q), (H, W, q, f)
+
+
+def test_png_kernels_emulated_match_oracle_stream(png_emu, oracle):
+    """csrc/png.cu (quantise + Sub filter + in-group run tokens + fixed-Huffman bit packing + Adler-32 + chunk
+    CRC folding) under the emulator: the file equals the oracle's restatement byte for byte and Pillow decodes it
+    (verifying every checksum) to the reference client's uint16 pixels (vlm_client_modular.py:354-355)."""
+    from PIL import Image
+    rng = np.random.default_rng(11)
+    cases = [rng.uniform(-1, 8, size=(9, 21)).astype(np.float32),
+             np.full((6, 40), 6.5, np.float32),
+             np.array([[0.5]], np.float32),
+             np.clip(rng.uniform(0, 9, size=(20, 17000 // 20)).astype(np.float32), 0.1, 6.5)]     # > one 32 KB IDAT chunk
+    z = np.zeros((5, 64), np.float32)
+    z[:, 14:18] = 3.0
+    cases.append(z)
+    for depth in cases:
+        H, W = depth.shape
+        h = C.c_void_p()
+        assert png_emu.sage_png_create(C.byref(h), 0, W, H, 1) == 0, png_emu.sage_last_error()
+        cap = C.c_int64(0)
+        png_emu.sage_png_max_bytes(h, C.byref(cap))
+        out = np.zeros(cap.value, np.uint8)
+        twin = np.zeros((H, W), np.uint16)
+        n = C.c_int64(0)
+        d = np.ascontiguousarray(depth)
+        rc = png_emu.sage_depth_png_encode_host(h, d.ctypes.data, 0.0, 6.5, 10000.0, out.ctypes.data, cap.value, C.byref(n),
+                                                twin.ctypes.data, None)
+        png_emu.sage_png_destroy(h)
+        assert rc == 0, png_emu.sage_last_error()
+        got = out[:n.value].tobytes()
+        want = (np.clip(depth, 0.0, 6.5) * 10000.0).astype(np.uint16)
+        assert np.array_equal(twin, want)
+        assert got == oracle.depth_png_encode(depth), depth.shape
+        im = Image.open(io.BytesIO(got))
+        im.load()
+        assert np.array_equal(np.asarray(im).astype(np.uint16), want)
 
 
 def test_plan_kernels_emulated_match_reference_goldens(plan_emu, oracle):

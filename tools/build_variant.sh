@@ -8,7 +8,7 @@ CSRC="$HERE/../sage-3d_official_b200/csrc"
 OBJ=/tmp/sage_variant_$TAG
 mkdir -p "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O2 $*"
-for f in api scene_api frame project sort bin composite collide jpeg plan; do
+for f in api scene_api frame project sort bin composite collide jpeg png plan; do
     nvcc $FLAGS -c "$CSRC/$f.cu" -o "$OBJ/$f.o" &
 done
 wait

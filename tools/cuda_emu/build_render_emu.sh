@@ -8,7 +8,7 @@ OUT=${1:-/tmp/emu/librender_emu.so}
 DIR=$(dirname "$OUT")
 mkdir -p "$DIR"
 FLAGS="-std=c++20 -O1 -DSAGE_CUDA_EMU -fPIC -pthread -w -ffp-contract=off -fno-fast-math -mfma"
-for f in project sort bin composite frame scene_api jpeg; do
+for f in project sort bin composite frame scene_api jpeg png; do
     g++ $FLAGS -x c++ -c "$CSRC/$f.cu" -o "$DIR/emu_$f.o" &
 done
 g++ $FLAGS -c "$HERE/render_emu.cpp" -o "$DIR/emu_main.o" &

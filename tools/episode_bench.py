@@ -34,16 +34,22 @@ def main():
                          "(run_benchmark.py:1421 + vlm_client_modular.py:445-455): Image.fromarray(rgb), 8-frame "
                          "history, convert('RGB') + JPEG + base64 of every history frame")
     ap.add_argument("--jpeg-handoff", action="store_true", help="device-side JPEG + Pillow hook (handoff.py)")
+    ap.add_argument("--stage-timing", action="store_true", help="per-stage device times (serialises the frame: slower)")
     args = ap.parse_args()
     import sage3d_official_b200 as sage
     from sage3d_official_b200.simple_env import SimpleVLNEnv
     from sage3d_official_b200.scenes import write_semantic_map, collision_ellipsoids, layout_semantic_map
     from sage3d_official_b200.scene_io import morton_order
 
+    from sage3d_official_b200.scenes import to_trajectory_frame
+    from sage3d_official_b200.collision_detector import build_obstacle_grid
     cloud, layout = sage.synthetic_interior(1, args.n)
     cloud = cloud.subset(morton_order(cloud.xyz))
     tmp = Path(tempfile.mkdtemp())
     map_path = write_semantic_map(layout, tmp / "map.json")
+    # the stage (and the agent) live in the trajectory frame; the generator's layout is in map coordinates
+    _, bounds = build_obstacle_grid(json.loads(Path(map_path).read_text()), 0.08, 0.05)
+    cloud.xyz[:] = to_trajectory_frame(cloud.xyz, bounds)
     env = SimpleVLNEnv(str(tmp / "scene_in_memory.npz"), resolution=(args.width, args.height),
                        map_json_path=str(map_path), gaussians=cloud, jpeg_handoff=args.jpeg_handoff)
     history, t_client, payload = [], 0.0, 0
@@ -51,7 +57,7 @@ def main():
     bodies = None
     if args.capsule:
         mu, ls, q = collision_ellipsoids(layout, per_m2=400.0)
-        bodies = sage.CollisionBodies(mu, ls, q)
+        bodies = sage.CollisionBodies(to_trajectory_frame(mu, bounds), ls, q)
     # start pose: free space, trajectory-frame coordinates (x3 = x2 - (min+max), trajectory_2d_to_3d.py:56-63)
     det = env.collision_detector
     p0, h0 = sage.camera_path(layout, 1, seed=3)[0]
@@ -63,7 +69,8 @@ def main():
     moved = 0
     frame_ms, inst = [], []
     env.get_rgb()                                                   # warm-up frame
-    env._scene.set_stage_timing(1)
+    if args.stage_timing:
+        env._scene.set_stage_timing(1)      # serialises the frame's stages on one stream: slower frames
     stage_acc = {k: 0.0 for k in env._scene.STAGES}
     t0 = time.perf_counter()
     timed = 0
@@ -75,7 +82,7 @@ def main():
         b = time.perf_counter()
         frame_ms.append(1000 * (b - a))
         inst.append(env._scene.stats()["n_instances_wanted"])
-        if env.render_calls > calls0:
+        if env.render_calls > calls0 and args.stage_timing:
             timed += 1
             for k_, v_ in env._scene.stage_times(0).items():
                 stage_acc[k_] += v_
@@ -130,7 +137,8 @@ def main():
         "python_other_ms": 1000 * (total - t_render - t_collide - t_capsule - t_client) / args.steps,
         "render_ms_p50_p90_max": [float(np.percentile(frame_ms, 50)), float(np.percentile(frame_ms, 90)), float(np.max(frame_ms))],
         "instances_p50_p90_max": [int(np.percentile(inst, 50)), int(np.percentile(inst, 90)), int(np.max(inst))],
-        "stage_ms_mean": {k_: v_ / max(timed, 1) for k_, v_ in stage_acc.items()},
+        "stage_ms_mean": {k_: v_ / max(timed, 1) for k_, v_ in stage_acc.items()} if args.stage_timing else None,
+        "depth_mean_m": float(depth.mean()),
         "engine_frames": env.render_calls, "collide_launches": env.collide_launches, "steps_that_moved": moved,
         "frame_shape": list(rgb.shape), "depth_range": [float(depth.min()), float(depth.max())],
     }

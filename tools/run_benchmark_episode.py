@@ -47,13 +47,16 @@ def write_assets(tmp: Path, n: int, seed: int = 1, n_points: int = 6):
     from sage3d_official_b200.scene_io import morton_order, save_npz
     from sage3d_official_b200.scenes import write_semantic_map
     from sage3d_official_b200.collision_detector import build_obstacle_grid
+    from sage3d_official_b200.scenes import to_trajectory_frame
     cloud, layout = sage.synthetic_interior(seed, n)
     cloud = cloud.subset(morton_order(cloud.xyz))
-    save_npz(tmp / "scene_0001.npz", cloud)
     map_path = write_semantic_map(layout, tmp / "map.json")
     inst = json.loads(Path(map_path).read_text())
     _, (min_x, max_x, min_y, max_y) = build_obstacle_grid(inst, 0.08, 0.05)
     sx, sy = min_x + max_x, min_y + max_y
+    # the stage (and the agent) live in the trajectory frame; the generator's layout is in map coordinates
+    cloud.xyz[:] = to_trajectory_frame(cloud.xyz, (min_x, max_x, min_y, max_y))
+    save_npz(tmp / "scene_0001.npz", cloud)
     # trajectory frame: x3 = x2 - (min+max) (trajectory_2d_to_3d.py:56-63); rotation [-sin(psi'/2),0,0,cos(psi'/2)]
     path = sage.camera_path(layout, n_points, seed=3)
     pts = []
