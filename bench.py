@@ -436,7 +436,7 @@ def run_native(args):
                 scene.render(cam, out=(rgb[b], dep[b]))
             else:
                 scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
-                peers.close_frame()      # device-side: every rank's strips have landed everywhere
+                peers.close_frame(b)     # device-side: every rank's strips have landed everywhere
 
     def sync_all():
         torch.cuda.synchronize()
@@ -490,7 +490,7 @@ def run_native(args):
         sync_all()
         with torch.cuda.stream(streams[0]):
             scene.render_peers(cam, rows, peers.rgb[0], peers.depth[0])
-            peers.close_frame()
+            peers.close_frame(0)
         sync_all()
         ref_rgb, ref_dep = scene.render(cam)
         torch.cuda.synchronize()

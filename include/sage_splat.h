@@ -159,6 +159,14 @@ int sage_project(sage_scene* s, const sage_camera* cam, int row0_tiles, int row1
 int sage_ipc_export(void* dev_ptr, uint8_t handle_out[64], uint64_t* offset_out);
 int sage_ipc_open(const uint8_t handle[64], uint64_t offset, void** dev_ptr_out);
 int sage_ipc_close(void* dev_ptr, uint64_t offset);
+/* Device-side frame barrier between the ranks of one node, enqueued on `stream`: flag_peers[r] is rank
+ * r's flag row (uint32 [n_peers], device memory, mapped with sage_ipc_open; flag_peers[my_rank] is this
+ * rank's own).  After the stream's earlier work (the peer stores of sage_render_peers) it publishes
+ * `value` to every peer and waits until every peer has published `value` (or later) here: the frame
+ * is then complete in every rank's buffers.  Replaces a per-frame NCCL all-reduce;
+ * `value` must increase from call to call on the same rows. */
+int sage_peer_barrier(uint32_t* const* flag_peers, int n_peers, int my_rank, uint32_t value,
+                      sage_stream_t stream);
 
 /* ---- 2-D grid collide -------------------------------------------------------------------
  * Obstacle grid of SemanticMap2DCollisionDetector (collision_detector.py:95-132), uploaded once.

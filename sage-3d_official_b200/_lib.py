@@ -20,7 +20,7 @@ EXPORTS = [
     "sage_scene_set_rgba", "sage_scene_set_graph", "sage_scene_graph_stats",
     "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_pipeline_depth", "sage_render_peers", "sage_frame_stats_get", "sage_project",
     "sage_frame_row_instances", "sage_set_stage_timing", "sage_stage_times_get",
-    "sage_ipc_export", "sage_ipc_open", "sage_ipc_close",
+    "sage_ipc_export", "sage_ipc_open", "sage_ipc_close", "sage_peer_barrier",
     "sage_grid_create", "sage_grid_destroy", "sage_collide_grid", "sage_collide_grid_f64",
     "sage_collide_grid_dev",
     "sage_bodies_create", "sage_bodies_destroy", "sage_collide_capsule",
@@ -100,6 +100,7 @@ def lib():
     L.sage_ipc_export.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.sage_ipc_open.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.sage_ipc_close.argtypes = [vp, C.c_uint64]
+    L.sage_peer_barrier.argtypes = [vp, i32, i32, C.c_uint32, vp]
     dbl = C.c_double
     L.sage_grid_create.argtypes = [C.POINTER(vp), i32, vp, i32, i32, dbl, dbl, dbl, dbl, dbl]
     L.sage_grid_destroy.argtypes = [vp]

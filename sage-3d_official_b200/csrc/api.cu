@@ -89,6 +89,49 @@ int sage_ipc_close(void* dev_ptr, uint64_t offset)
     return 0;
 }
 
+// ---- device-side frame barrier between the ranks of a node (flags in peer memory) ----------------
+// flag_peers[r] -> rank r's flag row (n_peers words, one per writer), mapped here with sage_ipc_open.
+// One thread per peer: publish `value` in the peer's row (slot = this rank) with a system-scope release
+// after this stream's earlier work (the composite's peer stores) has completed, then wait until this
+// rank's own row shows `value` from that peer.  No rank waits on anything but the other ranks reaching
+// the same point of their own streams; a peer that never arrives traps after 20 s instead of hanging.
+struct SagePeerFlags {
+    uint32_t* row[SAGE_MAX_PEERS];
+};
+
+static __global__ void __launch_bounds__(32) k_peer_barrier(SagePeerFlags f, int n, int me, uint32_t value)
+{
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.row[r] + me), "r"(value) : "memory");
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.row[me] + r) : "memory");
+        if ((int32_t)(v - value) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) __trap();
+        __nanosleep(200);
+    }
+}
+
+int sage_peer_barrier(uint32_t* const* flag_peers, int n_peers, int my_rank, uint32_t value, sage_stream_t stream)
+{
+    REQUIRE(flag_peers != nullptr && n_peers >= 1 && n_peers <= SAGE_MAX_PEERS, "sage_peer_barrier: n_peers must be in [1, 8]");
+    REQUIRE(my_rank >= 0 && my_rank < n_peers, "sage_peer_barrier: my_rank out of range");
+    SagePeerFlags f{};
+    for (int r = 0; r < n_peers; ++r) {
+        REQUIRE(flag_peers[r] != nullptr, "sage_peer_barrier: NULL flag row");
+        f.row[r] = flag_peers[r];
+    }
+    SAGE_KLAUNCH(k_peer_barrier, 1, 32, (cudaStream_t)stream, f, n_peers, my_rank, value);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ---- grid --------------------------------------------------------------------------------
 
 int sage_grid_create(sage_grid** out, int device, const uint8_t* map_host, int H, int W,

@@ -39,11 +39,6 @@ constexpr int C_CTAS_PER_SM = SAGE_COMPOSITE_CTAS;
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
-// Loop-invariant values the entry loop wants in REGISTERS (see k_composite): kept in global memory
-// so that ptxas cannot fold them back into immediates or re-materialise them per iteration.
-__device__ float g_loop_consts[2] = {0x1.c3f760p-5f, -1.0f};    // exp2 leading coefficient, -1
-__device__ int g_one_trip = 1;
-
 #ifdef SAGE_CUDA_EMU
 inline void cp_async16(void* dst_smem, const void* src) { memcpy(dst_smem, src, 16); }
 inline void cp_async_commit() {}
@@ -59,16 +54,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
-// packed deterministic degree-3 exp2 (mirrors so_exp2_fast); valid for x in [L255, L099].  The
-// polynomial's leading coefficient comes in a register (k3): an immediate there makes the compiler
-// re-materialise it with a move in every iteration.
-__device__ __forceinline__ float2 sage_exp2_fast_x2(float2 x, float k3)
+// packed deterministic degree-3 exp2 (mirrors so_exp2_fast); valid for x in [L255, L099]
+__device__ __forceinline__ float2 sage_exp2_fast_x2(float2 x)
 {
     const float magic = 12582912.0f;
     float2 t = __fadd2_rn(x, f2(magic));
     float2 n = __fadd2_rn(t, f2(-magic));
     float2 f = __ffma2_rn(n, f2(-1.0f), x);          // x - n, exact product => same rounding
-    float2 p = __ffma2_rn(f2(k3), f, f2(0x1.f0de1ap-3f));
+    float2 p = f2(0x1.c3f760p-5f);
+    p = __ffma2_rn(p, f, f2(0x1.f0de1ap-3f));
     p = __ffma2_rn(p, f, f2(0x1.62f31ap-1f));
     p = __ffma2_rn(p, f, f2(0x1.fff692p-1f));
     float2 r;
@@ -99,10 +93,6 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
     }
     const uint32_t n_nonempty = __shfl_sync(0xffffffffu, cls_incl, 31);
     const float NAN_X = __uint_as_float(0x7fc00000u);
-    // values the compiler must keep in registers instead of re-creating them inside the entry loop
-    const float k3 = *(const volatile float*)&g_loop_consts[0];
-    const float neg1 = *(const volatile float*)&g_loop_consts[1];
-    const int one_trip = *(const volatile int*)&g_one_trip;
 
     // Not persistent on purpose: as CTAs retire, the SM's registers and shared memory go to the
     // (higher-priority) front-half kernels of the next frame instead of staying pinned to this kernel.
@@ -161,48 +151,42 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             cp_async_wait<1>();
             __syncwarp();
             const float4* s_rec = srec[w][st];
-            const float4* e = s_rec;
-            const float4* const e_end = s_rec + 3 * cnt;
 #pragma unroll 2
-            for (; e != e_end; e += 3) {
-                const float4 a = e[0];                                                // gx gy qa lo
-                const float2 bq = *reinterpret_cast<const float2*>(&e[1]);            // qb qc
+            for (int j = 0; j < cnt; ++j) {
+                const float4 a = s_rec[3 * j];                                        // gx gy qa lo
+                const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1]);   // qb qc
                 const float dy = pyc - a.y;
                 const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
                 const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
                 const float2 dx = __fadd2_rn(pxc, f2(-a.x));
                 const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
                 float2 pw = __ffma2_rn(dx, wv, f2(c2));                               // log2(alpha)
-                const bool v0 = pw.x >= SAGE_L255;                                    // false for NaN (finished pixels)
-                if (!(v0 || pw.y >= SAGE_L255)) continue;
-                const bool v1 = pw.y >= SAGE_L255;
+                const bool v0 = pw.x >= SAGE_L255, v1 = pw.y >= SAGE_L255;            // false for NaN (finished pixels)
+                if (!(v0 || v1)) continue;
                 pw.x = fminf(pw.x, SAGE_L099);
                 pw.y = fminf(pw.y, SAGE_L099);
-                float2 al = sage_exp2_fast_x2(pw, k3);
+                float2 al = sage_exp2_fast_x2(pw);
                 al.x = v0 ? al.x : 0.0f;                  // alpha 0: T, C, Dz stay bit-identical
                 al.y = v1 ? al.y : 0.0f;
-                const float2 om = __ffma2_rn(al, f2(neg1), f2(1.0f));                 // 1 - alpha
+                const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));                // 1 - alpha
+                float2 Tn = __fmul2_rn(T, om);
                 float2 wgt = __fmul2_rn(al, T);
-                const float2 Tn = __fmul2_rn(T, om);
                 // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
-                // Once per pixel, against dozens of blended splats: a real (rarely taken) branch — the
-                // one-trip loop with an opaque bound keeps ptxas from if-converting the fix-up into eight
-                // predicated instructions that would issue for every splat.
+                // ptxas if-converts this block into eight predicated instructions that issue for every splat;
+                // forcing a real branch (opaque one-trip loop) and pinning the loop constants in registers was
+                // measured (profiles/r02_variants.md): 3 fewer instructions per splat, but 2 % SLOWER
+                // (0.2146 vs 0.2098 ms: the extra BSSY/BSYNC pair and 8 more registers) - left as is.
                 if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
-#pragma unroll 1
-                    for (int once = 0; once < one_trip; ++once) {
-                        const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
-                        wgt.x = s0 ? 0.0f : wgt.x;
-                        wgt.y = s1 ? 0.0f : wgt.y;
-                        T.x = s0 ? T.x : Tn.x;
-                        T.y = s1 ? T.y : Tn.y;
-                        pxc.x = s0 ? NAN_X : pxc.x;
-                        pxc.y = s1 ? NAN_X : pxc.y;
-                    }
-                } else {
-                    T = Tn;
+                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                    wgt.x = s0 ? 0.0f : wgt.x;
+                    wgt.y = s1 ? 0.0f : wgt.y;
+                    Tn.x = s0 ? T.x : Tn.x;
+                    Tn.y = s1 ? T.y : Tn.y;
+                    pxc.x = s0 ? NAN_X : pxc.x;
+                    pxc.y = s1 ? NAN_X : pxc.y;
                 }
-                const float4 c = e[2];                                                // r g b z
+                T = Tn;
+                const float4 c = s_rec[3 * j + 2];                                    // r g b z
                 Cr = __ffma2_rn(f2(c.x), wgt, Cr);
                 Cg = __ffma2_rn(f2(c.y), wgt, Cg);
                 Cb = __ffma2_rn(f2(c.z), wgt, Cb);

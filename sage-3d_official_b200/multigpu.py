@@ -14,6 +14,7 @@ Two exchange paths:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import List, Sequence, Tuple
 
@@ -100,7 +101,11 @@ class PeerFrames:
             check(L.sage_ipc_export(C.c_void_p(t.data_ptr()), C.cast(h, C.c_void_p), C.byref(off)))
             return bytes(h), int(off.value)
 
-        mine = {"rgb": [export(t) for t in rgb_buffers], "depth": [export(t) for t in depth_buffers]}
+        # one row of frame counters per buffer slot: flags[b][r] = last frame rank r completed into slot b
+        self._flags = torch.zeros((len(rgb_buffers), 8), dtype=torch.int32, device=rgb_buffers[0].device)
+        self._seq = [0] * len(rgb_buffers)
+        mine = {"rgb": [export(t) for t in rgb_buffers], "depth": [export(t) for t in depth_buffers],
+                "flags": [export(self._flags[b]) for b in range(len(rgb_buffers))]}
         everyone = [None] * world
         dist.all_gather_object(everyone, mine)
         torch.cuda.synchronize()
@@ -124,14 +129,25 @@ class PeerFrames:
 
         self.rgb = open_all("rgb", rgb_buffers)
         self.depth = open_all("depth", depth_buffers)
+        self.flags = open_all("flags", [self._flags[b] for b in range(len(rgb_buffers))])
         self._flag = torch.zeros(1, dtype=torch.int32, device=rgb_buffers[0].device)
+        self.use_nccl = os.environ.get("SAGE_PEER_BARRIER", "flags") == "nccl"
         dist.barrier()
 
-    def close_frame(self):
-        """Device-side frame barrier on the current stream: once it has run on every rank, all
-        ranks' strips have landed in all frame buffers."""
-        import torch.distributed as dist
-        dist.all_reduce(self._flag)
+    def close_frame(self, b: int = 0):
+        """Device-side frame barrier on the current stream for buffer slot ``b``: once it has run on every
+        rank, all ranks' strips have landed in all copies of the slot.  Counters in peer memory
+        (``sage_peer_barrier``: one 32-thread kernel, no collective); ``SAGE_PEER_BARRIER=nccl`` switches back
+        to the one-element NCCL all-reduce for comparison."""
+        if self.use_nccl:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag)
+            return
+        import torch
+        self._seq[b] += 1
+        rows = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in self.flags[b]])
+        check(_lib.lib().sage_peer_barrier(rows, self.world, self.rank, self._seq[b],
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
     def close(self):
         L = _lib.lib()

@@ -62,16 +62,29 @@ def connectivity_labels(grid, device: int = 0) -> np.ndarray:
 class GridPlanner:
     """Batched A* on one grid (handle of ``sage_planner``): ``slots`` searches run side by side."""
 
+    #: device memory the search slots may take (each slot: g f64 + came_from i32 per cell, 16 B per heap entry)
+    MEMORY_BUDGET = 4 << 30
+
     def __init__(self, grid, slots: int = 4096, max_path: int = 0, heap_capacity: int = 0, device: int = 0):
         _lib.require_gpu()
         self.grid = _u8(grid)
         self.H, self.W = self.grid.shape
-        self.slots, self.device = int(slots), int(device)
+        self.max_slots, self.device = int(slots), int(device)
+        self.slots = self.max_slots
         self._h = C.c_void_p()
         self._make(int(max_path), int(heap_capacity))
 
+    def _fit_slots(self, heap_capacity: int) -> int:
+        """As many side-by-side searches as the memory budget holds (a 600 x 600 map at 4096 slots would be
+        ~30 GB; after a capacity retry the heaps are 4x larger and the slot count shrinks accordingly)."""
+        cells = self.H * self.W
+        heap = heap_capacity if heap_capacity > 0 else cells // 2 + 1024          # sage_planner_create's default
+        per_slot = 12 * cells + 16 * heap
+        return int(max(1, min(self.max_slots, self.MEMORY_BUDGET // max(per_slot, 1))))
+
     def _make(self, max_path: int, heap_capacity: int):
         self.close()
+        self.slots = self._fit_slots(heap_capacity)
         h = C.c_void_p()
         check(_lib.lib().sage_planner_create(C.byref(h), self.device, self.grid.ctypes.data, self.H, self.W,
                                              self.slots, max_path, heap_capacity))

@@ -85,9 +85,14 @@ def _gpu_worker(rank, world, port, q):
     dep = [torch.zeros_like(ref_dep)]
     peers = PeerFrames(rgb, dep, rank, world)
     scene.render_peers(cam, rows_of(rank, cam.height, world), peers.rgb[0], peers.depth[0])
+    peers.close_frame(0)            # flags in peer memory: returns once BOTH ranks' strips are in this buffer
     torch.cuda.synchronize()
-    dist.barrier()
     ok = bool(torch.equal(rgb[0], ref_rgb)) and bool(torch.equal(dep[0], ref_dep))
+    # a second frame through the same slot: the counter moves on
+    scene.render_peers(cam, rows_of(rank, cam.height, world), peers.rgb[0], peers.depth[0])
+    peers.close_frame(0)
+    torch.cuda.synchronize()
+    ok = ok and int(peers._flags[0, :world].min().item()) == 2
     dist.barrier()
     peers.close()
     q.put((rank, ok))
@@ -213,7 +218,7 @@ def _two_gpu_worker(rank, world, port, q):
     for i, cam in enumerate(cams):
         b = i % 2
         scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
-        peers.close_frame()
+        peers.close_frame(b)
         torch.cuda.synchronize()
         dist.barrier()
         ref_rgb, ref_dep = scene.render(cam)
