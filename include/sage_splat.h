@@ -100,6 +100,10 @@ int sage_render_host(sage_scene* s, const sage_camera* cam, int row0_tiles, int 
 
 /* Number of frame contexts of a scene = frames that can be in flight at once (3). */
 int sage_pipeline_depth(void);
+/* Frame contexts (frames in flight) of scenes created from now on: 1..8, default 3 (or the
+ * SAGE_PIPELINE_DEPTH environment variable).  The ranks of a tile-row split render a fraction of a
+ * frame per step and profit from a deeper pipeline (6); a context costs ~0.4 GB at 2 M Gaussians. */
+int sage_set_pipeline_depth(int depth);
 
 /* Pipelined host path: sage_pipeline_depth() frames can be in flight (slot 0 .. depth-1, each with
  * its own frame context and internal stream).  sage_render_host_async returns at once; sage_host_wait(slot) blocks until that

@@ -16,6 +16,6 @@ repository root).
 from ._lib import SageError, LIB_PATH, EXPORTS, build as build_library  # noqa: F401
 from .camera import Camera  # noqa: F401
 from .scenes import GaussianCloud, synthetic_room, synthetic_interior, camera_path  # noqa: F401
-from .api import GaussianScene, ObstacleGrid, CollisionBodies, JpegEncoder, DepthPngEncoder, render, collide  # noqa: F401
+from .api import GaussianScene, ObstacleGrid, CollisionBodies, JpegEncoder, DepthPngEncoder, render, collide, set_pipeline_depth  # noqa: F401
 
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ EXPORTS = [
     "sage_last_error", "sage_abi_version", "sage_device_count",
     "sage_scene_create", "sage_scene_reserve", "sage_scene_destroy", "sage_scene_set_depth_clip",
     "sage_scene_set_rgba", "sage_scene_set_graph", "sage_scene_graph_stats",
-    "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_pipeline_depth", "sage_render_peers", "sage_frame_stats_get", "sage_project",
+    "sage_render", "sage_render_host", "sage_render_host_async", "sage_host_wait", "sage_pipeline_depth", "sage_set_pipeline_depth", "sage_render_peers", "sage_frame_stats_get", "sage_project",
     "sage_frame_row_instances", "sage_set_stage_timing", "sage_stage_times_get",
     "sage_ipc_export", "sage_ipc_open", "sage_ipc_close", "sage_peer_barrier",
     "sage_grid_create", "sage_grid_destroy", "sage_collide_grid", "sage_collide_grid_f64",

@@ -573,6 +573,11 @@ class DepthPngEncoder:
         return (data, twin) if want_pixels else data
 
 
+def set_pipeline_depth(depth: int) -> None:
+    """Frame contexts (frames in flight) of scenes created from now on (1..8; default 3)."""
+    check(_lib.lib().sage_set_pipeline_depth(int(depth)))
+
+
 # ---- functional surface (north_star) ---------------------------------------------------------
 
 _scene_cache: dict = {}
@@ -609,4 +614,4 @@ def collide(agent_pose, collision, **kw):
     raise TypeError("collision must be an ObstacleGrid or CollisionBodies")
 
 
-__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "JpegEncoder", "DepthPngEncoder", "render", "collide", "SageError", "Camera"]
+__all__ = ["GaussianScene", "ObstacleGrid", "CollisionBodies", "JpegEncoder", "DepthPngEncoder", "set_pipeline_depth", "render", "collide", "SageError", "Camera"]

@@ -17,8 +17,22 @@
 #include "api_common.cuh"
 
 #ifndef SAGE_N_CTX
-#define SAGE_N_CTX 3      // measured (round 1): 1975 / 2077 / 2050 frames/s with 2 / 3 / 4 contexts in flight
+#define SAGE_N_CTX 8      // most frame contexts a scene can own
 #endif
+// Contexts a scene is created with (frames in flight).  One GPU rendering whole frames: 3 (measured, round 1:
+// 1975 / 2077 / 2050 frames/s with 2 / 3 / 4).  A rank of a tile-row split renders a fraction of a frame per
+// step: its kernels are smaller and more latency-bound, and deeper pipelining pays (4 GPUs: 5773 -> 6489
+// frames/s with 6); the multi-GPU callers raise it with sage_set_pipeline_depth / SAGE_PIPELINE_DEPTH.
+static int g_pipeline_depth = 0;
+static int pipeline_depth_now()
+{
+    if (g_pipeline_depth == 0) {
+        int d = 3;
+        if (const char* v = getenv("SAGE_PIPELINE_DEPTH")) d = atoi(v);
+        g_pipeline_depth = d < 1 ? 1 : (d > SAGE_N_CTX ? SAGE_N_CTX : d);
+    }
+    return g_pipeline_depth;
+}
 
 namespace {
 
@@ -75,6 +89,7 @@ struct sage_scene {
     int device = 0;
     SageSceneDev sc{};
     FrameCtx ctx[SAGE_N_CTX];
+    int n_ctx = 3;                   // contexts in use (pipeline depth at creation)
     uint32_t* n_dev = nullptr;       // device copy of n (element count of the first depth-sort pass)
     long frame_index = 0;
     int last_ctx = -1;
@@ -303,7 +318,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     if (make_cam(cam, row0, row1, &cd)) return 1;
     cd.depth_lo = s->depth_lo; cd.depth_hi = s->depth_hi;
     CK(cudaSetDevice(s->device));
-    if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
+    if (ci < 0) ci = (int)(s->frame_index % s->n_ctx);
     FrameCtx& c = s->ctx[ci];
     // the context's pinned parameter block and counters are reused: the frame that used them
     // SAGE_N_CTX frames ago must have drained (normally long done; bounds the host's run-ahead)
@@ -400,7 +415,8 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     uint32_t n32 = (uint32_t)n;
     CKB(cudaMemcpy(s->n_dev, &n32, sizeof n32, cudaMemcpyHostToDevice));
     const int64_t cap = max_instances > 0 ? max_instances : (8 * n > (1 << 24) ? 8 * n : (1 << 24));
-    for (int k = 0; k < SAGE_N_CTX; ++k)
+    s->n_ctx = pipeline_depth_now();
+    for (int k = 0; k < s->n_ctx; ++k)
         if (alloc_ctx(s, s->ctx[k], cap)) return bail(1);
 
     if (n > 0) {
@@ -432,7 +448,7 @@ int sage_scene_reserve(sage_scene* s, int64_t max_instances)
     REQUIRE(max_instances > 0 && max_instances < (int64_t)0xFFFFFFFF, "sage_scene_reserve: bad capacity");
     CK(cudaSetDevice(s->device));
     CK(cudaDeviceSynchronize());
-    for (int k = 0; k < SAGE_N_CTX; ++k) {
+    for (int k = 0; k < s->n_ctx; ++k) {
         drop_graphs(s->ctx[k]);
         if (alloc_instances(s, s->ctx[k], max_instances)) return 1;
     }
@@ -478,7 +494,7 @@ static int render_to_host(sage_scene* s, int ci, const sage_camera* cam, int row
     REQUIRE(s != nullptr, "sage_render_host: NULL scene");
     REQUIRE(cam != nullptr && rgb_host != nullptr, "sage_render_host: NULL camera or rgb buffer");
     CK(cudaSetDevice(s->device));
-    if (ci < 0) ci = (int)(s->frame_index % SAGE_N_CTX);
+    if (ci < 0) ci = (int)(s->frame_index % s->n_ctx);
     FrameCtx& c = s->ctx[ci];
     if (ensure_out(c, (size_t)cam->width * (size_t)cam->height)) return 1;
     uint8_t* rgbs[1] = {c.out_rgb};
@@ -511,16 +527,23 @@ int sage_render_host_async(sage_scene* s, const sage_camera* cam, int row0_tiles
                            uint8_t* rgb_host, float* depth_host, int slot)
 {
     REQUIRE(s != nullptr, "sage_render_host_async: NULL scene");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_host_async: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_render_host_async: slot must be in [0, sage_pipeline_depth())");
     return render_to_host(s, slot, cam, row0_tiles, row1_tiles, rgb_host, depth_host, s->ctx[slot].stream);
 }
 
-int sage_pipeline_depth(void) { return SAGE_N_CTX; }
+int sage_pipeline_depth(void) { return pipeline_depth_now(); }
+
+int sage_set_pipeline_depth(int depth)
+{
+    REQUIRE(depth >= 1 && depth <= SAGE_N_CTX, "sage_set_pipeline_depth: depth must be in [1, 8]");
+    g_pipeline_depth = depth;
+    return 0;
+}
 
 int sage_host_wait(sage_scene* s, int slot)
 {
     REQUIRE(s != nullptr, "sage_host_wait: NULL scene");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_host_wait: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_host_wait: slot must be in [0, sage_pipeline_depth())");
     CK(cudaSetDevice(s->device));
     CK(cudaStreamSynchronize(s->ctx[slot].stream));
     return 0;
@@ -548,7 +571,7 @@ int sage_render_jpeg_async2(sage_scene* s, const sage_camera* cam, sage_jpeg* j,
                             uint8_t* rgb_host, float* depth_host, uint8_t* rgb_twin_host)
 {
     REQUIRE(s != nullptr && cam != nullptr && j != nullptr, "sage_render_jpeg_async: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_async: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_render_jpeg_async: slot must be in [0, sage_pipeline_depth())");
     REQUIRE(sage_jpeg_device(j) == s->device, "sage_render_jpeg_async: encoder lives on another device");
     REQUIRE(sage_jpeg_width(j) == cam->width && sage_jpeg_height(j) == cam->height,
             "sage_render_jpeg_async: encoder resolution differs from the camera's");
@@ -597,7 +620,7 @@ int sage_render_jpeg_async2(sage_scene* s, const sage_camera* cam, sage_jpeg* j,
 int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_host, int64_t cap, int64_t* size_out)
 {
     REQUIRE(s != nullptr && j != nullptr && jpeg_host != nullptr && size_out != nullptr, "sage_render_jpeg_wait: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_render_jpeg_wait: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_render_jpeg_wait: slot must be in [0, sage_pipeline_depth())");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     CK(cudaStreamSynchronize(c.stream));
@@ -622,7 +645,7 @@ int sage_render_jpeg_wait(sage_scene* s, sage_jpeg* j, int slot, uint8_t* jpeg_h
 int sage_frame_depth_png_async(sage_scene* s, sage_png* p, int slot, float lo, float hi, float scale, uint16_t* twin_host)
 {
     REQUIRE(s != nullptr && p != nullptr, "sage_frame_depth_png_async: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_frame_depth_png_async: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_frame_depth_png_async: slot must be in [0, sage_pipeline_depth())");
     REQUIRE(sage_png_device(p) == s->device, "sage_frame_depth_png_async: encoder lives on another device");
     REQUIRE(sage_png_max_batch(p) > slot, "sage_frame_depth_png_async: encoder needs max_batch > slot (one scratch slot per frame in flight)");
     CK(cudaSetDevice(s->device));
@@ -646,7 +669,7 @@ int sage_frame_depth_png_async(sage_scene* s, sage_png* p, int slot, float lo, f
 int sage_frame_depth_png_wait(sage_scene* s, sage_png* p, int slot, uint8_t* png_host, int64_t cap, int64_t* size_out)
 {
     REQUIRE(s != nullptr && p != nullptr && png_host != nullptr && size_out != nullptr, "sage_frame_depth_png_wait: NULL argument");
-    REQUIRE(slot >= 0 && slot < SAGE_N_CTX, "sage_frame_depth_png_wait: slot must be in [0, sage_pipeline_depth())");
+    REQUIRE(slot >= 0 && slot < s->n_ctx, "sage_frame_depth_png_wait: slot must be in [0, sage_pipeline_depth())");
     CK(cudaSetDevice(s->device));
     FrameCtx& c = s->ctx[slot];
     CK(cudaStreamSynchronize(c.stream));
