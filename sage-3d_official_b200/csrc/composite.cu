@@ -74,7 +74,7 @@ __device__ __forceinline__ float2 sage_exp2_fast_x2(float2 x)
 __global__ void __launch_bounds__(C_THREADS, C_CTAS_PER_SM)
 k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 {
-    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3];   // per warp: two stages of 32 x 48-byte records
+    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3 + 3];   // per warp: two stages of 32 x 48-byte records (+ one of padding)
     const SageFrameParams* __restrict__ fp = fr.fp;
     const int W = fp->cam.W, H = fp->cam.H, bins_x = fp->cam.bins_x, bin_row0 = fp->cam.bin_row0;
     const int n_bins = fp->cam.n_bins;
@@ -151,6 +151,56 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             cp_async_wait<1>();
             __syncwarp();
             const float4* s_rec = srec[w][st];
+#ifdef SAGE_COMPOSITE_PIPELINED
+            // software-pipelined entry loop: the exponent of entry j+1 (two shared-memory loads and six
+            // flops, independent of the blend) is computed BEFORE entry j is blended, so a warp that runs
+            // alone on its scheduler (the tail of a single-wave launch at low resolution) overlaps the two
+            // dependency chains instead of walking them one after the other.  Reading one record past the
+            // last entry is harmless (the stages are padded; the value is never used).
+            auto exponent = [&](int j) -> float2 {
+                const float4 a = s_rec[3 * j];                                        // gx gy qa lo
+                const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1]);   // qb qc
+                const float dy = pyc - a.y;
+                const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
+                const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
+                const float2 dx = __fadd2_rn(pxc, f2(-a.x));
+                const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
+                return __ffma2_rn(dx, wv, f2(c2));                                    // log2(alpha)
+            };
+            float2 pwn = exponent(0);
+#pragma unroll 2
+            for (int j = 0; j < cnt; ++j) {
+                float2 pw = pwn;
+                pwn = exponent(j + 1);
+                const bool v0 = pw.x >= SAGE_L255, v1 = pw.y >= SAGE_L255;            // false for NaN (finished pixels)
+                if (!(v0 || v1)) continue;
+                pw.x = fminf(pw.x, SAGE_L099);
+                pw.y = fminf(pw.y, SAGE_L099);
+                float2 al = sage_exp2_fast_x2(pw);
+                al.x = v0 ? al.x : 0.0f;
+                al.y = v1 ? al.y : 0.0f;
+                const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
+                float2 Tn = __fmul2_rn(T, om);
+                float2 wgt = __fmul2_rn(al, T);
+                if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
+                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                    wgt.x = s0 ? 0.0f : wgt.x;
+                    wgt.y = s1 ? 0.0f : wgt.y;
+                    Tn.x = s0 ? T.x : Tn.x;
+                    Tn.y = s1 ? T.y : Tn.y;
+                    pxc.x = s0 ? NAN_X : pxc.x;
+                    pxc.y = s1 ? NAN_X : pxc.y;
+                    pwn.x = s0 ? NAN_X : pwn.x;           // the exponent already taken for the next entry saw the live pixel
+                    pwn.y = s1 ? NAN_X : pwn.y;
+                }
+                T = Tn;
+                const float4 c = s_rec[3 * j + 2];                                    // r g b z
+                Cr = __ffma2_rn(f2(c.x), wgt, Cr);
+                Cg = __ffma2_rn(f2(c.y), wgt, Cg);
+                Cb = __ffma2_rn(f2(c.z), wgt, Cb);
+                Dz = __ffma2_rn(f2(c.w), wgt, Dz);
+            }
+#else
 #pragma unroll 2
             for (int j = 0; j < cnt; ++j) {
                 const float4 a = s_rec[3 * j];                                        // gx gy qa lo
@@ -192,6 +242,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
                 Cb = __ffma2_rn(f2(c.z), wgt, Cb);
                 Dz = __ffma2_rn(f2(c.w), wgt, Dz);
             }
+#endif
             if (!__any_sync(0xffffffffu, SAGE_LIVE())) break;
             __syncwarp();                                  // stage st is free for the gather after next
         }

@@ -81,7 +81,10 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
         tp.keys[0] = fr.ikey[0]; tp.keys[1] = fr.ikey[1];
         tp.vals[0] = fr.ival[0]; tp.vals[1] = fr.ival[1];
         tp.n_first = tp.n_rest = fr.counters + CNT_INSTANCES;
-        tp.lo_bit = 0; tp.n_bits = 8 * shape.tile_passes; tp.digit_bits = 8; tp.passes = shape.tile_passes;
+        // digits just wide enough for the tile ids (1080p: 8160 tiles = 13 bits -> two passes of 7 bits, not 8:
+        // half the warp-private counters to clear and combine, one ballot fewer per item)
+        tp.lo_bit = 0; tp.passes = shape.tile_passes; tp.digit_bits = shape.tile_digit_bits;
+        tp.n_bits = tp.digit_bits * tp.passes;
         static const int tile_ipt = env_ipt("SAGE_TILE_IPT", 8);
         tp.vals_are_iota = false; tp.compact_first = false; tp.items_per_thread = tile_ipt;
         tp.H = fr.sort_h; tp.ld = fr.sort_ld; tp.totals = fr.sort_totals; tp.ranges = fr.ranges;

@@ -92,7 +92,8 @@ struct SageCamDev {
     int bins_x;            // 8 x 8 bins per image row
     int bin_row0, bin_row1;    // bin rows rendered by this call
     int n_bins;            // bins_x * (bin_row1 - bin_row0)
-    int tile_passes;       // radix passes of the by-bin sort (8 bits each)
+    int tile_passes;       // radix passes of the by-tile sort
+    int tile_digit_bits;   // their digit width: ceil(bits of the tile ids / passes), 5..8
 };
 
 // destination frame buffers of one render call (several: peer GPUs, NVLink)
@@ -371,7 +372,8 @@ void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int
 // line on `cs`.  Returns the number of kernel launches, or -1 for an unsupported sort shape.
 struct SageFrameShape {
     int depth_bits;      // significant bits of the depth keys
-    int tile_passes;     // 8-bit passes of the by-bin sort
+    int tile_passes;     // passes of the by-tile sort
+    int tile_digit_bits; // digit width of those passes (5..8)
 };
 int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFrameShape& shape,
                        const uint32_t* n_dev, cudaStream_t cs, cudaStream_t fs, cudaStream_t ss,

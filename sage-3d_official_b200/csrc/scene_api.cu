@@ -226,6 +226,9 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     while ((1 << tbits) < d->n_bins) ++tbits;
     d->tile_passes = (tbits + 7) / 8;
     REQUIRE(d->tile_passes <= 3, "sage_render: too many bins");
+    d->tile_digit_bits = (tbits + d->tile_passes - 1) / d->tile_passes;
+    if (d->tile_digit_bits < 5) d->tile_digit_bits = 5;
+    if (d->tile_passes > 2) d->tile_digit_bits = 8;             // (> 65536 tiles: 8-bit digits, as before)
     return 0;
 }
 
@@ -341,6 +344,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     SageFrameShape shape;
     shape.depth_bits = depth_key_bits(cd);
     shape.tile_passes = cd.tile_passes;
+    shape.tile_digit_bits = cd.tile_digit_bits;
     {
         int rb = 0, np = 0;
         sage_sort_shape(shape.depth_bits, &rb, &np);

@@ -320,6 +320,7 @@ void sort_cfg()
 // dynamic shared-memory opt-in of every scatter instantiation (per device; outside graph capture)
 void sage_sort_configure(void)
 {
+    sort_cfg<5, 8>(); sort_cfg<5, 16>(); sort_cfg<6, 8>(); sort_cfg<6, 16>(); sort_cfg<7, 8>(); sort_cfg<7, 16>();
     sort_cfg<8, 8>(); sort_cfg<8, 16>(); sort_cfg<9, 8>(); sort_cfg<9, 16>();
 }
 
@@ -354,6 +355,7 @@ int sage_radix_sort(const SageSortPlan& pl, int* launches, cudaStream_t st)
         if (launches) *launches += 3 * NP_;                                          \
         return np & 1;                                                               \
     }
+    SAGE_SORT_CASE(5, 1) SAGE_SORT_CASE(5, 2) SAGE_SORT_CASE(6, 1) SAGE_SORT_CASE(6, 2) SAGE_SORT_CASE(7, 1) SAGE_SORT_CASE(7, 2)
     SAGE_SORT_CASE(8, 1) SAGE_SORT_CASE(8, 2) SAGE_SORT_CASE(8, 3) SAGE_SORT_CASE(8, 4)
     SAGE_SORT_CASE(9, 1) SAGE_SORT_CASE(9, 2) SAGE_SORT_CASE(9, 3)
 #undef SAGE_SORT_CASE
