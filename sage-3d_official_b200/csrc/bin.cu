@@ -1,7 +1,7 @@
 // K2 (instance emission, fused with its offset scan) and the tiles' work queue (the tile ranges, K4,
 // come out of the last pass of the by-tile sort: sort.cu).
 //
-// Binning is by 16 x 16 tiles, each instance carrying the mask of the tile's four 8 x 8 quadrants
+// Binning is by 32 x 16 tiles, each instance carrying the mask of the tile's eight 8 x 8 quadrants
 // the splat really reaches (exact culling: its {alpha >= 1/255} ellipse against the two 8-row halves
 // of every tile row).  The composite blends a quadrant per warp and drops the instances whose mask
 // bit is clear while it gathers, so the lists stay tile-sized (D ~ 2.4 M at 1080p) while the blend
@@ -121,8 +121,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
             g = __ldg(&order[r]);
             rc = __ldg(&fr.rect[g]);
             const int px0 = rc.x & 0xFFFF, px1 = rc.x >> 16, py0 = rc.y & 0xFFFF, py1 = rc.y >> 16;
-            nrows = (uint32_t)(py1 / SAGE_BIN - py0 / SAGE_BIN + 1);
-            c = (uint32_t)(px1 / SAGE_BIN - px0 / SAGE_BIN + 1) * nrows;
+            nrows = (uint32_t)(py1 / SAGE_BIN_H - py0 / SAGE_BIN_H + 1);
+            c = (uint32_t)(px1 / SAGE_BIN_W - px0 / SAGE_BIN_W + 1) * nrows;
             if (sage_box_cullable(px0, px1, py0, py1)) s_cull[atomicAdd(&s_ncull, 1u)] = threadIdx.x;
             const uint32_t it0 = atomicAdd(&s_nitem, nrows);
             if (it0 + nrows <= ITEM_POOL) {
@@ -142,8 +142,8 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
             const uint32_t t = s_cull[k];
             const uint2 q = s_rc[t];
             const int px0 = q.x & 0xFFFF, px1 = q.x >> 16, py0 = q.y & 0xFFFF, py1 = q.y >> 16;
-            const int ty0 = py0 / SAGE_BIN;
-            const uint32_t nr = (uint32_t)(py1 / SAGE_BIN - ty0 + 1);
+            const int ty0 = py0 / SAGE_BIN_H;
+            const uint32_t nr = (uint32_t)(py1 / SAGE_BIN_H - ty0 + 1);
             const uint32_t at = atomicAdd(&s_pool_used, nr);
             if (at + nr > ROW_POOL) continue;            // (a full pool only costs the culling, never correctness)
             const uint32_t gg = s_g[t];
@@ -218,11 +218,11 @@ k_emit(SageFrame fr, const uint32_t* __restrict__ order, uint32_t* __restrict__ 
         auto emit_row = [&](uint32_t t, uint32_t j) {
             const uint2 q = s_rc[t];
             const int px0 = q.x & 0xFFFF, px1 = q.x >> 16, py0 = q.y & 0xFFFF, py1 = q.y >> 16;
-            const int ty = py0 / SAGE_BIN + (int)j;
-            const uint32_t at = s_rows[t], gv = s_g[t] << 4;
+            const int ty = py0 / SAGE_BIN_H + (int)j;
+            const uint32_t at = s_rows[t], gv = s_g[t] << SAGE_MASK_BITS;
             const uint32_t rowtile = (uint32_t)((ty - bin_row0) * bins_x);
             if (at == ROWS_NONE) {
-                const int t0 = px0 / SAGE_BIN, t1 = px1 / SAGE_BIN;
+                const int t0 = px0 / SAGE_BIN_W, t1 = px1 / SAGE_BIN_W;
                 uint32_t slot = base + s_off[t] + j * (uint32_t)(t1 - t0 + 1);
                 for (int tx = t0; tx <= t1; ++tx) put(slot++, rowtile + (uint32_t)tx, gv | sage_box_quad_mask(px0, px1, py0, py1, tx, ty));
             } else {

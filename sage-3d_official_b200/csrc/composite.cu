@@ -3,10 +3,10 @@
 // Replaces cam.get_rgba() (simple_env.py:1380; generate_images.py:428) and
 // frame['distance_to_image_plane'] (simple_env.py:1425-1432).
 //
-// One WARP = one 8 x 8 quadrant of a 16 x 16 tile: lane -> row lane>>2, two horizontally adjacent
+// One WARP = one 8 x 8 quadrant of a 32 x 16 tile: lane -> row lane>>2, two horizontally adjacent
 // pixels (lane&3)*2, so the blend arithmetic runs on Blackwell's packed binary32 pipe
 // (FFMA2/FMUL2/FADD2: fma.rn.f32x2), which is IEEE per lane and therefore bit-identical to the
-// scalar statement in the oracle.  Warps are independent: CTA b holds the four quadrants of the b-th
+// scalar statement in the oracle.  Warps are independent: CTA b holds the eight quadrants of the b-th
 // heaviest tile (k_bin_order's length classes; CTAs are dispatched in index order, so the longest
 // lists start first), each warp walks the tile's
 // depth-sorted list 32 instances at a time, keeps those whose quadrant bit is set (ballot + popc: the
@@ -30,7 +30,11 @@
 
 namespace {
 
+// A CTA = four warps = the four 8 x 8 quadrants of one 16 x 16 HALF of a 32 x 16 tile; two CTAs per tile.
+// (One CTA of eight warps per tile was measured: +5 % kernel time — a CTA holds its registers and shared
+// memory until its slowest warp is done, and eight warps wait longer for one than four do.)
 constexpr int C_WARPS = 4;
+constexpr int C_HALVES = SAGE_BIN_W / 16;
 constexpr int C_THREADS = C_WARPS * 32;
 #ifndef SAGE_COMPOSITE_CTAS
 #define SAGE_COMPOSITE_CTAS 8
@@ -96,8 +100,10 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 
     // Not persistent on purpose: as CTAs retire, the SM's registers and shared memory go to the
     // (higher-priority) front-half kernels of the next frame instead of staying pinned to this kernel.
-    for (uint32_t tt = blockIdx.x; tt < (uint32_t)n_bins; tt += gridDim.x) {     // (one trip: the grid is n_bins)
-        const int quad = w;                                      // quadrant: bit qy*2 + qx of the instance masks
+    for (uint32_t wi = blockIdx.x; wi < (uint32_t)n_bins * C_HALVES; wi += gridDim.x) {     // (one trip: the grid is n_bins x halves)
+        const uint32_t tt = wi / C_HALVES;                       // tile rank in the heaviest-first order
+        const int half = (int)(wi % C_HALVES);
+        const int quad = (w >> 1) * SAGE_QUADS_X + half * 2 + (w & 1);   // quadrant: bit qy*4 + qx of the instance masks
         uint32_t cls, idx;
         if (tt < n_nonempty) {
             const unsigned m = __ballot_sync(0xffffffffu, cls_incl > tt);
@@ -111,7 +117,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
         uint2 rg = fr.ranges[bin];                               // (~begin, end); (0, 0) = empty
         rg.x = rg.y ? ~rg.x : 0u;
         const int bx = bin % bins_x, by = bin_row0 + bin / bins_x;
-        const int qx0 = bx * SAGE_BIN + (quad & 1) * 8, qy0 = by * SAGE_BIN + (quad >> 1) * 8;
+        const int qx0 = bx * SAGE_BIN_W + (quad % SAGE_QUADS_X) * 8, qy0 = by * SAGE_BIN_H + (quad / SAGE_QUADS_X) * 8;
         if (qx0 >= W || qy0 >= H) continue;                      // quadrant entirely outside the image
         const int px = qx0 + (lane & 3) * 2;
         const int py = qy0 + (lane >> 2);
@@ -128,7 +134,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             const bool rel = have && ((v >> quad) & 1u);
             const unsigned m = __ballot_sync(0xffffffffu, rel);
             if (rel) {
-                const float4* src = rec + (size_t)(v >> 4) * 3;
+                const float4* src = rec + (size_t)(v >> SAGE_MASK_BITS) * 3;
                 float4* dst = &srec[w][stage][__popc(m & ((1u << lane) - 1u)) * 3];
                 cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
             }
@@ -331,7 +337,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st)
 {
     if (n_bins <= 0) return;
-    SAGE_KLAUNCH(k_composite, n_bins, C_THREADS, st, fr, sorted_vals);
+    SAGE_KLAUNCH(k_composite, n_bins * C_HALVES, C_THREADS, st, fr, sorted_vals);
 }
 
 void sage_composite_configure(void)

@@ -149,8 +149,8 @@ k_project(SageSceneDev sc, SageFrame fr)
                     int ix0 = (int)fmax(xlo, 0.0), ix1 = (int)fmin(xhi, Wm);
                     int iy0 = (int)fmax(ylo, 0.0), iy1 = (int)fmin(yhi, Hm);
                     // clip to the rows this call renders (multi-GPU row sharding)
-                    iy0 = max(iy0, cam.bin_row0 * SAGE_BIN);
-                    iy1 = min(iy1, min(cam.bin_row1 * SAGE_BIN, cam.H) - 1);
+                    iy0 = max(iy0, cam.bin_row0 * SAGE_BIN_H);
+                    iy1 = min(iy1, min(cam.bin_row1 * SAGE_BIN_H, cam.H) - 1);
                     if (iy0 <= iy1 && ix0 <= ix1) {
                         vis = true;
                         key = __float_as_uint(tz) - __float_as_uint(cam.near_z);

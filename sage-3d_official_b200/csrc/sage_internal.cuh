@@ -67,12 +67,17 @@ __device__ __forceinline__ void sage_dep_launch() { asm volatile("griddepcontrol
 #define SAGE_L255 (-7.99435344f)      /* log2(1/255): skip where log2(alpha) < this */
 #define SAGE_L099 (-0.0144995697f)    /* log2(0.99): alpha cap, applied to the exponent */
 #define SAGE_T_MIN 1e-4f
-#define SAGE_BIN 16                   /* binning granularity: 16 x 16 pixel tiles; a warp blends one 8 x 8 quadrant */
+/* binning granularity: tiles of 32 x 16 pixels (W x H); a warp blends one of a tile's eight 8 x 8 quadrants.
+ * (16 x 16 tiles, rounds 1-2a: 1.41x the (tile, Gaussian) instances through emission and the tile sort.) */
+#define SAGE_BIN_W 32
+#define SAGE_BIN_H 16
+#define SAGE_QUADS_X (SAGE_BIN_W / 8)
+#define SAGE_MASK_BITS 8              /* instance value = Gaussian id << 8 | quadrant mask (bit qy * 4 + qx) */
 #define SAGE_BLUR 0.3f
 #define SAGE_LOG2E 1.44269504f
 #define SAGE_KEY_CULLED 0xFFFFFFFFu
-// instance value = Gaussian id (28 bits) << 4 | 8x8-quadrant overlap mask of the tile (4 bits)
-#define SAGE_ID_MASK 0x0FFFFFFFu      /* scene size limit (2^28 - 1 Gaussians) */
+// instance value = Gaussian id (24 bits) << 8 | 8x8-quadrant overlap mask of the tile (8 bits)
+#define SAGE_ID_MASK 0x00FFFFFFu      /* scene size limit (2^24 - 1 = 16.7 M Gaussians) */
 #define SAGE_MAX_PEERS 8
 
 // device counters (uint32 each)
@@ -163,10 +168,12 @@ __device__ __forceinline__ float sage_log2(float x)
 // sqrt to ~2 ulp (one MUFU + one multiply); the spans carry 0.1 % of slack.  Negative -> 0.
 __device__ __forceinline__ float sage_sqrt_fast(float x) { return x > 0.0f ? x * rsqrtf(x) : 0.0f; }
 
-// true: the pixel box spans at least 2 x 2 tiles — only then can the ellipse test remove a tile
+// true: the pixel box spans at least 2 x 2 blocks of 16 x 16 pixels — the splats worth intersecting with
+// the row bands (the ellipse test then removes tiles AND tightens the quadrant masks; a 32-px-wide tile
+// criterion would leave splats of 17-32 px with loose box masks: measured +6 % composite time)
 __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int iy1)
 {
-    return (ix0 / SAGE_BIN != ix1 / SAGE_BIN) && (iy0 / SAGE_BIN != iy1 / SAGE_BIN);
+    return (ix0 / 16 != ix1 / 16) && (iy0 / 16 != iy1 / 16);
 }
 
 struct SageBand {
@@ -239,18 +246,18 @@ __device__ __forceinline__ SageRowItem sage_band_row(const SageBand& b, int ix0,
     it.top = it.bot = SAGE_SPAN_EMPTY;
     int lo = 1 << 30, hi = -1;
     int xs, xe;
-    const int ya = max(ty * SAGE_BIN, iy0), yb = min(ty * SAGE_BIN + 7, iy1);
+    const int ya = max(ty * SAGE_BIN_H, iy0), yb = min(ty * SAGE_BIN_H + 7, iy1);
     if (ya <= yb && sage_band_span(b, ix0, ix1, ya, yb, &xs, &xe)) {
         it.top = (uint32_t)xs | ((uint32_t)xe << 16);
         lo = min(lo, xs); hi = max(hi, xe);
     }
-    const int yc = max(ty * SAGE_BIN + 8, iy0), yd = min(ty * SAGE_BIN + 15, iy1);
+    const int yc = max(ty * SAGE_BIN_H + 8, iy0), yd = min(ty * SAGE_BIN_H + 15, iy1);
     if (yc <= yd && sage_band_span(b, ix0, ix1, yc, yd, &xs, &xe)) {
         it.bot = (uint32_t)xs | ((uint32_t)xe << 16);
         lo = min(lo, xs); hi = max(hi, xe);
     }
     if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
-    else { it.tx0 = lo / SAGE_BIN; it.tx1 = hi / SAGE_BIN; }
+    else { it.tx0 = lo / SAGE_BIN_W; it.tx1 = hi / SAGE_BIN_W; }
     return it;
 }
 
@@ -263,29 +270,36 @@ __device__ __forceinline__ SageRowItem sage_row_from_spans(uint32_t top, uint32_
     if ((top & 0xFFFFu) <= (top >> 16)) { lo = min(lo, (int)(top & 0xFFFFu)); hi = max(hi, (int)(top >> 16)); }
     if ((bot & 0xFFFFu) <= (bot >> 16)) { lo = min(lo, (int)(bot & 0xFFFFu)); hi = max(hi, (int)(bot >> 16)); }
     if (hi < 0) { it.tx0 = 0; it.tx1 = -1; }
-    else { it.tx0 = lo / SAGE_BIN; it.tx1 = hi / SAGE_BIN; }
+    else { it.tx0 = lo / SAGE_BIN_W; it.tx1 = hi / SAGE_BIN_W; }
     return it;
 }
 
-// 8x8-quadrant mask (bit qy*2+qx, the work-item -> quadrant map of the composite kernel) of tile tx
+// 8x8-quadrant mask (bit qy*4+qx, the warp -> quadrant map of the composite kernel) of tile tx
 __device__ __forceinline__ uint32_t sage_row_quad_mask(uint32_t top, uint32_t bot, int tx)
 {
-    const int bx = tx * SAGE_BIN;
+    const int bx = tx * SAGE_BIN_W;
     const int t0 = (int)(top & 0xFFFFu), t1 = (int)(top >> 16);
     const int b0 = (int)(bot & 0xFFFFu), b1 = (int)(bot >> 16);
     uint32_t m = 0;
-    if (t0 <= t1) m |= ((t0 <= bx + 7 && t1 >= bx) ? 1u : 0u) | ((t0 <= bx + 15 && t1 >= bx + 8) ? 2u : 0u);
-    if (b0 <= b1) m |= ((b0 <= bx + 7 && b1 >= bx) ? 4u : 0u) | ((b0 <= bx + 15 && b1 >= bx + 8) ? 8u : 0u);
+#pragma unroll
+    for (int qx = 0; qx < SAGE_QUADS_X; ++qx) {
+        const int x0 = bx + 8 * qx, x1 = x0 + 7;
+        if (t0 <= t1 && t0 <= x1 && t1 >= x0) m |= 1u << qx;
+        if (b0 <= b1 && b0 <= x1 && b1 >= x0) m |= 1u << (SAGE_QUADS_X + qx);
+    }
     return m;
 }
 
 // the same from the inclusive pixel box of a splat that is not culled per row
 __device__ __forceinline__ uint32_t sage_box_quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
 {
-    const int bx = tx * SAGE_BIN, by = ty * SAGE_BIN;
-    const uint32_t xl = (px0 <= bx + 7) ? 1u : 0u, xr = (px1 >= bx + 8) ? 1u : 0u;
-    const uint32_t yt = (py0 <= by + 7) ? 1u : 0u, yb = (py1 >= by + 8) ? 1u : 0u;
-    return (yt & xl) | ((yt & xr) << 1) | ((yb & xl) << 2) | ((yb & xr) << 3);
+    const int bx = tx * SAGE_BIN_W, by = ty * SAGE_BIN_H;
+    const bool yt = py0 <= by + 7, yb = py1 >= by + 8;
+    uint32_t cols = 0;
+#pragma unroll
+    for (int qx = 0; qx < SAGE_QUADS_X; ++qx)
+        if (px0 <= bx + 8 * qx + 7 && px1 >= bx + 8 * qx) cols |= 1u << qx;
+    return (yt ? cols : 0u) | (yb ? cols << SAGE_QUADS_X : 0u);
 }
 
 // ---- frame workspace ---------------------------------------------------------------------
@@ -304,7 +318,7 @@ struct SageFrame {
     uint2* rect;         // inclusive PIXEL bounding box: x = x0 | x1<<16, y = y0 | y1<<16
     // per-instance (capacity cap)
     uint32_t* ikey[2];   // tile id, ping-pong
-    uint32_t* ival[2];   // Gaussian id << 4 | quadrant mask, ping-pong
+    uint32_t* ival[2];   // Gaussian id << 8 | quadrant mask, ping-pong
     // sort / scan state
     uint32_t* sort_h;       // [SAGE_RADIX_MAX_BINS][sort_ld] per-tile digit histograms / exclusive prefixes of a pass
     uint32_t* sort_totals;  // [SAGE_RADIX_MAX_BINS] digit totals of a pass

@@ -215,9 +215,10 @@ static int make_cam(const sage_camera* cam, int row0, int row1, SageCamDev* d)
     REQUIRE(row0 >= 0 && row0 <= row1 && row1 <= d->tiles_y, "tile-row range out of bounds");
     d->row0 = row0; d->row1 = row1;
     d->depth_lo = 1.0f; d->depth_hi = 0.0f;
-    const int per = SAGE_TILE / SAGE_BIN;
-    const int bins_y = (cam->height + SAGE_BIN - 1) / SAGE_BIN;
-    d->bins_x = (cam->width + SAGE_BIN - 1) / SAGE_BIN;
+    static_assert(SAGE_TILE % SAGE_BIN_H == 0, "public tile rows are whole bin rows");
+    const int per = SAGE_TILE / SAGE_BIN_H;
+    const int bins_y = (cam->height + SAGE_BIN_H - 1) / SAGE_BIN_H;
+    d->bins_x = (cam->width + SAGE_BIN_W - 1) / SAGE_BIN_W;
     d->bin_row0 = row0 * per;
     d->bin_row1 = row1 * per < bins_y ? row1 * per : bins_y;
     if (d->bin_row1 < d->bin_row0) d->bin_row1 = d->bin_row0;
@@ -394,7 +395,7 @@ int sage_scene_create(sage_scene** out, int device, int64_t n, int sh_degree, co
     REQUIRE(out != nullptr, "sage_scene_create: out is NULL");
     *out = nullptr;
     REQUIRE(sage_device_count() > 0, "sage_scene_create: no CUDA device (this library has no CPU fallback)");
-    REQUIRE(n >= 0 && n <= (int64_t)SAGE_ID_MASK, "sage_scene_create: n out of range (max 2^28-1 Gaussians)");
+    REQUIRE(n >= 0 && n <= (int64_t)SAGE_ID_MASK, "sage_scene_create: n out of range (max 2^24-1 = 16 777 215 Gaussians per scene)");
     REQUIRE(sh_degree >= 0 && sh_degree <= 3, "sage_scene_create: sh_degree must be 0..3");
     REQUIRE(n == 0 || (xyz && log_scale && quat_wxyz && opacity_raw && sh), "sage_scene_create: NULL attribute pointer");
     CK(cudaSetDevice(device));
@@ -748,8 +749,8 @@ int sage_frame_row_instances(sage_scene* s, int64_t* rows_out_host, int n_rows)
     CK(cudaEventSynchronize(c.done));
     const int rows = c.last_row1 - c.last_row0;
     REQUIRE(n_rows == rows, "sage_frame_row_instances: n_rows must equal the rows of the last frame");
-    const int per = SAGE_TILE / SAGE_BIN;
-    const int bins_y = (c.last_H + SAGE_BIN - 1) / SAGE_BIN;
+    const int per = SAGE_TILE / SAGE_BIN_H;
+    const int bins_y = (c.last_H + SAGE_BIN_H - 1) / SAGE_BIN_H;
     int bin_rows = rows * per;
     if (c.last_row0 * per + bin_rows > bins_y) bin_rows = bins_y - c.last_row0 * per;
     if (bin_rows < 0) bin_rows = 0;
