@@ -274,32 +274,29 @@ __device__ __forceinline__ SageRowItem sage_row_from_spans(uint32_t top, uint32_
     return it;
 }
 
+// quadrant columns (bits 0 .. SAGE_QUADS_X-1) of the tile starting at pixel bx that the inclusive pixel span
+// [x0, x1] touches; 0 if the span is empty or misses the tile
+__device__ __forceinline__ uint32_t sage_span_cols(int x0, int x1, int bx)
+{
+    const int lo = max(x0 - bx, 0) >> 3, hi = min(x1 - bx, SAGE_BIN_W - 1) >> 3;      // first / last quadrant column
+    const uint32_t m = ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+    return (x0 <= x1 && x1 >= bx && x0 <= bx + SAGE_BIN_W - 1) ? m : 0u;
+}
+
 // 8x8-quadrant mask (bit qy*4+qx, the warp -> quadrant map of the composite kernel) of tile tx
 __device__ __forceinline__ uint32_t sage_row_quad_mask(uint32_t top, uint32_t bot, int tx)
 {
     const int bx = tx * SAGE_BIN_W;
-    const int t0 = (int)(top & 0xFFFFu), t1 = (int)(top >> 16);
-    const int b0 = (int)(bot & 0xFFFFu), b1 = (int)(bot >> 16);
-    uint32_t m = 0;
-#pragma unroll
-    for (int qx = 0; qx < SAGE_QUADS_X; ++qx) {
-        const int x0 = bx + 8 * qx, x1 = x0 + 7;
-        if (t0 <= t1 && t0 <= x1 && t1 >= x0) m |= 1u << qx;
-        if (b0 <= b1 && b0 <= x1 && b1 >= x0) m |= 1u << (SAGE_QUADS_X + qx);
-    }
-    return m;
+    return sage_span_cols((int)(top & 0xFFFFu), (int)(top >> 16), bx) |
+           (sage_span_cols((int)(bot & 0xFFFFu), (int)(bot >> 16), bx) << SAGE_QUADS_X);
 }
 
 // the same from the inclusive pixel box of a splat that is not culled per row
 __device__ __forceinline__ uint32_t sage_box_quad_mask(int px0, int px1, int py0, int py1, int tx, int ty)
 {
-    const int bx = tx * SAGE_BIN_W, by = ty * SAGE_BIN_H;
-    const bool yt = py0 <= by + 7, yb = py1 >= by + 8;
-    uint32_t cols = 0;
-#pragma unroll
-    for (int qx = 0; qx < SAGE_QUADS_X; ++qx)
-        if (px0 <= bx + 8 * qx + 7 && px1 >= bx + 8 * qx) cols |= 1u << qx;
-    return (yt ? cols : 0u) | (yb ? cols << SAGE_QUADS_X : 0u);
+    const int by = ty * SAGE_BIN_H;
+    const uint32_t cols = sage_span_cols(px0, px1, tx * SAGE_BIN_W);
+    return (py0 <= by + 7 ? cols : 0u) | (py1 >= by + 8 ? cols << SAGE_QUADS_X : 0u);
 }
 
 // ---- frame workspace ---------------------------------------------------------------------
