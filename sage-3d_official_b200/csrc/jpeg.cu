@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(J1_WARPS * 32) k_jpeg_dct(const JpegDev* __res
     __shared__ uint32_t s_ac[2][256];
     __shared__ uint8_t s_zz[64];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_launch();
     for (int i = tid; i < 128; i += blockDim.x) s_qdiv[i >> 6][i & 63] = jd->qdiv[i >> 6][i & 63];
     for (int i = tid; i < 512; i += blockDim.x) s_ac[i >> 8][i & 255] = jd->ac_tab[i >> 8][i & 255];
     if (tid < 64) s_zz[tid] = c_zigzag[tid];
@@ -407,8 +408,10 @@ __global__ void __launch_bounds__(1024) k_jpeg_scan(const JpegDev* __restrict__ 
     __shared__ uint32_t s_dc[2][12];
     __shared__ uint32_t s_wsum[32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_launch();                       // (PDL: the next kernel of the chain may be scheduled; it waits below)
     if (tid < 24) s_dc[tid / 12][tid % 12] = jd->dc_tab[tid / 12][tid % 12];
     __syncthreads();
+    sage_dep_wait();                         // the DCT kernel's coefficients are complete and visible
     const int f = blockIdx.x;
     const int nmcu = jd->nmcu;
     const int16_t* dcs = dcs_all + (size_t)f * jd->nblk;
@@ -489,9 +492,11 @@ __global__ void __launch_bounds__(J3_WARPS * 32) k_jpeg_huff(const JpegDev* __re
     __shared__ uint32_t s_ac[2][256];
     __shared__ uint32_t s_dc[2][12];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_launch();
     for (int i = tid; i < 512; i += blockDim.x) s_ac[i >> 8][i & 255] = jd->ac_tab[i >> 8][i & 255];
     if (tid < 24) s_dc[tid / 12][tid % 12] = jd->dc_tab[tid / 12][tid % 12];
     __syncthreads();
+    sage_dep_wait();                         // bit offsets of every MCU (k_jpeg_scan)
     const int f = blockIdx.y;
     const int m = blockIdx.x * J3_WARPS + wid;
     if (m >= jd->nmcu || info_all[f].overflow) return;
@@ -604,6 +609,8 @@ __global__ void __launch_bounds__(256) k_jpeg_ffcount(const JpegDev* __restrict_
 {
     __shared__ int s_w[8];
     const int f = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_launch();
+    sage_dep_wait();
     const JpegFrameInfo inf = info_all[f];
     if (inf.overflow || (uint32_t)chunk * JPEG_CHUNK >= inf.raw_bytes) return;      // CTA-uniform
     int nv;
@@ -628,6 +635,8 @@ __global__ void __launch_bounds__(256) k_jpeg_ffscan(const JpegDev* __restrict__
     __shared__ uint32_t s_w[8];
     __shared__ uint32_t s_carry;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_launch();
+    sage_dep_wait();
     JpegFrameInfo& inf = info_all[f];
     uint8_t* out = out_all + (size_t)f * (size_t)out_stride;
     if (inf.overflow) {
@@ -675,6 +684,7 @@ __global__ void __launch_bounds__(256) k_jpeg_stuff(const JpegDev* __restrict__ 
 {
     __shared__ int s_w[8];
     const int f = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    sage_dep_wait();
     const JpegFrameInfo inf = info_all[f];
     if (inf.overflow || (uint32_t)chunk * JPEG_CHUNK >= inf.raw_bytes) return;      // CTA-uniform
     const long long size = (long long)jd->header_len + (long long)inf.raw_bytes + (long long)inf.ff_total + 2;
@@ -764,11 +774,13 @@ int sage_jpeg_enqueue(sage_jpeg* j, const uint8_t* rgb_dev, int bpp, int batch, 
     JpegFrameInfo* info = j->info + z;
     CK(cudaMemsetAsync(raw, 0, (size_t)batch * h.raw_words * 4, st));
     SAGE_KLAUNCH(k_jpeg_dct, dim3((h.nmcu + J1_WARPS - 1) / J1_WARPS, batch), J1_WARPS * 32, st, j->dev, rgb_dev, bpp, coef, acbits, dcs);
-    SAGE_KLAUNCH(k_jpeg_scan, batch, 1024, st, j->dev, dcs, acbits, bitoff, raw, info);
-    SAGE_KLAUNCH(k_jpeg_huff, dim3((h.nmcu + J3_WARPS - 1) / J3_WARPS, batch), J3_WARPS * 32, st, j->dev, coef, bitoff, info, raw);
-    SAGE_KLAUNCH(k_jpeg_ffcount, dim3(h.n_chunks, batch), 256, st, j->dev, info, raw, ffcnt);
-    SAGE_KLAUNCH(k_jpeg_ffscan, batch, 256, st, j->dev, info, ffcnt, out_dev, (long long)out_stride, sizes_dev);
-    SAGE_KLAUNCH(k_jpeg_stuff, dim3(h.n_chunks, batch), 256, st, j->dev, info, raw, ffcnt, out_dev, (long long)out_stride);
+    // the five kernels after the DCT are launched with programmatic stream serialisation: each may be scheduled
+    // while its predecessor drains, loads its tables, then waits (griddepcontrol.wait) for the predecessor's data
+    SAGE_KLAUNCH_PDL(k_jpeg_scan, batch, 1024, 0, st, j->dev, dcs, acbits, bitoff, raw, info);
+    SAGE_KLAUNCH_PDL(k_jpeg_huff, dim3((h.nmcu + J3_WARPS - 1) / J3_WARPS, batch), J3_WARPS * 32, 0, st, j->dev, coef, bitoff, info, raw);
+    SAGE_KLAUNCH_PDL(k_jpeg_ffcount, dim3(h.n_chunks, batch), 256, 0, st, j->dev, info, raw, ffcnt);
+    SAGE_KLAUNCH_PDL(k_jpeg_ffscan, batch, 256, 0, st, j->dev, info, ffcnt, out_dev, (long long)out_stride, sizes_dev);
+    SAGE_KLAUNCH_PDL(k_jpeg_stuff, dim3(h.n_chunks, batch), 256, 0, st, j->dev, info, raw, ffcnt, out_dev, (long long)out_stride);
     CK(cudaGetLastError());
     return 0;
 }

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(128) k_png_rows(const PngDev* __restrict__ pd,
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row = blockIdx.x * 4 + w;
     const int W = pd->W, H = pd->H, L = pd->L;
+    sage_dep_launch();
+    if (WRITE) sage_dep_wait();               // (second pass: the rows' bit offsets come from k_png_scan)
     if (row >= H) return;
     const float* drow = depth + (size_t)row * W;
     if (!WRITE && twin != nullptr) {
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(1024) k_png_scan(const PngDev* __restrict__ pd
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
     const int H = pd->H, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    sage_dep_launch();
+    sage_dep_wait();
     if (threadIdx.x == 0) s_carry = 3u;                       // three block-header bits come first
     __syncthreads();
     for (int base = 0; base < H; base += 1024) {
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(256) k_png_chunks(const PngDev* __restrict__ p
                                                     long long out_cap, long long* __restrict__ size_out)
 {
     __shared__ uint32_t s_crc[256];
+    sage_dep_wait();
     const uint32_t zlen = info->zlen;
     const uint32_t nchunks = (zlen + PNG_CHUNK - 1) / PNG_CHUNK;
     const long long total = 33ll + (long long)nchunks * 12ll + (long long)zlen + 12ll;
@@ -432,9 +437,9 @@ int sage_png_enqueue(sage_png* p, const float* depth_dev, float lo, float hi, fl
     CK(cudaMemsetAsync(info, 0, sizeof(PngInfo), st));
     const int blocks = (h.H + 3) / 4;
     SAGE_KLAUNCH(k_png_rows<false>, blocks, 128, st, p->dev, depth_dev, lo, hi, scale, row_bits, stream, info, twin_dev);
-    SAGE_KLAUNCH(k_png_scan, 1, 1024, st, p->dev, row_bits, stream, info);
-    SAGE_KLAUNCH(k_png_rows<true>, blocks, 128, st, p->dev, depth_dev, lo, hi, scale, row_bits, stream, info, (uint16_t*)nullptr);
-    SAGE_KLAUNCH(k_png_chunks, h.max_chunks, 256, st, p->dev, stream, info, out_dev, (long long)out_cap, size_dev);
+    SAGE_KLAUNCH_PDL(k_png_scan, 1, 1024, 0, st, p->dev, row_bits, stream, info);
+    SAGE_KLAUNCH_PDL(k_png_rows<true>, blocks, 128, 0, st, p->dev, depth_dev, lo, hi, scale, row_bits, stream, info, (uint16_t*)nullptr);
+    SAGE_KLAUNCH_PDL(k_png_chunks, h.max_chunks, 256, 0, st, p->dev, stream, info, out_dev, (long long)out_cap, size_dev);
     CK(cudaGetLastError());
     return 0;
 }

@@ -132,22 +132,28 @@ k_project(SageSceneDev sc, SageFrame fr)
                 float qc = conic_c * (-0.5f * SAGE_LOG2E);
                 float chk = gx + gy + qa + qb + qc;
 
-                // Conservative bounding rectangle of {alpha >= 1/255}: derived in binary64 from
-                // the *rounded* conic the blend kernel will use, with 0.2 % + 0.02 slack on the
-                // log2 threshold.  Not part of the spec: it only has to be conservative.
+                // Conservative bounding rectangle of {alpha >= 1/255}, from the *rounded* conic the blend kernel
+                // will use.  Not part of the spec: it only has to be conservative.  binary32 (round 1 used binary64:
+                // two DSQRT and two DDIV sequences per visible splat, half of this kernel's instructions) with the
+                // determinant by Kahan's fused-error form, so that a thin ellipse (A C ~ B^2) does not lose it to
+                // cancellation, 0.3 % + 0.02 of slack on the log2 threshold and 0.1 % + 0.01 px on the half extents —
+                // three orders above the rounding of the few operations involved.
                 const float l2 = lo - SAGE_L255;                 // log2(255 o)
-                const double t2 = (double)l2 * 1.002 + 0.02;
-                const double A = -(double)qa, Bq = -0.5 * (double)qb, Cq = -(double)qc;
-                const double det2 = A * Cq - Bq * Bq;
-                const bool unbounded = !(det2 > 0.0) || !(A > 0.0) || !(Cq > 0.0);
-                const double hx = unbounded ? 1e30 : sqrt(t2 * Cq / det2);
-                const double hy = unbounded ? 1e30 : sqrt(t2 * A / det2);
-                double xlo = floor((double)gx - hx - 0.5), xhi = ceil((double)gx + hx - 0.5);
-                double ylo = floor((double)gy - hy - 0.5), yhi = ceil((double)gy + hy - 0.5);
-                const double Wm = (double)(cam.W - 1), Hm = (double)(cam.H - 1);
-                if ((chk - chk == 0.0f) && xhi >= 0.0 && xlo <= Wm && yhi >= 0.0 && ylo <= Hm) {
-                    int ix0 = (int)fmax(xlo, 0.0), ix1 = (int)fmin(xhi, Wm);
-                    int iy0 = (int)fmax(ylo, 0.0), iy1 = (int)fmin(yhi, Hm);
+                const float t2 = l2 * 1.003f + 0.02f;
+                const float A = -qa, Bq = -0.5f * qb, Cq = -qc;
+                const float det2 = sage_det_kahan(A, Cq, Bq);
+                const bool unbounded = !(det2 > 0.0f) || !(A > 0.0f) || !(Cq > 0.0f);
+                float hx = unbounded ? 1e30f : sqrtf(t2 * Cq / det2);
+                float hy = unbounded ? 1e30f : sqrtf(t2 * A / det2);
+                if (!(hx < 1e9f)) hx = 1e30f;                    // overflow / NaN: cover everything
+                if (!(hy < 1e9f)) hy = 1e30f;
+                const float slack = 1e-3f * fmaxf(hx, hy) + 0.01f;
+                const float xlo = floorf((gx - hx) - slack - 0.5f), xhi = ceilf((gx + hx) + slack - 0.5f);
+                const float ylo = floorf((gy - hy) - slack - 0.5f), yhi = ceilf((gy + hy) + slack - 0.5f);
+                const float Wm = (float)(cam.W - 1), Hm = (float)(cam.H - 1);
+                if ((chk - chk == 0.0f) && xhi >= 0.0f && xlo <= Wm && yhi >= 0.0f && ylo <= Hm) {
+                    int ix0 = (int)fmaxf(xlo, 0.0f), ix1 = (int)fminf(xhi, Wm);
+                    int iy0 = (int)fmaxf(ylo, 0.0f), iy1 = (int)fminf(yhi, Hm);
                     // clip to the rows this call renders (multi-GPU row sharding)
                     iy0 = max(iy0, cam.bin_row0 * SAGE_BIN_H);
                     iy1 = min(iy1, min(cam.bin_row1 * SAGE_BIN_H, cam.H) - 1);

@@ -176,6 +176,16 @@ __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int
     return (ix0 / 16 != ix1 / 16) && (iy0 / 16 != iy1 / 16);
 }
 
+// A C - B^2 without the cancellation of the plain form (Kahan): w = B B rounded, e = its rounding error (exact,
+// by fma), f = A C - w fused; the sum is within ~2 ulp of the true determinant
+__device__ __forceinline__ float sage_det_kahan(float A, float C, float B)
+{
+    const float w = B * B;
+    const float e = fmaf(-B, B, w);
+    const float f = fmaf(A, C, -w);
+    return f + e;
+}
+
 struct SageBand {
     float gx, gy, A, B, C, t2, det2, invA;
     float hx, hy;       // half extents of the ellipse
@@ -191,7 +201,7 @@ __device__ __forceinline__ SageBand sage_band_make(float gx, float gy, float qa,
     b.t2 = l2 * 1.003f + 0.02f;
     b.gx = gx; b.gy = gy;
     b.A = -qa; b.B = -0.5f * qb; b.C = -qc;
-    b.det2 = b.A * b.C - b.B * b.B;
+    b.det2 = sage_det_kahan(b.A, b.C, b.B);
     b.unbounded = (!(b.det2 > 0.0f) || !(b.A > 0.0f) || !(b.C > 0.0f) || !(b.t2 > 0.0f)) ? 1 : 0;
     b.hx = b.unbounded ? 1e30f : sqrtf(b.t2 * b.C / b.det2);
     b.hy = b.unbounded ? 1e30f : sqrtf(b.t2 * b.A / b.det2);
