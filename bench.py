@@ -309,7 +309,7 @@ def collide_leg(sage, layout, device):
                     "grid_sweep_device_us: positions resident, CUDA events; reference: collision_detector.py:191 on one host core"}
 
 
-def batch_leg(args, sage, world, rank, local, n_scenes, steps=24):
+def batch_leg(args, sage, world, rank, local, n_scenes, steps=48):
     """BASELINE config 4: a batch of n_scenes scenes (seeds 1..n), one 1080p frame each per step.
     tilerow : every scene resident on every rank, every frame split into tile-row blocks (peer stores)
     replicas: scene s lives on rank s % world and is rendered whole there (the reference's scale-out:
@@ -329,8 +329,12 @@ def batch_leg(args, sage, world, rank, local, n_scenes, steps=24):
         cams.append([sage.Camera.look_heading(p, h, W, H) for p, h in sage.camera_path(layout, 16, seed=s)])
     out = {"n_scenes": n_scenes, "n_gaussians_per_scene": n_small, "frames_per_mode": steps * n_scenes}
 
+    from sage3d_official_b200 import _lib as _sage_lib
+    depth = int(_sage_lib.lib().sage_pipeline_depth())
+    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+
     def timed(fn, frames):
-        for i in range(2):
+        for i in range(2 * depth + 2):          # every frame context of every scene has captured its graph
             fn(i)
         torch.cuda.synchronize()
         if world > 1:
@@ -338,7 +342,9 @@ def batch_leg(args, sage, world, rank, local, n_scenes, steps=24):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
-            fn(2 + i)
+            fn(2 * depth + 2 + i)
+        for st_ in streams:
+            torch.cuda.current_stream().wait_stream(st_)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -348,30 +354,31 @@ def batch_leg(args, sage, world, rank, local, n_scenes, steps=24):
             ms = float(t.item())
         return frames / (ms / 1000.0)
 
-    # replicas
+    # replicas: scene s lives on rank s % N and is rendered whole there (the reference's only scale-out,
+    # generate_images.py:136-139); frames rotate over the frame contexts / streams as in the main loop
     mine = [s for s in range(n_scenes) if s % world == rank]
     scenes = {s: sage.GaussianScene(clouds[s], device=local) for s in mine}
-    rgb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
-    dep = torch.zeros((H, W), dtype=torch.float32, device=dev)
+    rgb = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev) for _ in range(depth)]
+    dep = [torch.zeros((H, W), dtype=torch.float32, device=dev) for _ in range(depth)]
 
     def step_rep(i):
+        b = i % depth
         for s in mine:
-            scenes[s].render(cams[s][i % 16], out=(rgb, dep))
+            scenes[s].render(cams[s][i % 16], out=(rgb[b], dep[b]), stream=streams[b])
     out["replicas_fps"] = timed(step_rep, steps * n_scenes)
     for sc in scenes.values():
         sc.close()
-    # tile rows
+    # tile rows: every scene resident on every rank, every frame split into N tile-row blocks
     if world > 1:
         scenes = [sage.GaussianScene(c, device=local) for c in clouds]
         rows = rows_of(rank, H, world)
-        rgbs = [torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)]
-        deps = [torch.zeros((H, W), dtype=torch.float32, device=dev)]
-        peers = PeerFrames(rgbs, deps, rank, world)
+        peers = PeerFrames(rgb, dep, rank, world)
 
         def step_rows(i):
+            b = i % depth
             for s in range(n_scenes):
-                scenes[s].render_peers(cams[s][i % 16], rows, peers.rgb[0], peers.depth[0])
-            peers.close_frame()
+                scenes[s].render_peers(cams[s][i % 16], rows, peers.rgb[b], peers.depth[b], stream=streams[b])
+            peers.close_frame(b, stream=streams[b])
         out["tilerow_fps"] = timed(step_rows, steps * n_scenes)
         peers.close()
         for sc in scenes:
@@ -435,12 +442,11 @@ def run_native(args):
     def step(i):
         cam = cams[i % len(cams)]
         b = i % nbuf
-        with torch.cuda.stream(streams[b]):
-            if world == 1:
-                scene.render(cam, out=(rgb[b], dep[b]))
-            else:
-                scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b])
-                peers.close_frame(b)     # device-side: every rank's strips have landed everywhere
+        if world == 1:
+            scene.render(cam, out=(rgb[b], dep[b]), stream=streams[b])
+        else:
+            scene.render_peers(cam, rows, peers.rgb[b], peers.depth[b], stream=streams[b])
+            peers.close_frame(b, stream=streams[b])     # device-side: every rank's strips have landed everywhere
 
     def sync_all():
         torch.cuda.synchronize()

@@ -25,6 +25,11 @@ def _torch():
 
 
 def _ccam(cam: Camera) -> CCamera:
+    """The C struct of a camera; cached on the object (a Camera is a value: callers that move the camera
+    build a new one, so the cache cannot go stale unless fields are assigned in place — then `meta` is cleared)."""
+    cached = cam.meta.get("_ccam")
+    if cached is not None:
+        return cached
     c = CCamera()
     c.R[:] = [float(v) for v in np.asarray(cam.R, np.float32).reshape(9)]
     c.t[:] = [float(v) for v in np.asarray(cam.t, np.float32).reshape(3)]
@@ -32,6 +37,7 @@ def _ccam(cam: Camera) -> CCamera:
     c.fx, c.fy, c.cx, c.cy = float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy)
     c.width, c.height = int(cam.width), int(cam.height)
     c.near_z, c.far_z = float(cam.near), float(cam.far)
+    cam.meta["_ccam"] = c
     return c
 
 
@@ -151,20 +157,20 @@ class GaussianScene:
             rgb, depth = out
         r0, r1 = self._rows(cam, rows)
         cc = _ccam(cam)
-        with torch.cuda.device(dev):
-            check(_lib.lib().sage_render(self._h, C.byref(cc), r0, r1, _ptr(rgb), _ptr(depth), _stream_ptr(stream)))
+        check(_lib.lib().sage_render(self._h, C.byref(cc), r0, r1, _ptr(rgb), _ptr(depth), _stream_ptr(stream)))
         return rgb, depth
 
     def render_peers(self, cam: Camera, rows, rgb_ptrs: Sequence[int], depth_ptrs: Optional[Sequence[int]], stream=None):
         """Composite rows straight into several (peer-mapped) frame buffers given as raw addresses."""
-        torch = _torch()
         n = len(rgb_ptrs)
-        RA = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in rgb_ptrs])
-        DA = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in depth_ptrs]) if depth_ptrs else None
+        # (multigpu.PeerFrames hands in ready-made ctypes arrays: nothing is rebuilt per frame)
+        RA = rgb_ptrs if isinstance(rgb_ptrs, C.Array) else (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in rgb_ptrs])
+        DA = None
+        if depth_ptrs is not None and len(depth_ptrs):
+            DA = depth_ptrs if isinstance(depth_ptrs, C.Array) else (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in depth_ptrs])
         cc = _ccam(cam)
-        with torch.cuda.device(self.device):
-            check(_lib.lib().sage_render_peers(self._h, C.byref(cc), int(rows[0]), int(rows[1]), n, RA, DA,
-                                               _stream_ptr(stream)))
+        check(_lib.lib().sage_render_peers(self._h, C.byref(cc), int(rows[0]), int(rows[1]), n, RA, DA,
+                                           _stream_ptr(stream)))
 
     def render_host(self, cam: Camera, rows=None, want_depth: bool = True, stream=None):
         """Synchronous frame into pinned host memory: (rgb u8 ndarray, depth f32 ndarray | None)."""

@@ -130,11 +130,16 @@ class PeerFrames:
         self.rgb = open_all("rgb", rgb_buffers)
         self.depth = open_all("depth", depth_buffers)
         self.flags = open_all("flags", [self._flags[b] for b in range(len(rgb_buffers))])
+        # ready-made pointer tables for sage_render_peers / sage_peer_barrier: nothing is rebuilt per frame
+        tab = lambda ptrs: (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in ptrs])
+        self.rgb = [tab(p) for p in self.rgb]
+        self.depth = [tab(p) for p in self.depth]
+        self._flag_rows = [tab(p) for p in self.flags]
         self._flag = torch.zeros(1, dtype=torch.int32, device=rgb_buffers[0].device)
         self.use_nccl = os.environ.get("SAGE_PEER_BARRIER", "flags") == "nccl"
         dist.barrier()
 
-    def close_frame(self, b: int = 0):
+    def close_frame(self, b: int = 0, stream=None):
         """Device-side frame barrier on the current stream for buffer slot ``b``: once it has run on every
         rank, all ranks' strips have landed in all copies of the slot.  Counters in peer memory
         (``sage_peer_barrier``: one 32-thread kernel, no collective); ``SAGE_PEER_BARRIER=nccl`` switches back
@@ -145,9 +150,8 @@ class PeerFrames:
             return
         import torch
         self._seq[b] += 1
-        rows = (C.c_void_p * self.world)(*[C.c_void_p(int(p)) for p in self.flags[b]])
-        check(_lib.lib().sage_peer_barrier(rows, self.world, self.rank, self._seq[b],
-                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st = stream if stream is not None else torch.cuda.current_stream()
+        check(_lib.lib().sage_peer_barrier(self._flag_rows[b], self.world, self.rank, self._seq[b], C.c_void_p(st.cuda_stream)))
 
     def close(self):
         L = _lib.lib()
