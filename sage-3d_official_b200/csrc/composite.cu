@@ -78,7 +78,7 @@ __device__ __forceinline__ float2 sage_exp2_fast_x2(float2 x)
 __global__ void __launch_bounds__(C_THREADS, C_CTAS_PER_SM)
 k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 {
-    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3 + 9];   // per warp: two stages of 32 x 48-byte records (+ three of padding: the batched loops read past the last entry)
+    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3 + 3];   // per warp: two stages of 32 x 48-byte records (+ one of padding)
     const SageFrameParams* __restrict__ fp = fr.fp;
     const int W = fp->cam.W, H = fp->cam.H, bins_x = fp->cam.bins_x, bin_row0 = fp->cam.bin_row0;
     const int n_bins = fp->cam.n_bins;
@@ -157,57 +157,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             cp_async_wait<1>();
             __syncwarp();
             const float4* s_rec = srec[w][st];
-#if defined(SAGE_COMPOSITE_BATCH4)
-            // Entry loop in batches of four, free of per-lane branches: the four exponents and alphas are
-            // independent of T, so they are evaluated side by side (instruction-level parallelism for a warp that
-            // is alone on its scheduler), then the four blends run in order.  In SIMT terms nothing is lost against
-            // the per-lane "continue": a warp executes the alpha path whenever ANY lane needs it.
-            bool dead0 = !(pxc.x == pxc.x), dead1 = !(pxc.y == pxc.y);
-            for (int j = 0; j < cnt; j += 4) {
-                float2 al[4];
-                bool ok0[4], ok1[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 a = s_rec[3 * (j + u)];                              // gx gy qa lo (slots past cnt: stale, masked below)
-                    const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * (j + u) + 1]);
-                    const float dy = pyc - a.y;
-                    const float2 t2 = __fmul2_rn(bq, f2(dy));
-                    const float c2 = fmaf(t2.y, dy, a.w);
-                    const float2 dx = __fadd2_rn(pxc, f2(-a.x));
-                    const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
-                    float2 pw = __ffma2_rn(dx, wv, f2(c2));
-                    const bool in_list = j + u < cnt;                                 // warp-uniform
-                    ok0[u] = in_list && pw.x >= SAGE_L255;
-                    ok1[u] = in_list && pw.y >= SAGE_L255;
-                    pw.x = fminf(fmaxf(pw.x, SAGE_L255), SAGE_L099);                  // keep the exponent split in range for masked lanes
-                    pw.y = fminf(fmaxf(pw.y, SAGE_L255), SAGE_L099);
-                    al[u] = sage_exp2_fast_x2(pw);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float2 a2;
-                    a2.x = (ok0[u] && !dead0) ? al[u].x : 0.0f;                       // alpha 0: T, C, Dz stay bit-identical
-                    a2.y = (ok1[u] && !dead1) ? al[u].y : 0.0f;
-                    const float2 om = __ffma2_rn(a2, f2(-1.0f), f2(1.0f));
-                    float2 Tn = __fmul2_rn(T, om);
-                    float2 wgt = __fmul2_rn(a2, T);
-                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;        // stop: finished, the splat not blended
-                    wgt.x = s0 ? 0.0f : wgt.x;
-                    wgt.y = s1 ? 0.0f : wgt.y;
-                    T.x = s0 ? T.x : Tn.x;
-                    T.y = s1 ? T.y : Tn.y;
-                    dead0 = dead0 || s0;
-                    dead1 = dead1 || s1;
-                    const float4 c = s_rec[3 * (j + u) + 2];                          // r g b z
-                    Cr = __ffma2_rn(f2(c.x), wgt, Cr);
-                    Cg = __ffma2_rn(f2(c.y), wgt, Cg);
-                    Cb = __ffma2_rn(f2(c.z), wgt, Cb);
-                    Dz = __ffma2_rn(f2(c.w), wgt, Dz);
-                }
-            }
-            pxc.x = dead0 ? NAN_X : pxc.x;
-            pxc.y = dead1 ? NAN_X : pxc.y;
-#elif defined(SAGE_COMPOSITE_PIPELINED)
+#if defined(SAGE_COMPOSITE_PIPELINED)
             // software-pipelined entry loop: the exponent of entry j+1 (two shared-memory loads and six
             // flops, independent of the blend) is computed BEFORE entry j is blended, so a warp that runs
             // alone on its scheduler (the tail of a single-wave launch at low resolution) overlaps the two

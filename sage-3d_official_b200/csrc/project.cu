@@ -80,12 +80,23 @@ void sage_launch_precompute(const SageSceneDev& sc, const float* xyz, const floa
 // per-Gaussian stream is a 16-byte-per-lane coalesced access.  Emits the depth key
 // (bits(z) - bits(near), or CULLED) that the first radix pass compacts and sorts in one go.
 // ---------------------------------------------------------------------------------------------
+#ifdef SAGE_CUDA_EMU
+constexpr int SAGE_STREAM_GRID = 3;
+#else
+constexpr int SAGE_STREAM_GRID = 148 * 8;      // fixed grid of the two streaming kernels (grid-stride loops)
+#endif
+
 __global__ void __launch_bounds__(256)
 k_project(SageSceneDev sc, SageFrame fr)
 {
     const SageCamDev& cam = fr.fp->cam;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     SAGE_DEP_LAUNCH_TOP();
+    // grid-stride over the Gaussians (a fixed grid of 148 x 8 CTAs): at 2 M Gaussians one CTA per 256 of them was
+    // 7813 CTA launches per frame for this kernel alone - at multi-GPU frame rates the CTA launch rate of the
+    // chip, not the work, was the limit
+    uint32_t n_vis = 0;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x; i0 < sc.n; i0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = i0 + threadIdx.x;
     bool vis = false;
     uint32_t key = SAGE_KEY_CULLED;
     if (i < sc.n) {
@@ -172,9 +183,10 @@ k_project(SageSceneDev sc, SageFrame fr)
         }
         fr.dkey_src[i] = key;
     }
+    n_vis += (uint32_t)__popc(__ballot_sync(0xffffffffu, vis));
+    }
     // one atomic per warp for the visible counter
-    const unsigned m = __ballot_sync(0xffffffffu, vis);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&fr.counters[CNT_VISIBLE], (uint32_t)__popc(m));
+    if ((threadIdx.x & 31) == 0 && n_vis) atomicAdd(&fr.counters[CNT_VISIBLE], n_vis);
     SAGE_DEP_LAUNCH_END();
 }
 
@@ -202,9 +214,8 @@ k_sh_color(SageSceneDev sc, SageFrame fr)
     constexpr int NF = 3 * NB;
     constexpr int NC = (NF + 3) / 4;
     const SageCamDev& cam = fr.fp->cam;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= sc.n) return;
-    if (__ldg(&fr.dkey_src[i]) == SAGE_KEY_CULLED) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sc.n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (__ldg(&fr.dkey_src[i]) == SAGE_KEY_CULLED) continue;
     const float4 g0 = __ldg(&sc.geo0[i]);
     float shv[NC * 4];
     const float4* sp = sc.shc + (size_t)i * NC;
@@ -252,12 +263,14 @@ k_sh_color(SageSceneDev sc, SageFrame fr)
     const float* R = cam.R;
     const float tz = fmaf(R[8], g0.z, fmaf(R[7], g0.y, fmaf(R[6], g0.x, cam.t[2])));
     fr.rec[3 * (size_t)i + 2] = make_float4(acc[0], acc[1], acc[2], tz);
+    }
 }
 
 void sage_launch_project(const SageSceneDev& sc, const SageFrame& fr, cudaStream_t st)
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
+    if (blocks > SAGE_STREAM_GRID) blocks = SAGE_STREAM_GRID;
     SAGE_KLAUNCH(k_project, blocks, 256, st, sc, fr);
 }
 
@@ -265,6 +278,7 @@ void sage_launch_sh_color(const SageSceneDev& sc, const SageFrame& fr, cudaStrea
 {
     if (sc.n <= 0) return;
     int blocks = (int)((sc.n + 255) / 256);
+    if (blocks > SAGE_STREAM_GRID) blocks = SAGE_STREAM_GRID;
     switch (sc.deg) {
         case 0: SAGE_KLAUNCH(k_sh_color<0>, blocks, 256, st, sc, fr); break;
         case 1: SAGE_KLAUNCH(k_sh_color<1>, blocks, 256, st, sc, fr); break;
