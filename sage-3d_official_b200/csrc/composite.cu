@@ -6,20 +6,21 @@
 // One WARP = one 8 x 8 quadrant of a 32 x 16 tile: lane -> row lane>>2, two horizontally adjacent
 // pixels (lane&3)*2, so the blend arithmetic runs on Blackwell's packed binary32 pipe
 // (FFMA2/FMUL2/FADD2: fma.rn.f32x2), which is IEEE per lane and therefore bit-identical to the
-// scalar statement in the oracle.  Warps are independent: CTA b holds the eight quadrants of the b-th
+// scalar statement in the oracle.  Warps are independent: CTA b holds four quadrants of the b/2-th
 // heaviest tile (k_bin_order's length classes; CTAs are dispatched in index order, so the longest
-// lists start first), each warp walks the tile's
-// depth-sorted list 32 instances at a time, keeps those whose quadrant bit is set (ballot + popc: the
-// survivors' records are gathered straight into consecutive slots of the stage) and never
-// synchronises with another warp.  (Round 1 blended a tile with a CTA of four warps that met at a
-// barrier per batch — 24 % of its stall samples — and filtered every entry with a ballot/ffs loop.)
+// lists start first) and a warp never synchronises with another warp.  (Round 1 blended a tile with a
+// CTA of four warps that met at a barrier per batch — 24 % of its stall samples — and filtered every
+// entry with a ballot/ffs loop.)
 //
-// Splat records (one 48-byte block per Gaussian, L2-resident) are gathered into the warp's private
-// shared-memory stage with cp.async (LDGSTS, 16 bytes x 3 per lane), two stages: the gather of chunk
-// c+1 is in flight while chunk c is blended.  (Round 1 issued one 48-byte TMA bulk copy per record:
-// UBLKCP is a uniform-datapath instruction, so a warp issued its 32 copies one lane at a time — ~8 %
-// of the kernel's instructions.  A per-lane gather is what LDGSTS is for.)  The entry loop is
-// warp-uniform: no ballots, no masks.
+// A warp walks the tile's depth-sorted list in three decoupled steps: it SCANS the raw list 128 entries
+// at a time and appends the ids whose quadrant bit is set to a small id ring in shared memory (ballot +
+// popc), GATHERS the next 32 ids' splat records (one 48-byte block per Gaussian, L2-resident) into one of
+// two private stages with cp.async (LDGSTS, 16 bytes x 3 per lane), and BLENDS the stage that has landed
+// while the next gather is in flight.  Every stage therefore holds 32 entries of this quadrant, however
+// sparse they are in the tile's list.  (Round 1 issued one 48-byte TMA bulk copy per record: UBLKCP is a
+// uniform-datapath instruction, so a warp issued its 32 copies one lane at a time — ~8 % of the kernel's
+// instructions.  A per-lane gather is what LDGSTS is for.)  The entry loop is warp-uniform: no ballots,
+// no masks.
 //
 // The blend: log2(alpha) = qa dx^2 + qb dx dy + qc dy^2 + lo with the opacity
 // already in the exponent; skip below log2(1/255); cap at log2(0.99); alpha by the degree-3
@@ -40,6 +41,17 @@ constexpr int C_THREADS = C_WARPS * 32;
 #define SAGE_COMPOSITE_CTAS 8
 #endif
 constexpr int C_CTAS_PER_SM = SAGE_COMPOSITE_CTAS;
+#ifndef SAGE_COMPOSITE_SCAN
+#define SAGE_COMPOSITE_SCAN 4
+#endif
+constexpr int C_SCAN = SAGE_COMPOSITE_SCAN;          // 32-entry chunks of the raw list per scan step
+constexpr int C_RING = C_SCAN >= 2 ? 64 * C_SCAN : 128;   // ids (power of two >= 64 + 32 C_SCAN): < 32 waiting + one scan step, never
+                                                          // overtaking the 32 a slower lane may still be reading for its gather
+#ifndef SAGE_COMPOSITE_CTAS_WIDE
+#define SAGE_COMPOSITE_CTAS_WIDE 6
+#endif
+constexpr int C_CTAS_PER_SM_WIDE = SAGE_COMPOSITE_CTAS_WIDE;   // register budget of the 4-entries-per-trip instantiation
+constexpr int C_LIVE_CHECK = 8;                      // entries between two "is any pixel of the quadrant still live" votes
 
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 
@@ -75,16 +87,27 @@ __device__ __forceinline__ float2 sage_exp2_fast_x2(float2 x)
     return r;
 }
 
-__global__ void __launch_bounds__(C_THREADS, C_CTAS_PER_SM)
+#ifdef SAGE_COMPOSITE_PROFILE
+// development build only (tools/build_variant.sh prof -DSAGE_COMPOSITE_PROFILE): per-warp walk statistics of the last launch
+constexpr int CPROF_WORDS = 8, CPROF_WARPS = 1 << 16;
+__device__ uint32_t g_cprof[CPROF_WARPS * CPROF_WORDS];
+__device__ __forceinline__ uint32_t cprof_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (uint32_t)t; }
+#endif
+
+// E = entries of the stage blended per trip of the inner loop (2: frames of many waves of CTAs; 4: small frames)
+template <int E>
+__global__ void __launch_bounds__(C_THREADS, E <= 2 ? C_CTAS_PER_SM : C_CTAS_PER_SM_WIDE)
 k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 {
-    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3 + 3];   // per warp: two stages of 32 x 48-byte records (+ one of padding)
+    __shared__ __align__(16) float4 srec[C_WARPS][2][32 * 3];       // per warp: two stages of 32 x 48-byte records
+    __shared__ uint32_t sring[C_WARPS][C_RING];                     // per warp: ring of Gaussian ids waiting to be gathered
     const SageFrameParams* __restrict__ fp = fr.fp;
     const int W = fp->cam.W, H = fp->cam.H, bins_x = fp->cam.bins_x, bin_row0 = fp->cam.bin_row0;
     const int n_bins = fp->cam.n_bins;
     const float depth_lo = fp->cam.depth_lo, depth_hi = fp->cam.depth_hi;
     const float4* __restrict__ rec = fr.rec;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     // work queue: tiles by descending length class, 4 work items (quadrants) each; lane l holds the
     // running count of classes 32 .. 32-l
@@ -129,132 +152,164 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 
         const uint32_t n = rg.y - rg.x;
         const uint32_t* lst = vals + rg.x;
-        // chunk c = list entries [32c, 32c+32); its survivors (quadrant bit set) land in slots 0 .. cnt-1
-        auto gather = [&](uint32_t v, bool have, int stage) -> int {
-            const bool rel = have && ((v >> quad) & 1u);
-            const unsigned m = __ballot_sync(0xffffffffu, rel);
-            if (rel) {
-                const float4* src = rec + (size_t)(v >> SAGE_MASK_BITS) * 3;
-                float4* dst = &srec[w][stage][__popc(m & ((1u << lane) - 1u)) * 3];
+#ifdef SAGE_COMPOSITE_PROFILE
+        const long long prof_c0 = clock64();
+        const uint32_t prof_t0 = cprof_ns();
+        uint32_t prof_visited = 0, prof_hits = 0;
+#endif
+        // The walk, in three decoupled steps:
+        //   scan    the tile's list C_SCAN x 32 entries at a time (loads issued one step ahead); the ids of the entries
+        //           whose quadrant bit is set are appended to the warp's id ring (ballot + popc)
+        //   gather  the next 32 ids of the ring -> their 48-byte records into the other stage (cp.async)
+        //   blend   the stage that has landed
+        // so every stage holds 32 entries of THIS quadrant however sparse they are in the tile's list.  (Until run W
+        // a stage was filled from one 32-entry chunk of the raw list: in the longest lists only a quarter of a chunk
+        // belongs to a given quadrant, the blend of those ~8 entries was shorter than the L2 round trip of the next
+        // gather, and the warps that finish last - the kernel's tail at 640 x 480 - ran at memory latency:
+        // 210-290 cycles per gathered entry, profiles/r02_variants.md.)
+#if defined(SAGE_CUDA_EMU) && defined(SAGE_EMU_POISON)
+        for (int k = lane; k < 2 * 32 * 3; k += 32) (&srec[w][0][0])[k] = make_float4(NAN_X, NAN_X, NAN_X, NAN_X);   // emulator test: stale stage contents
+        __syncwarp();
+#endif
+        uint32_t* ring = sring[w];
+        uint32_t q_head = 0, q_tail = 0, scan = 0;               // warp-uniform
+        uint32_t vq[C_SCAN];
+        auto prefetch = [&]() {
+#pragma unroll
+            for (int k = 0; k < C_SCAN; ++k) {
+                const uint32_t idx = scan + 32u * k + lane;
+                vq[k] = idx < n ? __ldg(&lst[idx]) : 0u;          // 0: no quadrant bit, never kept
+            }
+        };
+        auto fill = [&]() {
+            while (q_tail - q_head < 32u && scan < n) {
+#pragma unroll
+                for (int k = 0; k < C_SCAN; ++k) {
+                    const bool rel = (vq[k] >> quad) & 1u;
+                    const unsigned m = __ballot_sync(0xffffffffu, rel);
+                    if (rel) ring[(q_tail + __popc(m & lt_mask)) & (C_RING - 1)] = vq[k] >> SAGE_MASK_BITS;
+                    q_tail += __popc(m);
+                }
+                scan += 32u * C_SCAN;
+                prefetch();
+            }
+            __syncwarp();                                   // the ring's new ids are visible to every lane
+        };
+        auto gather = [&](int stage) -> int {
+            const int c = (int)min(q_tail - q_head, 32u);
+            if (lane < c) {
+                const float4* src = rec + (size_t)ring[(q_head + lane) & (C_RING - 1)] * 3;
+                float4* dst = &srec[w][stage][lane * 3];
                 cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
             }
+            // count not a multiple of E: the entry loop reads the slots up to the next multiple as (masked) partners of
+            // the last entries - whatever is left there from an earlier stage, their colours must be finite
+            if (E > 1 && lane >= c && lane < ((c + E - 1) & ~(E - 1))) srec[w][stage][lane * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             cp_async_commit();                             // (possibly empty: keeps the group count uniform)
-            return __popc(m);
+            q_head += (uint32_t)c;
+            return c;
         };
-        int cnt = 0, cnt_next = 0;
-        uint32_t v_next = 0;
+        int cnt_next = 0;
         if (n > 0) {
-            const uint32_t v0 = lane < n ? __ldg(&lst[lane]) : 0u;
-            cnt_next = gather(v0, lane < n, 0);
-            v_next = 32 + lane < n ? __ldg(&lst[32 + lane]) : 0u;
+            prefetch();
+            fill();
+            cnt_next = gather(0);
         }
-        int st = 0;
-        for (uint32_t base = 0; base < n; base += 32, st ^= 1) {
-            cnt = cnt_next;
-            // next chunk: gather in flight while this one is blended
-            cnt_next = gather(v_next, base + 32 + lane < n, st ^ 1);
-            v_next = base + 64 + lane < n ? __ldg(&lst[base + 64 + lane]) : 0u;
+        for (int st = 0; cnt_next > 0; st ^= 1) {
+            const int cnt = cnt_next;
+            fill();
+            cnt_next = gather(st ^ 1);                     // in flight while stage st is blended
             cp_async_wait<1>();
             __syncwarp();
             const float4* s_rec = srec[w][st];
-#if defined(SAGE_COMPOSITE_PIPELINED)
-            // software-pipelined entry loop: the exponent of entry j+1 (two shared-memory loads and six
-            // flops, independent of the blend) is computed BEFORE entry j is blended, so a warp that runs
-            // alone on its scheduler (the tail of a single-wave launch at low resolution) overlaps the two
-            // dependency chains instead of walking them one after the other.  Reading one record past the
-            // last entry is harmless (the stages are padded; the value is never used).
-            auto exponent = [&](int j) -> float2 {
-                const float4 a = s_rec[3 * j];                                        // gx gy qa lo
-                const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1]);   // qb qc
-                const float dy = pyc - a.y;
-                const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
-                const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
-                const float2 dx = __fadd2_rn(pxc, f2(-a.x));
-                const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
-                return __ffma2_rn(dx, wv, f2(c2));                                    // log2(alpha)
-            };
-            float2 pwn = exponent(0);
-#pragma unroll 2
-            for (int j = 0; j < cnt; ++j) {
-                float2 pw = pwn;
-                pwn = exponent(j + 1);
-                const bool v0 = pw.x >= SAGE_L255, v1 = pw.y >= SAGE_L255;            // false for NaN (finished pixels)
-                if (!(v0 || v1)) continue;
-                pw.x = fminf(pw.x, SAGE_L099);
-                pw.y = fminf(pw.y, SAGE_L099);
-                float2 al = sage_exp2_fast_x2(pw);
-                al.x = v0 ? al.x : 0.0f;
-                al.y = v1 ? al.y : 0.0f;
-                const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));
-                float2 Tn = __fmul2_rn(T, om);
-                float2 wgt = __fmul2_rn(al, T);
-                if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
-                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
-                    wgt.x = s0 ? 0.0f : wgt.x;
-                    wgt.y = s1 ? 0.0f : wgt.y;
-                    Tn.x = s0 ? T.x : Tn.x;
-                    Tn.y = s1 ? T.y : Tn.y;
-                    pxc.x = s0 ? NAN_X : pxc.x;
-                    pxc.y = s1 ? NAN_X : pxc.y;
-                    pwn.x = s0 ? NAN_X : pwn.x;           // the exponent already taken for the next entry saw the live pixel
-                    pwn.y = s1 ? NAN_X : pwn.y;
-                }
-                T = Tn;
-                const float4 c = s_rec[3 * j + 2];                                    // r g b z
-                Cr = __ffma2_rn(f2(c.x), wgt, Cr);
-                Cg = __ffma2_rn(f2(c.y), wgt, Cg);
-                Cb = __ffma2_rn(f2(c.z), wgt, Cb);
-                Dz = __ffma2_rn(f2(c.w), wgt, Dz);
-            }
-#else
-#pragma unroll 2
-            for (int j = 0; j < cnt; ++j) {
-                const float4 a = s_rec[3 * j];                                        // gx gy qa lo
-                const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * j + 1]);   // qb qc
-                const float dy = pyc - a.y;
-                const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
-                const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
-                const float2 dx = __fadd2_rn(pxc, f2(-a.x));
-                const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
-                float2 pw = __ffma2_rn(dx, wv, f2(c2));                               // log2(alpha)
-                const bool v0 = pw.x >= SAGE_L255, v1 = pw.y >= SAGE_L255;            // false for NaN (finished pixels)
-                if (!(v0 || v1)) continue;
-                pw.x = fminf(pw.x, SAGE_L099);
-                pw.y = fminf(pw.y, SAGE_L099);
-                float2 al = sage_exp2_fast_x2(pw);
-                al.x = v0 ? al.x : 0.0f;                  // alpha 0: T, C, Dz stay bit-identical
-                al.y = v1 ? al.y : 0.0f;
-                const float2 om = __ffma2_rn(al, f2(-1.0f), f2(1.0f));                // 1 - alpha
-                float2 Tn = __fmul2_rn(T, om);
-                float2 wgt = __fmul2_rn(al, T);
-                // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
-                // ptxas if-converts this block into eight predicated instructions that issue for every splat;
-                // forcing a real branch (opaque one-trip loop) and pinning the loop constants in registers was
-                // measured (profiles/r02_variants.md): 3 fewer instructions per splat, but 2 % SLOWER
-                // (0.2146 vs 0.2098 ms: the extra BSSY/BSYNC pair and 8 more registers) - left as is.
-                if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
-                    const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
-                    wgt.x = s0 ? 0.0f : wgt.x;
-                    wgt.y = s1 ? 0.0f : wgt.y;
-                    Tn.x = s0 ? T.x : Tn.x;
-                    Tn.y = s1 ? T.y : Tn.y;
-                    pxc.x = s0 ? NAN_X : pxc.x;
-                    pxc.y = s1 ? NAN_X : pxc.y;
-                }
-                T = Tn;
-                const float4 c = s_rec[3 * j + 2];                                    // r g b z
-                Cr = __ffma2_rn(f2(c.x), wgt, Cr);
-                Cg = __ffma2_rn(f2(c.y), wgt, Cg);
-                Cb = __ffma2_rn(f2(c.z), wgt, Cb);
-                Dz = __ffma2_rn(f2(c.w), wgt, Dz);
-            }
+#ifdef SAGE_COMPOSITE_PROFILE
+            prof_visited += (uint32_t)cnt;
 #endif
-            if (!__any_sync(0xffffffffu, SAGE_LIVE())) break;
+            for (int j0 = 0; j0 < cnt; j0 += C_LIVE_CHECK) {
+                const int j1 = min(j0 + C_LIVE_CHECK, cnt);
+                // E entries per trip: their exponents and alphas are evaluated side by side (E independent dependency
+                // chains in one basic block), then the E blends run in order.  A warp is latency-bound on this loop
+                // whenever it has its scheduler to itself - the tail of every frame, most of a small frame (run X: 130
+                // cycles per skipped and 270 per blended entry, one at a time) - and E chains overlap; where the kernel is
+                // issue-bound the price is the alpha path of an entry no lane needed whenever a partner needed it.
+                for (int j = j0; j < j1; j += E) {
+                    float2 pw[E];
+                    bool v0[E], v1[E], any = false;
+#pragma unroll
+                    for (int u = 0; u < E; ++u) {
+                        const float4 a = s_rec[3 * (j + u)];                                  // gx gy qa lo
+                        const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * (j + u) + 1]);   // qb qc
+                        const float dy = pyc - a.y;
+                        const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
+                        const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
+                        const float2 dx = __fadd2_rn(pxc, f2(-a.x));
+                        const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
+                        pw[u] = __ffma2_rn(dx, wv, f2(c2));                                   // log2(alpha)
+                        const bool has = (E == 1) || (u == 0) || (j + u < cnt);               // warp-uniform (slots past cnt are stale)
+                        v0[u] = has && pw[u].x >= SAGE_L255;                                  // false for NaN (finished pixels)
+                        v1[u] = has && pw[u].y >= SAGE_L255;
+                        any = any || v0[u] || v1[u];
+                    }
+#ifdef SAGE_COMPOSITE_PROFILE
+                    if (__any_sync(0xffffffffu, any)) prof_hits++;
+#endif
+                    if (!any) continue;
+                    float2 al[E];
+#pragma unroll
+                    for (int u = 0; u < E; ++u) {
+                        pw[u].x = fminf(pw[u].x, SAGE_L099);
+                        pw[u].y = fminf(pw[u].y, SAGE_L099);
+                        al[u] = sage_exp2_fast_x2(pw[u]);
+                        al[u].x = v0[u] ? al[u].x : 0.0f;          // alpha 0: T, C, Dz stay bit-identical
+                        al[u].y = v1[u] ? al[u].y : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < E; ++u) {
+                        const float2 om = __ffma2_rn(al[u], f2(-1.0f), f2(1.0f));             // 1 - alpha
+                        float2 Tn = __fmul2_rn(T, om);
+                        float2 wgt = __fmul2_rn(al[u], T);
+                        // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
+                        // (ptxas if-converts this block into predicated instructions that issue for every splat; forcing a
+                        // real branch was measured 2 % slower, profiles/r02_variants.md.)
+                        if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
+                            const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                            wgt.x = s0 ? 0.0f : wgt.x;
+                            wgt.y = s1 ? 0.0f : wgt.y;
+                            Tn.x = s0 ? T.x : Tn.x;
+                            Tn.y = s1 ? T.y : Tn.y;
+                            pxc.x = s0 ? NAN_X : pxc.x;
+                            pxc.y = s1 ? NAN_X : pxc.y;
+#pragma unroll
+                            for (int u2 = u + 1; u2 < E; ++u2) {                              // finished: the later entries of the trip no longer see the pixel
+                                al[u2].x = s0 ? 0.0f : al[u2].x;
+                                al[u2].y = s1 ? 0.0f : al[u2].y;
+                            }
+                        }
+                        T = Tn;
+                        const float4 c = s_rec[3 * (j + u) + 2];                              // r g b z
+                        Cr = __ffma2_rn(f2(c.x), wgt, Cr);
+                        Cg = __ffma2_rn(f2(c.y), wgt, Cg);
+                        Cb = __ffma2_rn(f2(c.z), wgt, Cb);
+                        Dz = __ffma2_rn(f2(c.w), wgt, Dz);
+                    }
+                }
+                if (!__any_sync(0xffffffffu, SAGE_LIVE())) { cnt_next = 0; break; }      // every pixel of the quadrant is finished
+            }
             __syncwarp();                                  // stage st is free for the gather after next
         }
         cp_async_wait<0>();                                // nothing may land in the stages after this bin
         __syncwarp();
 #undef SAGE_LIVE
+#ifdef SAGE_COMPOSITE_PROFILE
+        if (lane == 0) {
+            const uint32_t wid = blockIdx.x * C_WARPS + w;
+            if (wid < (uint32_t)CPROF_WARPS) {
+                uint32_t* o = g_cprof + (size_t)wid * CPROF_WORDS;
+                o[0] = (uint32_t)(clock64() - prof_c0); o[1] = prof_visited; o[2] = min(scan, n); o[3] = prof_hits;
+                o[4] = prof_t0; o[5] = cprof_ns(); o[6] = n; o[7] = (uint32_t)bin;
+            }
+        }
+#endif
 
         // epilogue: quantise and store to every destination frame.  Wide path (frame width a multiple
         // of 8, 8-byte aligned buffers, quadrant inside the image): the 24 RGB bytes of a bin row (4 lanes x
@@ -334,15 +389,32 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 
 }  // namespace
 
+#ifdef SAGE_COMPOSITE_PROFILE
+extern "C" int sage_debug_composite_profile(uint32_t* host, int n_warps)
+{
+    if (n_warps > CPROF_WARPS) n_warps = CPROF_WARPS;
+    return cudaMemcpyFromSymbol(host, g_cprof, sizeof(uint32_t) * CPROF_WORDS * (size_t)n_warps) == cudaSuccess ? 0 : 1;
+}
+#endif
+
+// Entries per trip: 2 where the frame is many waves of CTAs (the SMs stay full, the kernel is issue-bound and a wider
+// trip only adds alpha evaluations nobody needed), 4 for frames of at most SAGE_COMPOSITE_WIDE_MAX_CTAS CTAs (640 x 480:
+// 1200 CTAs, a single wave - the kernel's time is its longest walk, latency-bound).
+static int g_wide_max_ctas = 2400;
+
 void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st)
 {
     if (n_bins <= 0) return;
-    SAGE_KLAUNCH(k_composite, n_bins * C_HALVES, C_THREADS, st, fr, sorted_vals);
+    const int ctas = n_bins * C_HALVES;
+    if (ctas <= g_wide_max_ctas) SAGE_KLAUNCH(k_composite<4>, ctas, C_THREADS, st, fr, sorted_vals);
+    else SAGE_KLAUNCH(k_composite<2>, ctas, C_THREADS, st, fr, sorted_vals);
 }
 
 void sage_composite_configure(void)
 {
 #ifndef SAGE_CUDA_EMU
-    sage_prefer_smem(k_composite);
+    sage_prefer_smem(k_composite<2>);
+    sage_prefer_smem(k_composite<4>);
 #endif
+    if (const char* v = getenv("SAGE_COMPOSITE_WIDE_MAX_CTAS")) g_wide_max_ctas = atoi(v);
 }

@@ -19,15 +19,16 @@
 #ifndef SAGE_N_CTX
 #define SAGE_N_CTX 8      // most frame contexts a scene can own
 #endif
-// Contexts a scene is created with (frames in flight).  One GPU rendering whole frames: 3 (measured, round 1:
-// 1975 / 2077 / 2050 frames/s with 2 / 3 / 4).  A rank of a tile-row split renders a fraction of a frame per
+// Contexts a scene is created with (frames in flight).  One GPU rendering whole frames: 5 (run V, same box:
+// 2677 / 2766 / 2792 / 2800 frames/s device-resident and 2282 / 2539 / 2612 / 2651 end to end with 2 / 3 / 4 / 5;
+// ~0.4 GB of frame state each at 2 M Gaussians).  A rank of a tile-row split renders a fraction of a frame per
 // step: its kernels are smaller and more latency-bound, and deeper pipelining pays (4 GPUs: 5773 -> 6489
 // frames/s with 6); the multi-GPU callers raise it with sage_set_pipeline_depth / SAGE_PIPELINE_DEPTH.
 static int g_pipeline_depth = 0;
 static int pipeline_depth_now()
 {
     if (g_pipeline_depth == 0) {
-        int d = 3;
+        int d = 5;
         if (const char* v = getenv("SAGE_PIPELINE_DEPTH")) d = atoi(v);
         g_pipeline_depth = d < 1 ? 1 : (d > SAGE_N_CTX ? SAGE_N_CTX : d);
     }

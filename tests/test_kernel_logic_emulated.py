@@ -149,7 +149,7 @@ def test_plan_kernels_emulated_match_reference_goldens(plan_emu, oracle):
         assert plen[k] == z["path_len"][k] and np.array_equal(pxy[k, :plen[k]], want), k
 
 
-def test_render_pipeline_emulated_matches_oracle(oracle, sage, tmp_path_factory):
+def test_render_pipeline_emulated_matches_oracle(oracle, sage, tmp_path_factory, monkeypatch):
     """The whole render path (project, 3-kernel radix passes, SH colour, load-balanced emission,
     by-bin sort with fused ranges, bin order, warp-per-bin composite, C-ABI layer with its direct-launch
     path) under the emulator, bit for bit against the oracle: RGB, RGBA, depth, tile-row shards, an
@@ -175,3 +175,7 @@ def test_render_pipeline_emulated_matches_oracle(oracle, sage, tmp_path_factory)
     cam = sage.Camera.look_heading((0.2, 2.0, 1.2), np.radians(180.0), 192, 112)      # footprints of hundreds of bins
     assert R.check(L, sage, oracle, wall, cam, "wall close-up")
     assert R.check(L, sage, oracle, wall.subset(np.zeros(0, np.int64)), cam, "empty")
+    # the composite's other instantiation (2 entries per trip; these small frames get 4 by default)
+    monkeypatch.setenv("SAGE_COMPOSITE_WIDE_MAX_CTAS", "0")
+    cam = sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 160, 120)
+    assert R.check(L, sage, oracle, cloud, cam, "room, 2 entries per trip")

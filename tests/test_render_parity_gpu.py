@@ -162,6 +162,26 @@ def test_long_bin_lists(sage, oracle):
     _check_frame(sage, oracle, cloud, cam)
 
 
+@pytest.mark.parametrize("wide_max", ["0", "100000000"])
+def test_composite_both_trip_widths(sage, oracle, monkeypatch, wide_max):
+    """k_composite blends 2 entries per trip on large frames and 4 on small ones (composite.cu); the choice is made
+    per launch from the CTA count.  Force each instantiation on frames that would get the other: long lists whose
+    length is not a multiple of the trip width, early saturation inside a trip, a 640 x 480 frame and a 1080p one."""
+    monkeypatch.setenv("SAGE_COMPOSITE_WIDE_MAX_CTAS", wide_max)        # read when a scene is created
+    rng = np.random.default_rng(12)
+    n = 7001
+    cloud, _ = sage.synthetic_room(6, n)
+    cam = sage.Camera.look_heading((0.0, 0.0, 1.2), 0.0, 96, 64)
+    cloud.xyz[:, 0] = rng.uniform(2.0, 6.0, n).astype(np.float32)
+    cloud.xyz[:, 1] = rng.uniform(-0.15, 0.15, n).astype(np.float32)
+    cloud.xyz[:, 2] = rng.uniform(1.05, 1.35, n).astype(np.float32)
+    cloud.opacity[:] = rng.uniform(-4.0, 3.0, n).astype(np.float32)       # faint and opaque mixed: pixels finish mid-trip
+    _check_frame(sage, oracle, cloud, cam)
+    room, _ = sage.synthetic_room(0, 50_000)
+    _check_frame(sage, oracle, room, sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 640, 480))
+    _check_frame(sage, oracle, room, sage.Camera.look_heading((5.2, 3.4, 1.2), np.radians(-135.0), 1920, 1080))
+
+
 def test_two_frames_in_flight_match_serial_frames(sage, oracle):
     import torch
     cloud, layout = sage.synthetic_room(0, 30_000)
