@@ -63,28 +63,36 @@ class GridPlanner:
     """Batched A* on one grid (handle of ``sage_planner``): ``slots`` searches run side by side."""
 
     #: device memory the search slots may take (each slot: g f64 + came_from i32 per cell, 16 B per heap entry)
-    MEMORY_BUDGET = 4 << 30
+    MEMORY_BUDGET = 16 << 30
 
-    def __init__(self, grid, slots: int = 4096, max_path: int = 0, heap_capacity: int = 0, device: int = 0):
+    def __init__(self, grid, slots: int = 16384, max_path: int = 0, heap_capacity: int = 0, device: int = 0,
+                 memory_budget: Optional[int] = None, expect_queries: int = 256):
+        """``slots``: most searches run side by side (one per thread: throughput follows the searches in flight, run Z
+        in profiles/r02_variants.md).  The device arrays are sized for ``expect_queries`` at first and grown when a
+        larger batch arrives, so a single ``astar_pixel`` call does not allocate gigabytes."""
         _lib.require_gpu()
+        if memory_budget is not None:           # bytes
+            self.MEMORY_BUDGET = int(memory_budget)
         self.grid = _u8(grid)
         self.H, self.W = self.grid.shape
         self.max_slots, self.device = int(slots), int(device)
-        self.slots = self.max_slots
+        self.slots = 0
         self._h = C.c_void_p()
-        self._make(int(max_path), int(heap_capacity))
+        self._make(int(max_path), int(heap_capacity), int(expect_queries))
 
-    def _fit_slots(self, heap_capacity: int) -> int:
-        """As many side-by-side searches as the memory budget holds (a 600 x 600 map at 4096 slots would be
-        ~30 GB; after a capacity retry the heaps are 4x larger and the slot count shrinks accordingly)."""
+    def _fit_slots(self, heap_capacity: int, want: int) -> int:
+        """As many side-by-side searches as asked for, as the memory budget holds (a 600 x 600 map at 4096 slots would
+        be ~30 GB; after a capacity retry the heaps are 4x larger and the slot count shrinks accordingly)."""
         cells = self.H * self.W
         heap = heap_capacity if heap_capacity > 0 else cells // 2 + 1024          # sage_planner_create's default
         per_slot = 12 * cells + 16 * heap
-        return int(max(1, min(self.max_slots, self.MEMORY_BUDGET // max(per_slot, 1))))
+        want = 1 << max(8, int(max(want, 1) - 1).bit_length())                     # >= 256, power of two
+        return int(max(1, min(self.max_slots, want, self.MEMORY_BUDGET // max(per_slot, 1))))
 
-    def _make(self, max_path: int, heap_capacity: int):
+    def _make(self, max_path: int, heap_capacity: int, want: int):
         self.close()
-        self.slots = self._fit_slots(heap_capacity)
+        self._asked = (max_path, heap_capacity)
+        self.slots = self._fit_slots(heap_capacity, want)
         h = C.c_void_p()
         check(_lib.lib().sage_planner_create(C.byref(h), self.device, self.grid.ctypes.data, self.H, self.W,
                                              self.slots, max_path, heap_capacity))
@@ -125,6 +133,8 @@ class GridPlanner:
         out: List[Optional[np.ndarray]] = [None] * Q
         nexp_all = np.zeros(Q, np.int64)
         todo = np.arange(Q)
+        if Q > self.slots and self._fit_slots(self._asked[1], Q) > self.slots:     # a larger batch than any before: more slots
+            self._make(self._asked[0], self._asked[1], Q)
         for _ in range(6):
             if todo.size == 0:
                 break
@@ -138,7 +148,7 @@ class GridPlanner:
                     redo.append(q)
             todo = np.asarray(redo, dtype=np.int64)
             if todo.size:
-                self._make(min(self.max_path * 4, self.H * self.W), min(self.heap_capacity * 4, 8 * self.H * self.W + 16))
+                self._make(min(self.max_path * 4, self.H * self.W), min(self.heap_capacity * 4, 8 * self.H * self.W + 16), todo.size)
         if todo.size:
             raise SageError("A* search exceeded the planner's capacity even at the theoretical maximum")
         return (out, nexp_all) if want_expansions else out
