@@ -602,8 +602,10 @@ class SimpleVLNEnv:
         self._yaw += total_dyaw
         self._yaw = ((self._yaw + math.pi) % (2 * math.pi)) - math.pi
         self._update_camera_position()
-        self.perf["collide_s"] += time.perf_counter() - t_apply
+        t_pre = time.perf_counter()
+        self.perf["collide_s"] += t_pre - t_apply
         self._prefetch()
+        self.perf["prefetch_s"] = self.perf.get("prefetch_s", 0.0) + (time.perf_counter() - t_pre)
 
     def _safe_gradual_movement(self, start_pos, target_pos, target_distance) -> float:
         current_pos = self._pos.copy()

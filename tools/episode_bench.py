@@ -141,6 +141,8 @@ def main():
         "depth_mean_m": float(depth.mean()),
         "engine_frames": env.render_calls, "collide_launches": env.collide_launches, "steps_that_moved": moved,
         "frame_shape": list(rgb.shape), "depth_range": [float(depth.min()), float(depth.max())],
+        "facade_perf": {k: (round(v, 6) if isinstance(v, float) else v) for k, v in env.perf.items() if not k.endswith("_t")},
+        "pipeline_depth": int(getattr(env._scene, "pipeline_depth", 0)),
     }
     print(json.dumps(out))
 
