@@ -398,15 +398,17 @@ extern "C" int sage_debug_composite_profile(uint32_t* host, int n_warps)
 #endif
 
 // Entries per trip: 2 where the frame is many waves of CTAs (the SMs stay full, the kernel is issue-bound and a wider
-// trip only adds alpha evaluations nobody needed), 4 for frames of at most SAGE_COMPOSITE_WIDE_MAX_CTAS CTAs (640 x 480:
-// 1200 CTAs, a single wave - the kernel's time is its longest walk, latency-bound).
+// trip only adds alpha evaluations nobody needed), 4 for WHOLE frames of at most SAGE_COMPOSITE_WIDE_MAX_CTAS CTAs (640 x 480:
+// 1200 CTAs, a single wave - the kernel's time is its longest walk, latency-bound, and the caller of such a frame is the
+// synchronous facade: run CC, 1449 against 1366 agent steps/s).  A tile-row block of a multi-GPU split is as small, but
+// its rank keeps six frames in flight and lives on throughput: E = 2 turns a block over 3 - 5 % faster (run DD).
 static int g_wide_max_ctas = 2400;
 
-void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st)
+void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, bool whole_frame, cudaStream_t st)
 {
     if (n_bins <= 0) return;
     const int ctas = n_bins * C_HALVES;
-    if (ctas <= g_wide_max_ctas) SAGE_KLAUNCH(k_composite<4>, ctas, C_THREADS, st, fr, sorted_vals);
+    if (whole_frame && ctas <= g_wide_max_ctas) SAGE_KLAUNCH(k_composite<4>, ctas, C_THREADS, st, fr, sorted_vals);
     else SAGE_KLAUNCH(k_composite<2>, ctas, C_THREADS, st, fr, sorted_vals);
 }
 

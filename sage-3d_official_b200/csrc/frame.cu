@@ -98,7 +98,7 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
             cudaStreamWaitEvent(cs, fork_join[3], 0);
             cudaStreamWaitEvent(cs, fork_join[2], 0);
         }
-        sage_launch_composite(fr, fr.ival[ires], n_bins, cs);
+        sage_launch_composite(fr, fr.ival[ires], n_bins, shape.whole_frame != 0, cs);
         launches += 1;
         MARK(6);
     } else {
@@ -111,7 +111,7 @@ int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFr
             cudaEventRecord(fork_join[3], fs);
             cudaStreamWaitEvent(cs, fork_join[3], 0);
         }
-        if (n_bins > 0) { sage_launch_composite(fr, fr.ival[0], n_bins, cs); launches += 1; }
+        if (n_bins > 0) { sage_launch_composite(fr, fr.ival[0], n_bins, shape.whole_frame != 0, cs); launches += 1; }
         MARK(6);
     }
 #undef MARK

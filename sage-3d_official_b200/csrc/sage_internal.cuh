@@ -384,7 +384,7 @@ size_t sage_sort_matrix_words(int64_t capacity);
 
 void sage_launch_emit(const SageFrame& fr, const uint32_t* order, cudaStream_t st);
 void sage_launch_bin_order(const SageFrame& fr, cudaStream_t st);
-void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, cudaStream_t st);
+void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, bool whole_frame, cudaStream_t st);
 
 // One whole frame (every launch between the parameter upload and the counter read-back): the front
 // half on stream `fs`, the view-dependent colours on `ss`, the composite on the caller's stream
@@ -395,6 +395,7 @@ struct SageFrameShape {
     int depth_bits;      // significant bits of the depth keys
     int tile_passes;     // passes of the by-tile sort
     int tile_digit_bits; // digit width of those passes (5..8)
+    int whole_frame;     // the rows are the whole frame (not a tile-row block of a multi-GPU split)
 };
 int sage_frame_enqueue(const SageSceneDev& sc, const SageFrame& fr, const SageFrameShape& shape,
                        const uint32_t* n_dev, cudaStream_t cs, cudaStream_t fs, cudaStream_t ss,

@@ -347,6 +347,7 @@ static int render_impl(sage_scene* s, int ci, const sage_camera* cam, int row0, 
     shape.depth_bits = depth_key_bits(cd);
     shape.tile_passes = cd.tile_passes;
     shape.tile_digit_bits = cd.tile_digit_bits;
+    shape.whole_frame = (row0 == 0 && row1 >= cd.tiles_y) ? 1 : 0;
     {
         int rb = 0, np = 0;
         sage_sort_shape(shape.depth_bits, &rb, &np);
