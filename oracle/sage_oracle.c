@@ -389,12 +389,31 @@ int so_render(const so_camera* cam, int64_t n, int deg, const float* xyz, const 
         int32_t* rect = (int32_t*)malloc((size_t)(V > 0 ? V : 1) * 4 * sizeof(int32_t));
         if (!cnt || !rect) { free(cnt); free(rect); free(order); free(sp); free(vis); return 2; }
         /* conservative pixel bbox in double: alpha >= 1/255 needs d^T conic d <= 2 ln(255 o);
-           1 % + 1 px of slack swallows every binary32 rounding in the blend path. */
+           1 % + 1 px of slack swallows the binary32 rounding of the blend path for ordinary splats.  For needle-like
+           splats it does not: the exponent's terms (|qa| dx^2, |qb dx dy|, |qc| dy^2) reach 1e5 - 1e6 where their
+           sum is ~ -8, so the ROUNDED exponent of the spec passes the threshold up to ~10 % beyond the exact ellipse
+           along the needle (found by tests/test_render_parity_gpu.py::test_needle_splats..., where this mode dropped a
+           contribution the brute-force mode - the definition - and the GPU both had).  Hence a second box from the
+           rounded conic deflated by that rounding allowance, eps (|term| sum) with |dx dy| <= (dx^2 + dy^2) / 2:
+           A' = A - eps (A + |B|), C' = C - eps (C + |B|); unbounded when the deflated form is no longer definite. */
         for (int64_t r = 0; r < V; ++r) {
             const so_splat* s = &sp[order[r].idx];
             double tau = 2.0 * (((double)s->lo - (double)SO_L255) / 1.4426950408889634) * 1.01 + 0.01;
             if (tau < 0.01) tau = 0.01;
             double hx = sqrt(tau * (double)s->cov_a) + 1.0, hy = sqrt(tau * (double)s->cov_c) + 1.0;
+            {
+                const double eps = 1e-6;
+                double A = -(double)s->qa, B = -0.5 * (double)s->qb, C = -(double)s->qc;
+                const double t2 = ((double)s->lo - (double)SO_L255) * 1.01 + 0.02;
+                A -= eps * (A + fabs(B)); C -= eps * (C + fabs(B));
+                const double det = A * C - B * B;
+                if (!(det > 0.0) || !(A > 0.0) || !(C > 0.0)) { hx = 1e30; hy = 1e30; }
+                else if (t2 > 0.0) {
+                    const double hx2 = sqrt(t2 * C / det) * 1.001 + 1.0, hy2 = sqrt(t2 * A / det) * 1.001 + 1.0;
+                    if (!(hx2 <= hx)) hx = hx2;
+                    if (!(hy2 <= hy)) hy = hy2;
+                }
+            }
             double x0 = floor(((double)s->gx - hx) / SO_TILE), x1 = floor(((double)s->gx + hx) / SO_TILE);
             double y0 = floor(((double)s->gy - hy) / SO_TILE), y1 = floor(((double)s->gy + hy) / SO_TILE);
             int ix0 = x0 < 0 ? 0 : (x0 > TX ? TX : (int)x0), ix1 = x1 < -1 ? -1 : (x1 >= TX ? TX - 1 : (int)x1);

@@ -94,8 +94,9 @@ __device__ uint32_t g_cprof[CPROF_WARPS * CPROF_WORDS];
 __device__ __forceinline__ uint32_t cprof_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return (uint32_t)t; }
 #endif
 
-// E = entries of the stage blended per trip of the inner loop (2: frames of many waves of CTAs; 4: small frames)
-template <int E>
+// E = entries of the stage blended per trip of the inner loop (2: frames of many waves of CTAs; 4: small frames);
+// PRE = once per stage, a lane-parallel test of every entry against the box of the quadrant's live pixels comes first
+template <int E, bool PRE>
 __global__ void __launch_bounds__(C_THREADS, E <= 2 ? C_CTAS_PER_SM : C_CTAS_PER_SM_WIDE)
 k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 {
@@ -155,7 +156,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 #ifdef SAGE_COMPOSITE_PROFILE
         const long long prof_c0 = clock64();
         const uint32_t prof_t0 = cprof_ns();
-        uint32_t prof_visited = 0, prof_hits = 0;
+        uint32_t prof_visited = 0, prof_hits = 0, prof_cand = 0;
 #endif
         // The walk, in three decoupled steps:
         //   scan    the tile's list C_SCAN x 32 entries at a time (loads issued one step ahead); the ids of the entries
@@ -202,9 +203,9 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
                 float4* dst = &srec[w][stage][lane * 3];
                 cp_async16(dst, src); cp_async16(dst + 1, src + 1); cp_async16(dst + 2, src + 2);
             }
-            // count not a multiple of E: the entry loop reads the slots up to the next multiple as (masked) partners of
-            // the last entries - whatever is left there from an earlier stage, their colours must be finite
-            if (E > 1 && lane >= c && lane < ((c + E - 1) & ~(E - 1))) srec[w][stage][lane * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            // count not a multiple of E: the index walk (!PRE) reads the slots up to the next multiple as masked partners of
+            // the last entries - whatever an earlier stage left there, their colours must be finite
+            if (!PRE && E > 1 && lane >= c && lane < ((c + E - 1) & ~(E - 1))) srec[w][stage][lane * 3 + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             cp_async_commit();                             // (possibly empty: keeps the group count uniform)
             q_head += (uint32_t)c;
             return c;
@@ -225,76 +226,145 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
 #ifdef SAGE_COMPOSITE_PROFILE
             prof_visited += (uint32_t)cnt;
 #endif
-            for (int j0 = 0; j0 < cnt; j0 += C_LIVE_CHECK) {
-                const int j1 = min(j0 + C_LIVE_CHECK, cnt);
-                // E entries per trip: their exponents and alphas are evaluated side by side (E independent dependency
-                // chains in one basic block), then the E blends run in order.  A warp is latency-bound on this loop
-                // whenever it has its scheduler to itself - the tail of every frame, most of a small frame (run X: 130
-                // cycles per skipped and 270 per blended entry, one at a time) - and E chains overlap; where the kernel is
-                // issue-bound the price is the alpha path of an entry no lane needed whenever a partner needed it.
-                for (int j = j0; j < j1; j += E) {
-                    float2 pw[E];
-                    bool v0[E], v1[E], any = false;
-#pragma unroll
-                    for (int u = 0; u < E; ++u) {
-                        const float4 a = s_rec[3 * (j + u)];                                  // gx gy qa lo
-                        const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * (j + u) + 1]);   // qb qc
-                        const float dy = pyc - a.y;
-                        const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
-                        const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
-                        const float2 dx = __fadd2_rn(pxc, f2(-a.x));
-                        const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
-                        pw[u] = __ffma2_rn(dx, wv, f2(c2));                                   // log2(alpha)
-                        const bool has = (E == 1) || (u == 0) || (j + u < cnt);               // warp-uniform (slots past cnt are stale)
-                        v0[u] = has && pw[u].x >= SAGE_L255;                                  // false for NaN (finished pixels)
-                        v1[u] = has && pw[u].y >= SAGE_L255;
-                        any = any || v0[u] || v1[u];
+            // Which entries of the stage can reach a pixel that is still live?  PRE: one entry per lane against the
+            // bounding box of the quadrant's live pixels - the exact maximum of the (concave) exponent over the box, on
+            // its four edges, plus a rounding allowance - so the serial loop below only walks the survivors.  In the
+            // walks that make the kernel's tail two thirds of the gathered entries touch nothing that is still live
+            // (profiles/r02_variants.md) and each costs the serial loop a full dependency chain; here they cost one
+            // lane a few dozen independent flops.  Skipping is exact: an entry is dropped only if no live pixel can
+            // pass the alpha >= 1/255 test, and pixels only ever leave the live set during the stage.
+            unsigned cand = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+            if (PRE) {
+                const bool l0 = pxc.x == pxc.x, l1 = pxc.y == pxc.y;
+                const uint32_t INF_U = 0x7f800000u;                            // pixel centres are positive: uint order = float order
+                const uint32_t ux0 = l0 ? __float_as_uint(pxc.x) : (l1 ? __float_as_uint(pxc.y) : INF_U);
+                const uint32_t ux1 = l1 ? __float_as_uint(pxc.y) : (l0 ? __float_as_uint(pxc.x) : 0u);
+                const uint32_t uy0 = (l0 || l1) ? __float_as_uint(pyc) : INF_U, uy1 = (l0 || l1) ? __float_as_uint(pyc) : 0u;
+                const float X0 = __uint_as_float(__reduce_min_sync(0xffffffffu, ux0)), X1 = __uint_as_float(__reduce_max_sync(0xffffffffu, ux1));
+                const float Y0 = __uint_as_float(__reduce_min_sync(0xffffffffu, uy0)), Y1 = __uint_as_float(__reduce_max_sync(0xffffffffu, uy1));
+                bool keep = false;
+                if (lane < cnt) {
+                    const float4 a = s_rec[3 * lane];                                           // gx gy qa lo
+                    const float2 bq = *reinterpret_cast<const float2*>(&s_rec[3 * lane + 1]);     // qb qc
+                    const float ax0 = X0 - a.x, ax1 = X1 - a.x, ay0 = Y0 - a.y, ay1 = Y1 - a.y;   // the box, relative to the splat's centre
+                    const float qa = a.z, qb = bq.x, qc = bq.y;
+                    auto form = [&](float dx, float dy) { return dx * (qa * dx + qb * dy) + (qc * dy) * dy; };
+                    float fmax = 0.0f;                                                          // centre inside the box
+                    if (!(ax0 <= 0.0f && ax1 >= 0.0f && ay0 <= 0.0f && ay1 >= 0.0f)) {
+                        const float kc = (-0.5f * qb) / qc, ka = (-0.5f * qb) / qa;             // argmax of dy given dx: kc dx; of dx given dy: ka dy
+                        fmax = form(ax0, fminf(fmaxf(kc * ax0, ay0), ay1));
+                        fmax = fmaxf(fmax, form(ax1, fminf(fmaxf(kc * ax1, ay0), ay1)));
+                        fmax = fmaxf(fmax, form(fminf(fmaxf(ka * ay0, ax0), ax1), ay0));
+                        fmax = fmaxf(fmax, form(fminf(fmaxf(ka * ay1, ax0), ax1), ay1));
                     }
-#ifdef SAGE_COMPOSITE_PROFILE
-                    if (__any_sync(0xffffffffu, any)) prof_hits++;
-#endif
-                    if (!any) continue;
-                    float2 al[E];
-#pragma unroll
-                    for (int u = 0; u < E; ++u) {
-                        pw[u].x = fminf(pw[u].x, SAGE_L099);
-                        pw[u].y = fminf(pw[u].y, SAGE_L099);
-                        al[u] = sage_exp2_fast_x2(pw[u]);
-                        al[u].x = v0[u] ? al[u].x : 0.0f;          // alpha 0: T, C, Dz stay bit-identical
-                        al[u].y = v1[u] ? al[u].y : 0.0f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < E; ++u) {
-                        const float2 om = __ffma2_rn(al[u], f2(-1.0f), f2(1.0f));             // 1 - alpha
-                        float2 Tn = __fmul2_rn(T, om);
-                        float2 wgt = __fmul2_rn(al[u], T);
-                        // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
-                        // (ptxas if-converts this block into predicated instructions that issue for every splat; forcing a
-                        // real branch was measured 2 % slower, profiles/r02_variants.md.)
-                        if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
-                            const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
-                            wgt.x = s0 ? 0.0f : wgt.x;
-                            wgt.y = s1 ? 0.0f : wgt.y;
-                            Tn.x = s0 ? T.x : Tn.x;
-                            Tn.y = s1 ? T.y : Tn.y;
-                            pxc.x = s0 ? NAN_X : pxc.x;
-                            pxc.y = s1 ? NAN_X : pxc.y;
-#pragma unroll
-                            for (int u2 = u + 1; u2 < E; ++u2) {                              // finished: the later entries of the trip no longer see the pixel
-                                al[u2].x = s0 ? 0.0f : al[u2].x;
-                                al[u2].y = s1 ? 0.0f : al[u2].y;
-                            }
-                        }
-                        T = Tn;
-                        const float4 c = s_rec[3 * (j + u) + 2];                              // r g b z
-                        Cr = __ffma2_rn(f2(c.x), wgt, Cr);
-                        Cg = __ffma2_rn(f2(c.y), wgt, Cg);
-                        Cb = __ffma2_rn(f2(c.z), wgt, Cb);
-                        Dz = __ffma2_rn(f2(c.w), wgt, Dz);
-                    }
+                    // allowance for the binary32 rounding of this bound and of the loop's own exponent (a few ulp of the
+                    // largest term each; thin diagonal splats cancel terms of 1e5 - 1e6 down to ~10)
+                    const float mx = fmaxf(fabsf(ax0), fabsf(ax1)), my = fmaxf(fabsf(ay0), fabsf(ay1));
+                    const float mag = fabsf(qa) * mx * mx + fabsf(qb) * mx * my + fabsf(qc) * my * my;
+                    keep = !(a.w + fmax + (0.02f + 2e-6f * mag) < SAGE_L255);                   // (NaN anywhere: keep)
                 }
-                if (!__any_sync(0xffffffffu, SAGE_LIVE())) { cnt_next = 0; break; }      // every pixel of the quadrant is finished
+                cand = __ballot_sync(0xffffffffu, keep);
             }
+#ifdef SAGE_COMPOSITE_PROFILE
+            prof_cand += (uint32_t)__popc(cand);
+#endif
+            // E entries per trip: their exponents and alphas are evaluated side by side (E independent dependency
+            // chains in one basic block), then the E blends run in order.  A warp is latency-bound on this loop
+            // whenever it has its scheduler to itself - the tail of every frame, most of a small frame (run X: 130
+            // cycles per skipped and 270 per blended entry, one at a time) - and E chains overlap; where the kernel is
+            // issue-bound the price is the alpha path of an entry no lane needed whenever a partner needed it.
+            // one trip: rp[u] -> the 48-byte record of entry u of the trip, has_u[u]: it exists (warp-uniform)
+            auto blend_trip = [&](const float4* const (&rp)[E], const bool (&has_u)[E]) {
+                float2 pw[E];
+                bool v0[E], v1[E], any = false;
+#pragma unroll
+                for (int u = 0; u < E; ++u) {
+                    const float4 a = rp[u][0];                                  // gx gy qa lo
+                    const float2 bq = *reinterpret_cast<const float2*>(&rp[u][1]);   // qb qc
+                    const float dy = pyc - a.y;
+                    const float2 t2 = __fmul2_rn(bq, f2(dy));                             // bdy, cdy
+                    const float c2 = fmaf(t2.y, dy, a.w);                                 // cdy dy + lo
+                    const float2 dx = __fadd2_rn(pxc, f2(-a.x));
+                    const float2 wv = __ffma2_rn(f2(a.z), dx, f2(t2.x));
+                    pw[u] = __ffma2_rn(dx, wv, f2(c2));                                   // log2(alpha)
+                    const bool has = (u == 0) || has_u[u];                                 // warp-uniform (a missing partner is masked)
+                    v0[u] = has && pw[u].x >= SAGE_L255;                                  // false for NaN (finished pixels)
+                    v1[u] = has && pw[u].y >= SAGE_L255;
+                    any = any || v0[u] || v1[u];
+                }
+#ifdef SAGE_COMPOSITE_PROFILE
+                if (__any_sync(0xffffffffu, any)) prof_hits++;
+#endif
+                if (!any) return;
+                float2 al[E];
+#pragma unroll
+                for (int u = 0; u < E; ++u) {
+                    pw[u].x = fminf(pw[u].x, SAGE_L099);
+                    pw[u].y = fminf(pw[u].y, SAGE_L099);
+                    al[u] = sage_exp2_fast_x2(pw[u]);
+                    al[u].x = v0[u] ? al[u].x : 0.0f;          // alpha 0: T, C, Dz stay bit-identical
+                    al[u].y = v1[u] ? al[u].y : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < E; ++u) {
+                    const float2 om = __ffma2_rn(al[u], f2(-1.0f), f2(1.0f));             // 1 - alpha
+                    float2 Tn = __fmul2_rn(T, om);
+                    float2 wgt = __fmul2_rn(al[u], T);
+                    // stop: the splat would push T below 1e-4 -> the pixel is finished, the splat not blended.
+                    // (ptxas if-converts this block into predicated instructions that issue for every splat; forcing a
+                    // real branch was measured 2 % slower, profiles/r02_variants.md.)
+                    if (fminf(Tn.x, Tn.y) < SAGE_T_MIN) {
+                        const bool s0 = Tn.x < SAGE_T_MIN, s1 = Tn.y < SAGE_T_MIN;
+                        wgt.x = s0 ? 0.0f : wgt.x;
+                        wgt.y = s1 ? 0.0f : wgt.y;
+                        Tn.x = s0 ? T.x : Tn.x;
+                        Tn.y = s1 ? T.y : Tn.y;
+                        pxc.x = s0 ? NAN_X : pxc.x;
+                        pxc.y = s1 ? NAN_X : pxc.y;
+#pragma unroll
+                        for (int u2 = u + 1; u2 < E; ++u2) {                              // finished: the later entries of the trip no longer see the pixel
+                            al[u2].x = s0 ? 0.0f : al[u2].x;
+                            al[u2].y = s1 ? 0.0f : al[u2].y;
+                        }
+                    }
+                    T = Tn;
+                    const float4 c = rp[u][2];                              // r g b z
+                    Cr = __ffma2_rn(f2(c.x), wgt, Cr);
+                    Cg = __ffma2_rn(f2(c.y), wgt, Cg);
+                    Cb = __ffma2_rn(f2(c.z), wgt, Cb);
+                    Dz = __ffma2_rn(f2(c.w), wgt, Dz);
+                }
+            };
+            if (PRE) {
+                for (int trips = 0; cand != 0u; ) {                // the surviving entries, in list order
+                    const float4* rp[E];
+                    bool has_u[E];
+#pragma unroll
+                    for (int u = 0; u < E; ++u) {
+                        has_u[u] = cand != 0u;
+                        rp[u] = has_u[u] ? s_rec + 3 * (__ffs((int)cand) - 1) : rp[0];
+                        cand &= cand - 1u;                         // (0 & 0xffffffff = 0)
+                    }
+                    blend_trip(rp, has_u);
+                    if (((++trips) & (C_LIVE_CHECK / E - 1)) == 0 && cand != 0u && !__any_sync(0xffffffffu, SAGE_LIVE())) break;
+                }
+            } else {
+                for (int j0 = 0; j0 < cnt; j0 += C_LIVE_CHECK) {   // every entry of the stage, by index
+                    const int j1 = min(j0 + C_LIVE_CHECK, cnt);
+                    for (int j = j0; j < j1; j += E) {
+                        const float4* rp[E];
+                        bool has_u[E];
+#pragma unroll
+                        for (int u = 0; u < E; ++u) {
+                            has_u[u] = j + u < cnt;                // (a slot past cnt is stale, masked; its colour was zeroed by the gather)
+                            rp[u] = s_rec + 3 * (j + u);
+                        }
+                        blend_trip(rp, has_u);
+                    }
+                    if (j1 < cnt && !__any_sync(0xffffffffu, SAGE_LIVE())) break;
+                }
+            }
+            if (!__any_sync(0xffffffffu, SAGE_LIVE())) cnt_next = 0;       // every pixel of the quadrant is finished: the walk ends here
             __syncwarp();                                  // stage st is free for the gather after next
         }
         cp_async_wait<0>();                                // nothing may land in the stages after this bin
@@ -306,7 +376,7 @@ k_composite(SageFrame fr, const uint32_t* __restrict__ vals)
             if (wid < (uint32_t)CPROF_WARPS) {
                 uint32_t* o = g_cprof + (size_t)wid * CPROF_WORDS;
                 o[0] = (uint32_t)(clock64() - prof_c0); o[1] = prof_visited; o[2] = min(scan, n); o[3] = prof_hits;
-                o[4] = prof_t0; o[5] = cprof_ns(); o[6] = n; o[7] = (uint32_t)bin;
+                o[4] = prof_t0; o[5] = cprof_ns(); o[6] = n; o[7] = prof_cand;
             }
         }
 #endif
@@ -403,20 +473,36 @@ extern "C" int sage_debug_composite_profile(uint32_t* host, int n_warps)
 // synchronous facade: run CC, 1449 against 1366 agent steps/s).  A tile-row block of a multi-GPU split is as small, but
 // its rank keeps six frames in flight and lives on throughput: E = 2 turns a block over 3 - 5 % faster (run DD).
 static int g_wide_max_ctas = 2400;
+// The per-stage box test (PRE) pays where walks are long and mostly miss: together with E = 4 on whole frames of a single wave
+// of CTAs (640 x 480: composite 0.216 -> 0.188 ms, frames/s +2 %, frame latency 0.51 -> 0.49 ms, run II).  With E = 2 its
+// candidate walk (a find-first-set per entry instead of an index) is not won back: 1024 x 768 -3 % frames/s, 1080p -6 %.
+// SAGE_COMPOSITE_PREFILTER: 1 always, 0 never, unset: exactly the launches that get E = 4.
+static int g_prefilter = -1;
 
 void sage_launch_composite(const SageFrame& fr, const uint32_t* sorted_vals, int n_bins, bool whole_frame, cudaStream_t st)
 {
     if (n_bins <= 0) return;
     const int ctas = n_bins * C_HALVES;
-    if (whole_frame && ctas <= g_wide_max_ctas) SAGE_KLAUNCH(k_composite<4>, ctas, C_THREADS, st, fr, sorted_vals);
-    else SAGE_KLAUNCH(k_composite<2>, ctas, C_THREADS, st, fr, sorted_vals);
+    const bool wide = whole_frame && ctas <= g_wide_max_ctas;
+    const bool pre = g_prefilter >= 0 ? g_prefilter == 1 : wide;
+    if (wide) {
+        if (pre) SAGE_KLAUNCH((k_composite<4, true>), ctas, C_THREADS, st, fr, sorted_vals);
+        else SAGE_KLAUNCH((k_composite<4, false>), ctas, C_THREADS, st, fr, sorted_vals);
+    } else {
+        if (pre) SAGE_KLAUNCH((k_composite<2, true>), ctas, C_THREADS, st, fr, sorted_vals);
+        else SAGE_KLAUNCH((k_composite<2, false>), ctas, C_THREADS, st, fr, sorted_vals);
+    }
 }
 
 void sage_composite_configure(void)
 {
 #ifndef SAGE_CUDA_EMU
-    sage_prefer_smem(k_composite<2>);
-    sage_prefer_smem(k_composite<4>);
+    sage_prefer_smem(k_composite<2, false>);
+    sage_prefer_smem(k_composite<2, true>);
+    sage_prefer_smem(k_composite<4, false>);
+    sage_prefer_smem(k_composite<4, true>);
 #endif
     if (const char* v = getenv("SAGE_COMPOSITE_WIDE_MAX_CTAS")) g_wide_max_ctas = atoi(v);
+    if (const char* v = getenv("SAGE_COMPOSITE_PREFILTER")) g_prefilter = atoi(v);
+
 }

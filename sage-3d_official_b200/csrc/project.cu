@@ -151,7 +151,9 @@ k_project(SageSceneDev sc, SageFrame fr)
                 // three orders above the rounding of the few operations involved.
                 const float l2 = lo - SAGE_L255;                 // log2(255 o)
                 const float t2 = l2 * 1.003f + 0.02f;
-                const float A = -qa, Bq = -0.5f * qb, Cq = -qc;
+                float A = -qa, Cq = -qc;
+                const float Bq = -0.5f * qb;
+                sage_conic_deflate(&A, Bq, &Cq);                 // (the rounded exponent reaches further than the exact one: sage_internal.cuh)
                 const float det2 = sage_det_kahan(A, Cq, Bq);
                 const bool unbounded = !(det2 > 0.0f) || !(A > 0.0f) || !(Cq > 0.0f);
                 float hx = unbounded ? 1e30f : sqrtf(t2 * Cq / det2);

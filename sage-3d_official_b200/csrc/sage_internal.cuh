@@ -176,6 +176,20 @@ __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int
     return (ix0 / 16 != ix1 / 16) && (iy0 / 16 != iy1 / 16);
 }
 
+// The blend evaluates the exponent in binary32: at an offset d from the centre its rounding error is a few ulp of the
+// LARGEST term (|qa| dx^2, |qb dx dy|, |qc| dy^2), which for needle-like splats is 1e5 - 1e6 times the sum - the rounded
+// exponent of the spec can pass the 1/255 threshold up to ~10 % beyond the exact ellipse along the needle.  Culling has to
+// bound where the ROUNDED exponent can pass: the ellipse of the conic deflated by that allowance, with
+// |dx dy| <= (dx^2 + dy^2) / 2:  A' = A - eps (A + |B|),  C' = C - eps (C + |B|)  (eps = 1e-6, four times the worst case of
+// the blend's operation sequence).  When the deflated form is no longer definite the caller covers everything.
+#define SAGE_CULL_EPS 1e-6f
+__device__ __forceinline__ void sage_conic_deflate(float* A, float B, float* C)
+{
+    const float ab = fabsf(B);
+    *A -= SAGE_CULL_EPS * (*A + ab);
+    *C -= SAGE_CULL_EPS * (*C + ab);
+}
+
 // A C - B^2 without the cancellation of the plain form (Kahan): w = B B rounded, e = its rounding error (exact,
 // by fma), f = A C - w fused; the sum is within ~2 ulp of the true determinant
 __device__ __forceinline__ float sage_det_kahan(float A, float C, float B)
@@ -201,6 +215,7 @@ __device__ __forceinline__ SageBand sage_band_make(float gx, float gy, float qa,
     b.t2 = l2 * 1.003f + 0.02f;
     b.gx = gx; b.gy = gy;
     b.A = -qa; b.B = -0.5f * qb; b.C = -qc;
+    sage_conic_deflate(&b.A, b.B, &b.C);
     b.det2 = sage_det_kahan(b.A, b.C, b.B);
     b.unbounded = (!(b.det2 > 0.0f) || !(b.A > 0.0f) || !(b.C > 0.0f) || !(b.t2 > 0.0f)) ? 1 : 0;
     b.hx = b.unbounded ? 1e30f : sqrtf(b.t2 * b.C / b.det2);

@@ -138,3 +138,17 @@ def test_exp2_polynomial_accuracy(oracle):
     got = np.array([oracle.exp2(float(x)) for x in xs])
     assert np.max(np.abs(got / 2.0 ** xs - 1)) < 4e-7
     assert oracle.exp2(-1000.0) < 1e-37 and oracle.exp2(0.0) == pytest.approx(1.0, abs=2e-7)
+
+
+def test_oracle_tile_mode_equals_brute_force_on_needle_splats(sage, oracle):
+    """The oracle's tile-list mode is an acceleration of its brute-force mode (every splat against every pixel: the
+    definition).  Needle-like splats are where a bounding box from the exact ellipse is NOT enough - the binary32
+    exponent's rounding passes the 1/255 test beyond it (seed 2 at 1080p, pixel (462, 974), until round 2)."""
+    from conftest import oracle_camera
+    from test_render_parity_gpu import needle_scene
+    for seed, res in ((2, (1920, 1080)), (0, (640, 480)), (1, (640, 480)), (3, (333, 187))):
+        cloud, cam = needle_scene(sage, seed, *res)
+        oc = oracle_camera(oracle, cam)
+        a_rgb, a_dep, _ = oracle.render(oc, *cloud.as_tuple())
+        b_rgb, b_dep, _ = oracle.render(oc, *cloud.as_tuple(), brute=True)
+        assert np.array_equal(a_rgb, b_rgb) and np.array_equal(a_dep.view(np.uint32), b_dep.view(np.uint32)), (seed, res)

@@ -168,6 +168,7 @@ def test_composite_both_trip_widths(sage, oracle, monkeypatch, wide_max):
     per launch from the CTA count.  Force each instantiation on frames that would get the other: long lists whose
     length is not a multiple of the trip width, early saturation inside a trip, a 640 x 480 frame and a 1080p one."""
     monkeypatch.setenv("SAGE_COMPOSITE_WIDE_MAX_CTAS", wide_max)        # read when a scene is created
+    monkeypatch.setenv("SAGE_COMPOSITE_PREFILTER", "1" if wide_max == "0" else "0")   # and the per-stage box test on frames that would not get it / off where they would
     rng = np.random.default_rng(12)
     n = 7001
     cloud, _ = sage.synthetic_room(6, n)
@@ -180,6 +181,38 @@ def test_composite_both_trip_widths(sage, oracle, monkeypatch, wide_max):
     room, _ = sage.synthetic_room(0, 50_000)
     _check_frame(sage, oracle, room, sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 640, 480))
     _check_frame(sage, oracle, room, sage.Camera.look_heading((5.2, 3.4, 1.2), np.radians(-135.0), 1920, 1080))
+
+
+def needle_scene(sage, seed, W, H):
+    """Needle-like splats (metres long, a millimetre thin, every orientation) in front of and behind opaque blobs:
+    exponents whose terms cancel from 1e5 - 1e6 down to ~10 far from the splat's centre, on quadrants whose live set
+    shrinks to a few pixels - what the composite's per-stage box test (composite.cu, PRE) must stay conservative on."""
+    rng = np.random.default_rng(4200 + seed)
+    n = 2400
+    cloud, _ = sage.synthetic_room(seed, n)
+    k = n // 2
+    cloud.xyz[:, 0] = rng.uniform(1.0, 5.0, n).astype(np.float32)
+    cloud.xyz[:, 1] = rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    cloud.xyz[:, 2] = rng.uniform(0.4, 2.0, n).astype(np.float32)
+    cloud.log_scale[:k] = np.array([1.0, -7.0, -7.0], np.float32) + rng.uniform(-0.5, 0.5, size=(k, 3)).astype(np.float32)
+    cloud.log_scale[k:] = rng.uniform(-3.5, -1.5, size=(n - k, 3)).astype(np.float32)      # blobs, 3 - 20 cm
+    cloud.quat[:] = rng.normal(size=(n, 4)).astype(np.float32)
+    cloud.opacity[:k] = rng.uniform(-3.0, 2.0, k).astype(np.float32)
+    cloud.opacity[k:] = rng.uniform(0.0, 6.0, n - k).astype(np.float32)                   # many nearly opaque: pixels finish early
+    cam = sage.Camera.look_heading((0.0, 0.0, 1.2), 0.0, W, H)
+    return cloud, cam
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("res", [(640, 480), (1920, 1080)])
+@pytest.mark.parametrize("prefilter", ["0", "1"])
+def test_needle_splats_against_shrinking_live_sets(sage, oracle, monkeypatch, seed, res, prefilter):
+    """Seed 2 at 1080p is the frame on which the ORACLE's tile mode used to drop a contribution at a needle's tip (its
+    box came from the exact ellipse; the rounded exponent of the spec reaches further) - the GPU and the oracle's
+    brute-force mode agreed.  Both sides now cull against the conic deflated by the rounding allowance."""
+    monkeypatch.setenv("SAGE_COMPOSITE_PREFILTER", prefilter)
+    cloud, cam = needle_scene(sage, seed, *res)
+    _check_frame(sage, oracle, cloud, cam)
 
 
 def test_two_frames_in_flight_match_serial_frames(sage, oracle):

@@ -124,6 +124,28 @@ inline unsigned __ballot_sync(unsigned, int pred)
     return m;
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+inline unsigned __reduce_min_sync(unsigned, unsigned v)
+{
+    const int tid = cuda_emu::lin_tid(), w0 = tid & ~31;
+    cuda_emu::t_cta->slots[tid] = v;
+    cuda_emu::warp_sync();
+    unsigned r = 0xFFFFFFFFu;
+    for (int l = 0; l < 32 && w0 + l < cuda_emu::t_cta->nthreads; ++l)
+        if ((unsigned)cuda_emu::t_cta->slots[w0 + l] < r) r = (unsigned)cuda_emu::t_cta->slots[w0 + l];
+    cuda_emu::warp_sync();
+    return r;
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v)
+{
+    const int tid = cuda_emu::lin_tid(), w0 = tid & ~31;
+    cuda_emu::t_cta->slots[tid] = v;
+    cuda_emu::warp_sync();
+    unsigned r = 0u;
+    for (int l = 0; l < 32 && w0 + l < cuda_emu::t_cta->nthreads; ++l)
+        if ((unsigned)cuda_emu::t_cta->slots[w0 + l] > r) r = (unsigned)cuda_emu::t_cta->slots[w0 + l];
+    cuda_emu::warp_sync();
+    return r;
+}
 inline int __all_sync(unsigned m, int pred)
 {
     const int tid = cuda_emu::lin_tid(), w0 = tid & ~31;
