@@ -670,6 +670,8 @@ def run_native(args):
         # against 148 SMs x 4 schedulers x the SM clock sampled during this run
         issue = None
         try:
+            if not (world == 1 and (W, H) == (1920, 1080) and args.n == 2_000_000):
+                raise KeyError("the committed instruction count is for the headline workload only")
             wi = float(tj[dom]["warp_instr"])
             mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
             peak_issue = 148 * 4 * mhz * 1e6
