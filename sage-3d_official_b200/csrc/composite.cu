@@ -19,8 +19,10 @@
 // while the next gather is in flight.  Every stage therefore holds 32 entries of this quadrant, however
 // sparse they are in the tile's list.  (Round 1 issued one 48-byte TMA bulk copy per record: UBLKCP is a
 // uniform-datapath instruction, so a warp issued its 32 copies one lane at a time — ~8 % of the kernel's
-// instructions.  A per-lane gather is what LDGSTS is for.)  The entry loop is warp-uniform: no ballots,
-// no masks.
+// instructions.  A per-lane gather is what LDGSTS is for.)  The entry loop is warp-uniform and blends E entries
+// per trip (their exponents and alphas side by side - the loop is bound by its own dependency chain whenever a
+// warp has its scheduler to itself); small whole frames also get a lane-parallel box test per stage (PRE) that
+// leaves only the entries which can still reach a live pixel for that loop.
 //
 // The blend: log2(alpha) = qa dx^2 + qb dx dy + qc dy^2 + lo with the opacity
 // already in the exponent; skip below log2(1/255); cap at log2(0.99); alpha by the degree-3
