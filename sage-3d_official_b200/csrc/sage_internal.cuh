@@ -182,7 +182,9 @@ __device__ __forceinline__ bool sage_box_cullable(int ix0, int ix1, int iy0, int
 // bound where the ROUNDED exponent can pass: the ellipse of the conic deflated by that allowance, with
 // |dx dy| <= (dx^2 + dy^2) / 2:  A' = A - eps (A + |B|),  C' = C - eps (C + |B|)  (eps = 1e-6, four times the worst case of
 // the blend's operation sequence).  When the deflated form is no longer definite the caller covers everything.
-#define SAGE_CULL_EPS 1e-6f
+#ifndef SAGE_CULL_EPS
+#define SAGE_CULL_EPS 1e-6f        /* (overridable so that tools/cuda_emu/run_band_check.py can show what happens without it) */
+#endif
 __device__ __forceinline__ void sage_conic_deflate(float* A, float B, float* C)
 {
     const float ab = fabsf(B);

@@ -80,3 +80,23 @@ def test_composite_box_bound_is_conservative():
     r = subprocess.run([sys.executable, str(tool), "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "wrong skips 0" in r.stdout
+
+
+def test_culling_is_conservative_against_the_rounded_exponent():
+    """tools/cuda_emu/run_band_check.py: K1a's pixel box and K2's band / quadrant-mask helpers (compiled from
+    csrc/sage_internal.cuh with g++) against the blend's own binary32 exponent at every pixel of a 1080p image, for
+    random splats from blobs to needles thousands of pixels long: no pixel that passes the alpha >= 1/255 test may lie
+    outside the box, in a tile that is not emitted, or in a quadrant whose bit is clear."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    from pathlib import Path
+    import pytest
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    tool = Path(__file__).resolve().parents[1] / "tools" / "cuda_emu" / "run_band_check.py"
+    r = subprocess.run([sys.executable, str(tool), "300", "7"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["violations"] == 0 and out["pixels_passing_the_rounded_test"] > 1_000_000
