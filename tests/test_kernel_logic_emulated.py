@@ -175,7 +175,12 @@ def test_render_pipeline_emulated_matches_oracle(oracle, sage, tmp_path_factory,
     cam = sage.Camera.look_heading((0.2, 2.0, 1.2), np.radians(180.0), 192, 112)      # footprints of hundreds of bins
     assert R.check(L, sage, oracle, wall, cam, "wall close-up")
     assert R.check(L, sage, oracle, wall.subset(np.zeros(0, np.int64)), cam, "empty")
-    # the composite's other instantiation (2 entries per trip; these small frames get 4 by default)
-    monkeypatch.setenv("SAGE_COMPOSITE_WIDE_MAX_CTAS", "0")
+    # the composite's other instantiations (these small whole frames get E = 4 + the per-stage box test by default)
     cam = sage.Camera.look_heading((1.5, 1.0, 1.2), np.radians(30.0), 160, 120)
-    assert R.check(L, sage, oracle, cloud, cam, "room, 2 entries per trip")
+    monkeypatch.setenv("SAGE_COMPOSITE_WIDE_MAX_CTAS", "0")
+    assert R.check(L, sage, oracle, cloud, cam, "room, 2 entries per trip, index walk")
+    monkeypatch.setenv("SAGE_COMPOSITE_PREFILTER", "1")
+    assert R.check(L, sage, oracle, cloud, cam, "room, 2 entries per trip, box test")
+    monkeypatch.delenv("SAGE_COMPOSITE_WIDE_MAX_CTAS")
+    monkeypatch.setenv("SAGE_COMPOSITE_PREFILTER", "0")
+    assert R.check(L, sage, oracle, cloud, cam, "room, 4 entries per trip, index walk")
