@@ -90,3 +90,24 @@ def test_trajectory_points_known_answer(sage):
     assert pts[0]["rotation"][2] == 0.0 and pts[0]["rotation"][3] == 1.0             # heading +x
     assert abs(pts[1]["rotation"][2] - np.sin(np.pi / 4)) < 1e-15                     # heading +y
     assert pts[2]["rotation"] == [0.0, 0.0, 0.0, 1.0] and pts[2]["focal_length"] == 7.0
+
+
+def test_planner_slots_follow_the_batch_and_the_memory_budget(sage):
+    """GridPlanner sizes its device arrays (12 B per cell + 16 B per heap entry, per search slot) by the largest batch it
+    has seen, never beyond its slot limit or its memory budget - a single astar_pixel call must not allocate gigabytes
+    (ADVICE round 1), a 16 384-query batch gets 16 384 searches in flight (throughput follows them: run Z)."""
+    from sage3d_official_b200.planner import GridPlanner
+    p = GridPlanner.__new__(GridPlanner)                 # the sizing rule alone: no device
+    p.H, p.W, p.max_slots = 201, 241, 16384
+    per_slot = 12 * 201 * 241 + 16 * (201 * 241 // 2 + 1024)
+    assert p._fit_slots(0, 1) == 256                      # one query: the smallest array
+    assert p._fit_slots(0, 300) == 512                    # next power of two
+    assert p._fit_slots(0, 16384) == 16384                # fits the default 16 GiB budget on this map
+    assert 16384 * per_slot < GridPlanner.MEMORY_BUDGET
+    p.MEMORY_BUDGET = 1 << 30
+    assert p._fit_slots(0, 16384) == (1 << 30) // per_slot
+    p.H, p.W = 600, 600                                   # a large map: the budget, not the batch, decides
+    p.MEMORY_BUDGET = 16 << 30
+    big = 12 * 360000 + 16 * (180000 + 1024)
+    assert p._fit_slots(0, 16384) == (16 << 30) // big
+    assert p._fit_slots(8 * 360000 + 16, 16384) == (16 << 30) // (12 * 360000 + 16 * (8 * 360000 + 16))   # after capacity retries
