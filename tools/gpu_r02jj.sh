@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU round-2 run JJ (1 GPU): final evidence pass - per-stage box test on frames of <= 4000 CTAs, conic deflated by the rounding
+# GPU round-2 run JJ (1 GPU): final evidence pass - per-stage box test on the E = 4 launches (an intermediate build of run HH still used it on frames of <= 4000 CTAs), conic deflated by the rounding
 # allowance in every culling step, needle-splat tests: tests, bench (default + k20 + reference arm), resolutions, ncu launch list +
 # full capture, facade.
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU round-2 run LL (8 GPUs): the tile-row split after the composite work (E = 2 index walk on blocks): N = 4 bench line.
+# GPU round-2 run LL (8 GPUs): the tile-row split after the composite work (E = 2 index walk on blocks): N = 8 bench line.
 mkdir -p gpurun_out
 T=r02ll
 Q="--steps 100 --warmup 20 --no-cpu-baseline --batch-scenes 0 --no-collide --no-handoff"
