@@ -174,7 +174,11 @@ def astar_pixel_batch(grid, starts, goals) -> List[Optional[List[Tuple[int, int]
 
 
 def astar_pixel(grid, start: Tuple[int, int], goal: Tuple[int, int]) -> Optional[List[Tuple[int, int]]]:
-    """Drop-in for vln_trajectory_generator.astar_pixel: list of (x, y) from start to goal, or None."""
+    """Drop-in for vln_trajectory_generator.astar_pixel: list of (x, y) from start to goal, or None.
+
+    One documented difference: a START outside the grid returns None here, while the reference - which keys its
+    scores by coordinate tuples - would expand from it (its callers only pass cells of the map: instance centroids
+    and free cells found on it, vln_trajectory_generator.py:309-344,487-559)."""
     return astar_pixel_batch(grid, [start], [goal])[0]
 
 
